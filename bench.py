@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- SBR env-steps/sec on N B200s, FP64 roofline fraction, next to the CPU scipy-odeint path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--envs-per-gpu M] [--mode rk4|dp45]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...)
+
+A "step" is one pass of the hot path over one batch: every env of the rank's shard advances by ONE SBR-v2
+env-step = one whole 12-h cycle = 528 PID intervals + settle/draw (gym_SBR_env2.py:131-171), in ONE kernel launch.
+Workload (BASELINE.json configs[4] at one GPU, named in config.workload): 2^20 envs per GPU, random DO set-point
+actions, per-env influent draws, one cycle each; envs are independent, so ranks shard them with no data-path
+collective ("scaling": "weak"); the only collective is an all_gather of 5 reward statistics per step.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the flop/byte accounting.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sbr_env_steps_per_sec"
+UNIT = "cycle-steps/s"          # one env-step of SBR-v2 = one 12-h cycle = 528 PID intervals (72 s each)
+INTERVALS_PER_CYCLE = 528
+
+# algorithmic flops (add/mul/div = 1, FMA = 2; CSE-minimal RHS)
+F_REACT, F_FILL = 66, 106
+OVH_REACT = 2 * (3 * 9 + 4 * 11)     # RK4 step: 3 stage-input + 4 accumulate FMAs over 9 / 11 active components
+OVH_FILL = 2 * (3 * 14 + 4 * 14)
+F_EPILOGUE = 400
+BYTES_PER_ENV = (14 + 14 + 3) * 8 + (14 + 3 + 1 + 12) * 8 + 4 + 8   # SoA reads + writes per env per cycle
+
+
+def cycle_flops_rk4(sched):
+    fill = sched.n_int[0] * sched.n_sub[0]
+    react = sum(sched.n_int[k] * sched.n_sub[k] for k in (1, 2, 3, 4, 7))
+    return fill * (4 * F_FILL + OVH_FILL) + react * (4 * F_REACT + OVH_REACT) + F_EPILOGUE, fill + react
+
+
+class ClockSampler(object):
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak(core, torch, device):
+    """Measured FP64 FMA-pipe peak (TFLOP/s): DFMA probe, 8 independent chains/thread, best of 5 (burst) and
+    the mean over a ~1 s back-to-back loop (sustained, under the power cap)."""
+    blocks, threads, iters = 148 * 16, 256, 20000
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        core.fp64_probe(blocks, threads, iters, device)
+    torch.cuda.synchronize()
+    best, flops = 0.0, 0.0
+    for _ in range(5):
+        e0.record()
+        _, flops = core.fp64_probe(blocks, threads, iters, device)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    reps = max(3, int(1.0 / (flops / (best * 1e12))))
+    e0.record()
+    for _ in range(reps):
+        core.fp64_probe(blocks, threads, iters, device)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = reps * flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return best, sustained
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port of the scipy-odeint
+    path, all host cores), same metric/unit/config.  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import cpu_baseline
+    cores = cpu_baseline.usable_cores()
+    per_proc = max(1, args.ref_steps_per_proc)
+    times, total = [], 0
+    for _ in range(args.warmup):
+        cpu_baseline.run(steps_per_proc=1, procs=cores, warmup=0)
+    t_all = 0.0
+    for _ in range(args.steps):
+        r = cpu_baseline.run(steps_per_proc=per_proc, procs=cores, warmup=1)
+        times.append(r["wall_s"]); total += r["steps"]; t_all += r["wall_s"]
+    value = total / t_all
+    sample = "%d procs x %d SBR-v2 cycle-steps per bench step (reset influent draw + step), scipy LSODA" % (cores, per_proc)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "envs_per_gpu": args.envs_per_gpu, "integrator": "lsoda"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "interval_steps_per_sec": value * INTERVALS_PER_CYCLE, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(args):
+    return ("configs[4] at one GPU per rank: %d SBR-v2 envs per GPU, random DO-setpoint actions, per-env influent, "
+            "one full cycle each" % args.envs_per_gpu)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--mode", default="rk4", choices=["rk4", "dp45"])
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--atol", type=float, default=1e-10)
+    ap.add_argument("--ref-steps-per-proc", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as tdist
+    from gym_sbr2_b200 import _abi, core, dist
+    from gym_sbr2_b200.vec_env import SbrV2VecEnv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device: there is no CPU fallback")
+    rank, world, local = dist.init_from_env()
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    n = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+
+    env = SbrV2VecEnv(n, device=device, seed=1234 + rank, mode=args.mode, rtol=args.rtol, atol=args.atol)
+    env.reset()
+    gen = torch.Generator(device=device).manual_seed(99 + rank)
+    action = torch.rand((n, 3), dtype=torch.float64, device=device, generator=gen)
+    stats = torch.empty((5,), dtype=torch.float64, device=device)
+
+    def hot_step():
+        o = env.step_async(action)
+        core.reward_stats(o.reward, o.status, out=stats)
+        if world > 1:
+            return dist.gather_stats(stats, async_op=True)
+        return stats.reshape(1, 5), None
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        g, work = hot_step()
+        if work is not None:
+            work.wait()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    works = []
+    for _ in range(K):
+        g, work = hot_step()
+        if work is not None:
+            works.append(work)
+    for w_ in works:
+        w_.wait()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        tdist.all_reduce(t_ms, op=tdist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = world * n * K / (ms_total * 1e-3)
+    reward_stats = dist.combine_stats(g)
+
+    # ---- dominant kernel alone: per-launch CUDA-event time of sbr_cycle_v2 on its launching stream ----------
+    kern_ms = []
+    for _ in range(K):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        o = core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=env.mode,
+                          tol=env.tol)
+        eb.record()
+        torch.cuda.synchronize()
+        kern_ms.append(ea.elapsed_time(eb))
+    kern_avg = sum(kern_ms) / len(kern_ms)
+    if args.mode == "rk4":
+        flops_env, steps_env = cycle_flops_rk4(env.sched)
+        rhs_mean, rej_mean = 4.0 * steps_env, 0.0
+    else:
+        cnt = o.counters.to(torch.float64)
+        rhs_mean, rej_mean = float(cnt[0].mean()), float(cnt[1].mean())
+        n_intervals = sum(env.sched.n_int[k] for k in (0, 1, 2, 3, 4, 7))
+        dp_steps = (rhs_mean - n_intervals) / 6.0
+        ovh = 2 * 9 * (1 + 2 + 3 + 4 + 5) + 2 * 11 * 5 + 2 * 11 * 6 + 5 * 11
+        flops_env = rhs_mean * F_REACT + dp_steps * ovh + F_EPILOGUE      # fill RHS counted as react: conservative
+    achieved_tf = n * flops_env / (kern_avg * 1e-3) / 1e12
+    peak_burst, peak_sustained = measure_fp64_peak(core, torch, device)
+    peak = peak_sustained if kern_avg * K > 500 else peak_burst
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        try:
+            traffic = json.load(open(tj)).get("sbr_cycle_v2_bytes_per_env") * n
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
+                "traffic": traffic, "kernel": "sbr_cycle_v2_kernel<%s>" % args.mode, "kernel_ms": kern_avg,
+                "flops_per_env": flops_env, "rhs_per_env": rhs_mean, "rejected_per_env": rej_mean,
+                "peak_source": "in-run DFMA probe (MEASURED_PEAKS.json has no FP64 entry); burst %.2f, sustained %.2f"
+                               % (peak_burst, peak_sustained),
+                "hbm": {"bytes_per_env": BYTES_PER_ENV, "achieved_gbs": n * BYTES_PER_ENV / (kern_avg * 1e-3) / 1e9,
+                        "peak_gbs": _hbm_peak()}}
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------------------------
+    act_h = torch.rand((n, 3), dtype=torch.float64).pin_memory()
+    infl_h = env.influent.cpu().pin_memory()
+    obs_h = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
+    done_h = torch.empty((n,), dtype=torch.bool).pin_memory()
+    act_d = torch.empty((n, 3), dtype=torch.float64, device=device)
+    infl_d = torch.empty((14, n), dtype=torch.float64, device=device)
+
+    def e2e_step():
+        infl_d.copy_(infl_h, non_blocking=True)
+        act_d.copy_(act_h, non_blocking=True)
+        env.reset(influent=infl_d)
+        obs, reward, done, info = env.step(act_d)
+        obs_h.copy_(obs, non_blocking=True)
+        rew_h.copy_(reward, non_blocking=True)
+        done_h.copy_(done, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        tdist.all_reduce(t_e, op=tdist.ReduceOp.MAX)
+    e2e = {"value": world * n * K / float(t_e.item()), "unit": UNIT,
+           "h2d_bytes_per_step": world * (act_h.numel() + infl_h.numel()) * 8,
+           "d2h_bytes_per_step": world * ((obs_h.numel() + rew_h.numel()) * 8 + done_h.numel()),
+           "api": "SbrV2VecEnv.reset(influent) + step(action), pinned host buffers, result read back every step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        r = cpu_baseline.run(steps_per_proc=2, procs=cpu_baseline.usable_cores(), warmup=1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "per_core": r["per_core"],
+               "sample": "%d SBR-v2 cycle-steps (%d procs x 2, scipy LSODA oracle port), %.1f s wall"
+                         % (r["steps"], r["cores"], r["wall_s"])}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args), "envs_per_gpu": n, "integrator": args.mode,
+                           "rtol": args.rtol if args.mode == "dp45" else None,
+                           "l2": "inputs %d MB per step > 126 MB L2" % (n * 31 * 8 >> 20),
+                           "parallelism": "env-sharded x%d, no step-path collective" % world},
+                "interval_steps_per_sec": value * INTERVALS_PER_CYCLE,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
+                "gpu_launch_names": ["sbr_cycle_v2_kernel", "sbr_reward_stats_init_kernel", "sbr_reward_stats_kernel"],
+                "clocks": clocks, "reward_stats": reward_stats}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+    return 0
+
+
+def _hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,113 @@
+"""ctypes binding of the C ABI declared in include/sbr_b200.h (the CUDA library libsbr_b200.so).
+
+There is no CPU fallback: if the library is missing this module raises at first use, and every compute entry
+point fails when no CUDA device is present.  Struct layouts mirror include/sbr_b200.h field for field.
+"""
+import ctypes as C
+import os
+
+NX = 14
+NPHASE = 8
+MODE_RK4, MODE_DP45 = 0, 1
+TAIL_REACT, TAIL_FILL, TAIL_EC = 0, 1, 2
+ST_NONFINITE, ST_WASTE, ST_STEPLIMIT, ST_LAYERS = 1, 2, 4, 8
+AUX_ROWS = 12
+AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
+             "kla3_mean", "kla5_mean", "kla8_mean")
+ABI_VERSION = 1
+
+_PARAM_FIELDS = [
+    "muh", "Ks", "Koh", "Kno", "bh", "etag", "etah", "kh", "Kx", "mua", "Knh", "ba", "Koa", "ka",
+    "Ya", "Yh", "fp", "ixb", "ixp", "so_sat",
+    "pid_Kc", "pid_tauI", "pid_tauD", "pid_dt", "kla_min", "kla_max",
+    "WV", "Qin", "Qeff", "biomass_setpoint", "settler_area", "settler_vmax", "kla0", "action_scale",
+    "os_Kc_DO", "os_tauI_DO", "os_tauD_DO", "os_Kc_EC", "os_tauI_EC", "os_tauD_EC",
+    "os_pid_dt", "ec_min", "ec_max", "ec_conc", "do_sp_max", "no_sp_max",
+]
+
+
+class SbrParams(C.Structure):
+    _fields_ = [(name, C.c_double) for name in _PARAM_FIELDS]
+
+
+class SbrSchedule(C.Structure):
+    _fields_ = [("n_int", C.c_int32 * NPHASE), ("n_sub", C.c_int32 * NPHASE),
+                ("interval", C.c_double * NPHASE), ("settle_time", C.c_double)]
+
+
+class SbrTol(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SbrLibraryError(RuntimeError):
+    pass
+
+
+_LIB = None
+LIB_NAME = "libsbr_b200.so"
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+
+_P = C.c_void_p
+_PROTOS = {
+    "sbr_abi_version": (C.c_int, []),
+    "sbr_last_error": (C.c_char_p, []),
+    "sbr_device_count": (C.c_int, []),
+    "sbr_params_default": (None, [C.POINTER(SbrParams)]),
+    "sbr_cycle_v2": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrSchedule),
+                               _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_integrate_interval": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int,
+                                         C.c_double, C.c_int, C.c_int, C.POINTER(SbrTol), _P, _P]),
+    "sbr_rhs": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int, _P, _P]),
+    "sbr_reward_stats_init": (C.c_int, [_P, _P]),
+    "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
+    "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite against include/sbr_b200.h)."""
+    return sorted(_PROTOS)
+
+
+def load():
+    """Load libsbr_b200.so (built in-tree by __graft_entry__.build()).  Raises if it is missing or stale."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SbrLibraryError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise SbrLibraryError("%s does not export %s (stale build?)" % (path, name))
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sbr_abi_version() != ABI_VERSION:
+        raise SbrLibraryError("ABI version mismatch: library %d, binding %d" % (lib.sbr_abi_version(), ABI_VERSION))
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().sbr_last_error()
+        raise SbrLibraryError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def default_params():
+    p = SbrParams()
+    load().sbr_params_default(C.byref(p))
+    return p
+
+
+def make_tol(rtol=1e-8, atol=1e-10, max_steps=4000):
+    return SbrTol(float(rtol), float(atol), int(max_steps), 0)

@@ -1,0 +1,137 @@
+"""Torch-facing wrappers of the C ABI (include/sbr_b200.h).  PyTorch is plumbing here: it owns device memory
+and streams; all arithmetic happens in the sm_100a kernels of libsbr_b200.so.  No CPU fallback -- tensors that
+are not CUDA float64 SoA are rejected."""
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+
+def _dev_ptr(t, rows, n, dtype=torch.float64, name="tensor"):
+    if t is None:
+        return None, n
+    if not t.is_cuda:
+        raise _abi.SbrLibraryError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if rows == 1:
+        if t.dim() != 1 or t.shape[0] != n or t.stride(0) != 1:
+            raise ValueError("%s must be a contiguous [%d] vector" % (name, n))
+        return C.c_void_p(t.data_ptr()), n
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n or t.stride(1) != 1:
+        raise ValueError("%s must be SoA [%d, %d] with unit stride along envs, got %s" % (name, rows, n, tuple(t.shape)))
+    return C.c_void_p(t.data_ptr()), t.stride(0)
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _same_ld(lds, what):
+    lds = {ld for ld in lds if ld is not None}
+    if len(lds) != 1:
+        raise ValueError("%s: all SoA tensors must share one row stride, got %s" % (what, sorted(lds)))
+    return lds.pop()
+
+
+class CycleV2Out(object):
+    """Output buffers of sbr_cycle_v2; allocated once and reused by the env."""
+
+    def __init__(self, n, device):
+        f = dict(dtype=torch.float64, device=device)
+        self.x_last = torch.empty((_abi.NX, n), **f)
+        self.obs = torch.empty((3, n), **f)
+        self.reward = torch.empty((n,), **f)
+        self.aux = torch.empty((_abi.AUX_ROWS, n), **f)
+        self.status = torch.empty((n,), dtype=torch.int32, device=device)
+        self.counters = torch.empty((2, n), dtype=torch.int32, device=device)
+
+
+def cycle_v2(x0, influent, action, params, sched, out=None, mode=_abi.MODE_RK4, tol=None, stream=None):
+    """One whole cycle for a batch (SbrEnv2.step, gym_SBR_env2.py:131-171).  x0, influent [14,n]; action [3,n]."""
+    lib = _abi.load()
+    n = x0.shape[1]
+    if out is None:
+        out = CycleV2Out(n, x0.device)
+    px0, l0 = _dev_ptr(x0, _abi.NX, n, name="x0")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    pac, l2 = _dev_ptr(action, 3, n, name="action")
+    pxl, l3 = _dev_ptr(out.x_last, _abi.NX, n, name="x_last")
+    pob, l4 = _dev_ptr(out.obs, 3, n, name="obs")
+    prw, _ = _dev_ptr(out.reward, 1, n, name="reward")
+    pax, l5 = _dev_ptr(out.aux, _abi.AUX_ROWS, n, name="aux")
+    pst, _ = _dev_ptr(out.status, 1, n, dtype=torch.int32, name="status")
+    pct, l6 = _dev_ptr(out.counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1, l2, l3, l4, l5, l6], "cycle_v2")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(x0.device):
+        rc = lib.sbr_cycle_v2(n, ld, px0, pin, pac, C.byref(params), C.byref(sched), pxl, pob, prw, pax, pst, pct,
+                              int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_cycle_v2")
+    return out
+
+
+def integrate_interval(x, kla, params, tail, T, n_sub, mode=_abi.MODE_RK4, tol=None, ec=None, loading=None,
+                       counters=None, stream=None):
+    """In-place advance of x [14,n] over one interval (replaces one odeint call, sub_phases_FB.py:252,480)."""
+    lib = _abi.load()
+    n = x.shape[1]
+    px, l0 = _dev_ptr(x, _abi.NX, n, name="x")
+    pk, _ = _dev_ptr(kla, 1, n, name="kla")
+    pe, _ = _dev_ptr(ec, 1, n, name="ec")
+    pl, l1 = _dev_ptr(loading, _abi.NX, n, name="loading")
+    pc, l2 = _dev_ptr(counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1 if loading is not None else None, l2 if counters is not None else None],
+                  "integrate_interval")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(x.device):
+        rc = lib.sbr_integrate_interval(n, ld, px, pk, pe, pl, C.byref(params), int(tail), float(T), int(n_sub),
+                                        int(mode), C.byref(tol), pc, _stream_ptr(stream))
+    _abi.check(rc, "sbr_integrate_interval")
+    return x
+
+
+def rhs(x, kla, params, tail, ec=None, loading=None, stream=None):
+    """dx = f(x): the kinetic right-hand side (rxn.dxdt / filling.dxdt / reaction_dxdt)."""
+    lib = _abi.load()
+    n = x.shape[1]
+    dx = torch.zeros_like(x)
+    px, l0 = _dev_ptr(x, _abi.NX, n, name="x")
+    pd, l1 = _dev_ptr(dx, _abi.NX, n, name="dx")
+    pk, _ = _dev_ptr(kla, 1, n, name="kla")
+    pe, _ = _dev_ptr(ec, 1, n, name="ec")
+    pl, l2 = _dev_ptr(loading, _abi.NX, n, name="loading")
+    ld = _same_ld([l0, l1, l2 if loading is not None else None], "rhs")
+    with torch.cuda.device(x.device):
+        rc = lib.sbr_rhs(n, ld, px, pk, pe, pl, C.byref(params), int(tail), pd, _stream_ptr(stream))
+    _abi.check(rc, "sbr_rhs")
+    return dx
+
+
+def reward_stats(reward, status=None, out=None, stream=None):
+    """[sum, sumsq, min, max, count] of the rewards of healthy envs, on the device (feeds the NCCL gather)."""
+    lib = _abi.load()
+    n = reward.shape[0]
+    if out is None:
+        out = torch.empty((5,), dtype=torch.float64, device=reward.device)
+    pr, _ = _dev_ptr(reward, 1, n, name="reward")
+    ps, _ = _dev_ptr(status, 1, n, dtype=torch.int32, name="status")
+    sp = _stream_ptr(stream)
+    with torch.cuda.device(reward.device):
+        _abi.check(lib.sbr_reward_stats_init(C.c_void_p(out.data_ptr()), sp), "sbr_reward_stats_init")
+        _abi.check(lib.sbr_reward_stats(n, pr, ps, C.c_void_p(out.data_ptr()), sp), "sbr_reward_stats")
+    return out
+
+
+def fp64_probe(blocks, threads, iters, device, stream=None):
+    """Launch the DFMA probe once; returns (sink tensor, flops issued).  Time it with CUDA events."""
+    lib = _abi.load()
+    sink = torch.empty((blocks * threads,), dtype=torch.float64, device=device)
+    flops = C.c_double(0.0)
+    with torch.cuda.device(device):
+        rc = lib.sbr_fp64_probe(int(blocks), int(threads), int(iters), C.c_void_p(sink.data_ptr()), C.byref(flops),
+                                _stream_ptr(stream))
+    _abi.check(rc, "sbr_fp64_probe")
+    return sink, flops.value

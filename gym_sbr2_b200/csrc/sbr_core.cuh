@@ -1,0 +1,571 @@
+// sbr_core.cuh -- per-environment arithmetic of the batched SBR stepper (one env = one thread).
+//
+// Everything here is a pure function of registers: the kinetic right-hand side with its three tails, the
+// RK4 and Dormand-Prince steppers, the DO->KLa PID, the settler closed form, the draw/waste algebra and the
+// reward/observation epilogues.  The kernels in sbr_kernels.cu only add SoA loads/stores around these.
+// The functions are SBR_HD (host+device) so that tests can compile the same source with g++ into a CPU twin
+// (oracle/twin/, test infrastructure) and debug the logic without a GPU; the product only ships the CUDA build.
+//
+// Reference behaviour is cited as file:line relative to /root/reference/gym_SBR/envs.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/sbr_b200.h"
+
+#ifdef __CUDACC__
+#define SBR_HD __host__ __device__ __forceinline__
+#define SBR_HD_NOINLINE __host__ __device__
+#else
+#define SBR_HD inline
+#define SBR_HD_NOINLINE inline
+#endif
+
+namespace sbr {
+
+enum { TAIL_REACT = 0, TAIL_FILL = 1, TAIL_EC = 2 };
+enum { iV = 0, iSi, iSs, iXi, iXs, iXbh, iXba, iXp, iSo, iSno, iSnh, iSnd, iXnd, iSalk };
+
+// ---------------------------------------------------------------------------------------------------------
+// Derived constants: stoichiometric coefficients folded on the host with the reference's own expressions
+// (sub_phases_FB.py:307-343).  Passed by value as a kernel argument (constant bank), never a global symbol.
+// ---------------------------------------------------------------------------------------------------------
+struct Coef {
+    double Ks, Koh, Kno, Knh, Koa, Kx;                 // half-saturation constants
+    double muh, muh_etag, mua, bh, ba, ka, kh, etah;   // rate constants
+    double n_invYh;       // nu2_1 = nu2_2 = -1/Yh
+    double one_m_ixp;     // nu4_4 = nu4_5 = 1 - ixp   (sic: ixp where ASM1 has fp)
+    double ixp;           // nu7_4 = nu7_5
+    double c81, c83;      // So:  -(1-Yh)/Yh , -(4.57-Ya)/Ya
+    double c92, c93;      // Sno: -(1-Yh)/(2.86 Yh) , 1/Ya
+    double n_ixb, c103;   // Snh: -ixb , -ixb - 1/Ya
+    double c124;          // Xnd: ixb - fp*ixp
+    double c131, c132, c133, c136;  // Salk
+    double so_sat;
+};
+
+inline Coef make_coef(const SbrParams& p) {
+    Coef c;
+    c.Ks = p.Ks; c.Koh = p.Koh; c.Kno = p.Kno; c.Knh = p.Knh; c.Koa = p.Koa; c.Kx = p.Kx;
+    c.muh = p.muh; c.muh_etag = p.muh * p.etag; c.mua = p.mua; c.bh = p.bh; c.ba = p.ba; c.ka = p.ka;
+    c.kh = p.kh; c.etah = p.etah;
+    c.n_invYh = -1 / p.Yh;
+    c.one_m_ixp = 1 - p.ixp;
+    c.ixp = p.ixp;
+    c.c81 = -(1 - p.Yh) / p.Yh;
+    c.c83 = -(4.57 - p.Ya) / p.Ya;
+    c.c92 = -((1 - p.Yh) / (2.86 * p.Yh));
+    c.c93 = 1 / p.Ya;
+    c.n_ixb = -p.ixb;
+    c.c103 = -p.ixb - 1 / p.Ya;
+    c.c124 = p.ixb - p.fp * p.ixp;
+    c.c131 = -p.ixb / 14;
+    c.c132 = (1 - p.Yh) / (14 * 2.86 * p.Yh) - p.ixb / 14;
+    c.c133 = -p.ixb / 14 - 1 / (7 * p.Ya);
+    c.c136 = 1.0 / 14;
+    c.so_sat = p.so_sat;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 reciprocal: MUFU.RCP64H seed (>= 20 good bits) + one cubic Newton correction (3 DFMA) -> ~2^-60.
+// An IEEE divide costs ~10 FP64-pipe slots; the RHS has 6-7 of them per evaluation.
+// ---------------------------------------------------------------------------------------------------------
+SBR_HD double rcp(double d) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    double t = fma(e, e, e);
+    return fma(r, t, r);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// Which components have a non-zero derivative / are read by the RHS, per tail.  React: V, Si, Xi are frozen
+// (sub_phases_FB.py:348,352,376); Xp and Salk are outputs that feed no rate.
+SBR_HD constexpr bool integ(int tail, int i) { return tail != TAIL_REACT || !(i == iV || i == iSi || i == iXi); }
+SBR_HD constexpr bool staged(int tail, int i) {
+    return tail != TAIL_REACT || (integ(tail, i) && i != iXp && i != iSalk);
+}
+
+// Influent loading accessor: component i at p[i * stride] (shared memory column on the GPU).
+struct Loading {
+    const double* p;
+    int stride;
+    SBR_HD double operator()(int i) const { return p[i * stride]; }
+};
+
+struct TailArgs {
+    double kla;        // oxygen transfer coefficient, constant over one PID interval
+    double q;          // FILL: inflow m3/d ; EC: carbon dosing flow m3/d
+    double ec_conc;    // EC: dosing concentration gCOD/m3
+    Loading load;      // FILL: influent concentrations
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Kinetic RHS (sub_phases_FB.py:278-404; tails :146-176 and gym_SBR_oneshot.py:1757-1787).
+// CSE-minimal form: 6 Monod denominators -> 6 reciprocals; hydrolysis written as Xs*g / Xnd*g so no divide
+// by Xs or Xbh is needed ((Xs/Xbh)/(Kx+Xs/Xbh) == Xs/(Kx*Xbh+Xs)).  Only masked components are written.
+// ---------------------------------------------------------------------------------------------------------
+template <int TAIL>
+SBR_HD void rhs(const double (&y)[SBR_NX], double (&k)[SBR_NX], const Coef& c, const TailArgs& a) {
+    const double Ss = y[iSs], Xs = y[iXs], Xbh = y[iXbh], Xba = y[iXba], So = y[iSo], Sno = y[iSno],
+                 Snh = y[iSnh], Snd = y[iSnd], Xnd = y[iXnd];
+    const double r1 = rcp(c.Ks + Ss);
+    const double r2 = rcp(c.Koh + So);
+    const double r3 = rcp(c.Kno + Sno);
+    const double r4 = rcp(c.Knh + Snh);
+    const double r5 = rcp(c.Koa + So);
+    const double r6 = rcp(fma(c.Kx, Xbh, Xs));
+    const double mSs = Ss * r1;
+    const double mOh = So * r2;      // So/(Koh+So)
+    const double iOh = c.Koh * r2;   // Koh/(Koh+So)
+    const double mNo = Sno * r3;
+    const double mNh = Snh * r4;
+    const double mOa = So * r5;
+    const double anox = iOh * mNo;
+    const double gh = mSs * Xbh;
+    const double rho1 = (c.muh * gh) * mOh;
+    const double rho2 = (c.muh_etag * gh) * anox;
+    const double rho3 = (c.mua * mNh) * (mOa * Xba);
+    const double rho4 = c.bh * Xbh;
+    const double rho5 = c.ba * Xba;
+    const double rho6 = (c.ka * Snd) * Xbh;
+    const double g = ((c.kh * Xbh) * r6) * fma(c.etah, anox, mOh);
+    const double rho7 = Xs * g;
+    const double rho8 = Xnd * g;
+    const double s12 = rho1 + rho2;
+    const double s45 = rho4 + rho5;
+    k[iSs] = fma(c.n_invYh, s12, rho7);
+    k[iXs] = fma(c.one_m_ixp, s45, -rho7);
+    k[iXbh] = s12 - rho4;
+    k[iXba] = rho3 - rho5;
+    k[iXp] = c.ixp * s45;
+    k[iSo] = fma(a.kla, c.so_sat - So, fma(c.c81, rho1, c.c83 * rho3));
+    k[iSno] = fma(c.c92, rho2, c.c93 * rho3);
+    k[iSnh] = fma(c.n_ixb, s12, fma(c.c103, rho3, rho6));
+    k[iSnd] = rho8 - rho6;
+    k[iXnd] = fma(c.c124, s45, -rho8);
+    k[iSalk] = fma(c.c131, rho1, fma(c.c132, rho2, fma(c.c133, rho3, c.c136 * rho6)));
+    if (TAIL == TAIL_FILL) {
+        // dV/dt = q ; dx_i/dt = r_i + (q/V)(c_in,i - x_i)   (sub_phases_FB.py:146-176)
+        const double qV = a.q * rcp(y[iV]);
+        k[iV] = a.q;
+        k[iSi] = qV * (a.load(iSi) - y[iSi]);
+        k[iXi] = qV * (a.load(iXi) - y[iXi]);
+#pragma unroll
+        for (int i = 2; i < SBR_NX; ++i)
+            if (i != iXi) k[i] = fma(qV, a.load(i) - y[i], k[i]);
+    } else if (TAIL == TAIL_EC) {
+        // dV/dt = ec ; dx_i/dt = r_i - (ec/V) x_i ; Ss additionally + (ec/V) EC_conc  (gym_SBR_oneshot.py:1757-1787)
+        const double eV = a.q * rcp(y[iV]);
+        k[iV] = a.q;
+        k[iSi] = -eV * y[iSi];
+        k[iXi] = -eV * y[iXi];
+#pragma unroll
+        for (int i = 2; i < SBR_NX; ++i)
+            if (i != iXi) k[i] = fma(-eV, y[i], k[i]);
+        k[iSs] = fma(eV, a.ec_conc, k[iSs]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Classical RK4, one step of size h.  Low-storage form: x (state), acc (weighted sum), y (stage input), k.
+// Output-only components (react: Xp, Salk) skip the stage-input FMAs.
+// ---------------------------------------------------------------------------------------------------------
+template <int TAIL>
+SBR_HD void rk4_step(double (&x)[SBR_NX], double h, const Coef& c, const TailArgs& a) {
+    double y[SBR_NX], k[SBR_NX], acc[SBR_NX];
+    const double h2 = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
+    rhs<TAIL>(y, k, c, a);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) {
+        if (integ(TAIL, i)) acc[i] = fma(h6, k[i], x[i]);
+        if (staged(TAIL, i)) y[i] = fma(h2, k[i], x[i]);
+    }
+    rhs<TAIL>(y, k, c, a);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) {
+        if (integ(TAIL, i)) acc[i] = fma(h3, k[i], acc[i]);
+        if (staged(TAIL, i)) y[i] = fma(h2, k[i], x[i]);
+    }
+    rhs<TAIL>(y, k, c, a);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) {
+        if (integ(TAIL, i)) acc[i] = fma(h3, k[i], acc[i]);
+        if (staged(TAIL, i)) y[i] = fma(h, k[i], x[i]);
+    }
+    rhs<TAIL>(y, k, c, a);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i)
+        if (integ(TAIL, i)) x[i] = fma(h6, k[i], acc[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4) with FSAL, per-env adaptive step.
+// ---------------------------------------------------------------------------------------------------------
+struct Dp45State {
+    double h;          // current step-size proposal, carried across PID intervals
+    uint32_t n_rhs;    // RHS evaluations (accepted + rejected)
+    uint32_t n_rej;    // rejected steps
+};
+
+// Per-component absolute-tolerance scale: atol_i = atol * scale_i, scale from the reference's own
+// normalisation vector x_1_state (gym_SBR_oneshot.py:153) so that So ~ 1e-15 in anoxic phases does not
+// drive the step to zero.
+SBR_HD constexpr double tol_scale(int i) {
+    return i == iV ? 1.32 : i == iSi ? 30.0 : i == iSs ? 30.0 : i == iXi ? 1500.0 : i == iXs ? 150.0
+         : i == iXbh ? 3000.0 : i == iXba ? 2000.0 : i == iXp ? 600.0 : i == iSo ? 8.0 : i == iSno ? 20.0
+         : i == iSnh ? 20.0 : i == iSnd ? 10.0 : i == iXnd ? 10.0 : 10.0;
+}
+
+// Integrate x over [0, T] with constant tail arguments.  Returns status bits (0 or SBR_ST_STEPLIMIT).
+template <int TAIL>
+SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Coef& c, const TailArgs& a, const SbrTol& tol,
+                         Dp45State& st) {
+    // Butcher tableau (Dormand & Prince 1980)
+    const double a21 = 1.0 / 5;
+    const double a31 = 3.0 / 40, a32 = 9.0 / 40;
+    const double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+    const double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+    const double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176,
+                 a65 = -5103.0 / 18656;
+    const double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+    const double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200,
+                 e6 = 22.0 / 525, e7 = -1.0 / 40;
+    double k1[SBR_NX], k2[SBR_NX], k3[SBR_NX], k4[SBR_NX], k5[SBR_NX], k6[SBR_NX], y[SBR_NX];
+    double t = 0.0;
+    double h = st.h;
+    int status = 0;
+    int steps = 0;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
+    rhs<TAIL>(y, k1, c, a);   // the PID changes KLa at every interval start, so FSAL restarts here
+    st.n_rhs += 1;
+    while (t < T) {
+        if (steps >= tol.max_steps) { status = SBR_ST_STEPLIMIT; break; }
+        ++steps;
+        bool last = false;
+        double hs = h;
+        if (t + hs * 1.0000001 >= T) { hs = T - t; last = true; }
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (staged(TAIL, i)) y[i] = fma(hs * a21, k1[i], x[i]);
+        rhs<TAIL>(y, k2, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (staged(TAIL, i)) y[i] = fma(hs * a32, k2[i], fma(hs * a31, k1[i], x[i]));
+        rhs<TAIL>(y, k3, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (staged(TAIL, i)) y[i] = fma(hs * a43, k3[i], fma(hs * a42, k2[i], fma(hs * a41, k1[i], x[i])));
+        rhs<TAIL>(y, k4, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (staged(TAIL, i))
+                y[i] = fma(hs * a54, k4[i], fma(hs * a53, k3[i], fma(hs * a52, k2[i], fma(hs * a51, k1[i], x[i]))));
+        rhs<TAIL>(y, k5, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (staged(TAIL, i))
+                y[i] = fma(hs * a65, k5[i], fma(hs * a64, k4[i], fma(hs * a63, k3[i],
+                       fma(hs * a62, k2[i], fma(hs * a61, k1[i], x[i])))));
+        rhs<TAIL>(y, k6, c, a);
+        // 5th-order solution (into y) ; k2 is free from here on and receives k7 = f(y)
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (integ(TAIL, i))
+                y[i] = fma(hs * b6, k6[i], fma(hs * b5, k5[i], fma(hs * b4, k4[i],
+                       fma(hs * b3, k3[i], fma(hs * b1, k1[i], x[i])))));
+        rhs<TAIL>(y, k2, c, a);
+        st.n_rhs += 6;
+        // error estimate, RMS norm over integrated components
+        double en = 0.0;
+        int ncomp = 0;
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (integ(TAIL, i)) {
+                const double err = hs * fma(e7, k2[i], fma(e6, k6[i], fma(e5, k5[i], fma(e4, k4[i],
+                                   fma(e3, k3[i], e1 * k1[i])))));
+                const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(y[i])), tol.atol * tol_scale(i));
+                const double q = err * rcp(sc);
+                en = fma(q, q, en);
+                ++ncomp;
+            }
+        en = en * (1.0 / ncomp);   // mean square
+        const bool finite = en < 1e300;   // false for NaN/Inf
+        if (en <= 1.0 || !finite) {
+            // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
+            t = last ? T : t + hs;
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (integ(TAIL, i)) { x[i] = y[i]; k1[i] = k2[i]; }
+            if (!finite) { t = T; }
+        } else {
+            st.n_rej += 1;
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (staged(TAIL, i)) y[i] = x[i];
+        }
+        // step-size controller: h *= clamp(0.9 * en^(-1/10), 0.2, 5)  (en is the SQUARED norm)
+        float fac = 5.0f;
+        if (en > 1e-20) {
+            fac = 0.9f * exp2f(-0.1f * log2f((float)en));
+            fac = fminf(5.0f, fmaxf(0.2f, fac));
+        }
+        if (en > 1.0) fac = fminf(fac, 1.0f);
+        if (!(last && en <= 1.0)) h = hs * (double)fac;   // a truncated final step does not shrink the carry
+        else h = fmax(h, hs * (double)fac);
+    }
+    st.h = h;
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One PID interval of length T: RK4 with n_sub equal sub-steps, or DP45.
+// ---------------------------------------------------------------------------------------------------------
+template <int TAIL, int MODE>
+SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
+                              const TailArgs& a, const SbrTol& tol, Dp45State& st) {
+    if (MODE == SBR_MODE_RK4) {
+        const double h = T / (double)n_sub;
+        for (int s = 0; s < n_sub; ++s) rk4_step<TAIL>(x, h, c, a);
+        st.n_rhs += 4u * (uint32_t)n_sub;
+        return 0;
+    }
+    return dp45_interval<TAIL>(x, T, c, a, tol, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DO -> KLa positional PID of the cycle-per-step path (sub_phases_FB.py:233-250).
+// ---------------------------------------------------------------------------------------------------------
+struct PidA {
+    double Kc, Kc_tauI, Kc_tauD, dt, lo, hi;
+};
+
+SBR_HD PidA make_pid_a(const SbrParams& p) {
+    PidA q;
+    q.Kc = p.pid_Kc; q.Kc_tauI = p.pid_Kc / p.pid_tauI; q.Kc_tauD = p.pid_Kc * p.pid_tauD;
+    q.dt = p.pid_dt; q.lo = p.kla_min; q.hi = p.kla_max;
+    return q;
+}
+
+struct PhaseOut {
+    double kla_sum;
+    double kla_last;
+};
+
+// One PID-controlled phase = filling.sim_rxn / rxn.sim_rxn (sub_phases_FB.py:178-271, 406-500).
+// The bias of intervals i >= 1 is the clamped output of interval 0 (:218,243); So is sampled at interval
+// starts; two independent clamp checks each undo the integral update (:245-250).
+template <int TAIL, int MODE>
+SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double sp, double kla_in,
+                     const Coef& c, TailArgs a, const PidA& pid, const SbrTol& tol, Dp45State& st,
+                     PhaseOut& out) {
+    double bias = kla_in, ie = 0.0, so_prev = 0.0, so_i = x[iSo];
+    double ksum = 0.0, kla = kla_in;
+    int status = 0;
+    for (int i = 0; i < n_int; ++i) {
+        const double e = sp - so_i;
+        double dcv = 0.0;
+        if (i >= 1) {
+            dcv = (so_i - so_prev) / pid.dt;
+            ie = ie + e * pid.dt;
+        }
+        kla = pid.Kc * e + pid.Kc_tauI * ie + pid.Kc_tauD * dcv + bias;
+        if (kla > pid.hi) { kla = pid.hi; ie = ie - e * pid.dt; }
+        if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
+        if (i == 0) bias = kla;
+        a.kla = kla;
+        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st);
+        ksum += kla;
+        so_prev = so_i;
+        so_i = x[iSo];
+    }
+    out.kla_sum = ksum;
+    out.kla_last = kla;
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Settler: the reference's 10-layer flux model takes max(vmax, exp-exp) (sub_phases_FB.py:677-686), and
+// exp(-rh d) - exp(-rp d) < 1 for every real d, so v == vmax in every layer and the ODE is the linear chain
+//   s0' = a s1 ; s_i' = a (s_{i+1} - s_i) (1<=i<=8) ; s9' = -a s9 ,  a = vmax * As / V, equal initial layers Xf.
+// Closed form: s_{9-k}(T) = Xf e^{-aT} sum_{j<=k} (aT)^j / j!  (k = 0..8), s0 = 10 Xf - sum_{i>=1} s_i
+// (matches the reference's odeint to 6e-8).  Layer 0 = bottom.
+// ---------------------------------------------------------------------------------------------------------
+SBR_HD void settle_closed_form(const double (&x)[SBR_NX], double T, double area, double vmax, double (&sX)[10],
+                               double& Xf) {
+    Xf = 0.75 * (x[iXi] + x[iXs] + x[iXbh] + x[iXba] + x[iXp]);   // sub_phases_FB.py:730
+    const double aT = vmax * area / x[iV] * T;
+    const double ex = exp(-aT) * Xf;
+    double term = 1.0, part = 1.0, rest = 0.0;
+    sX[9] = ex;
+    rest = sX[9];
+#pragma unroll
+    for (int kk = 1; kk <= 8; ++kk) {
+        term = term * aT / (double)kk;
+        part += term;
+        sX[9 - kk] = ex * part;
+        rest += sX[9 - kk];
+    }
+    sX[0] = 10.0 * Xf - rest;
+}
+
+struct DrawOut {
+    double Qw, EQI;
+    double eff[6];   // [0.66, Ntot, COD, Snh, BOD5, Sno]
+    int status;
+};
+
+// drawing.sim_drawing + cal_eq (sub_phases_FB.py:780-915).  x is replaced by the post-draw reactor state.
+SBR_HD void draw_and_waste(double (&x)[SBR_NX], const double (&sX)[10], double Xf, double Qeff, double biomass_sp,
+                           DrawOut& o) {
+    const double V0 = x[iV];
+    const double lv = V0 / 10;
+    double resV = V0 - Qeff;
+    // m = int(ceil(round(Qeff / lv)))  -- Python round = half-to-even = rint
+    const double mr = rint(Qeff / lv);
+    int m = (int)mr;
+    o.status = 0;
+    if (!(mr >= 1.0 && mr <= 9.0)) { o.status |= SBR_ST_LAYERS; m = m < 1 ? 1 : 9; }
+    // effluent solids: layers [10-m, 8]; the top layer is left out by the reference's [-m:-1] slice (:794)
+    double sX_eff = 0.0;
+#pragma unroll
+    for (int i = 1; i < 9; ++i)
+        if (i >= 10 - m) sX_eff += sX[i] * lv;
+    double xe[SBR_NX];
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) xe[i] = x[i];
+    xe[iXs] = x[iXs] * (1 / 0.75) * sX_eff / Xf;
+    xe[iXp] = x[iXp] * (1 / 0.75) * sX_eff / Xf;
+    xe[iXi] = x[iXi] * (1 / 0.75) * sX_eff / Xf;
+    xe[iXbh] = x[iXbh] * (1 / 0.75) * sX_eff / Xf;
+    xe[iXba] = x[iXba] * (1 / 0.75) * sX_eff / Xf;
+    // waste sludge bottom-up (:805-836)
+    double wl[10];
+    double total = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        wl[i] = (i < 10 - m) ? lv * sX[i] : 0.0;
+        if (i < 10 - m) total += wl[i];
+    }
+    double waste = total - biomass_sp * resV;
+    double Qw = NAN;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (i < 10 - m && !found) {
+            const double left = waste - wl[i];
+            if (left > 0) {
+                waste = left;
+                wl[i] = 0.0;
+                resV -= lv;
+            } else {
+                Qw = waste / (sX[i] - biomass_sp);
+                wl[i] = wl[i] - Qw * sX[i];
+                resV -= Qw;
+                found = true;
+            }
+        }
+    }
+    if (!found) o.status |= SBR_ST_WASTE;
+    double rem = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i < 10 - m) rem += wl[i];
+    const double sX2 = rem / resV;
+    x[iV] = resV;
+    x[iXs] = x[iXs] * (1 / 0.75) * sX2 / Xf;
+    x[iXp] = x[iXp] * (1 / 0.75) * sX2 / Xf;
+    x[iXi] = x[iXi] * (1 / 0.75) * sX2 / Xf;
+    x[iXbh] = x[iXbh] * (1 / 0.75) * sX2 / Xf;
+    x[iXba] = x[iXba] * (1 / 0.75) * sX2 / Xf;
+    // cal_eq (:868-915) on the effluent
+    const double Snkj = xe[iSnh] + xe[iSnd] + xe[iXnd] + 0.08 * (xe[iXbh] + xe[iXba]) + 0.06 * (xe[iXp] + xe[iXi]);
+    const double Ntot = xe[iSno] + Snkj;
+    const double SS = 0.75 * (xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp]);
+    const double BOD5 = 0.25 * (xe[iSs] + xe[iXs] + (1 - 0.08) * (xe[iXbh] + xe[iXba]));
+    const double COD = xe[iSs] + xe[iSi] + xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp];
+    o.EQI = (2 * SS + 1 * COD + 30 * Snkj + 10 * xe[iSno] + 2 * BOD5) * (1.0 / 1000) * 0.66;
+    o.eff[0] = 0.66; o.eff[1] = Ntot; o.eff[2] = COD; o.eff[3] = xe[iSnh]; o.eff[4] = BOD5; o.eff[5] = xe[iSno];
+    o.Qw = Qw;
+}
+
+// module_reward.sbr_reward (module_reward.py:4-51): means of the per-interval KLa of phases 3, 5, 8.
+SBR_HD void reward_v2(const SbrParams& p, double kla3_mean, double kla5_mean, double kla8_mean, double Qw, double Snh,
+                      double& reward, double& OCI) {
+    const double ME = 0.005 * 1.32 * 24 + 0.005 * 1.32 * 24;
+    const double AE = p.so_sat / (1.8 * 1000) * (1.32 * kla3_mean + 1.32 * kla5_mean + (1.32 - Qw) * kla8_mean);
+    const double PE = 0.004 * p.Qin + 0.05 * Qw + 0.004 * p.Qeff;
+    OCI = AE + PE + ME;
+    reward = (5 - OCI) + (Snh < 4 ? 0.0 : -20.0);
+}
+
+struct CycleOut {
+    double obs[3];
+    double reward;
+    double aux[SBR_AUX_ROWS];
+    int status;
+};
+
+// Whole cycle = SBR_model_FB.run (SBR_model_FB.py:8-295) + SbrEnv2.step epilogue (gym_SBR_env2.py:131-171).
+// x: in = start state, out = state after the idle phase.  action: raw, clipped here.
+template <int MODE>
+SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading load, double q_fill,
+                     const SbrParams& p, const Coef& c, const SbrSchedule& s, const SbrTol& tol,
+                     Dp45State& st, CycleOut& o) {
+    const PidA pid = make_pid_a(p);
+    double sp3[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sp3[j] = fmin(fmax(action[j], 0.0), 1.0) * p.action_scale;
+    TailArgs a;
+    a.kla = 0.0; a.q = q_fill; a.ec_conc = 0.0; a.load = load;
+    int status = 0;
+    PhaseOut po;
+    double kla_mean[3] = {0.0, 0.0, 0.0};
+    // phase 1: fill, set-point 0 (gym_SBR_env2.py:54)
+    status |= pid_phase<TAIL_FILL, MODE>(x, s.n_int[0], s.n_sub[0], s.interval[0], 0.0, p.kla0, c, a, pid, tol, st, po);
+    double kla = po.kla_last;
+    a.q = 0.0;
+    DrawOut d;
+    // phases 2..5 react with set-points [0, sp3[0], 0, sp3[1]], each biased by the previous phase's last KLa
+    // (SBR_model_FB.py:94,120,146,172); then settle + draw; then phase 8 idle with set-point sp3[2], biased
+    // by phase 5's last KLa (:266).  One loop so that the react stepper is instantiated once.
+    for (int j = 0; j < 5; ++j) {
+        const int ph = j < 4 ? j + 1 : 7;
+        if (j == 4) {
+            double sX[10], Xf;
+            settle_closed_form(x, s.settle_time, p.settler_area, p.settler_vmax, sX, Xf);
+            draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+            status |= d.status;
+        }
+        const double sp = j == 1 ? sp3[0] : (j == 3 ? sp3[1] : (j == 4 ? sp3[2] : 0.0));
+        status |= pid_phase<TAIL_REACT, MODE>(x, s.n_int[ph], s.n_sub[ph], s.interval[ph], sp, kla, c, a, pid, tol,
+                                              st, po);
+        const double mean = po.kla_sum / (double)s.n_int[ph];
+        if (j < 4) kla = po.kla_last;
+        if (j == 1) kla_mean[0] = mean;
+        if (j == 3) kla_mean[1] = mean;
+        if (j == 4) kla_mean[2] = mean;
+    }
+    double reward, OCI;
+    reward_v2(p, kla_mean[0], kla_mean[1], kla_mean[2], d.Qw, d.eff[3], reward, OCI);
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);
+    if (!finite || !(fabs(reward) < 1e300)) status |= SBR_ST_NONFINITE;
+    o.obs[0] = p.Qeff; o.obs[1] = d.eff[2]; o.obs[2] = d.eff[3] / 30;
+    o.reward = reward;
+    o.aux[SBR_AUX_OCI] = OCI; o.aux[SBR_AUX_QW] = d.Qw; o.aux[SBR_AUX_EQI] = d.EQI;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o.aux[SBR_AUX_EFF_Q + j] = d.eff[j];
+    o.aux[SBR_AUX_KLA3_MEAN] = kla_mean[0]; o.aux[SBR_AUX_KLA5_MEAN] = kla_mean[1];
+    o.aux[SBR_AUX_KLA8_MEAN] = kla_mean[2];
+    o.status = status;
+}
+
+}  // namespace sbr

@@ -1,0 +1,368 @@
+// sbr_kernels.cu -- sm_100a kernels and the C ABI (include/sbr_b200.h) of the batched SBR stepper.
+//
+// Mapping: one environment per thread, whole state + PID integrator + stepper stages register-resident for the
+// whole launch; global memory is touched only at the launch boundaries with coalesced SoA loads/stores
+// (component c of env i at base[c*ld + i]).  The path is FP64-FMA-pipe bound (no contraction => no tensor
+// cores); see DESIGN.md for the roofline arithmetic.  Per-env influent concentrations sit in a shared-memory
+// column (conflict-free: consecutive threads -> consecutive 8-byte words) so the fill tail costs no registers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sbr_core.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return SBR_ERR_CUDA;
+    }
+    return SBR_OK;
+}
+
+constexpr int kBlock = 64;   // 2 warps per CTA: fine-grained tail balancing across 148 SMs x 4 SMSPs
+
+struct CycleArgs {
+    int64_t n, ld;
+    const double* x0;
+    const double* influent;
+    const double* action;
+    double* x_last;
+    double* obs;
+    double* reward;
+    double* aux;
+    int32_t* status;
+    uint32_t* counters;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
+                                                              SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX], action[3];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0[k * g.ld + i];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) action[k] = g.action[k * g.ld + i];
+    sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    sbr::Dp45State st;
+    st.h = s.interval[0] / (double)s.n_sub[0];
+    st.n_rhs = 0;
+    st.n_rej = 0;
+    sbr::CycleOut o;
+    sbr::cycle_v2<MODE>(x, action, load, load(0), p, c, s, tol, st, o);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.x_last[k * g.ld + i] = x[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.obs[k * g.ld + i] = o.obs[k];
+    g.reward[i] = o.reward;
+    if (g.aux) {
+#pragma unroll
+        for (int k = 0; k < SBR_AUX_ROWS; ++k) g.aux[k * g.ld + i] = o.aux[k];
+    }
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) {
+        g.counters[i] = st.n_rhs;
+        g.counters[g.ld + i] = st.n_rej;
+    }
+}
+
+struct IntervalArgs {
+    int64_t n, ld;
+    double* x;
+    const double* kla;
+    const double* ec;
+    const double* loading;
+    uint32_t* counters;
+    double T;
+    int n_sub;
+};
+
+template <int TAIL, int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_interval_kernel(IntervalArgs g, SbrParams p, sbr::Coef c, SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x[k * g.ld + i];
+    sbr::TailArgs a;
+    a.kla = g.kla[i];
+    a.q = 0.0;
+    a.ec_conc = p.ec_conc;
+    a.load = sbr::Loading{&s_load[threadIdx.x], kBlock};
+    if (TAIL == sbr::TAIL_FILL) {
+#pragma unroll
+        for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.loading[k * g.ld + i];
+        a.q = a.load(0);
+    }
+    if (TAIL == sbr::TAIL_EC) a.q = g.ec[i];
+    sbr::Dp45State st;
+    st.h = g.T / (double)g.n_sub;
+    st.n_rhs = 0;
+    st.n_rej = 0;
+    sbr::integrate_interval<TAIL, MODE>(x, g.T, g.n_sub, c, a, tol, st);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.x[k * g.ld + i] = x[k];
+    if (g.counters) {
+        g.counters[i] = st.n_rhs;
+        g.counters[g.ld + i] = st.n_rej;
+    }
+}
+
+struct RhsArgs {
+    int64_t n, ld;
+    const double* x;
+    const double* kla;
+    const double* ec;
+    const double* loading;
+    double* dx;
+};
+
+template <int TAIL>
+__global__ void __launch_bounds__(kBlock) sbr_rhs_kernel(RhsArgs g, SbrParams p, sbr::Coef c) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX], k[SBR_NX];
+#pragma unroll
+    for (int j = 0; j < SBR_NX; ++j) { x[j] = g.x[j * g.ld + i]; k[j] = 0.0; }
+    sbr::TailArgs a;
+    a.kla = g.kla[i];
+    a.q = 0.0;
+    a.ec_conc = p.ec_conc;
+    a.load = sbr::Loading{&s_load[threadIdx.x], kBlock};
+    if (TAIL == sbr::TAIL_FILL) {
+#pragma unroll
+        for (int j = 0; j < SBR_NX; ++j) s_load[j * kBlock + threadIdx.x] = g.loading[j * g.ld + i];
+        a.q = a.load(0);
+    }
+    if (TAIL == sbr::TAIL_EC) a.q = g.ec[i];
+    sbr::rhs<TAIL>(x, k, c, a);
+#pragma unroll
+    for (int j = 0; j < SBR_NX; ++j) g.dx[j * g.ld + i] = k[j];
+}
+
+// FP64 pipe probe: 8 independent DFMA chains per thread, `iters` rounds of 8 DFMAs each.
+__global__ void sbr_fp64_probe_kernel(int iters, double* sink) {
+    const double a = 1.0000001, b = 1e-9 * (double)(threadIdx.x + 1);
+    double v0 = 1.0, v1 = 1.1, v2 = 1.2, v3 = 1.3, v4 = 1.4, v5 = 1.5, v6 = 1.6, v7 = 1.7;
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+// Reward statistics: grid-stride partial sums, warp shuffle + one atomic per warp.
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double(assumed) <= v) break;
+        old = atomicCAS(a, assumed, __double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (__longlong_as_double(assumed) >= v) break;
+        old = atomicCAS(a, assumed, __double_as_longlong(v));
+    } while (assumed != old);
+}
+
+__global__ void sbr_reward_stats_init_kernel(double* stats) {
+    stats[0] = 0.0; stats[1] = 0.0; stats[2] = INFINITY; stats[3] = -INFINITY; stats[4] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) sbr_reward_stats_kernel(int64_t n, const double* __restrict__ reward,
+                                                               const int32_t* __restrict__ status, double* stats) {
+    double s = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY, cnt = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (status && status[i] != 0) continue;
+        const double r = reward[i];
+        s += r; ss = fma(r, r, ss); mn = fmin(mn, r); mx = fmax(mx, r); cnt += 1.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        ss += __shfl_down_sync(0xffffffffu, ss, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+        atomicAdd(&stats[0], s);
+        atomicAdd(&stats[1], ss);
+        atomic_min_f64(&stats[2], mn);
+        atomic_max_f64(&stats[3], mx);
+        atomicAdd(&stats[4], cnt);
+    }
+}
+
+int check_common(int64_t n, int64_t ld, const SbrParams* p) {
+    if (n <= 0) return fail(SBR_ERR_ARG, "n must be positive%s");
+    if (ld < n) return fail(SBR_ERR_ARG, "ld must be >= n%s");
+    if (!p) return fail(SBR_ERR_ARG, "params pointer is NULL%s");
+    if ((n + kBlock - 1) / kBlock > 2147483647LL) return fail(SBR_ERR_ARG, "n too large for one launch%s");
+    return SBR_OK;
+}
+
+SbrTol tol_or_default(const SbrTol* tol) {
+    SbrTol t;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 4000; t.reserved = 0;
+    if (tol) t = *tol;
+    return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sbr_abi_version(void) { return SBR_ABI_VERSION; }
+
+const char* sbr_last_error(void) { return g_err; }
+
+int sbr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void sbr_params_default(SbrParams* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->muh = 4.0; p->Ks = 10.0; p->Koh = 0.2; p->Kno = 0.5; p->bh = 0.3; p->etag = 0.8; p->etah = 0.8;
+    p->kh = 3.0; p->Kx = 0.1; p->mua = 0.5; p->Knh = 1.0; p->ba = 0.05; p->Koa = 0.4; p->ka = 0.05;
+    p->Ya = 0.24; p->Yh = 0.67; p->fp = 0.08; p->ixb = 0.08; p->ixp = 0.06;
+    {   // module_temperature.py:3-20 at 15 C
+        const double tk = (15 + 273.15) / 100;
+        const double f = 56.12 * exp(-66.7354 + 87.4755 / tk + 24.4526 * log(tk));
+        p->so_sat = 0.9997743214 * (8 / 10.5) * 6791.5 * f;
+    }
+    p->pid_Kc = 5.0; p->pid_tauI = 0.00035; p->pid_tauD = 0.005; p->pid_dt = 0.02 / 24;
+    p->kla_min = 0.0; p->kla_max = 240.0;
+    p->WV = 1.32; p->Qin = 1.32 - 0.6161484733495801; p->Qeff = 0.66; p->biomass_setpoint = 2700.0;
+    p->settler_area = (1.25 / 2) * (1.25 / 2); p->settler_vmax = 474.0;
+    p->kla0 = 0.0; p->action_scale = 8.0;
+    p->os_Kc_DO = 100.0; p->os_tauI_DO = 20.0; p->os_tauD_DO = 0.0;
+    p->os_Kc_EC = 100.0; p->os_tauI_EC = 20.0; p->os_tauD_EC = 0.0;
+    p->os_pid_dt = 0.002 / 24; p->ec_min = 0.0; p->ec_max = 0.0005; p->ec_conc = 1200000.0 * 4;
+    p->do_sp_max = 8.0; p->no_sp_max = 15.0;
+}
+
+int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
+                 const SbrParams* p, const SbrSchedule* s, double* x_last, double* obs, double* reward,
+                 double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!x0 || !influent || !action || !s || !x_last || !obs || !reward)
+        return fail(SBR_ERR_ARG, "sbr_cycle_v2: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cycle_v2: bad mode%s");
+    for (int k = 0; k < SBR_NPHASE; ++k) {
+        if (k == 5 || k == 6) continue;
+        if (s->n_int[k] < 1 || s->n_sub[k] < 1 || !(s->interval[k] > 0))
+            return fail(SBR_ERR_ARG, "sbr_cycle_v2: schedule needs n_int, n_sub >= 1 and interval > 0%s");
+    }
+    CycleArgs g{n, ld, x0, influent, action, x_last, obs, reward, aux, status, counters};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4)
+        sbr_cycle_v2_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, st>>>(g, *p, c, *s, t);
+    else
+        sbr_cycle_v2_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, st>>>(g, *p, c, *s, t);
+    return check_launch("sbr_cycle_v2");
+}
+
+int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, const double* ec,
+                           const double* loading, const SbrParams* p, int tail, double T, int n_sub,
+                           int mode, const SbrTol* tol, uint32_t* counters, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!x || !kla) return fail(SBR_ERR_ARG, "sbr_integrate_interval: NULL buffer%s");
+    if (tail == sbr::TAIL_FILL && !loading) return fail(SBR_ERR_ARG, "sbr_integrate_interval: fill tail needs loading%s");
+    if (tail == sbr::TAIL_EC && !ec) return fail(SBR_ERR_ARG, "sbr_integrate_interval: EC tail needs ec%s");
+    if (!(T > 0) || n_sub < 1) return fail(SBR_ERR_ARG, "sbr_integrate_interval: T > 0 and n_sub >= 1 required%s");
+    IntervalArgs g{n, ld, x, kla, ec, loading, counters, T, n_sub};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SBR_LAUNCH(TAIL, MODE) sbr_interval_kernel<TAIL, MODE><<<grid, kBlock, 0, st>>>(g, *p, c, t)
+    if (mode == SBR_MODE_RK4) {
+        if (tail == sbr::TAIL_REACT) SBR_LAUNCH(sbr::TAIL_REACT, SBR_MODE_RK4);
+        else if (tail == sbr::TAIL_FILL) SBR_LAUNCH(sbr::TAIL_FILL, SBR_MODE_RK4);
+        else if (tail == sbr::TAIL_EC) SBR_LAUNCH(sbr::TAIL_EC, SBR_MODE_RK4);
+        else return fail(SBR_ERR_ARG, "sbr_integrate_interval: bad tail%s");
+    } else if (mode == SBR_MODE_DP45) {
+        if (tail == sbr::TAIL_REACT) SBR_LAUNCH(sbr::TAIL_REACT, SBR_MODE_DP45);
+        else if (tail == sbr::TAIL_FILL) SBR_LAUNCH(sbr::TAIL_FILL, SBR_MODE_DP45);
+        else if (tail == sbr::TAIL_EC) SBR_LAUNCH(sbr::TAIL_EC, SBR_MODE_DP45);
+        else return fail(SBR_ERR_ARG, "sbr_integrate_interval: bad tail%s");
+    } else {
+        return fail(SBR_ERR_ARG, "sbr_integrate_interval: bad mode%s");
+    }
+#undef SBR_LAUNCH
+    return check_launch("sbr_integrate_interval");
+}
+
+int sbr_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const double* ec, const double* loading,
+            const SbrParams* p, int tail, double* dx, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!x || !kla || !dx) return fail(SBR_ERR_ARG, "sbr_rhs: NULL buffer%s");
+    if (tail == sbr::TAIL_FILL && !loading) return fail(SBR_ERR_ARG, "sbr_rhs: fill tail needs loading%s");
+    if (tail == sbr::TAIL_EC && !ec) return fail(SBR_ERR_ARG, "sbr_rhs: EC tail needs ec%s");
+    RhsArgs g{n, ld, x, kla, ec, loading, dx};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tail == sbr::TAIL_REACT) sbr_rhs_kernel<sbr::TAIL_REACT><<<grid, kBlock, 0, st>>>(g, *p, c);
+    else if (tail == sbr::TAIL_FILL) sbr_rhs_kernel<sbr::TAIL_FILL><<<grid, kBlock, 0, st>>>(g, *p, c);
+    else if (tail == sbr::TAIL_EC) sbr_rhs_kernel<sbr::TAIL_EC><<<grid, kBlock, 0, st>>>(g, *p, c);
+    else return fail(SBR_ERR_ARG, "sbr_rhs: bad tail%s");
+    return check_launch("sbr_rhs");
+}
+
+int sbr_reward_stats_init(double* stats, void* stream) {
+    if (!stats) return fail(SBR_ERR_ARG, "sbr_reward_stats_init: NULL buffer%s");
+    sbr_reward_stats_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(stats);
+    return check_launch("sbr_reward_stats_init");
+}
+
+int sbr_reward_stats(int64_t n, const double* reward, const int32_t* status, double* stats, void* stream) {
+    if (n <= 0 || !reward || !stats) return fail(SBR_ERR_ARG, "sbr_reward_stats: bad arguments%s");
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sbr_reward_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, reward, status, stats);
+    return check_launch("sbr_reward_stats");
+}
+
+int sbr_fp64_probe(int blocks, int threads, int iters, double* sink, double* flops, void* stream) {
+    if (blocks < 1 || threads < 1 || threads > 1024 || iters < 1 || !sink)
+        return fail(SBR_ERR_ARG, "sbr_fp64_probe: bad arguments%s");
+    sbr_fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (flops) *flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    return check_launch("sbr_fp64_probe");
+}
+
+}  // extern "C"

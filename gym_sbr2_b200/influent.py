@@ -1,0 +1,79 @@
+"""Influent generator: the step before the hot path (buffer_tank3.influent.buffer_tank, buffer_tank3.py:13-1197).
+
+Eight scenarios (`switch` 0..7: dry / carbon-rich / high-load / N-rich x morning / evening) of 48-point mean
+profiles for the 13 concentrations and the flow; each draw perturbs every profile with ONE shared
+rnd ~ N(0,1)^48 (std = 0.1*mean for Ss, Xi, Xs, Xbh, Snh, Snd, Xnd and q, 0 for the rest, buffer_tank3.py:50-66)
+and returns the flow-weighted mean concentrations, `influent_mixed = [0.66, sum(c*q)/sum(q) ...]`
+(buffer_tank3.py:87-107).  Scenario 0 consumes one randn(48) from the RNG, scenarios 1..7 consume two and use
+the second (buffer_tank3.py:206,224).  The mean profiles are data, extracted from the reference by
+oracle/extract_influent_tables.py into data/influent_tables.npz.
+
+`mix_numpy` is bit-exact with the reference (sequential sums, same operation order) and serves the single-env
+Gym wrappers, where "identical seeds" means np.random.seed(s) before reset().  `mix_torch` is the batched
+device version used by the vector envs (same formula, parallel reduction order -> ~1e-16 relative).
+"""
+import os
+
+import numpy as np
+
+_TABLES = None
+N_POINTS = 48
+
+
+def tables():
+    global _TABLES
+    if _TABLES is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "influent_tables.npz")
+        z = np.load(path)
+        _TABLES = dict(mean=z["mean"], std_frac=z["std_frac"], draws=z["draws"])
+    return _TABLES
+
+
+def draws_per_reset(switch):
+    """How many randn(48) vectors one buffer_tank(switch) call consumes (the last one is used)."""
+    return int(tables()["draws"][int(switch)])
+
+
+def mix_numpy(switch, rnd):
+    """influent_mixed (14-vector, [0] = 0.66) for one env from one rnd[48]; bit-exact with the reference."""
+    t = tables()
+    mean, frac = t["mean"][int(switch)], t["std_frac"][int(switch)]
+    rnd = np.asarray(rnd, dtype=np.float64)
+    prof = np.empty((14, N_POINTS))
+    for j in range(14):
+        prof[j] = mean[j] + (frac[j] * mean[j]) * rnd if frac[j] != 0 else mean[j] + 0 * rnd
+    q = prof[0]
+    qsum = np.cumsum(q)[-1]                      # sequential, like the builtin sum() the reference uses
+    out = np.empty(14)
+    out[0] = 0.66
+    for j in range(1, 14):
+        out[j] = np.cumsum(prof[j] * q)[-1] / qsum
+    return out
+
+
+def sample_numpy(switch, rng=None):
+    """One buffer_tank(switch) call: consumes draws_per_reset(switch) x randn(48) from `rng` (default: the
+    global numpy RNG, as the reference does) and returns influent_mixed."""
+    rng = np.random if rng is None else rng
+    rnd = None
+    for _ in range(draws_per_reset(switch)):
+        rnd = rng.randn(N_POINTS)
+    return mix_numpy(switch, rnd)
+
+
+def mix_torch(switch, rnd):
+    """Batched device version: rnd [n, 48] (torch, float64) -> influent_mixed SoA [14, n]."""
+    import torch
+    t = tables()
+    mean = torch.as_tensor(t["mean"][int(switch)], dtype=torch.float64, device=rnd.device)          # [14,48]
+    std = torch.as_tensor(t["std_frac"][int(switch)][:, None] * t["mean"][int(switch)], dtype=torch.float64,
+                          device=rnd.device)
+    n = rnd.shape[0]
+    out = torch.empty((14, n), dtype=torch.float64, device=rnd.device)
+    out[0] = 0.66
+    q = mean[0][None, :] + std[0][None, :] * rnd                 # [n,48]
+    qsum = q.sum(dim=1)
+    for j in range(1, 14):
+        c = mean[j][None, :] + std[j][None, :] * rnd
+        out[j] = (c * q).sum(dim=1) / qsum
+    return out

@@ -1,0 +1,62 @@
+"""Host-side time schedule of one SBR cycle.
+
+The reference derives every loop count from `int(float_expr)` truncation:
+  * phase boundaries: phase 1 starts at 0, every later phase at previous end + t_delta, length
+    t_cycle * t_ratio[k]                                   (SBR_model_FB.py:17-25, 60-264)
+  * PID intervals per phase: len(linspace(t0, t1, int((t1-t0)/(10*t_delta)))) - 1
+                                                            (sub_phases_FB.py:183-184)
+  * output points per interval: int((te-ts)/t_delta)        (sub_phases_FB.py:231)
+so the schedule is computed here with the same numpy float64 expressions and shipped to the kernel as a small
+table (SbrSchedule) instead of being re-derived on the device, where FMA contraction could change a count.
+"""
+import numpy as np
+
+from . import _abi
+
+T_CYCLE = 12 / 24
+T_RATIO = (4.2 / 100, 8.3 / 100, 37.5 / 100, 31.2 / 100, 2.1 / 100, 8.3 / 100, 2.1 / 100, 6.3 / 100)
+T_DELTA = 0.002 / 24
+
+
+def phase_bounds(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
+    bounds = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + t_delta
+        t_end = t_start + t_cycle * t_ratio[k]
+        bounds.append((t_start, t_end))
+    return bounds
+
+
+def pid_grid(t_start, t_end, t_delta=T_DELTA):
+    """(interval boundaries, output points per interval) of one PID-controlled phase."""
+    t_save2 = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+    pts = [int((t_save2[i + 1] - t_save2[i]) / t_delta) for i in range(len(t_save2) - 1)]
+    return t_save2, pts
+
+
+def cycle_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
+    """SbrSchedule for the cycle-per-step path (SBR-v2)."""
+    s = _abi.SbrSchedule()
+    bounds = phase_bounds(t_cycle, t_ratio, t_delta)
+    for k in range(8):
+        t0, t1 = bounds[k]
+        if k in (5, 6):
+            s.n_int[k], s.n_sub[k], s.interval[k] = 0, 0, 0.0
+            continue
+        grid, pts = pid_grid(t0, t1, t_delta)
+        n_int = len(grid) - 1
+        if n_int < 1:
+            raise ValueError("phase %d has no PID interval" % (k + 1))
+        if len(set(pts)) != 1:
+            raise ValueError("phase %d: output points per interval are not uniform: %s" % (k + 1, sorted(set(pts))))
+        s.n_int[k] = n_int
+        s.n_sub[k] = pts[0] - 1                    # RK4 sub-steps = gaps between the reference's output points
+        s.interval[k] = (t1 - t0) / n_int
+    # the settler integrates over linspace(t0, t1, int((t1-t0)/t_delta)) -> total span t1 - t0
+    s.settle_time = bounds[5][1] - bounds[5][0]
+    return s
+
+
+def schedule_summary(s):
+    return dict(n_int=list(s.n_int), n_sub=list(s.n_sub), interval=list(s.interval), settle_time=s.settle_time)

@@ -1,0 +1,108 @@
+"""Vectorised SBR environments: N independent reactors stepped by one CUDA launch.
+
+`SbrV2VecEnv` is the batched drop-in for the reference's `SbrEnv2` (id `SBR-v2`, gym_SBR_env2.py:58-193):
+one `step` = one whole 12-h cycle (fill, 4 react phases, settle, draw, idle) with the DO->KLa PID inside.
+Observation / action / reward semantics are the reference's; tensors are torch CUDA float64.  The reference
+keeps its state in module globals, so two reference envs in one process share state;
+the semantics here are "N fresh processes each running one env".
+"""
+import numpy as np
+import torch
+
+from . import _abi, core, influent as influent_mod, schedule
+
+X0_INIT = (0.6161484733495801, 30, 0.571098000538576, 1440.01157895393, 31.254221999137, 2599.2714348941,
+           168.915006750837, 551.901552960823, 2.16607843793004, 13.3791460027604, 0.00562880208518134,
+           0.35996687629947, 1.86916737961228, 3.790463057094611)        # gym_SBR_env2.py:78-80
+WV = 1.32                                                                  # gym_SBR_env2.py:33
+IV = 0.6161484733495801                                                    # gym_SBR_env2.py:85
+
+
+class SbrV2VecEnv(object):
+    """N x `SBR-v2`.  reset() -> obs [N,3]; step(action [N,3]) -> (obs [N,3], reward [N], done [N], info).
+
+    action: raw, clipped to [0,1] in the kernel; DO set-points of phases 3, 5, 8 = 8*action
+            (gym_SBR_env2.py:133,184-186).
+    obs after reset: [V, (sum COD - 5145)/10, Snh/30] of the element-wise SUM x0 + influent_mixed
+            (gym_SBR_env2.py:108-118); after step: [Qeff, COD_eff, Snh_eff/30] (:162-168).
+    done is always True (one step = one episode, :160); like the reference, every step replays the cycle from
+    x0_init with the influent drawn at the last reset (:88-99,152-153).
+    info: x_last [14,N], status [N], counters [2,N], aux rows by name (OCI, Qw, EQI, eff_*, kla*_mean).
+    """
+
+    num_actions = 3
+    num_obs = 3
+    scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
+
+    def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=4000,
+                 params=None, rng="torch"):
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _abi.SbrLibraryError("SbrV2VecEnv needs a CUDA device: there is no CPU fallback")
+        self.lib = _abi.load()
+        self.params = params if params is not None else _abi.default_params()
+        self.sched = schedule.cycle_schedule()
+        self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
+        self.tol = _abi.make_tol(rtol, atol, max_steps)
+        self.rng = rng
+        self._gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self._gen.manual_seed(int(seed))
+        self._np_rng = np.random.RandomState(seed) if seed is not None else np.random
+        n = self.num_envs
+        f = dict(dtype=torch.float64, device=self.device)
+        self.x0 = torch.tensor(X0_INIT, **f)[:, None].repeat(1, n).contiguous()
+        self.influent = torch.zeros((_abi.NX, n), **f)
+        self.Qin = WV - IV
+        t_fill = schedule.T_CYCLE * schedule.T_RATIO[0]
+        self.fill_flow = self.Qin / t_fill                                    # gym_SBR_env2.py:144
+        self._loading = torch.zeros((_abi.NX, n), **f)
+        self._action = torch.zeros((3, n), **f)
+        self._out = core.CycleV2Out(n, self.device)
+        self._done = torch.ones((n,), dtype=torch.bool, device=self.device)
+
+    # -- influent ------------------------------------------------------------------------------------
+    def _draw_influent(self):
+        n = self.num_envs
+        if self.rng == "numpy":
+            # N sequential buffer_tank(0) calls on one numpy stream, as N reference resets would make
+            d = influent_mod.draws_per_reset(self.scenario)
+            r = self._np_rng.randn(n, d, influent_mod.N_POINTS)[:, -1, :]
+            rnd = torch.as_tensor(r, dtype=torch.float64).to(self.device)
+        else:
+            rnd = torch.randn((n, influent_mod.N_POINTS), dtype=torch.float64, device=self.device,
+                              generator=self._gen)
+        return influent_mod.mix_torch(self.scenario, rnd)
+
+    def reset(self, influent=None, x0=None):
+        """influent: optional [14,N] influent_mixed (row 0 ignored at step time); x0: optional [14,N]."""
+        if influent is None:
+            influent = self._draw_influent()
+        self.influent.copy_(influent.to(self.device, torch.float64))
+        if x0 is not None:
+            self.x0.copy_(x0.to(self.device, torch.float64))
+        s = self.x0 + self.influent
+        cod = s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7]
+        return torch.stack([s[0], (cod - 5145) / 10, s[10] / 30], dim=1)
+
+    # -- step ----------------------------------------------------------------------------------------
+    def step_async(self, action, stream=None):
+        """Launch one cycle for every env; returns the SoA output buffers without synchronising."""
+        if action.shape != (self.num_envs, 3):
+            raise ValueError("action must be [N,3], got %s" % (tuple(action.shape),))
+        self._action.copy_(action.to(self.device, torch.float64).t())
+        self._loading.copy_(self.influent)
+        self._loading[0] = self.fill_flow
+        return core.cycle_v2(self.x0, self._loading, self._action, self.params, self.sched, out=self._out,
+                             mode=self.mode, tol=self.tol, stream=stream)
+
+    def step(self, action):
+        o = self.step_async(action)
+        info = dict(x_last=o.x_last, status=o.status, counters=o.counters)
+        for k, name in enumerate(_abi.AUX_NAMES):
+            info[name] = o.aux[k]
+        return o.obs.t(), o.reward, self._done, info
+
+    def render(self, mode="human", close=False):
+        print("Reward for this episode: {}".format(self._out.reward))

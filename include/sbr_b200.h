@@ -1,0 +1,149 @@
+/*
+ * sbr_b200.h -- C ABI of the B200-native batched sequencing-batch-reactor stepper.
+ *
+ * The reference (SungKu/gym-SBR2) has no FFI layer: its boundary is the Gym API and, underneath, one
+ * `scipy.integrate.odeint(func, y0, t, args)` call per PID interval with a Python RHS callback
+ * (sub_phases_FB.py:252,480,769-770; gym_SBR_oneshot.py:1647,1953,2041,2318-2319,2587).  Each entry point
+ * below replaces a whole reference call tree for a BATCH of n independent environments; the reference
+ * function each one stands in for is cited on the declaration.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is a DEVICE pointer owned by the caller (torch tensors on the Python
+ *     side); the library allocates nothing and keeps no mutable global state; launches are asynchronous on the
+ *     `stream` argument (a cudaStream_t passed as void*, NULL = legacy default stream); no implicit sync.
+ *   - struct-of-arrays: component c of env i lives at  base[c * ld + i]  (ld >= n, in elements), so loads and
+ *     stores of consecutive envs are coalesced.
+ *   - state component order (SBR_model_FB.py:199-203):
+ *       0=V 1=Si 2=Ss 3=Xi 4=Xs 5=Xbh 6=Xba 7=Xp 8=So 9=Sno 10=Snh 11=Snd 12=Xnd 13=Salk ; time unit = day.
+ *   - return value: 0 = ok; < 0 = argument / launch error (text via sbr_last_error(), thread-local).
+ *     Per-env numerical trouble never raises: it is reported in status[i] (SBR_ST_* bits).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SBR_ERR_CUDA.
+ */
+#ifndef SBR_B200_H
+#define SBR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBR_ABI_VERSION 1
+#define SBR_NX 14            /* state components per env */
+#define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
+
+/* integrator modes */
+#define SBR_MODE_RK4 0       /* fixed step on the reference's own output grid (len(t_range)-1 sub-steps) */
+#define SBR_MODE_DP45 1      /* Dormand-Prince 5(4), per-env adaptive step, FSAL */
+
+/* status bits */
+#define SBR_ST_NONFINITE 1   /* state left the finite range                                             */
+#define SBR_ST_WASTE 2       /* waste loop ended without fixing Qw (reference: NameError, sub_phases_FB.py:817-836) */
+#define SBR_ST_STEPLIMIT 4   /* DP45 hit max_steps inside one interval                                 */
+#define SBR_ST_LAYERS 8      /* decant layer count m outside 1..9                                       */
+
+/* error codes */
+#define SBR_OK 0
+#define SBR_ERR_ARG -1
+#define SBR_ERR_CUDA -2
+
+/* aux[] rows written by sbr_cycle_v2 (aux[r * ld + i]) */
+enum {
+    SBR_AUX_OCI = 0, SBR_AUX_QW, SBR_AUX_EQI, SBR_AUX_EFF_Q, SBR_AUX_EFF_NTOT, SBR_AUX_EFF_COD,
+    SBR_AUX_EFF_SNH, SBR_AUX_EFF_BOD5, SBR_AUX_EFF_SNO, SBR_AUX_KLA3_MEAN, SBR_AUX_KLA5_MEAN,
+    SBR_AUX_KLA8_MEAN, SBR_AUX_ROWS
+};
+
+/* Model / plant / controller constants.  Defaults = SURVEY.md appendix A (sbr_params_default). */
+typedef struct SbrParams {
+    /* kinetic, Kpar (SBR_model_FB.py:38) */
+    double muh, Ks, Koh, Kno, bh, etag, etah, kh, Kx, mua, Knh, ba, Koa, ka;
+    /* stoichiometric, Spar (SBR_model_FB.py:36) */
+    double Ya, Yh, fp, ixb, ixp;
+    double so_sat;                 /* module_temperature.py:3-20, DO_set(15) */
+    /* DO->KLa PID of the cycle-per-step path (gym_SBR_env2.py:48): Kc, tauI, tauD, PID dt, clamps */
+    double pid_Kc, pid_tauI, pid_tauD, pid_dt, kla_min, kla_max;
+    /* plant (gym_SBR_env2.py:33,85,93; SBR_model_FB.py:224-226; sub_phases_FB.py:737,662) */
+    double WV, Qin, Qeff, biomass_setpoint, settler_area, settler_vmax;
+    double kla0;                   /* initial KLa bias of phase 1 (gym_SBR_env2.py:56) */
+    double action_scale;           /* DO set-point = action * action_scale (gym_SBR_env2.py:184-186) */
+    /* interval-per-step path (gym_SBR_oneshot.py:83-96): DO and NO3 PIDs, EC dosing */
+    double os_Kc_DO, os_tauI_DO, os_tauD_DO, os_Kc_EC, os_tauI_EC, os_tauD_EC;
+    double os_pid_dt, ec_min, ec_max, ec_conc, do_sp_max, no_sp_max;
+} SbrParams;
+
+/* Time schedule of one cycle (computed on the host with the reference's own float expressions,
+ * sub_phases_FB.py:183-184,231; SBR_model_FB.py:17-25): per phase the number of PID intervals, the
+ * number of RK4 sub-steps per interval and the interval length in days.  Phases 5 and 6 (settle, draw)
+ * only use settle_time. */
+typedef struct SbrSchedule {
+    int32_t n_int[SBR_NPHASE];
+    int32_t n_sub[SBR_NPHASE];
+    double interval[SBR_NPHASE];
+    double settle_time;
+} SbrSchedule;
+
+/* Adaptive-step controls (SBR_MODE_DP45). */
+typedef struct SbrTol {
+    double rtol, atol;     /* mixed tolerance: err_i <= atol * scale_i + rtol * |x_i|          */
+    int32_t max_steps;     /* per PID interval, accepted + rejected                            */
+    int32_t reserved;
+} SbrTol;
+
+int sbr_abi_version(void);
+const char* sbr_last_error(void);
+/* number of CUDA devices visible to the library (0 = none, compute entry points will fail) */
+int sbr_device_count(void);
+
+void sbr_params_default(SbrParams* p);
+
+/*
+ * One whole 12-h cycle for n envs = SbrEnv2.step (gym_SBR_env2.py:131-171) -> SBR_model_FB.run
+ * (SBR_model_FB.py:8-295) -> filling/rxn.sim_rxn + odeint (sub_phases_FB.py:178-271, 406-500), settling
+ * (:716-775), drawing + cal_eq (:780-915), module_reward.sbr_reward (module_reward.py:4-51).
+ *   x0        [14][ld] in   start state
+ *   influent  [14][ld] in   row 0 = fill flow m3/d (gym_SBR_env2.py:144), rows 1..13 = influent concentrations
+ *   action    [3][ld]  in   raw action, clipped to [0,1] inside (gym_SBR_env2.py:133)
+ *   x_last    [14][ld] out  state at the end of the idle phase
+ *   obs       [3][ld]  out  [Qeff, COD_eff, Snh_eff/30]
+ *   reward    [n]      out
+ *   aux       [SBR_AUX_ROWS][ld] out (may be NULL)
+ *   status    [n] out (may be NULL);  counters [2][ld] out: RHS evaluations, rejected steps (may be NULL)
+ */
+int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
+                 const SbrParams* p, const SbrSchedule* s, double* x_last, double* obs, double* reward,
+                 double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+
+/*
+ * Stage-level entry (unit tests, and the seam where the reference calls odeint): advance n envs over ONE
+ * interval of length T with constant KLa (and EC dosing / fill loading) -- replaces a single
+ * `odeint(dxdt, x, t_range, args=(..., Kla[i], ...))` call (sub_phases_FB.py:252,480; gym_SBR_oneshot.py:1953).
+ *   tail: 0 = react, 1 = fill (loading [14][ld] required), 2 = react + EC dosing (ec [n] required)
+ *   x [14][ld] in/out; kla [n]; n_sub = RK4 sub-steps (ignored by DP45)
+ */
+int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, const double* ec,
+                           const double* loading, const SbrParams* p, int tail, double T, int n_sub,
+                           int mode, const SbrTol* tol, uint32_t* counters, void* stream);
+
+/* Kinetic right-hand side only: dx [14][ld] = f(x) -- replaces rxn.dxdt / filling.dxdt / reaction_dxdt
+ * (sub_phases_FB.py:51-176, 278-404; gym_SBR_oneshot.py:1658-1787). */
+int sbr_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const double* ec,
+            const double* loading, const SbrParams* p, int tail, double* dx, void* stream);
+
+/* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
+ * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the
+ * envs whose status is 0 (all envs if status == NULL).  stats must be zero-initialised by the caller with
+ * stats[2] = +inf, stats[3] = -inf (sbr_reward_stats_init does it on the stream). */
+int sbr_reward_stats_init(double* stats, void* stream);
+int sbr_reward_stats(int64_t n, const double* reward, const int32_t* status, double* stats, void* stream);
+
+/* FP64 pipe probe: runs `iters` rounds of 8 independent DFMA chains per thread on `blocks` x `threads`
+ * and returns the number of floating-point operations issued (2 per DFMA) in *flops; time it with CUDA events
+ * around the call to get the measured FP64 roofline denominator.  sink [blocks*threads] out. */
+int sbr_fp64_probe(int blocks, int threads, int iters, double* sink, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBR_B200_H */

@@ -1,0 +1,340 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+A numpy/scipy restatement of the reference's sequencing-batch-reactor hot path, written from the
+reference's behaviour (file:line citations on every function, all relative to /root/reference/gym_SBR/envs).
+It is the checker the CUDA path is compared with; it is also timed as the CPU baseline (`bench.py`,
+`cpu_baseline.kind == "port"`).  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import it.  The product package `gym_sbr2_b200` never does.
+
+Arithmetic: like the reference, every ODE solve is `scipy.integrate.odeint` (ODEPACK LSODA, default
+rtol = atol = 1.49e-8) called once per PID interval with a Python RHS callback -- the integrator is a
+third-party dependency the reference does not pin (setup.py:3 lists only `gym`); the golden vectors in
+tests/golden/ were produced by the *unmodified reference* under scipy 1.18.1 / numpy 2.3.5 (recorded in the
+fixtures).  Parity pin: tests/test_oracle_golden.py checks this file against those reference outputs
+(whole-cycle state, reward, OCI, Qw, EQI, per-phase interval counts; per-step rewards/obs/done for SBROS-v1).
+The reference holds no tests or golden vectors of its own, so these fixtures, generated
+from the reference itself by oracle/make_golden.py, are the pin.
+
+State vector (all files): 0=V 1=Si 2=Ss 3=Xi 4=Xs 5=Xbh 6=Xba 7=Xp 8=So 9=Sno 10=Snh 11=Snd 12=Xnd 13=Salk
+(SBR_model_FB.py:199-203).  Time unit: day.
+"""
+import math
+
+import numpy as np
+from scipy.integrate import odeint
+
+# ----------------------------------------------------------------------------------------------------------
+# constants
+# ----------------------------------------------------------------------------------------------------------
+WV = 1.32                                   # gym_SBR_env2.py:33
+IV = 0.6161484733495801                     # gym_SBR_env2.py:85
+QIN = WV - IV                               # gym_SBR_env2.py:93
+QEFF = 0.66                                 # SBR_model_FB.py:226
+BIOMASS_SETPOINT = 2700                     # SBR_model_FB.py:224
+T_CYCLE = 12 / 24                           # gym_SBR_env2.py:39
+T_RATIO = [4.2 / 100, 8.3 / 100, 37.5 / 100, 31.2 / 100, 2.1 / 100, 8.3 / 100, 2.1 / 100, 6.3 / 100]
+DT = 0.002 / 24                             # gym_SBR_env2.py:36 (`t_delta`)
+X0_INIT = [0.6161484733495801, 30, 0.571098000538576, 1440.01157895393,
+           31.254221999137, 2599.2714348941, 168.915006750837, 551.901552960823, 2.16607843793004,
+           13.3791460027604, 0.00562880208518134, 0.35996687629947, 1.86916737961228,
+           3.790463057094611]              # gym_SBR_env2.py:78-80
+SPAR = dict(Ya=0.24, Yh=0.67, fp=0.08, ixb=0.08, ixp=0.06)                       # SBR_model_FB.py:36
+KPAR = dict(muh=4.0, Ks=10.0, Koh=0.2, Kno=0.5, bh=0.3, etag=0.8, etah=0.8, kh=3.0, Kx=0.1,
+            mua=0.5, Knh=1.0, ba=0.05, Koa=0.4, ka=0.05)                          # SBR_model_FB.py:38
+
+
+def do_saturation(temp_c=15.0):
+    """Oxygen saturation vs temperature (module_temperature.py:3-20); 8.000000000006622 at 15 C."""
+    tk = (temp_c + 273.15) / 100
+    f = 56.12 * np.exp(-66.7354 + 87.4755 / tk + 24.4526 * np.log(tk))
+    return 0.9997743214 * (8 / 10.5) * 6791.5 * f
+
+
+SO_SAT = float(do_saturation(15))
+# Path-A controller: Kc, tauI, PID dt, Kla_min, Kla_max, tauD  (gym_SBR_env2.py:48)
+PID_A = dict(Kc=5.0, tauI=0.00035, dt=0.02 / 24, lo=0.0, hi=240.0, tauD=0.005)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# kinetics: one RHS, three tails
+# ----------------------------------------------------------------------------------------------------------
+def asm1_rates(x, kla, so_sat=SO_SAT):
+    """Component conversion rates r[1..13] of the ASM1-type model incl. aeration (sub_phases_FB.py:278-372).
+
+    Quirks kept on purpose: `ixp` is used where ASM1 has `fp` in the decay stoichiometry
+    (sub_phases_FB.py:325-333).
+    """
+    K, S = KPAR, SPAR
+    Ss, Xs, Xbh, Xba, So, Sno, Snh, Snd, Xnd = x[2], x[4], x[5], x[6], x[8], x[9], x[10], x[11], x[12]
+    # process rates (sub_phases_FB.py:280-303)
+    rho1 = K['muh'] * (Ss / (K['Ks'] + Ss)) * (So / (K['Koh'] + So)) * Xbh
+    rho2 = K['muh'] * (Ss / (K['Ks'] + Ss)) * (K['Koh'] / (So + K['Koh'])) * (Sno / (K['Kno'] + Sno)) * K['etag'] * Xbh
+    rho3 = K['mua'] * (Snh / (K['Knh'] + Snh)) * (So / (K['Koa'] + So)) * Xba
+    rho4 = K['bh'] * Xbh
+    rho5 = K['ba'] * Xba
+    rho6 = K['ka'] * Snd * Xbh
+    rho7 = K['kh'] * ((Xs / Xbh) / (K['Kx'] + (Xs / Xbh))) * (
+        (So / (K['Koh'] + So)) + K['etah'] * (K['Koh'] / (So + K['Koh'])) * (Sno / (K['Kno'] + Sno))) * Xbh
+    rho8 = (Xnd / Xs) * rho7
+    Ya, Yh, fp, ixb, ixp = S['Ya'], S['Yh'], S['fp'], S['ixb'], S['ixp']
+    r = np.zeros(14)
+    r[2] = (-1 / Yh) * rho1 + (-1 / Yh) * rho2 + rho7
+    r[4] = (1 - ixp) * rho4 + (1 - ixp) * rho5 - rho7
+    r[5] = rho1 + rho2 - rho4
+    r[6] = rho3 - rho5
+    r[7] = ixp * rho4 + ixp * rho5
+    r[8] = (-(1 - Yh) / Yh) * rho1 + (-(4.57 - Ya) / Ya) * rho3 + kla * (so_sat - So)
+    r[9] = (-((1 - Yh) / (2.86 * Yh))) * rho2 + (1 / Ya) * rho3
+    r[10] = (-ixb) * rho1 + (-ixb) * rho2 + (-ixb - 1 / Ya) * rho3 + rho6
+    r[11] = -rho6 + rho8
+    r[12] = (ixb - fp * ixp) * rho4 + (ixb - fp * ixp) * rho5 - rho8
+    r[13] = (-ixb / 14) * rho1 + ((1 - Yh) / (14 * 2.86 * Yh) - ixb / 14) * rho2 \
+        + (-ixb / 14 - 1 / (7 * Ya)) * rho3 + (1 / 14) * rho6
+    return r
+
+
+def rhs_react(x, t, kla):
+    """React tail: dx_i/dt = r_i, dV/dt = 0 (sub_phases_FB.py:374-404)."""
+    return asm1_rates(x, kla)
+
+
+def rhs_fill(x, t, kla, loading):
+    """Fill tail: dV/dt = q, dx_i/dt = r_i + (q/V)(c_in,i - x_i) (sub_phases_FB.py:146-176)."""
+    d = asm1_rates(x, kla)
+    q = loading[0]
+    for i in range(1, 14):
+        d[i] = d[i] + (q / x[0]) * (loading[i] - x[i])
+    d[0] = q
+    return d
+
+
+def rhs_react_ec(x, t, kla, ec, ec_conc):
+    """React + external-carbon dosing tail (gym_SBR_oneshot.py:1757-1787)."""
+    d = asm1_rates(x, kla)
+    for i in range(1, 14):
+        d[i] = d[i] + (ec / x[0]) * (-x[i])
+    d[2] = d[2] + (ec / x[0]) * ec_conc
+    d[0] = ec
+    return d
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Path A (SBR-v2): PID-controlled phases, settle, draw, reward
+# ----------------------------------------------------------------------------------------------------------
+def phase_grid(t_start, t_end, t_delta=DT):
+    """Interval boundaries of one PID-controlled phase (sub_phases_FB.py:183-184, 226-231).
+
+    Returns (t_save2, points_per_interval).  Both sizes come from int(float) truncation in the reference.
+    """
+    t_save2 = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+    pts = [int((t_save2[i + 1] - t_save2[i]) / t_delta) for i in range(len(t_save2) - 1)]
+    return t_save2, pts
+
+
+def cycle_schedule():
+    """[(t_start, t_end)] for the 8 phases exactly as SBR_model_FB.run sequences them (SBR_model_FB.py:17-25,
+    60-264): phase 1 starts at 0, every later phase starts at the previous end + t_delta."""
+    out = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + DT
+        t_end = t_start + T_CYCLE * T_RATIO[k]
+        out.append((t_start, t_end))
+    return out
+
+
+def pid_phase(x, t_start, t_end, sp, kla_bias, rhs, rhs_args=(), pid=PID_A, ode_kw=None, tap=None):
+    """One PID-controlled phase: filling.sim_rxn / rxn.sim_rxn (sub_phases_FB.py:178-271, 406-500).
+
+    Positional PID on So sampled at interval starts; the bias is the *clamped* output of interval 0
+    (Kla[0] is overwritten, sub_phases_FB.py:218,243); two independent clamp checks with anti-windup
+    (:245-250).  Returns (x_end, Kla per interval).
+    """
+    ode_kw = ode_kw or {}
+    t_save2, pts = phase_grid(t_start, t_end)
+    n = len(t_save2) - 1
+    Kc, tauI, tauD, dtc = pid['Kc'], pid['tauI'], pid['tauD'], pid['dt']
+    So = np.zeros(n)
+    e = np.zeros(n)
+    ie = np.zeros(n)
+    dcv = np.zeros(n)
+    Kla = np.zeros(n)
+    So[0] = x[8]
+    Kla[0] = kla_bias
+    x = np.asarray(x, dtype=float)
+    for i in range(n):
+        t_range = np.linspace(t_save2[i], t_save2[i + 1], pts[i])
+        e[i] = sp - So[i]
+        if i >= 1:
+            dcv[i] = (So[i] - So[i - 1]) / dtc
+            ie[i] = ie[i - 1] + e[i] * dtc
+        Kla[i] = Kc * e[i] + Kc / tauI * ie[i] + Kc * tauD * dcv[i] + Kla[0]
+        if Kla[i] > pid['hi']:
+            Kla[i] = pid['hi']
+            ie[i] = ie[i] - e[i] * dtc
+        if Kla[i] < pid['lo']:
+            Kla[i] = pid['lo']
+            ie[i] = ie[i] - e[i] * dtc
+        soln = odeint(rhs, x, t_range, args=(Kla[i],) + tuple(rhs_args), **ode_kw)
+        if tap is not None:
+            tap.append(dict(x0=np.array(x), kla=float(Kla[i]), T=float(t_range[-1] - t_range[0]),
+                            pts=len(t_range), x1=np.array(soln[-1]), args=rhs_args))
+        if i < n - 1:
+            So[i + 1] = soln[-1][8]
+        x = soln[-1]
+    return x, Kla
+
+
+def settler_rhs(sX, t, z, Xf):
+    """10-layer solids flux model (sub_phases_FB.py:622-714).  The reference takes max(vmax, ...), so the
+    settling velocity is the constant vmax = 474 m/d in every layer (kept as written)."""
+    vmax, rh, rp, fns = 474, 0.000576, 0.00286, 0.00228
+    v = np.array([max(vmax, np.exp(-rh * (s - fns * Xf)) - np.exp(-rp * (s - fns * Xf))) for s in sX])
+    J = v * sX
+    d = np.zeros_like(sX)
+    d[0] = J[1] / z
+    for i in range(1, 9):
+        d[i] = (J[i + 1] - J[i]) / z
+    d[9] = (0 - J[9]) / z
+    return d
+
+
+def settle(x, t_start, t_end, ode_kw=None):
+    """settling.sim_settling (sub_phases_FB.py:716-775) without the unused Xnd layers (their result is never
+    read downstream: SBR_model_FB.py:196,234).  Returns (sX[10], Xf)."""
+    ode_kw = ode_kw or {}
+    t_save = np.linspace(t_start, t_end, int((t_end - t_start) / DT))
+    Xf = 0.75 * (x[3] + x[4] + x[5] + x[6] + x[7])
+    As = (1.25 / 2) ** 2
+    z = x[0] / As
+    sol = odeint(settler_rhs, [Xf] * 10, t_save, args=(z, Xf), **ode_kw)
+    return sol[-1], Xf
+
+
+def effluent_quality(xe):
+    """drawing.cal_eq (sub_phases_FB.py:868-915): EQI and eff = [0.66, Ntot, COD, Snh, BOD5, Sno]."""
+    Si, Ss, Xi, Xs, Xbh, Xba, Xp, So, Sno, Snh, Snd, Xnd = xe[1:13]
+    Snkj = Snh + Snd + Xnd + 0.08 * (Xbh + Xba) + 0.06 * (Xp + Xi)
+    Ntot = Sno + Snkj
+    SS = 0.75 * (Xs + Xi + Xbh + Xba + Xp)
+    BOD5 = 0.25 * (Ss + Xs + (1 - 0.08) * (Xbh + Xba))
+    COD = Ss + Si + Xs + Xi + Xbh + Xba + Xp
+    EQI = (2 * SS + 1 * COD + 30 * Snkj + 10 * Sno + 2 * BOD5) * (1 / 1000) * 0.66
+    return EQI, [0.66, Ntot, COD, Snh, BOD5, Sno]
+
+
+def draw(x, sX, Xf, Qeff=QEFF, biomass_setpoint=BIOMASS_SETPOINT):
+    """drawing.sim_drawing (sub_phases_FB.py:780-864): decant `Qeff` from the top layers (the very top layer
+    is left out of the effluent-solids sum by the `[-m:-1]` slice, :794), then waste sludge bottom-up until the
+    remaining solids equal biomass_setpoint * remaining volume.  Returns (x_after, Qw, EQI, eff, status) where
+    status = 1 flags the reference's unassigned-`Qw` path (loop ends without reaching the `else`, :817-836)."""
+    x = np.array(x, dtype=float)
+    sX = np.array(sX, dtype=float)
+    V0 = x[0]
+    lv = V0 / 10
+    resV = V0 - Qeff
+    m = int(math.ceil(round(Qeff / lv)))
+    sX_eff = sum(sX[-m:-1] * lv)
+    xe = x.copy()
+    xe[0] = Qeff
+    for i in (4, 7, 3, 5, 6):
+        xe[i] = xe[i] * (1 / 0.75) * sX_eff / Xf
+    res = sX[0:10 - m].copy()
+    w_layer = lv * res
+    waste = sum(w_layer) - biomass_setpoint * resV
+    Qw = float('nan')
+    status = 1
+    for i in range(10 - m):
+        left = waste - w_layer[i]
+        if left > 0:
+            waste = left
+            res[i] = 0
+            w_layer[i] = 0
+            resV -= lv
+        else:
+            Qw = waste / (res[i] - biomass_setpoint)
+            w_layer[i] = w_layer[i] - Qw * res[i]
+            resV -= Qw
+            res[i] = w_layer[i] / (lv - Qw)
+            status = 0
+            break
+    sX2 = sum(w_layer) / resV
+    x7 = x.copy()
+    x7[0] = resV
+    for i in (4, 7, 3, 5, 6):
+        x7[i] = x[i] * (1 / 0.75) * sX2 / Xf
+    EQI, eff = effluent_quality(xe)
+    return x7, Qw, EQI, eff, status
+
+
+def reward_v2(kla3, kla5, kla8, Qw, Qin, Qeff, Snh, so_sat=SO_SAT):
+    """module_reward.sbr_reward (module_reward.py:4-51) -> (reward, OCI)."""
+    t_delta = DT
+    ME = 0.005 * 1.32 * 24 + 0.005 * 1.32 * 24
+    AE_3 = 1.32 * sum(kla3) * t_delta / (len(kla3) * t_delta)
+    AE_5 = 1.32 * sum(kla5) * t_delta / (len(kla5) * t_delta)
+    AE_8 = (1.32 - Qw) * sum(kla8) * t_delta / (len(kla8) * t_delta)
+    AE = so_sat / (1.8 * 1000) * (AE_3 + AE_5 + AE_8)
+    PE = 0.004 * Qin + 0.05 * Qw + 0.004 * Qeff
+    OCI = AE + PE + ME
+    r_snh = 0 if Snh < 4 else -20
+    return (5 - OCI) + r_snh, OCI
+
+
+def fill_flow():
+    """Fill flow rate written into influent_mixed[0] by SbrEnv2.step (gym_SBR_env2.py:144)."""
+    return QIN / (T_CYCLE * T_RATIO[0])
+
+
+def cycle_v2(setpoints3, influent, x0=X0_INIT, kla0=0.0, ode_kw=None, tap=None):
+    """One whole 12-h cycle = SBR_model_FB.run (SBR_model_FB.py:8-295) for the SBR-v2 env.
+
+    setpoints3: DO set-points (g/m3) of phases 3, 5 and 8 (already scaled, i.e. 8*action).
+    influent:   14-vector, [0] = fill flow (m3/d), [1:] = influent concentrations.
+    Set-points of the other reacting phases are 0 (gym_SBR_env2.py:54,184-186); each phase's bias is the last
+    Kla of the previous reacting phase, the idle phase takes phase 5's (SBR_model_FB.py:94,120,146,172,266).
+    """
+    sched = cycle_schedule()
+    sp = [0, 0, setpoints3[0], 0, setpoints3[1], 0, 0, setpoints3[2]]
+    x = np.array(x0, dtype=float)
+    klas = {}
+    kla = kla0
+    taps = {k: ([] if tap is not None else None) for k in range(8)}
+    for k in range(5):
+        if k == 0:
+            x, K = pid_phase(x, sched[k][0], sched[k][1], sp[k], kla, rhs_fill, (list(influent),),
+                             ode_kw=ode_kw, tap=taps[k])
+        else:
+            x, K = pid_phase(x, sched[k][0], sched[k][1], sp[k], kla, rhs_react, ode_kw=ode_kw, tap=taps[k])
+        klas[k] = K
+        kla = K[-1]
+    x5 = x
+    sX, Xf = settle(x5, sched[5][0], sched[5][1], ode_kw=ode_kw)
+    x7, Qw, EQI, eff, status = draw(x5, sX, Xf)
+    x8, K8 = pid_phase(x7, sched[7][0], sched[7][1], sp[7], klas[4][-1], rhs_react, ode_kw=ode_kw, tap=taps[7])
+    klas[7] = K8
+    if tap is not None:
+        tap.update(taps)
+    return dict(x_last=np.array(x8), x5=np.array(x5), x7=np.array(x7), sX=np.array(sX), Xf=Xf, Qw=Qw, EQI=EQI,
+                eff=eff, kla=klas, status=status,
+                n_intervals=[len(klas[k]) if k in klas else 0 for k in range(8)])
+
+
+def sbr_v2_step(action, influent_mixed, x0=X0_INIT, ode_kw=None, tap=None):
+    """SbrEnv2.step (gym_SBR_env2.py:131-171): returns dict(obs[3], reward, done, OCI, ...)."""
+    a = np.clip(np.asarray(action, dtype=float), 0.0, 1.0)
+    infl = list(influent_mixed)
+    infl[0] = fill_flow()
+    out = cycle_v2([a[0] * 8, a[1] * 8, a[2] * 8], infl, x0=x0, ode_kw=ode_kw, tap=tap)
+    Snh = out['eff'][3]
+    reward, OCI = reward_v2(out['kla'][2], out['kla'][4], out['kla'][7], out['Qw'], QIN, QEFF, Snh)
+    out.update(reward=reward, OCI=OCI, done=True,
+               obs=np.array([QEFF, out['eff'][2], out['eff'][3] / 30]))
+    return out
+
+
+def sbr_v2_reset_obs(influent_mixed, x0=X0_INIT):
+    """SbrEnv2.reset observation (gym_SBR_env2.py:108-118): element-wise SUM of x0 and influent_mixed."""
+    s = np.asarray(x0, dtype=float) + np.asarray(influent_mixed, dtype=float)
+    cod = s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7]
+    return np.array([s[0], (cod - 5145) / 10, s[10] / 30])

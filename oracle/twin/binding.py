@@ -1,0 +1,101 @@
+"""ctypes binding of the CPU twin (TEST INFRASTRUCTURE ONLY; see sbr_twin.cpp).  numpy in / numpy out, SoA."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gym_sbr2_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD_DIR = os.path.join(os.path.dirname(HERE), "_build")
+LIB = os.path.join(BUILD_DIR, "libsbr_twin.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "sbr_twin.cpp")
+    core = os.path.join(os.path.dirname(os.path.dirname(HERE)), "gym_sbr2_b200", "csrc", "sbr_core.cuh")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if (not force and os.path.exists(LIB)
+            and os.path.getmtime(LIB) >= max(os.path.getmtime(src), os.path.getmtime(core))):
+        return LIB
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", LIB, src])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def default_params():
+    """Defaults without touching the CUDA library (mirrors sbr_params_default in sbr_kernels.cu)."""
+    p = _abi.SbrParams()
+    vals = dict(muh=4.0, Ks=10.0, Koh=0.2, Kno=0.5, bh=0.3, etag=0.8, etah=0.8, kh=3.0, Kx=0.1, mua=0.5, Knh=1.0,
+                ba=0.05, Koa=0.4, ka=0.05, Ya=0.24, Yh=0.67, fp=0.08, ixb=0.08, ixp=0.06,
+                pid_Kc=5.0, pid_tauI=0.00035, pid_tauD=0.005, pid_dt=0.02 / 24, kla_min=0.0, kla_max=240.0,
+                WV=1.32, Qin=1.32 - 0.6161484733495801, Qeff=0.66, biomass_setpoint=2700.0,
+                settler_area=(1.25 / 2) * (1.25 / 2), settler_vmax=474.0, kla0=0.0, action_scale=8.0,
+                os_Kc_DO=100.0, os_tauI_DO=20.0, os_tauD_DO=0.0, os_Kc_EC=100.0, os_tauI_EC=20.0, os_tauD_EC=0.0,
+                os_pid_dt=0.002 / 24, ec_min=0.0, ec_max=0.0005, ec_conc=1200000.0 * 4, do_sp_max=8.0,
+                no_sp_max=15.0)
+    tk = (15 + 273.15) / 100
+    vals["so_sat"] = 0.9997743214 * (8 / 10.5) * 6791.5 * (56.12 * np.exp(-66.7354 + 87.4755 / tk + 24.4526 * np.log(tk)))
+    for k, v in vals.items():
+        setattr(p, k, float(v))
+    return p
+
+
+def cycle_v2(x0, influent, action, params, sched, mode=0, tol=None):
+    """x0, influent: [14, n]; action: [3, n] float64 C-contiguous.  Returns dict of numpy arrays."""
+    lib = load()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    influent = np.ascontiguousarray(influent, dtype=np.float64)
+    action = np.ascontiguousarray(action, dtype=np.float64)
+    n = x0.shape[1]
+    x_last = np.empty((14, n)); obs = np.empty((3, n)); reward = np.empty(n); aux = np.empty((_abi.AUX_ROWS, n))
+    status = np.zeros(n, dtype=np.int32); counters = np.zeros((2, n), dtype=np.uint32)
+    tol = tol or _abi.make_tol()
+    rc = lib.twin_cycle_v2(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(influent), _ptr(action), C.byref(params),
+                           C.byref(sched), _ptr(x_last), _ptr(obs), _ptr(reward), _ptr(aux), _ptr(status),
+                           _ptr(counters), C.c_int(mode), C.byref(tol))
+    assert rc == 0
+    return dict(x_last=x_last, obs=obs, reward=reward, aux=aux, status=status, counters=counters)
+
+
+def integrate_interval(x, kla, params, tail, T, n_sub, mode=0, tol=None, ec=None, loading=None):
+    lib = load()
+    x = np.array(x, dtype=np.float64, order="C")
+    n = x.shape[1]
+    kla = np.ascontiguousarray(kla, dtype=np.float64)
+    ec = None if ec is None else np.ascontiguousarray(ec, dtype=np.float64)
+    loading = None if loading is None else np.ascontiguousarray(loading, dtype=np.float64)
+    counters = np.zeros((2, n), dtype=np.uint32)
+    tol = tol or _abi.make_tol()
+    rc = lib.twin_integrate_interval(C.c_int64(n), C.c_int64(n), _ptr(x), _ptr(kla), _ptr(ec), _ptr(loading),
+                                     C.byref(params), C.c_int(tail), C.c_double(T), C.c_int(n_sub), C.c_int(mode),
+                                     C.byref(tol), _ptr(counters))
+    assert rc == 0
+    return x, counters
+
+
+def rhs(x, kla, params, tail, ec=None, loading=None):
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[1]
+    kla = np.ascontiguousarray(kla, dtype=np.float64)
+    ec = None if ec is None else np.ascontiguousarray(ec, dtype=np.float64)
+    loading = None if loading is None else np.ascontiguousarray(loading, dtype=np.float64)
+    dx = np.zeros((14, n))
+    rc = lib.twin_rhs(C.c_int64(n), C.c_int64(n), _ptr(x), _ptr(kla), _ptr(ec), _ptr(loading), C.byref(params),
+                      C.c_int(tail), _ptr(dx))
+    assert rc == 0
+    return dx

@@ -1,0 +1,120 @@
+"""Host-side logic that needs no GPU: schedule tables, influent generator, C-ABI exports, argument errors."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gym_sbr2_b200 import _abi, influent, schedule
+from oracle import sbr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_schedule_matches_reference_counts(golden_v2):
+    s = schedule.cycle_schedule()
+    assert list(s.n_int) == [24, 48, 223, 186, 11, 0, 0, 36]
+    assert list(s.n_sub) == [9, 9, 9, 9, 10, 0, 0, 9]
+    assert (s.n_int[2], s.n_int[4], s.n_int[7]) == (golden_v2["n3"][0], golden_v2["n5"][0], golden_v2["n8"][0])
+    # same grid as the oracle (which is pinned to the reference)
+    for k, (t0, t1) in enumerate(O.cycle_schedule()):
+        if k in (5, 6):
+            continue
+        grid, pts = O.phase_grid(t0, t1)
+        assert len(grid) - 1 == s.n_int[k] and set(pts) == {s.n_sub[k] + 1}
+        assert np.isclose(s.interval[k], grid[1] - grid[0], rtol=1e-12)
+    assert np.isclose(s.settle_time, 0.5 * 0.083, rtol=1e-12)
+
+
+def test_influent_generator_bit_exact_with_reference(golden_v2):
+    g = golden_v2
+    for i in range(0, len(g["seed"]), 3):
+        np.random.seed(int(g["seed"][i]))
+        assert np.array_equal(influent.sample_numpy(0), g["influent"][i])
+
+
+def test_influent_draw_counts():
+    assert [influent.draws_per_reset(k) for k in range(8)] == [1, 2, 2, 2, 2, 2, 2, 2]
+
+
+def test_influent_torch_matches_numpy():
+    import torch
+    rnd = torch.randn(7, 48, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    for sw in range(8):
+        a = influent.mix_torch(sw, rnd).numpy()
+        b = np.stack([influent.mix_numpy(sw, r.numpy()) for r in rnd], axis=1)
+        assert np.allclose(a, b, rtol=1e-13, atol=0)
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "sbr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sbr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = _header_functions()
+    assert names == _abi.exported_symbols()
+    lib = C.CDLL(_abi.lib_path())
+    for n in names:
+        assert hasattr(lib, n), n
+    assert _abi.load().sbr_abi_version() == _abi.ABI_VERSION
+
+
+def test_struct_layouts_match_header(built):
+    text = open(os.path.join(ROOT, "include", "sbr_b200.h")).read()
+    body = re.search(r"typedef struct SbrParams \{(.*?)\} SbrParams;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"double\s+([^;]+);", body):
+        fields += [f.strip() for f in decl.split(",")]
+    assert fields == [f for f, _ in _abi.SbrParams._fields_]
+    assert C.sizeof(_abi.SbrSchedule) == 8 * 4 + 8 * 4 + 8 * 8 + 8
+    assert C.sizeof(_abi.SbrTol) == 24
+
+
+def test_default_params_match_reference_constants(built):
+    p = _abi.default_params()
+    assert p.so_sat == O.SO_SAT
+    for k, v in O.KPAR.items():
+        assert getattr(p, k) == v
+    for k, v in O.SPAR.items():
+        assert getattr(p, k) == v
+    assert (p.pid_Kc, p.pid_tauI, p.pid_tauD, p.pid_dt) == (5.0, 0.00035, 0.005, 0.02 / 24)
+    assert p.Qin == O.QIN and p.Qeff == 0.66 and p.biomass_setpoint == 2700 and p.ec_conc == 4800000.0
+    from oracle.twin import binding as twin
+    q = twin.default_params()
+    for f, _ in _abi.SbrParams._fields_:
+        assert getattr(p, f) == getattr(q, f), f
+
+
+def test_argument_errors_are_reported_without_gpu(built):
+    lib = _abi.load()
+    p = _abi.default_params()
+    s = schedule.cycle_schedule()
+    rc = lib.sbr_cycle_v2(0, 0, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
+                          None, None)
+    assert rc == -1 and b"n must be positive" in lib.sbr_last_error()
+    rc = lib.sbr_cycle_v2(4, 2, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
+                          None, None)
+    assert rc == -1 and b"ld" in lib.sbr_last_error()
+    rc = lib.sbr_cycle_v2(4, 4, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
+                          None, None)
+    assert rc == -1 and b"NULL" in lib.sbr_last_error()
+    with pytest.raises(_abi.SbrLibraryError):
+        _abi.check(rc, "sbr_cycle_v2")
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import the oracle, and the vector env refuses non-CUDA devices."""
+    import gym_sbr2_b200
+    pkg = os.path.dirname(gym_sbr2_b200.__file__)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+            assert not re.search(r"^\s*(from|import)\s+scipy", src, flags=re.M), fn
+    from gym_sbr2_b200.vec_env import SbrV2VecEnv
+    with pytest.raises(_abi.SbrLibraryError):
+        SbrV2VecEnv(4, device="cpu")
