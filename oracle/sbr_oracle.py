@@ -338,3 +338,223 @@ def sbr_v2_reset_obs(influent_mixed, x0=X0_INIT):
     s = np.asarray(x0, dtype=float) + np.asarray(influent_mixed, dtype=float)
     cod = s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7]
     return np.array([s[0], (cod - 5145) / 10, s[10] / 30])
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Path B (SBROS-v1): interval-per-step env with DO-PID (KLa) and NO3-PID (external carbon)
+# ----------------------------------------------------------------------------------------------------------
+OS_DT = 0.002 / 24                      # gym_SBR_oneshot.py:30  (`dt`)
+OS_T_DELTA = OS_DT * 10                 # gym_SBR_oneshot.py:31  (`t_delta`, one control interval)
+OS_PID = dict(Kc_DO=100, tauI_DO=20, tauD_DO=0, Kc_EC=100, tauI_EC=20, tauD_EC=0,
+              kla_lo=0, kla_hi=240, ec_lo=0, ec_hi=0.0005)              # gym_SBR_oneshot.py:80-94
+EC_CONC = 1200000 * 4                   # gym_SBR_oneshot.py:96
+X1_STATE = np.array([0.5, 1.32, 30, 30, 1500, 150, 3000, 2000, 600, 8, 20, 20, 10, 10, 10])   # :153
+OBS_IDX_DO, X1_DO = [0, 5, 6, 8, 10], np.array([0.5, 2000, 500, 8., 10])                        # :150,155
+OBS_IDX_EC, X1_EC = [0, 2, 5, 9, 10], np.array([0.5, 30, 2000, 10, 10])                         # :151,156
+
+
+def batch_time_marks(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=OS_T_DELTA):
+    """module_batch_time.batch_time (module_batch_time.py:3-116): first and last output stamp of each phase,
+    [(t_memoryK[0], t_memoryK[-1])] for K = 1..8, with the reference's int(float) point counts."""
+    marks = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + t_delta
+        t_end = t_start + t_cycle * t_ratio[k]
+        t_save = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+        mem = [t_save[0]]
+        for i in range(len(t_save) - 1):
+            t_range = np.linspace(t_save[i], t_save[i + 1], int((t_save[i + 1] - t_save[i]) / t_delta))
+            mem.extend(t_range[1:])
+        marks.append((float(mem[0]), float(mem[-1])))
+    return marks
+
+
+def reward_os(x, n_pts, span, kla_hist, ec_hist):
+    """module_reward_EQIOCI.sbr_reward (module_reward_EQIOCI.py:4-115).  kla_hist / ec_hist are the reference's
+    `Kla` / `EC` lists; note Kla holds ONE entry per interval, so Kla[-L:-1] sums the previous L-1 intervals."""
+    EQI, _ = effluent_quality(x)
+    t_delta = 0.002 / 24
+    AE = 8 / (span * 1.8 * 1000) * (1.32 * sum(kla_hist[-n_pts:-1]) * t_delta)
+    ECo = EC_CONC * sum(ec_hist[-n_pts:-1]) * t_delta / (span * 1000)
+    return (1 - ((EQI / 10) ** 2 + (AE + ECo) ** 2)) / 473
+
+
+def _clip1(v):
+    return 1 if v > 1 else (-1 if v < -1 else v)
+
+
+def _obs_os(t, x, x_first, x_last):
+    """obs_DO / obs_EC / state of SbrOS.step (gym_SBR_oneshot.py:1015-1112)."""
+    state = np.concatenate([[t], x]) / X1_STATE
+    full = np.concatenate([[t], x])
+    d = lambda i, s: _clip1((x_last[i] - x_first[i]) / s)
+    # note: index 0 of obs_idx_* is time; other indices address x directly (x[i], not [t,x][i])
+    o_do = np.array([t] + [x[i] for i in OBS_IDX_DO[1:]]) / X1_DO
+    o_ec = np.array([t] + [x[i] for i in OBS_IDX_EC[1:]]) / X1_EC
+    o_do = np.append(o_do, [d(5, 4000), d(6, 500), d(8, 8), d(10, 50)])
+    o_ec = np.append(o_ec, [d(2, 50), d(5, 4000), d(9, 50), d(10, 50)])
+    del full
+    return o_do, o_ec, state
+
+
+class SbrOsOracle(object):
+    """Restatement of the reference's SbrOS env (gym_SBR_oneshot.py:98-2644) with explicit per-env state instead
+    of module globals.  reset(influent_mixed) -> (obs_DO[9], obs_EC[9]); step(action[2]) ->
+    ((obs_DO, obs_EC), state[15], reward, done)."""
+
+    def __init__(self, ode_kw=None):
+        self.ode_kw = ode_kw or {}
+        self.marks = batch_time_marks()
+        self.n_rhs = 0
+
+    # -- controllers -------------------------------------------------------------------------------------
+    def _pid_do(self, sp, t_start, aerobic):
+        """DO-PID with incremental bias Kla[-1]; PID dt = 0.002/24, not the control interval
+        (gym_SBR_oneshot.py:1889-1909).  In anoxic intervals the PID state advances but Kla := 0 (:1990)."""
+        P = OS_PID
+        e = sp - self.So[-1]
+        if t_start > 0:
+            dcv = (self.So[-1] - self.So[-2]) / OS_DT
+            self.ie_DO = self.ie_DO + e * OS_DT
+        else:
+            dcv = 0
+            self.ie_DO = 0
+        if aerobic:
+            kla = P['Kc_DO'] * e + P['Kc_DO'] / P['tauI_DO'] * self.ie_DO + P['Kc_DO'] * P['tauD_DO'] * dcv + self.Kla[-1]
+        else:
+            kla = 0
+        if kla > P['kla_hi']:
+            kla = P['kla_hi']
+            self.ie_DO = self.ie_DO - e * OS_DT
+        if kla < P['kla_lo']:
+            kla = P['kla_lo']
+            self.ie_DO = self.ie_DO - e * OS_DT
+        self.Kla.append(kla)
+        return kla
+
+    def _pid_ec(self, sp, t_start, dosing, reversed_sign=True):
+        """NO3-PID: error = Sno - sp (sign reversed), output EC in [0, 0.0005] (gym_SBR_oneshot.py:1917-1948);
+        outside anoxic react intervals EC := 0 while the integral still advances (:1937)."""
+        P = OS_PID
+        e = (self.Sno[-1] - sp) if reversed_sign else (sp - self.Sno[-1])
+        if t_start > 0:
+            dcv = (self.Sno[-1] - self.Sno[-2]) / OS_DT
+            self.ie_EC = self.ie_EC + e * OS_DT
+        else:
+            dcv = 0
+            self.ie_EC = 0
+        if dosing:
+            ec = P['Kc_EC'] * e + P['Kc_EC'] / P['tauI_EC'] * self.ie_EC + P['Kc_EC'] * P['tauD_EC'] * dcv + self.EC[-1]
+        else:
+            ec = 0
+        if ec < P['ec_lo']:
+            ec = P['ec_lo']
+            self.ie_EC = self.ie_EC - e * OS_DT
+        elif ec > P['ec_hi']:
+            ec = P['ec_hi']
+            self.ie_EC = self.ie_EC - e * OS_DT
+        self.EC.append(ec)
+        return ec
+
+    # -- reset: fill phase -------------------------------------------------------------------------------
+    def reset(self, influent_mixed, x0=X0_INIT):
+        """SbrOS.reset + Sim_filling (gym_SBR_oneshot.py:168-438, 1585-1654)."""
+        self.infl = list(influent_mixed)
+        x0 = np.array(x0, dtype=float)
+        self.So, self.Ss, self.Sno = [x0[8]], [x0[2]], [x0[9]]
+        self.Kla, self.EC = [0], [0]
+        self.ie_DO = self.ie_EC = 0
+        self.u_DO, self.u_EC = 0, 15
+        self.infl[0] = QIN / self.marks[0][1]                                     # :287
+        t_end = 0 + T_RATIO[0] * 0.5
+        t_range = np.linspace(0, t_end, int((t_end - 0) / OS_DT))
+        kla = self._pid_do(0, 0, aerobic=True)                                     # sp 0 -> clamps to 0
+        # the fill-phase EC controller: error = 0 - Sno, EC := 0, clamp order upper-then-lower (:1620-1645)
+        self.ie_EC = 0
+        self.EC.append(0)
+        x_out = odeint(rhs_fill, x0, t_range, args=(kla, self.infl), **self.ode_kw)
+        self.So.append(x_out[-1][8])
+        self.Ss.append(x_out[-1][2])
+        self.Sno.append(x_out[-1][2])                                              # sic: Ss stored as Sno (:1652)
+        rep = int(len(x_out) / len(self.Kla))
+        self.Kla = self.Kla * rep                                                  # :322
+        self.EC = self.EC * int(len(x_out) / len(self.EC))                         # :323
+        self.t = float(t_range[-1])
+        self.x = x_out[-1]
+        self.n_pts_fill = len(t_range)
+        x = self.x
+        mix = lambda i: (QIN * self.infl[i] + x[i] * IV) / (QIN + IV)              # :347-364
+        o_do = np.array([self.t] + [mix(i) for i in OBS_IDX_DO[1:]]) / X1_DO
+        o_ec = np.array([self.t] + [mix(i) for i in OBS_IDX_EC[1:]]) / X1_EC
+        d = lambda i, s: _clip1((x_out[-1][i] - x_out[0][i]) / s)
+        o_do = np.append(o_do, [d(5, 4000), d(6, 500), d(8, 8), d(10, 50)])
+        o_ec = np.append(o_ec, [d(2, 50), d(5, 4000), d(9, 50), d(10, 50)])
+        self.schedule_log = []
+        return o_do, o_ec
+
+    # -- one control interval ----------------------------------------------------------------------------
+    def _interval(self, aerobic):
+        """run_aero_step / run_anaero_step + Sim_(an)aero_rxn (gym_SBR_oneshot.py:1331-1419, 1877-2051)."""
+        t_start = self.t
+        t_end = self.t + OS_T_DELTA
+        t_range = np.linspace(t_start, t_end, int((t_end - t_start) / OS_DT))
+        kla = self._pid_do(self.u_DO if aerobic else 0, t_range[0], aerobic)
+        ec = self._pid_ec(self.u_EC, t_range[0], dosing=not aerobic)
+        x_out = odeint(rhs_react_ec, self.x, t_range, args=(kla, ec, EC_CONC), **self.ode_kw)
+        for _ in range(len(t_range) - 2):
+            self.EC.append(self.EC[-1])
+        self.So.append(x_out[-1][8])
+        self.Ss.append(x_out[-1][2])
+        self.Sno.append(x_out[-1][9])
+        self.t = float(t_range[-1])
+        self.x_first, self.x = x_out[0], x_out[-1]
+        self.schedule_log.append((float(t_start), int(aerobic), len(t_range), float(t_range[-1] - t_range[0])))
+        return t_range
+
+    def step(self, action):
+        """SbrOS.step (gym_SBR_oneshot.py:843-1273): four NON-exclusive `if`s on the running time, so a step that
+        crosses a phase boundary runs two intervals."""
+        m = self.marks
+        tm3_0, tm3_1, tm4_1, tm5_1 = m[2][0], m[2][1], m[3][1], m[4][1]
+        t_range = None
+        if self.t < tm3_0:
+            self.u_EC, self.u_DO = min(max(action[1], 0), 15), 0
+            t_range = self._interval(aerobic=False)
+        if (self.t >= tm3_0) and (self.t <= tm3_1):
+            self.u_DO, self.u_EC = min(max(action[0], 0), 8), 0
+            t_range = self._interval(aerobic=True)
+        if (self.t > tm3_1) and (self.t <= tm4_1):
+            self.u_EC, self.u_DO = min(max(action[1], 0), 15), 0
+            t_range = self._interval(aerobic=False)
+        if self.t > tm4_1:
+            self.u_DO, self.u_EC = min(max(action[0], 0), 8), 0
+            t_range = self._interval(aerobic=True)
+        reward = reward_os(self.x, len(t_range), t_range[-1] - t_range[0], self.Kla, self.EC)
+        o_do, o_ec, state = _obs_os(self.t, self.x, self.x_first, self.x)
+        done = False
+        if self.t >= tm5_1:
+            done = True
+            x_react_end = self.x
+            # settle + draw (Sim_Settling_Drawing, :2264-2420): same algebra as Path A on a 49-point grid
+            t_set = np.linspace(self.t, self.t + T_RATIO[5] * T_CYCLE, int((T_RATIO[5] * T_CYCLE) / OS_T_DELTA))
+            Xf = 0.75 * (self.x[3] + self.x[4] + self.x[5] + self.x[6] + self.x[7])
+            z = self.x[0] / ((1.25 / 2) ** 2)
+            sX = odeint(settler_rhs, [Xf] * 10, t_set, args=(z, Xf), **self.ode_kw)[-1]
+            x_n, self.Qw, _, _, self.draw_status = draw(self.x, sX, Xf)
+            t_draw = np.linspace(t_set[-1], t_set[-1] + T_RATIO[6] * T_CYCLE, int((T_RATIO[6] * T_CYCLE) / OS_T_DELTA))
+            for _ in range(len(t_set) + len(t_draw) - 2):
+                self.EC.append(0)
+            self.So += [self.x[8]] * len(t_set) + [x_n[8]] * (len(t_draw) - 1)     # :2415-2416
+            # idle (Sim_idle, :2554-2597): one PID update with the last DO set-point, ONE solve to t_cycle
+            t_idle = np.linspace(t_draw[-1], T_CYCLE, int((T_CYCLE - t_draw[-1]) / OS_DT))
+            kla = self._pid_do(self.u_DO, t_idle[0], aerobic=True)
+            x_idle = odeint(rhs_react, x_n, t_idle, args=(kla,), **self.ode_kw)
+            self.So.append(x_idle[-1][8])
+            self.Ss.append(x_idle[-1][2])
+            self.Sno.append(x_idle[-1][9])
+            self.t = float(t_idle[-1])
+            self.x = x_idle[-1]
+            self.idle_pts = len(t_idle)
+            o_do, o_ec, state = _obs_os(self.t, self.x, x_react_end, self.x)
+        return (o_do, o_ec), state, reward, done
