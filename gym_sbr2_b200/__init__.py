@@ -1,2 +1,19 @@
-"""gym_sbr2_b200 -- B200-native batched sequencing-batch-reactor simulator behind the gym-SBR API."""
-__version__ = "0.1.0"
+"""gym_sbr2_b200 -- B200-native batched sequencing-batch-reactor simulator behind the gym-SBR API.
+
+    import gym_sbr2_b200 as sbr
+    env = sbr.make("SBR-v2")                    # per-instance Gym env (batch of one on cuda:0)
+    vec = sbr.SbrV2VecEnv(1 << 20, "cuda:0")    # the vectorised drop-in: torch CUDA tensors in and out
+
+Importing the package registers the reference's ten env ids (with gym / gymnasium too when installed).
+"""
+__version__ = "0.2.0"
+
+from .registration import ENV_TABLE, UnsupportedEnvError, make, register, registry, spec_ids  # noqa: F401
+
+
+def __getattr__(name):
+    # the vector envs import torch; keep `import gym_sbr2_b200` light
+    if name in ("SbrV2VecEnv", "SbrOsVecEnv"):
+        from . import vec_env
+        return getattr(vec_env, name)
+    raise AttributeError(name)

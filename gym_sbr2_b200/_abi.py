@@ -10,11 +10,16 @@ NX = 14
 NPHASE = 8
 MODE_RK4, MODE_DP45 = 0, 1
 TAIL_REACT, TAIL_FILL, TAIL_EC = 0, 1, 2
-ST_NONFINITE, ST_WASTE, ST_STEPLIMIT, ST_LAYERS = 1, 2, 4, 8
+ST_NONFINITE, ST_WASTE, ST_STEPLIMIT, ST_LAYERS, ST_DONE = 1, 2, 4, 8, 16
 AUX_ROWS = 12
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 1
+ABI_VERSION = 2
+# rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
+OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
+    0, 14, 15, 16, 17, 18, 19, 20, 21, 22
+OS_RETURN, OS_STEPS, OS_QW, OS_ROWS = 32, 33, 34, 35
+OS_NOBS, OS_NSTATE = 9, 15
 
 _PARAM_FIELDS = [
     "muh", "Ks", "Koh", "Kno", "bh", "etag", "etah", "kh", "Kx", "mua", "Knh", "ba", "Koa", "ka",
@@ -22,7 +27,7 @@ _PARAM_FIELDS = [
     "pid_Kc", "pid_tauI", "pid_tauD", "pid_dt", "kla_min", "kla_max",
     "WV", "Qin", "Qeff", "biomass_setpoint", "settler_area", "settler_vmax", "kla0", "action_scale",
     "os_Kc_DO", "os_tauI_DO", "os_tauD_DO", "os_Kc_EC", "os_tauI_EC", "os_tauD_EC",
-    "os_pid_dt", "ec_min", "ec_max", "ec_conc", "do_sp_max", "no_sp_max",
+    "os_pid_dt", "ec_min", "ec_max", "ec_conc", "do_sp_max", "no_sp_max", "IV",
 ]
 
 
@@ -33,6 +38,14 @@ class SbrParams(C.Structure):
 class SbrSchedule(C.Structure):
     _fields_ = [("n_int", C.c_int32 * NPHASE), ("n_sub", C.c_int32 * NPHASE),
                 ("interval", C.c_double * NPHASE), ("settle_time", C.c_double)]
+
+
+class SbrOsSchedule(C.Structure):
+    _fields_ = [("tm3_0", C.c_double), ("tm3_1", C.c_double), ("tm4_1", C.c_double), ("tm5_1", C.c_double),
+                ("dt", C.c_double), ("t_delta", C.c_double), ("t_fill", C.c_double),
+                ("settle_len", C.c_double), ("draw_len", C.c_double), ("t_cycle", C.c_double),
+                ("fill_pts", C.c_int32), ("rk4_sub_interval", C.c_int32), ("rk4_sub_fill", C.c_int32),
+                ("rk4_sub_idle", C.c_int32)]
 
 
 class SbrTol(C.Structure):
@@ -62,6 +75,10 @@ _PROTOS = {
     "sbr_integrate_interval": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int,
                                          C.c_double, C.c_int, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_rhs": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int, _P, _P]),
+    "sbr_os_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
+                               _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_os_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
+                              _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),

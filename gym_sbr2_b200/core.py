@@ -19,9 +19,23 @@ def _dev_ptr(t, rows, n, dtype=torch.float64, name="tensor"):
         if t.dim() != 1 or t.shape[0] != n or t.stride(0) != 1:
             raise ValueError("%s must be a contiguous [%d] vector" % (name, n))
         return C.c_void_p(t.data_ptr()), n
-    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n or t.stride(1) != 1:
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n or (n > 1 and t.stride(1) != 1):
         raise ValueError("%s must be SoA [%d, %d] with unit stride along envs, got %s" % (name, rows, n, tuple(t.shape)))
+    if n == 1:
+        # a [rows, 1] tensor may carry any stride on either axis; the ABI takes ONE row stride for all buffers
+        if t.stride(0) != 1:
+            raise ValueError("%s: [%d, 1] tensor must have row stride 1 (use core.soa1)" % (name, rows))
+        return C.c_void_p(t.data_ptr()), 1
     return C.c_void_p(t.data_ptr()), t.stride(0)
+
+
+def soa1(t):
+    """Normalise a [rows, 1] tensor to row stride 1 (a fresh buffer if needed)."""
+    if t is not None and t.dim() == 2 and t.shape[1] == 1 and t.stride(0) != 1:
+        out = torch.empty((t.shape[0], 1), dtype=t.dtype, device=t.device)
+        out.copy_(t)
+        return out
+    return t
 
 
 def _stream_ptr(stream=None):
@@ -108,6 +122,66 @@ def rhs(x, kla, params, tail, ec=None, loading=None, stream=None):
         rc = lib.sbr_rhs(n, ld, px, pk, pe, pl, C.byref(params), int(tail), pd, _stream_ptr(stream))
     _abi.check(rc, "sbr_rhs")
     return dx
+
+
+class OsBuffers(object):
+    """Device buffers of the interval-per-step path: persistent state + per-step outputs (allocated once)."""
+
+    def __init__(self, n, device):
+        f = dict(dtype=torch.float64, device=device)
+        self.st = torch.zeros((_abi.OS_ROWS, n), **f)
+        self.obs_do = torch.empty((_abi.OS_NOBS, n), **f)
+        self.obs_ec = torch.empty((_abi.OS_NOBS, n), **f)
+        self.state = torch.empty((_abi.OS_NSTATE, n), **f)
+        self.reward = torch.zeros((n,), **f)
+        self.done = torch.ones((n,), dtype=torch.uint8, device=device)     # nothing to step before reset
+        self.status = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.counters = torch.zeros((2, n), dtype=torch.int32, device=device)
+
+
+def os_reset(buf, influent, params, sched, x0=None, mask=None, mode=_abi.MODE_DP45, tol=None, stream=None):
+    """Episode start for a batch (SbrOS.reset + Sim_filling, gym_SBR_oneshot.py:168-438, 1585-1654).
+    influent [14,n] (row 0 = fill flow); x0 [14,n] or None (reference x0_init); mask [n] uint8 or None."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    pst, l0 = _dev_ptr(buf.st, _abi.OS_ROWS, n, name="st")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    px0, l2 = _dev_ptr(x0, _abi.NX, n, name="x0")
+    pmk, _ = _dev_ptr(mask, 1, n, dtype=torch.uint8, name="mask")
+    pod, l3 = _dev_ptr(buf.obs_do, _abi.OS_NOBS, n, name="obs_do")
+    poe, l4 = _dev_ptr(buf.obs_ec, _abi.OS_NOBS, n, name="obs_ec")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l5 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1, l2 if x0 is not None else None, l3, l4, l5], "os_reset")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_os_reset(n, ld, px0, pin, pmk, C.byref(params), C.byref(sched), pst, pod, poe, pdn, pss, pct,
+                              int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_os_reset")
+    return buf
+
+
+def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None):
+    """One env.step for a batch (SbrOS.step, gym_SBR_oneshot.py:843-1273).  action [2,n]: DO and NO3 set-points."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    pst, l0 = _dev_ptr(buf.st, _abi.OS_ROWS, n, name="st")
+    pac, l1 = _dev_ptr(action, 2, n, name="action")
+    pod, l2 = _dev_ptr(buf.obs_do, _abi.OS_NOBS, n, name="obs_do")
+    poe, l3 = _dev_ptr(buf.obs_ec, _abi.OS_NOBS, n, name="obs_ec")
+    pse, l4 = _dev_ptr(buf.state, _abi.OS_NSTATE, n, name="state")
+    prw, _ = _dev_ptr(buf.reward, 1, n, name="reward")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l5 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1, l2, l3, l4, l5], "os_step")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_os_step(n, ld, pst, pac, C.byref(params), C.byref(sched), pod, poe, pse, prw, pdn, pss, pct,
+                             int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_os_step")
+    return buf
 
 
 def reward_stats(reward, status=None, out=None, stream=None):

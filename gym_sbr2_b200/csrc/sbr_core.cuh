@@ -415,6 +415,18 @@ SBR_HD void settle_closed_form(const double (&x)[SBR_NX], double T, double area,
     sX[0] = 10.0 * Xf - rest;
 }
 
+// drawing.cal_eq (sub_phases_FB.py:868-915) == the EQI block of module_reward_EQIOCI.sbr_reward
+// (module_reward_EQIOCI.py:28-47).  eff = [0.66, Ntot, COD, Snh, BOD5, Sno].
+SBR_HD double effluent_quality(const double (&xe)[SBR_NX], double (&eff)[6]) {
+    const double Snkj = xe[iSnh] + xe[iSnd] + xe[iXnd] + 0.08 * (xe[iXbh] + xe[iXba]) + 0.06 * (xe[iXp] + xe[iXi]);
+    const double Ntot = xe[iSno] + Snkj;
+    const double SS = 0.75 * (xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp]);
+    const double BOD5 = 0.25 * (xe[iSs] + xe[iXs] + (1 - 0.08) * (xe[iXbh] + xe[iXba]));
+    const double COD = xe[iSs] + xe[iSi] + xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp];
+    eff[0] = 0.66; eff[1] = Ntot; eff[2] = COD; eff[3] = xe[iSnh]; eff[4] = BOD5; eff[5] = xe[iSno];
+    return (2 * SS + 1 * COD + 30 * Snkj + 10 * xe[iSno] + 2 * BOD5) * (1.0 / 1000) * 0.66;
+}
+
 struct DrawOut {
     double Qw, EQI;
     double eff[6];   // [0.66, Ntot, COD, Snh, BOD5, Sno]
@@ -485,13 +497,7 @@ SBR_HD void draw_and_waste(double (&x)[SBR_NX], const double (&sX)[10], double X
     x[iXbh] = x[iXbh] * (1 / 0.75) * sX2 / Xf;
     x[iXba] = x[iXba] * (1 / 0.75) * sX2 / Xf;
     // cal_eq (:868-915) on the effluent
-    const double Snkj = xe[iSnh] + xe[iSnd] + xe[iXnd] + 0.08 * (xe[iXbh] + xe[iXba]) + 0.06 * (xe[iXp] + xe[iXi]);
-    const double Ntot = xe[iSno] + Snkj;
-    const double SS = 0.75 * (xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp]);
-    const double BOD5 = 0.25 * (xe[iSs] + xe[iXs] + (1 - 0.08) * (xe[iXbh] + xe[iXba]));
-    const double COD = xe[iSs] + xe[iSi] + xe[iXs] + xe[iXi] + xe[iXbh] + xe[iXba] + xe[iXp];
-    o.EQI = (2 * SS + 1 * COD + 30 * Snkj + 10 * xe[iSno] + 2 * BOD5) * (1.0 / 1000) * 0.66;
-    o.eff[0] = 0.66; o.eff[1] = Ntot; o.eff[2] = COD; o.eff[3] = xe[iSnh]; o.eff[4] = BOD5; o.eff[5] = xe[iSno];
+    o.EQI = effluent_quality(xe, o.eff);
     o.Qw = Qw;
 }
 
@@ -565,6 +571,312 @@ SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading loa
     for (int j = 0; j < 6; ++j) o.aux[SBR_AUX_EFF_Q + j] = d.eff[j];
     o.aux[SBR_AUX_KLA3_MEAN] = kla_mean[0]; o.aux[SBR_AUX_KLA5_MEAN] = kla_mean[1];
     o.aux[SBR_AUX_KLA8_MEAN] = kla_mean[2];
+    o.status = status;
+}
+
+
+// =========================================================================================================
+// Path B: the interval-per-step env SbrOS (gym_SBR_oneshot.py).  One env.step = one (at phase boundaries two)
+// 72-s PID interval; DO-PID -> KLa in aerobic phases, NO3-PID -> external-carbon flow EC in anoxic phases; the
+// last step also runs settle + draw + idle.  The reference keeps So / Sno / Kla / EC as ever-growing Python
+// lists in module globals; what the arithmetic actually reads back is So[-2:], Sno[-2:], EC[-1], the two PID
+// integrals and the last 10 entries of Kla -- that is the persistent per-env state (SBR_OS_* rows).
+// =========================================================================================================
+
+// IEEE round-to-nearest add / sub / div that the compiler may neither contract nor re-associate: the number of
+// output points of an interval, L = int(((t + t_delta) - t) / dt), flips between 9 and 10 with the rounding of
+// the running time (gym_SBR_oneshot.py:1339,1384) and feeds the reward (module_reward_EQIOCI.py:70,79).
+SBR_HD double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+SBR_HD double sub_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    volatile double r = a - b;
+    return r;
+#endif
+}
+SBR_HD double div_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b;
+    return r;
+#endif
+}
+
+// true if the predicate holds for any env of the warp (CPU twin: for this env).  Used to pick the cheaper
+// react tail when no env of the warp doses carbon: with ec == 0 the EC tail IS the react tail.
+SBR_HD bool warp_any(bool pred) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(__activemask(), pred) != 0;
+#else
+    return pred;
+#endif
+}
+
+// One SoA column of an env: element j at p[j * stride].
+struct Column {
+    double* p;
+    int64_t stride;
+    SBR_HD double get(int j) const { return p[(int64_t)j * stride]; }
+    SBR_HD void set(int j, double v) const { p[(int64_t)j * stride] = v; }
+};
+
+struct OsPid {
+    double Kc_DO, KcI_DO, KcD_DO, Kc_EC, KcI_EC, KcD_EC, dt, kla_lo, kla_hi, ec_lo, ec_hi;
+};
+
+SBR_HD OsPid make_os_pid(const SbrParams& p) {
+    OsPid q;
+    q.Kc_DO = p.os_Kc_DO; q.KcI_DO = p.os_Kc_DO / p.os_tauI_DO; q.KcD_DO = p.os_Kc_DO * p.os_tauD_DO;
+    q.Kc_EC = p.os_Kc_EC; q.KcI_EC = p.os_Kc_EC / p.os_tauI_EC; q.KcD_EC = p.os_Kc_EC * p.os_tauD_EC;
+    q.dt = p.os_pid_dt; q.kla_lo = p.kla_min; q.kla_hi = p.kla_max; q.ec_lo = p.ec_min; q.ec_hi = p.ec_max;
+    return q;
+}
+
+// Controller scalars of one env.  So[-1] is always x[8] and is passed in.
+struct OsCtrl {
+    double t, so_prev, sno_last, sno_prev, ie_do, ie_ec, ec_last, kla_last;
+};
+
+// DO-PID (gym_SBR_oneshot.py:1889-1909; anoxic variant :1975-1990 advances the integral but sets Kla := 0).
+// Incremental bias Kla[-1]; PID dt = 0.002/24 (NOT the 72-s control interval); two independent clamp checks,
+// each undoing the integral update.  `first` = the t_start == 0 branch taken only by reset.
+SBR_HD double os_pid_do(OsCtrl& c, double so_last, double sp, bool first, bool aerobic, const OsPid& q) {
+    const double e = sp - so_last;
+    double dcv = 0.0;
+    if (!first) {
+        dcv = (so_last - c.so_prev) / q.dt;
+        c.ie_do = c.ie_do + e * q.dt;
+    } else {
+        c.ie_do = 0.0;
+    }
+    double kla = aerobic ? q.Kc_DO * e + q.KcI_DO * c.ie_do + q.KcD_DO * dcv + c.kla_last : 0.0;
+    if (kla > q.kla_hi) { kla = q.kla_hi; c.ie_do = c.ie_do - e * q.dt; }
+    if (kla < q.kla_lo) { kla = q.kla_lo; c.ie_do = c.ie_do - e * q.dt; }
+    return kla;
+}
+
+// NO3-PID -> external carbon flow (gym_SBR_oneshot.py:1917-1948; aerobic variant :1925-1937 sets EC := 0).
+// Error sign reversed (Sno - sp); lower clamp first, `elif` upper.
+SBR_HD double os_pid_ec(OsCtrl& c, double sp, bool dosing, const OsPid& q) {
+    const double e = c.sno_last - sp;
+    const double dcv = (c.sno_last - c.sno_prev) / q.dt;
+    c.ie_ec = c.ie_ec + e * q.dt;
+    double ec = dosing ? q.Kc_EC * e + q.KcI_EC * c.ie_ec + q.KcD_EC * dcv + c.ec_last : 0.0;
+    if (ec < q.ec_lo) { ec = q.ec_lo; c.ie_ec = c.ie_ec - e * q.dt; }
+    else if (ec > q.ec_hi) { ec = q.ec_hi; c.ie_ec = c.ie_ec - e * q.dt; }
+    return ec;
+}
+
+SBR_HD double clip1(double v) { return v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v); }
+
+// The six components whose change over the step enters the observations: Ss, Xbh, Xba, So, Sno, Snh.
+struct ObsRef { double Ss, Xbh, Xba, So, Sno, Snh; };
+SBR_HD ObsRef obs_ref(const double (&x)[SBR_NX]) {
+    ObsRef r;
+    r.Ss = x[iSs]; r.Xbh = x[iXbh]; r.Xba = x[iXba]; r.So = x[iSo]; r.Sno = x[iSno]; r.Snh = x[iSnh];
+    return r;
+}
+
+// Clipped deltas shared by the reset and step observations (gym_SBR_oneshot.py:388-429, 1069-1112).
+SBR_HD void os_emit_deltas(const double (&x)[SBR_NX], const ObsRef& f, const Column& obs_do, const Column& obs_ec) {
+    const double dXbh = clip1((x[iXbh] - f.Xbh) / 4000), dSnh = clip1((x[iSnh] - f.Snh) / 50);
+    obs_do.set(5, dXbh);
+    obs_do.set(6, clip1((x[iXba] - f.Xba) / 500));
+    obs_do.set(7, clip1((x[iSo] - f.So) / 8));
+    obs_do.set(8, dSnh);
+    obs_ec.set(5, clip1((x[iSs] - f.Ss) / 50));
+    obs_ec.set(6, dXbh);
+    obs_ec.set(7, clip1((x[iSno] - f.Sno) / 50));
+    obs_ec.set(8, dSnh);
+}
+
+// Step observation epilogue (gym_SBR_oneshot.py:1015-1112): obs_DO = [t, Xbh, Xba, So, Snh] / x_1_DO,
+// obs_EC = [t, Ss, Xbh, Sno, Snh] / x_1_EC (:150-156), each followed by 4 clipped deltas; state = [t, x] / x_1_state.
+SBR_HD void os_emit_obs(double t, const double (&x)[SBR_NX], const ObsRef& first, const Column& obs_do,
+                        const Column& obs_ec, const Column& state) {
+    obs_do.set(0, t / 0.5); obs_do.set(1, x[iXbh] / 2000); obs_do.set(2, x[iXba] / 500);
+    obs_do.set(3, x[iSo] / 8.0); obs_do.set(4, x[iSnh] / 10);
+    obs_ec.set(0, t / 0.5); obs_ec.set(1, x[iSs] / 30); obs_ec.set(2, x[iXbh] / 2000);
+    obs_ec.set(3, x[iSno] / 10); obs_ec.set(4, x[iSnh] / 10);
+    os_emit_deltas(x, first, obs_do, obs_ec);
+    state.set(0, t / 0.5);
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) state.set(i + 1, x[i] / tol_scale(i));   // tol_scale == x_1_state[1:]
+}
+
+// SbrOS.reset (gym_SBR_oneshot.py:168-438) + Sim_filling (:1585-1654).  x: in = x0, out = state after the fill.
+template <int MODE>
+SBR_HD int os_reset_env(double (&x)[SBR_NX], const Loading& load, const SbrParams& p, const Coef& coef,
+                        const SbrOsSchedule& s, const SbrTol& tol, Dp45State& dp, OsCtrl& c, const Column& ring,
+                        const Column& obs_do, const Column& obs_ec) {
+    const OsPid pid = make_os_pid(p);
+    const ObsRef x0r = obs_ref(x);
+    const double so0 = x[iSo], sno0 = x[iSno];
+    c.so_prev = so0; c.sno_prev = sno0; c.sno_last = sno0;
+    c.ie_do = 0.0; c.ie_ec = 0.0; c.ec_last = 0.0; c.kla_last = 0.0;
+    // one DO-PID update at set-point 0 on the t_start == 0 branch (:1597-1617): e < 0, KLa clamps to 0 and the
+    // anti-windup leaves ie_DO = So0 * dt; the fill-phase EC controller is forced to 0 (:1620-1645)
+    const double kla = os_pid_do(c, so0, 0.0, true, true, pid);
+    TailArgs a;
+    a.kla = kla; a.q = load(0); a.ec_conc = 0.0; a.load = load;
+    const int n_sub = s.rk4_sub_fill > 0 ? s.rk4_sub_fill : s.fill_pts - 1;
+    const int status = integrate_interval<TAIL_FILL, MODE>(x, s.t_fill, n_sub, coef, a, tol, dp);
+    c.so_prev = so0;                 // So  = [x0[8], x_fill[8]]
+    c.sno_prev = sno0;               // Sno = [x0[9], x_fill[2]]  -- sic, Ss stored as Sno (:1652)
+    c.sno_last = x[iSs];
+    c.kla_last = kla;
+    c.t = s.t_fill;
+    // `Kla` = [0, kla] replicated to the length of the fill trajectory (:320-324)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) ring.set(j, (j & 1) ? kla : 0.0);
+    // reset observation: flow-weighted mix of influent and reactor content (:347-364)
+    const double Qin = p.Qin, IV = p.IV;
+    const double den = Qin + IV;
+    obs_do.set(0, c.t / 0.5);
+    obs_do.set(1, (Qin * load(iXbh) + x[iXbh] * IV) / den / 2000);
+    obs_do.set(2, (Qin * load(iXba) + x[iXba] * IV) / den / 500);
+    obs_do.set(3, (Qin * load(iSo) + x[iSo] * IV) / den / 8.0);
+    obs_do.set(4, (Qin * load(iSnh) + x[iSnh] * IV) / den / 10);
+    obs_ec.set(0, c.t / 0.5);
+    obs_ec.set(1, (Qin * load(iSs) + x[iSs] * IV) / den / 30);
+    obs_ec.set(2, (Qin * load(iXbh) + x[iXbh] * IV) / den / 2000);
+    obs_ec.set(3, (Qin * load(iSno) + x[iSno] * IV) / den / 10);
+    obs_ec.set(4, (Qin * load(iSnh) + x[iSnh] * IV) / den / 10);
+    os_emit_deltas(x, x0r, obs_do, obs_ec);
+    return status;
+}
+
+struct OsStepOut {
+    double reward;
+    double Qw;       // only meaningful when done
+    int done;
+    int status;
+};
+
+// SbrOS.step (gym_SBR_oneshot.py:843-1273).  ring: the env's 10-entry Kla history (read after the integration,
+// so that it costs no registers while the stepper runs).
+template <int MODE>
+SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, double a_do, double a_ec,
+                        const SbrParams& p, const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol,
+                        Dp45State& dp, const Column& obs_do, const Column& obs_ec, const Column& state,
+                        OsStepOut& o) {
+    const OsPid pid = make_os_pid(p);
+    int status = 0, n_run = 0, L = 10;
+    double span = s.t_delta, u_do = 0.0, ec_before = c.ec_last;
+    double kla_new0 = 0.0, kla_new1 = 0.0;
+    ObsRef first = obs_ref(x);
+    TailArgs a;
+    a.kla = 0.0; a.q = 0.0; a.ec_conc = p.ec_conc; a.load = Loading{nullptr, 0};
+    // four NON-exclusive ifs on the running time (:860,896,931,963): anoxic / aerobic / anoxic / aerobic
+    for (int pass = 0; pass < 4; ++pass) {
+        const double t = c.t;
+        const bool cond = pass == 0 ? (t < s.tm3_0)
+                        : pass == 1 ? (t >= s.tm3_0 && t <= s.tm3_1)
+                        : pass == 2 ? (t > s.tm3_1 && t <= s.tm4_1)
+                                    : (t > s.tm4_1);
+        if (!cond) continue;
+        const bool aerobic = (pass & 1) != 0;
+        u_do = aerobic ? fmin(fmax(a_do, 0.0), p.do_sp_max) : 0.0;                  // :862-870, 898-906
+        const double u_ec = aerobic ? 0.0 : fmin(fmax(a_ec, 0.0), p.no_sp_max);
+        // run_aero_step / run_anaero_step (:1331-1419)
+        const double t_end = add_rn(t, s.t_delta);
+        span = sub_rn(t_end, t);
+        L = (int)div_rn(span, s.dt);
+        first = obs_ref(x);
+        const double so_start = x[iSo];
+        const double kla = os_pid_do(c, so_start, u_do, false, aerobic, pid);
+        ec_before = c.ec_last;
+        const double ec = os_pid_ec(c, u_ec, !aerobic, pid);
+        a.kla = kla; a.q = ec;
+        const int n_sub = s.rk4_sub_interval > 0 ? s.rk4_sub_interval : (L > 1 ? L - 1 : 1);
+        if (warp_any(ec != 0.0)) status |= integrate_interval<TAIL_EC, MODE>(x, span, n_sub, coef, a, tol, dp);
+        else status |= integrate_interval<TAIL_REACT, MODE>(x, span, n_sub, coef, a, tol, dp);
+        c.so_prev = so_start;
+        c.sno_prev = c.sno_last;
+        c.sno_last = x[iSno];
+        c.kla_last = kla;
+        c.ec_last = ec;
+        c.t = t_end;
+        if (n_run == 0) kla_new0 = kla; else kla_new1 = kla;
+        ++n_run;
+    }
+    // push the new KLa entries into the history, then reward = module_reward_EQIOCI.sbr_reward
+    // (module_reward_EQIOCI.py:4-115): `Kla` holds ONE entry per interval, so Kla[-L:-1] sums the previous L-1
+    // intervals and leaves the current one out (:70-71); `EC` holds L-1 copies per interval, so EC[-L:-1] is the
+    // previous interval's flow once plus the current one L-2 times (:79).
+    double r[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) r[j] = ring.get(j);
+    if (n_run >= 1) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+        r[9] = kla_new0;
+    }
+    if (n_run >= 2) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+        r[9] = kla_new1;
+    }
+    double ksum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+        if (j >= 10 - L) ksum += r[j];
+    double esum = 0.0 + ec_before;
+    for (int j = 0; j < L - 2; ++j) esum += c.ec_last;
+    double eff[6];
+    const double EQI = effluent_quality(x, eff);
+    const double EQI2 = EQI / 10;
+    const double AE = 8 / (span * 1.8 * 1000) * (1.32 * ksum * p.os_pid_dt);
+    const double ECO = p.ec_conc * esum * p.os_pid_dt / (span * 1000);
+    const double OCI = AE + ECO;
+    o.reward = (1 - (EQI2 * EQI2 + OCI * OCI)) / 473;
+    o.done = 0;
+    o.Qw = NAN;
+    if (c.t >= s.tm5_1) {
+        // end of the react phases (:1122): Sim_Settling_Drawing (:2264-2420) + Sim_idle (:2554-2597) in this step;
+        // the reward stays the pre-settle one, obs/state are recomputed from the post-idle state with deltas
+        // taken against the end-of-react state (:1167-1261)
+        o.done = 1;
+        first = obs_ref(x);
+        const double t_set_end = add_rn(c.t, s.settle_len);
+        const double T_set = sub_rn(t_set_end, c.t);
+        double sX[10], Xf;
+        settle_closed_form(x, T_set, p.settler_area, p.settler_vmax, sX, Xf);
+        DrawOut d;
+        draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+        status |= d.status;
+        o.Qw = d.Qw;
+        const double t_draw_end = add_rn(t_set_end, s.draw_len);
+        c.so_prev = x[iSo];                    // So padded with the frozen value over settle + draw (:2415-2416)
+        const double T_idle = sub_rn(s.t_cycle, t_draw_end);
+        const int pts = (int)div_rn(T_idle, s.dt);
+        const int n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
+        const double kla = os_pid_do(c, x[iSo], u_do, false, true, pid);
+        a.kla = kla; a.q = 0.0;
+        status |= integrate_interval<TAIL_REACT, MODE>(x, T_idle, n_sub, coef, a, tol, dp);
+        c.sno_prev = c.sno_last; c.sno_last = x[iSno];
+        c.kla_last = kla;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+        r[9] = kla;
+        c.t = s.t_cycle;
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) ring.set(j, r[j]);
+    bool finite = fabs(o.reward) < 1e300;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);
+    if (!finite) status |= SBR_ST_NONFINITE;
+    os_emit_obs(c.t, x, first, obs_do, obs_ec, state);
     o.status = status;
 }
 

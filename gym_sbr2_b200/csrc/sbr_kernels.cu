@@ -156,6 +156,118 @@ __global__ void __launch_bounds__(kBlock) sbr_rhs_kernel(RhsArgs g, SbrParams p,
     for (int j = 0; j < SBR_NX; ++j) g.dx[j * g.ld + i] = k[j];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Path B kernels: persistent per-env state st[SBR_OS_ROWS][ld] (SoA), one env per thread.
+// ---------------------------------------------------------------------------------------------------------
+struct OsArgs {
+    int64_t n, ld;
+    double* st;
+    const double* x0;         // reset only (may be NULL)
+    const double* influent;   // reset only
+    const uint8_t* mask;      // reset only (may be NULL)
+    const double* action;     // step only
+    double* obs_do;
+    double* obs_ec;
+    double* state;            // step only
+    double* reward;           // step only
+    uint8_t* done;
+    int32_t* status;
+    uint32_t* counters;
+};
+
+__constant__ double c_x0_init[SBR_NX] = {   // gym_SBR_oneshot.py:201-203
+    0.6161484733495801, 30, 0.571098000538576, 1440.01157895393, 31.254221999137, 2599.2714348941,
+    168.915006750837, 551.901552960823, 2.16607843793004, 13.3791460027604, 0.00562880208518134,
+    0.35996687629947, 1.86916737961228, 3.790463057094611};
+
+__device__ __forceinline__ void os_store_ctrl(double* st, int64_t ld, int64_t i, const sbr::OsCtrl& c, double h) {
+    st[SBR_OS_T * ld + i] = c.t;
+    st[SBR_OS_SO_PREV * ld + i] = c.so_prev;
+    st[SBR_OS_SNO_LAST * ld + i] = c.sno_last;
+    st[SBR_OS_SNO_PREV * ld + i] = c.sno_prev;
+    st[SBR_OS_IE_DO * ld + i] = c.ie_do;
+    st[SBR_OS_IE_EC * ld + i] = c.ie_ec;
+    st[SBR_OS_EC_LAST * ld + i] = c.ec_last;
+    st[SBR_OS_H * ld + i] = h;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_os_reset_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+                                                              SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    if (g.mask && g.mask[i] == 0) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0 ? g.x0[k * g.ld + i] : c_x0_init[k];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+    sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    sbr::Dp45State dp;
+    dp.h = s.t_fill / (double)(s.fill_pts > 1 ? s.fill_pts - 1 : 1);
+    dp.n_rhs = 0; dp.n_rej = 0;
+    sbr::OsCtrl ctl;
+    const sbr::Column ring{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld};
+    const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld};
+    int status = sbr::os_reset_env<MODE>(x, load, p, c, s, tol, dp, ctl, ring, od, oe);
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) { g.st[k * g.ld + i] = x[k]; finite = finite && (fabs(x[k]) < 1e300); }
+    if (!finite) status |= SBR_ST_NONFINITE;
+    os_store_ctrl(g.st, g.ld, i, ctl, s.t_delta / 9.0);
+    g.st[SBR_OS_RETURN * g.ld + i] = 0.0;
+    g.st[SBR_OS_STEPS * g.ld + i] = 0.0;
+    g.st[SBR_OS_QW * g.ld + i] = NAN;
+    g.done[i] = 0;
+    if (g.status) g.status[i] = status;
+    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+                                                             SbrTol tol) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
+    sbr::OsCtrl ctl;
+    ctl.t = g.st[SBR_OS_T * g.ld + i];
+    const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld}, os{g.state + i, g.ld};
+    if (g.done[i]) {
+        // stepping a finished episode is a no-op: same observation, zero deltas, reward 0
+        sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
+        g.reward[i] = 0.0;
+        if (g.status) g.status[i] = SBR_ST_DONE;
+        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
+        return;
+    }
+    ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
+    ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
+    ctl.sno_prev = g.st[SBR_OS_SNO_PREV * g.ld + i];
+    ctl.ie_do = g.st[SBR_OS_IE_DO * g.ld + i];
+    ctl.ie_ec = g.st[SBR_OS_IE_EC * g.ld + i];
+    ctl.ec_last = g.st[SBR_OS_EC_LAST * g.ld + i];
+    ctl.kla_last = g.st[(SBR_OS_KLA_RING + 9) * g.ld + i];
+    sbr::Dp45State dp;
+    dp.h = g.st[SBR_OS_H * g.ld + i];
+    dp.n_rhs = 0; dp.n_rej = 0;
+    const double a_do = g.action[i], a_ec = g.action[g.ld + i];
+    const sbr::Column ring{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld};
+    sbr::OsStepOut o;
+    sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, od, oe, os, o);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
+    os_store_ctrl(g.st, g.ld, i, ctl, dp.h);
+    g.st[SBR_OS_RETURN * g.ld + i] += o.reward;
+    g.st[SBR_OS_STEPS * g.ld + i] += 1.0;
+    if (o.done) { g.st[SBR_OS_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
+    g.reward[i] = o.reward;
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread, `iters` rounds of 8 DFMAs each.
 __global__ void sbr_fp64_probe_kernel(int iters, double* sink) {
     const double a = 1.0000001, b = 1e-9 * (double)(threadIdx.x + 1);
@@ -232,6 +344,15 @@ SbrTol tol_or_default(const SbrTol* tol) {
     return t;
 }
 
+int check_os_schedule(const SbrOsSchedule* s) {
+    if (!s) return fail(SBR_ERR_ARG, "schedule pointer is NULL%s");
+    if (!(s->dt > 0) || !(s->t_delta > 0) || !(s->t_fill > 0) || !(s->t_cycle > 0) || s->fill_pts < 2 ||
+        !(s->tm3_0 < s->tm3_1 && s->tm3_1 < s->tm4_1 && s->tm4_1 <= s->tm5_1) || !(s->settle_len > 0) ||
+        !(s->draw_len >= 0) || s->rk4_sub_interval < 0 || s->rk4_sub_fill < 0 || s->rk4_sub_idle < 0)
+        return fail(SBR_ERR_ARG, "SbrOsSchedule: inconsistent time constants%s");
+    return SBR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,6 +387,7 @@ void sbr_params_default(SbrParams* p) {
     p->os_Kc_EC = 100.0; p->os_tauI_EC = 20.0; p->os_tauD_EC = 0.0;
     p->os_pid_dt = 0.002 / 24; p->ec_min = 0.0; p->ec_max = 0.0005; p->ec_conc = 1200000.0 * 4;
     p->do_sp_max = 8.0; p->no_sp_max = 15.0;
+    p->IV = 0.6161484733495801;
 }
 
 int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
@@ -341,6 +463,43 @@ int sbr_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const dou
     else if (tail == sbr::TAIL_EC) sbr_rhs_kernel<sbr::TAIL_EC><<<grid, kBlock, 0, st>>>(g, *p, c);
     else return fail(SBR_ERR_ARG, "sbr_rhs: bad tail%s");
     return check_launch("sbr_rhs");
+}
+
+int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                 const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs_do, double* obs_ec,
+                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if ((rc = check_os_schedule(s))) return rc;
+    if (!influent || !st || !obs_do || !obs_ec || !done) return fail(SBR_ERR_ARG, "sbr_os_reset: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_reset: bad mode%s");
+    OsArgs g{n, ld, st, x0, influent, mask, nullptr, obs_do, obs_ec, nullptr, nullptr, done, status, counters};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4) sbr_os_reset_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    else sbr_os_reset_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    return check_launch("sbr_os_reset");
+}
+
+int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
+                const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if ((rc = check_os_schedule(s))) return rc;
+    if (!st || !action || !obs_do || !obs_ec || !state || !reward || !done)
+        return fail(SBR_ERR_ARG, "sbr_os_step: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_step: bad mode%s");
+    OsArgs g{n, ld, st, nullptr, nullptr, nullptr, action, obs_do, obs_ec, state, reward, done, status, counters};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    return check_launch("sbr_os_step");
 }
 
 int sbr_reward_stats_init(double* stats, void* stream) {

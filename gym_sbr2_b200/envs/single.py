@@ -1,0 +1,103 @@
+"""Per-instance Gym envs = batch-of-one views of the vector envs (drop-in for the reference's odeint path)."""
+import numpy as np
+import torch
+
+from .. import influent as influent_mod
+from ..registration import ENV_TABLE, UnsupportedEnvError
+from ..spaces import Box, env_base
+from ..vec_env import SbrOsVecEnv, SbrV2VecEnv
+
+_Base = env_base()
+
+
+def unsupported_class(env_id):
+    cls_name, ref_module, _, why = ENV_TABLE[env_id]
+
+    def __init__(self, *a, **k):
+        raise UnsupportedEnvError(
+            "%s (%s, reference %s) is registered for API compatibility only: %s. It has no working oracle; the "
+            "ids that step in the reference are SBR-v2 and SBROS-v1." % (env_id, cls_name, ref_module, why))
+
+    return type(cls_name, (_Base,), {"__init__": __init__, "metadata": {"render.modes": ["human"]},
+                                     "__doc__": "Unsupported: %s" % why})
+
+
+def _device(device):
+    if device is None:
+        device = "cuda:0"
+    return torch.device(device)
+
+
+class SbrEnv2(_Base):
+    """`SBR-v2` (gym_SBR_env2.py:58-193): one step = one whole 12-h cycle; action = 3 values in [0,1] -> DO
+    set-points 8*a of phases 3, 5, 8; obs = [Qeff, COD_eff, Snh_eff/30]; done = True after every step."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device=None, mode="rk4", rtol=1e-8, atol=1e-10):
+        self.action_space = Box(np.array([0., 0., 0.]), np.array([1.0, 1.0, 1.0]), dtype=np.float32)       # :64
+        self.observation_space = Box(low=np.array([0.5, 0, 0]), high=np.array([1.33, 2.5, 2]), dtype=np.float32)
+        self.reward = 0
+        self._vec = SbrV2VecEnv(1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
+        self.influent_mixed = None
+        self.info = {}
+
+    def reset(self):
+        # one buffer_tank(0) call on the GLOBAL numpy RNG, bit-exact with the reference (buffer_tank3.py:68)
+        self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)
+        obs = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
+        return obs[0].cpu().numpy()
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        action = np.clip(np.asarray(action, dtype=np.float64), self.action_space.low, self.action_space.high)
+        obs, reward, done, info = self._vec.step(torch.as_tensor(action, dtype=torch.float64)[None, :])
+        self.reward = float(reward[0])
+        self.info = {k: v[..., 0].cpu().numpy() for k, v in info.items()}
+        return obs[0].cpu().numpy(), self.reward, True, {}
+
+    def render(self, mode="human", close=False):
+        print("Reward for this episode: {}".format(self.reward))
+
+
+class SbrOS(_Base):
+    """`SBROS-v1` (gym_SBR_oneshot.py:98-2644): one step = one 72-s PID interval; action = [DO set-point, NO3
+    set-point]; returns the reference's 5-tuple (obs, state, reward, done, info) with obs = (obs_DO, obs_EC)."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device=None, mode="dp45", rtol=1e-8, atol=1e-10):
+        self.action_space = Box(np.array([-1]), np.array([1]), dtype=np.float32)                           # :106
+        self.observation_space = Box(low=np.array([0, 0, 0, -1, -1]), high=np.ones([5]) * 1.0, dtype=np.float32)
+        self._vec = SbrOsVecEnv(1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
+        self.influent_mixed = None
+        self.reward = 0
+
+    def reset(self):
+        self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)       # buffer_tank(6), :180
+        obs_do, obs_ec = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
+        return (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1, 2))
+        (obs_do, obs_ec), state, reward, done, info = self._vec.step(a)
+        self.reward = float(reward[0])
+        obs = (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
+        return obs, state[0].cpu().numpy().tolist(), self.reward, bool(done[0]), {}
+
+    def get_available_actions(self, pre_action, n_agents, n_action):
+        """Action masks of the reference's discrete multi-agent wrapper (gym_SBR_oneshot.py:440-459)."""
+        action_list = ([-0.1, 0, 0.1], [-5, 0, 5])
+        action_boundary = ([0, 8], [0, 15])
+        avail_us = []
+        for agent_i in range(0, n_agents):
+            avail_u = np.ones(n_action)
+            for i in range(0, n_action):
+                v = pre_action[agent_i] + action_list[agent_i][i]
+                avail_u[i] = 1 if action_boundary[agent_i][0] <= v <= action_boundary[agent_i][1] else 0
+            avail_us.append(avail_u)
+        return avail_us
+
+    def render(self, mode="human", close=False):
+        print("Reward for this step: {}".format(self.reward))

@@ -1,0 +1,84 @@
+"""Gym registration surface (the reference's drop-in boundary, gym_SBR/__init__.py:1-12).
+
+The reference registers ten ids with `gym.envs.registration.register(id=..., entry_point='gym_SBR.envs:<Class>')`
+and users call `gym.make(id)`.  The same ten ids are registered here, under the same class names:
+  * `SBR-v2` (`SbrEnv2`) and `SBROS-v1` (`SbrOS`) -- the two ids whose `step()` runs in the reference on a current
+    toolchain -- are served by the CUDA path;
+  * the other eight raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
+    (they crash inside `step()` there), instead of pretending to work.
+`gym` / `gymnasium` are optional: when one is importable the ids are registered with it as well (so `gym.make`
+works unchanged); otherwise `gym_sbr2_b200.make(id)` is the equivalent.
+"""
+import importlib
+
+ENTRY_PACKAGE = "gym_sbr2_b200.envs"
+
+# id -> (class name, reference module, supported?, reference failure mode when not)
+ENV_TABLE = {
+    "SBR-v0": ("SbrEnv", "gym_SBR_env0.py", False,
+               "reference step() raises TypeError: float `num` in np.linspace (sub_phases_batchPID_fbPID.py:144)"),
+    "SBR-v1": ("SbrEnv1", "gym_SBR_env1.py", False,
+               "reference step() raises TypeError: sbr_reward() arity mismatch (gym_SBR_env1.py:151 vs module_reward.py:4)"),
+    "SBR-v2": ("SbrEnv2", "gym_SBR_env2.py", True, None),
+    "SBR-v4": ("SbrEnv4", "gym_SBR_env4.py", False,
+               "reference step() raises TypeError: float `num` in np.linspace (gym_SBR_env4.py:286)"),
+    "SBRCnt-v0": ("SbrCnt0", "gym_SBR_continuous0.py", False,
+                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    "SBRCnt-v1": ("SbrCnt1", "gym_SBR_continuous1.py", False,
+                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    "SBRCnt-v2": ("SbrCnt2", "gym_SBR_continuous2.py", False,
+                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    "SBRCntMA-v1": ("SbrCntMA1", "gym_SBR_continuous_MA1.py", False,
+                    "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    "SBROS-v1": ("SbrOS", "gym_SBR_oneshot.py", True, None),
+    "SBROS-v2": ("SbrOS1", "gym_SBR_oneshot1.py", False,
+                 "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+}
+
+registry = {}
+
+
+class UnsupportedEnvError(NotImplementedError):
+    pass
+
+
+def register(id, entry_point, **kwargs):
+    """Same signature as gym.envs.registration.register (only `id` and `entry_point` are used by the reference)."""
+    registry[id] = dict(entry_point=entry_point, kwargs=dict(kwargs))
+
+
+def _load(entry_point):
+    mod, _, attr = entry_point.partition(":")
+    return getattr(importlib.import_module(mod), attr)
+
+
+def make(id, **kwargs):
+    """gym.make equivalent: instantiate the env registered under `id`."""
+    if id not in registry:
+        raise KeyError("no env registered under id %r (known: %s)" % (id, ", ".join(sorted(registry))))
+    spec = registry[id]
+    kw = dict(spec["kwargs"])
+    kw.update(kwargs)
+    return _load(spec["entry_point"])(**kw)
+
+
+def spec_ids():
+    return sorted(registry)
+
+
+def _register_all():
+    for env_id, (cls, _, _, _) in ENV_TABLE.items():
+        register(id=env_id, entry_point="%s:%s" % (ENTRY_PACKAGE, cls))
+    for name in ("gym", "gymnasium"):
+        try:
+            reg = importlib.import_module(name + ".envs.registration")
+        except Exception:
+            continue
+        for env_id, (cls, _, _, _) in ENV_TABLE.items():
+            try:
+                reg.register(id=env_id, entry_point="%s:%s" % (ENTRY_PACKAGE, cls))
+            except Exception:
+                pass                      # already registered (e.g. by the reference package itself)
+
+
+_register_all()

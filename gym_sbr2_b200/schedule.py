@@ -60,3 +60,48 @@ def cycle_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
 
 def schedule_summary(s):
     return dict(n_int=list(s.n_int), n_sub=list(s.n_sub), interval=list(s.interval), settle_time=s.settle_time)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# interval-per-step path (SBROS-v1)
+# ---------------------------------------------------------------------------------------------------------
+def batch_time_marks(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA * 10):
+    """First and last output stamp of each phase, [(t_memoryK[0], t_memoryK[-1])] for K = 1..8, as
+    module_batch_time.batch_time builds them (module_batch_time.py:3-116) when called with t_delta = 10*dt
+    (gym_SBR_oneshot.py:35-36): per phase a linspace of int(len/(10*t_delta)) stamps, each gap refilled with
+    int(gap/t_delta) points -- every count an int(float) truncation."""
+    marks = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + t_delta
+        t_end = t_start + t_cycle * t_ratio[k]
+        t_save = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+        first, last = t_save[0], t_save[0]
+        for i in range(len(t_save) - 1):
+            t_range = np.linspace(t_save[i], t_save[i + 1], int((t_save[i + 1] - t_save[i]) / t_delta))
+            if len(t_range) > 1:
+                last = t_range[-1]
+        marks.append((float(first), float(last)))
+    return marks
+
+
+def os_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, dt=T_DELTA, rk4_sub_interval=0, rk4_sub_fill=0, rk4_sub_idle=0):
+    """SbrOsSchedule: the time constants SbrOS.step / reset key on (gym_SBR_oneshot.py:28-36, 292, 860-963, 1122,
+    2264-2420, 2554-2597)."""
+    t_delta = dt * 10
+    m = batch_time_marks(t_cycle, t_ratio, t_delta)
+    s = _abi.SbrOsSchedule()
+    s.tm3_0, s.tm3_1, s.tm4_1, s.tm5_1 = m[2][0], m[2][1], m[3][1], m[4][1]
+    s.dt, s.t_delta = dt, t_delta
+    s.t_fill = 0 + t_ratio[0] * 0.5                      # Sim_filling(x0, t=0, t_ratio[0], ...) (:292,1585)
+    s.fill_pts = int((s.t_fill - 0) / dt)
+    s.settle_len = t_ratio[5] * t_cycle
+    s.draw_len = t_ratio[6] * t_cycle
+    s.t_cycle = t_cycle
+    s.rk4_sub_interval, s.rk4_sub_fill, s.rk4_sub_idle = int(rk4_sub_interval), int(rk4_sub_fill), int(rk4_sub_idle)
+    return s
+
+
+def os_fill_flow(qin, t_cycle=T_CYCLE, t_ratio=T_RATIO, dt=T_DELTA):
+    """influent_mixed[0] := Qin / t_memory1[-1] (gym_SBR_oneshot.py:287)."""
+    return qin / batch_time_marks(t_cycle, t_ratio, dt * 10)[0][1]

@@ -38,7 +38,7 @@ class SbrV2VecEnv(object):
                  params=None, rng="torch"):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
-        if self.device.type != "cuda":
+        if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _abi.SbrLibraryError("SbrV2VecEnv needs a CUDA device: there is no CPU fallback")
         self.lib = _abi.load()
         self.params = params if params is not None else _abi.default_params()
@@ -106,3 +106,92 @@ class SbrV2VecEnv(object):
 
     def render(self, mode="human", close=False):
         print("Reward for this episode: {}".format(self._out.reward))
+
+
+class SbrOsVecEnv(object):
+    """N x `SBROS-v1` (the reference's `SbrOS`, gym_SBR_oneshot.py:98-2644): one `step` = one 72-s PID interval
+    (two when the step crosses a phase boundary); 463 steps per episode; the last one also settles, draws and
+    idles.  One kernel launch per `step` for the whole batch; the per-env controller histories the reference keeps
+    in module-level lists live in a [35, N] SoA state tensor on the device.
+
+    reset()  -> (obs_DO [N,9], obs_EC [N,9])
+    step(a)  -> ((obs_DO [N,9], obs_EC [N,9]), state [N,15], reward [N], done [N] bool, info)   (the reference's
+                5-tuple, gym_SBR_oneshot.py:1273)
+    action [N,2]: a[:,0] = DO set-point (g/m3, clipped to [0,8], used in aerobic phases), a[:,1] = NO3 set-point
+                (clipped to [0,15], used in anoxic phases) (:862-906).  The declared action_space Box([-1],[1]) of
+                the reference does not describe what `step` consumes; neither is enforced.
+    autoreset: envs whose episode has ended are restarted (new influent draw, masked reset kernel) at the start of
+               the next `step` and then take that step like every other env; info["restarted"] marks them.
+               Without autoreset, stepping a finished env is a no-op (reward 0, status SBR_ST_DONE).
+    """
+
+    num_actions = 2
+    scenario = 6                     # buffer_tank(6), gym_SBR_oneshot.py:180
+    max_episode_steps = 463
+
+    def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=4000,
+                 params=None, rng="torch", autoreset=False, rk4_sub_interval=0):
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _abi.SbrLibraryError("SbrOsVecEnv needs a CUDA device: there is no CPU fallback")
+        self.lib = _abi.load()
+        self.params = params if params is not None else _abi.default_params()
+        self.sched = schedule.os_schedule(rk4_sub_interval=rk4_sub_interval)
+        self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
+        self.tol = _abi.make_tol(rtol, atol, max_steps)
+        self.rng = rng
+        self.autoreset = bool(autoreset)
+        self._gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self._gen.manual_seed(int(seed))
+        self._np_rng = np.random.RandomState(seed) if seed is not None else np.random
+        n = self.num_envs
+        f = dict(dtype=torch.float64, device=self.device)
+        self.buf = core.OsBuffers(n, self.device)
+        self.influent = torch.zeros((_abi.NX, n), **f)
+        self._loading = torch.zeros((_abi.NX, n), **f)
+        self._action = torch.zeros((2, n), **f)
+        self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_oneshot.py:287
+
+    _draw_influent = SbrV2VecEnv._draw_influent
+
+    def reset(self, influent=None, x0=None, mask=None):
+        """influent: optional [14,N] influent_mixed (row 0 is replaced by the fill flow); x0: optional [14,N];
+        mask: optional [N] bool/uint8 -- restart only these envs."""
+        if influent is None:
+            influent = self._draw_influent()
+        influent = influent.to(self.device, torch.float64)
+        if mask is None:
+            self.influent.copy_(influent)
+        else:
+            mask = mask.to(self.device).to(torch.uint8).contiguous()
+            self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
+        self._loading.copy_(self.influent)
+        self._loading[0] = self.fill_flow
+        if x0 is not None:
+            x0 = x0.to(self.device, torch.float64).contiguous()
+        core.os_reset(self.buf, self._loading, self.params, self.sched, x0=x0, mask=mask, mode=self.mode,
+                      tol=self.tol)
+        return self.buf.obs_do.t(), self.buf.obs_ec.t()
+
+    def step_async(self, action, stream=None):
+        if action.shape != (self.num_envs, 2):
+            raise ValueError("action must be [N,2], got %s" % (tuple(action.shape),))
+        self._action.copy_(action.to(self.device, torch.float64).t())
+        return core.os_step(self.buf, self._action, self.params, self.sched, mode=self.mode, tol=self.tol,
+                            stream=stream)
+
+    def step(self, action):
+        b = self.buf
+        restarted = None
+        if self.autoreset:
+            restarted = b.done.clone()
+            self.reset(mask=restarted)          # masked kernel: a no-op for running envs
+        self.step_async(action)
+        info = dict(status=b.status, counters=b.counters, t=b.st[_abi.OS_T], Qw=b.st[_abi.OS_QW],
+                    episode_return=b.st[_abi.OS_RETURN], episode_steps=b.st[_abi.OS_STEPS], restarted=restarted)
+        return (b.obs_do.t(), b.obs_ec.t()), b.state.t(), b.reward, b.done.bool(), info
+
+    def render(self, mode="human", close=False):
+        print("Reward for this step: {}".format(self.buf.reward))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 1
+#define SBR_ABI_VERSION 2
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -41,7 +41,8 @@ extern "C" {
 #define SBR_ST_NONFINITE 1   /* state left the finite range                                             */
 #define SBR_ST_WASTE 2       /* waste loop ended without fixing Qw (reference: NameError, sub_phases_FB.py:817-836) */
 #define SBR_ST_STEPLIMIT 4   /* DP45 hit max_steps inside one interval                                 */
-#define SBR_ST_LAYERS 8      /* decant layer count m outside 1..9                                       */
+#define SBR_ST_LAYERS 8      /* decant layer count m outside 1..9 (reference: round(inf) OverflowError, gym_SBR_oneshot.py:2338) */
+#define SBR_ST_DONE 16       /* sbr_os_step was called on an env whose episode had already ended (no-op) */
 
 /* error codes */
 #define SBR_OK 0
@@ -71,6 +72,7 @@ typedef struct SbrParams {
     /* interval-per-step path (gym_SBR_oneshot.py:83-96): DO and NO3 PIDs, EC dosing */
     double os_Kc_DO, os_tauI_DO, os_tauD_DO, os_Kc_EC, os_tauI_EC, os_tauD_EC;
     double os_pid_dt, ec_min, ec_max, ec_conc, do_sp_max, no_sp_max;
+    double IV;                     /* initial (post-draw) volume used by the reset observation mix (gym_SBR_oneshot.py:347-364) */
 } SbrParams;
 
 /* Time schedule of one cycle (computed on the host with the reference's own float expressions,
@@ -83,6 +85,43 @@ typedef struct SbrSchedule {
     double interval[SBR_NPHASE];
     double settle_time;
 } SbrSchedule;
+
+/* Rows of the persistent per-env state of the interval-per-step path (st[r * ld + i]); the reference keeps all
+ * of this in module globals and ever-growing Python lists (gym_SBR_oneshot.py:207-257). */
+enum {
+    SBR_OS_X = 0,            /* rows 0..13: reactor state                                                     */
+    SBR_OS_T = 14,           /* running time `t` (days)                                                       */
+    SBR_OS_SO_PREV,          /* So[-2] (So[-1] is x[8])                                                       */
+    SBR_OS_SNO_LAST,         /* Sno[-1]: x[9], except right after reset where the reference stores Ss (:1652)  */
+    SBR_OS_SNO_PREV,         /* Sno[-2]                                                                       */
+    SBR_OS_IE_DO,            /* DO-PID integral                                                               */
+    SBR_OS_IE_EC,            /* NO3-PID integral                                                              */
+    SBR_OS_EC_LAST,          /* EC[-1]: dosing flow of the last interval                                      */
+    SBR_OS_H,                /* DP45 step-size proposal carried across intervals                              */
+    SBR_OS_KLA_RING,         /* rows 22..31: last 10 entries of the `Kla` list, oldest first                  */
+    SBR_OS_RETURN = SBR_OS_KLA_RING + 10,   /* sum of rewards since reset                                     */
+    SBR_OS_STEPS,            /* env.step calls since reset                                                    */
+    SBR_OS_QW,               /* waste-sludge volume of the terminal draw (the reference's global `Qw`); NaN before */
+    SBR_OS_ROWS
+};
+#define SBR_OS_NOBS 9        /* len(obs_DO) = len(obs_EC): 5 normalised values + 4 clipped deltas             */
+#define SBR_OS_NSTATE 15     /* [t, x] / x_1_state                                                            */
+
+/* Time constants of the interval-per-step path, computed on the host with the reference's float expressions
+ * (module_batch_time.py:3-116 called with t_delta = 10*dt, gym_SBR_oneshot.py:28-36).  The per-interval output
+ * point count L = int(((t + t_delta) - t) / dt) (9 or 10, :1339,1384) depends on the running time and is
+ * evaluated in the kernel with IEEE round-to-nearest add/sub/div (no contraction), hence bit-identical. */
+typedef struct SbrOsSchedule {
+    double tm3_0, tm3_1, tm4_1, tm5_1;   /* t_memory3[0], t_memory3[-1], t_memory4[-1], t_memory5[-1]          */
+    double dt, t_delta;                  /* 0.002/24 and 10*dt                                                 */
+    double t_fill;                       /* end of the fill phase = t_ratio[0] * 0.5 (:292,1585)               */
+    double settle_len, draw_len;         /* t_ratio[5] * t_cycle, t_ratio[6] * t_cycle (:2264-2420)            */
+    double t_cycle;
+    int32_t fill_pts;                    /* int(t_fill / dt) = 252 output points of the fill solve (:1647)     */
+    int32_t rk4_sub_interval;            /* RK4 sub-steps per interval; 0 = the reference grid (L - 1)         */
+    int32_t rk4_sub_fill;                /* RK4 sub-steps of the fill solve; 0 = fill_pts - 1                  */
+    int32_t rk4_sub_idle;                /* RK4 sub-steps of the idle solve; 0 = int((t_cycle - t0)/dt) - 1    */
+} SbrOsSchedule;
 
 /* Adaptive-step controls (SBR_MODE_DP45). */
 typedef struct SbrTol {
@@ -130,6 +169,40 @@ int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, 
  * (sub_phases_FB.py:51-176, 278-404; gym_SBR_oneshot.py:1658-1787). */
 int sbr_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const double* ec,
             const double* loading, const SbrParams* p, int tail, double* dx, void* stream);
+
+/*
+ * Interval-per-step path, episode start = SbrOS.reset (gym_SBR_oneshot.py:168-438) -> Sim_filling (:1585-1654) ->
+ * odeint(filling_dxdt) (:1647): one PID update at set-point 0, ONE fill solve over [0, t_fill], history seeding
+ * (incl. the reference's `Sno := Ss` slip, :1652) and the reset observation from the flow-weighted mix of
+ * influent and reactor (:347-364) plus 4 clipped deltas each (:388-429).
+ *   x0        [14][ld] in   start state (NULL = the reference's x0_init for every env, :201-203)
+ *   influent  [14][ld] in   row 0 = fill flow Qin / t_memory1[-1] (:287), rows 1..13 = influent concentrations
+ *   mask      [n] in        reset only envs with mask[i] != 0 (NULL = all) -- lets a vector env restart finished
+ *                           episodes while the others keep running
+ *   st        [SBR_OS_ROWS][ld] out persistent per-env state
+ *   obs_do, obs_ec [9][ld] out; done [n] out (cleared); status [n], counters [2][ld] may be NULL
+ */
+int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                 const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs_do, double* obs_ec,
+                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+
+/*
+ * One env.step = SbrOS.step (gym_SBR_oneshot.py:843-1273): phase selection by the running time through four
+ * NON-exclusive `if`s (:860,896,931,963 -- a step that crosses a phase boundary runs two intervals),
+ * run_aero_step / run_anaero_step (:1331-1419) -> Sim_aero_rxn / Sim_anaero_rxn (:1877-2051: DO-PID -> KLa with
+ * incremental bias, NO3-PID -> external-carbon flow EC) -> odeint(reaction_dxdt) (:1953,2041), reward
+ * module_reward_EQIOCI.sbr_reward (module_reward_EQIOCI.py:4-115), observation epilogue (:1015-1114) and, when
+ * t >= t_memory5[-1] (:1122), Sim_Settling_Drawing (:2264-2420) + Sim_idle (:2554-2597) inside the same call.
+ *   st      [SBR_OS_ROWS][ld] in/out
+ *   action  [2][ld] in   row 0 = DO set-point (clipped to [0, do_sp_max], aerobic phases), row 1 = NO3 set-point
+ *                        (clipped to [0, no_sp_max], anoxic phases) (:862-906)
+ *   obs_do, obs_ec [9][ld] out; state [15][ld] out; reward [n] out; done [n] in/out
+ *   status [n] out (may be NULL); counters [2][ld] out (may be NULL)
+ * An env whose done flag is already set is left untouched (reward 0, status SBR_ST_DONE).
+ */
+int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
+                const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

@@ -46,7 +46,7 @@ def default_params():
                 settler_area=(1.25 / 2) * (1.25 / 2), settler_vmax=474.0, kla0=0.0, action_scale=8.0,
                 os_Kc_DO=100.0, os_tauI_DO=20.0, os_tauD_DO=0.0, os_Kc_EC=100.0, os_tauI_EC=20.0, os_tauD_EC=0.0,
                 os_pid_dt=0.002 / 24, ec_min=0.0, ec_max=0.0005, ec_conc=1200000.0 * 4, do_sp_max=8.0,
-                no_sp_max=15.0)
+                no_sp_max=15.0, IV=0.6161484733495801)
     tk = (15 + 273.15) / 100
     vals["so_sat"] = 0.9997743214 * (8 / 10.5) * 6791.5 * (56.12 * np.exp(-66.7354 + 87.4755 / tk + 24.4526 * np.log(tk)))
     for k, v in vals.items():
@@ -99,3 +99,45 @@ def rhs(x, kla, params, tail, ec=None, loading=None):
                       C.c_int(tail), _ptr(dx))
     assert rc == 0
     return dx
+
+
+class OsBatch(object):
+    """Host-memory twin of the interval-per-step path: same buffers and call sequence as the CUDA entry points
+    sbr_os_reset / sbr_os_step."""
+
+    def __init__(self, n, params=None, sched=None, mode=0, tol=None):
+        from gym_sbr2_b200 import schedule
+        self.n = n
+        self.params = params or default_params()
+        self.sched = sched or schedule.os_schedule()
+        self.mode = mode
+        self.tol = tol or _abi.make_tol()
+        self.st = np.zeros((_abi.OS_ROWS, n))
+        self.obs_do = np.zeros((9, n)); self.obs_ec = np.zeros((9, n)); self.state = np.zeros((15, n))
+        self.reward = np.zeros(n); self.done = np.zeros(n, dtype=np.uint8)
+        self.status = np.zeros(n, dtype=np.int32); self.counters = np.zeros((2, n), dtype=np.uint32)
+
+    def reset(self, influent, x0=None, mask=None):
+        lib = load()
+        influent = np.ascontiguousarray(influent, dtype=np.float64)
+        x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        n = self.n
+        rc = lib.twin_os_reset(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(influent), _ptr(mask),
+                               C.byref(self.params), C.byref(self.sched), _ptr(self.st), _ptr(self.obs_do),
+                               _ptr(self.obs_ec), _ptr(self.done), _ptr(self.status), _ptr(self.counters),
+                               C.c_int(self.mode), C.byref(self.tol))
+        assert rc == 0
+        return self.obs_do.copy(), self.obs_ec.copy()
+
+    def step(self, action):
+        lib = load()
+        action = np.ascontiguousarray(action, dtype=np.float64)
+        n = self.n
+        assert action.shape == (2, n)
+        rc = lib.twin_os_step(C.c_int64(n), C.c_int64(n), _ptr(self.st), _ptr(action), C.byref(self.params),
+                              C.byref(self.sched), _ptr(self.obs_do), _ptr(self.obs_ec), _ptr(self.state),
+                              _ptr(self.reward), _ptr(self.done), _ptr(self.status), _ptr(self.counters),
+                              C.c_int(self.mode), C.byref(self.tol))
+        assert rc == 0
+        return self.obs_do.copy(), self.obs_ec.copy(), self.state.copy(), self.reward.copy(), self.done.copy()

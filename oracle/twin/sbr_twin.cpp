@@ -97,4 +97,93 @@ int twin_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const do
     return 0;
 }
 
+static const double kX0Init[SBR_NX] = {   // gym_SBR_oneshot.py:201-203
+    0.6161484733495801, 30, 0.571098000538576, 1440.01157895393, 31.254221999137, 2599.2714348941,
+    168.915006750837, 551.901552960823, 2.16607843793004, 13.3791460027604, 0.00562880208518134,
+    0.35996687629947, 1.86916737961228, 3.790463057094611};
+
+static SbrTol tol_or_default(const SbrTol* tol) {
+    SbrTol t;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 4000; t.reserved = 0;
+    if (tol) t = *tol;
+    return t;
+}
+
+static void store_ctrl(double* st, int64_t ld, int64_t i, const OsCtrl& c, double h) {
+    st[SBR_OS_T * ld + i] = c.t; st[SBR_OS_SO_PREV * ld + i] = c.so_prev;
+    st[SBR_OS_SNO_LAST * ld + i] = c.sno_last; st[SBR_OS_SNO_PREV * ld + i] = c.sno_prev;
+    st[SBR_OS_IE_DO * ld + i] = c.ie_do; st[SBR_OS_IE_EC * ld + i] = c.ie_ec;
+    st[SBR_OS_EC_LAST * ld + i] = c.ec_last; st[SBR_OS_H * ld + i] = h;
+}
+
+int twin_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                  const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs_do, double* obs_ec,
+                  uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && mask[i] == 0) continue;
+        double x[SBR_NX], load[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) { x[k] = x0 ? x0[k * ld + i] : kX0Init[k]; load[k] = influent[k * ld + i]; }
+        Dp45State dp;
+        dp.h = s->t_fill / (double)(s->fill_pts > 1 ? s->fill_pts - 1 : 1); dp.n_rhs = 0; dp.n_rej = 0;
+        OsCtrl ctl;
+        const Column ring{st + SBR_OS_KLA_RING * ld + i, ld}, od{obs_do + i, ld}, oe{obs_ec + i, ld};
+        const Loading L{load, 1};
+        int stt = mode == SBR_MODE_RK4 ? os_reset_env<SBR_MODE_RK4>(x, L, *p, c, *s, t, dp, ctl, ring, od, oe)
+                                       : os_reset_env<SBR_MODE_DP45>(x, L, *p, c, *s, t, dp, ctl, ring, od, oe);
+        for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
+        store_ctrl(st, ld, i, ctl, s->t_delta / 9.0);
+        st[SBR_OS_RETURN * ld + i] = 0.0; st[SBR_OS_STEPS * ld + i] = 0.0; st[SBR_OS_QW * ld + i] = NAN;
+        done[i] = 0;
+        if (status) status[i] = stt;
+        if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
+    }
+    return 0;
+}
+
+int twin_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
+                 const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        double x[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) x[k] = st[k * ld + i];
+        OsCtrl ctl;
+        ctl.t = st[SBR_OS_T * ld + i];
+        const Column od{obs_do + i, ld}, oe{obs_ec + i, ld}, os{state + i, ld};
+        if (done[i]) {
+            os_emit_obs(ctl.t, x, obs_ref(x), od, oe, os);
+            reward[i] = 0.0;
+            if (status) status[i] = SBR_ST_DONE;
+            if (counters) { counters[i] = 0; counters[ld + i] = 0; }
+            continue;
+        }
+        ctl.so_prev = st[SBR_OS_SO_PREV * ld + i]; ctl.sno_last = st[SBR_OS_SNO_LAST * ld + i];
+        ctl.sno_prev = st[SBR_OS_SNO_PREV * ld + i]; ctl.ie_do = st[SBR_OS_IE_DO * ld + i];
+        ctl.ie_ec = st[SBR_OS_IE_EC * ld + i]; ctl.ec_last = st[SBR_OS_EC_LAST * ld + i];
+        ctl.kla_last = st[(SBR_OS_KLA_RING + 9) * ld + i];
+        Dp45State dp;
+        dp.h = st[SBR_OS_H * ld + i]; dp.n_rhs = 0; dp.n_rej = 0;
+        const Column ring{st + SBR_OS_KLA_RING * ld + i, ld};
+        OsStepOut o;
+        if (mode == SBR_MODE_RK4)
+            os_step_env<SBR_MODE_RK4>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, od, oe, os, o);
+        else
+            os_step_env<SBR_MODE_DP45>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, od, oe, os, o);
+        for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
+        store_ctrl(st, ld, i, ctl, dp.h);
+        st[SBR_OS_RETURN * ld + i] += o.reward;
+        st[SBR_OS_STEPS * ld + i] += 1.0;
+        if (o.done) { st[SBR_OS_QW * ld + i] = o.Qw; done[i] = 1; }
+        reward[i] = o.reward;
+        if (status) status[i] = o.status;
+        if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,147 @@
+"""GPU parity tests of the interval-per-step path (SBROS-v1): kernels sbr_os_reset / sbr_os_step through the C ABI
+against whole episodes of the unmodified reference, against the scipy oracle, and (every env of a 4096 batch)
+against the g++ twin of the same stepper."""
+import numpy as np
+import pytest
+import torch
+
+from gym_sbr2_b200 import _abi, core, parity, schedule
+from gym_sbr2_b200.vec_env import SbrOsVecEnv
+from oracle.twin import binding as twin
+from test_oracle_golden_os import EPISODES, load_episode
+from test_twin_parity_os import check_against_golden, run_episodes
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuOsBatch(object):
+    """numpy-in / numpy-out adapter over the CUDA entry points with the interface of oracle.twin.binding.OsBatch."""
+
+    def __init__(self, n, device, mode=_abi.MODE_DP45, sched=None, tol=None):
+        self.n, self.device, self.mode = n, device, mode
+        self.params = _abi.default_params()
+        self.sched = sched or schedule.os_schedule()
+        self.tol = tol or _abi.make_tol()
+        self.buf = core.OsBuffers(n, device)
+
+    def _dev(self, a, dtype=torch.float64):
+        return None if a is None else core.soa1(torch.as_tensor(np.ascontiguousarray(a)).to(self.device, dtype))
+
+    def _sync(self):
+        b = self.buf
+        torch.cuda.synchronize()
+        self.st = b.st.cpu().numpy()
+        self.status = b.status.cpu().numpy()
+        self.counters = b.counters.cpu().numpy().astype(np.uint32)
+        self.done = b.done.cpu().numpy()
+
+    def reset(self, influent, x0=None, mask=None):
+        core.os_reset(self.buf, self._dev(influent), self.params, self.sched, x0=self._dev(x0),
+                      mask=self._dev(mask, torch.uint8), mode=self.mode, tol=self.tol)
+        self._sync()
+        return self.buf.obs_do.cpu().numpy(), self.buf.obs_ec.cpu().numpy()
+
+    def step(self, action):
+        b = core.os_step(self.buf, self._dev(action), self.params, self.sched, mode=self.mode, tol=self.tol)
+        self._sync()
+        return (b.obs_do.cpu().numpy(), b.obs_ec.cpu().numpy(), b.state.cpu().numpy(), b.reward.cpu().numpy(),
+                self.done.copy())
+
+
+def test_dp45_episodes_match_reference(built, cuda_device):
+    G, rec = run_episodes(lambda n: GpuOsBatch(n, cuda_device, mode=_abi.MODE_DP45), EPISODES)
+    check_against_golden(G, rec, EPISODES)
+
+
+def test_rk4_episodes_match_reference(built, cuda_device):
+    names = ["seed0_const", "seed2_walk", "seed4_random", "seed5_walk"]
+    sched = schedule.os_schedule(rk4_sub_interval=20)
+    G, rec = run_episodes(lambda n: GpuOsBatch(n, cuda_device, mode=_abi.MODE_RK4, sched=sched), names)
+    check_against_golden(G, rec, names)
+
+
+def test_rk4_reference_grid_counters_and_double_steps(built, cuda_device):
+    """The 9/10 output-point pattern of the reference (bit-exact float truncation of the running time) shows in the
+    RK4 RHS counters: 32 or 36 per single interval, two intervals at steps 51 and 275."""
+    g = load_episode("seed0_const")
+    b = GpuOsBatch(1, cuda_device, mode=_abi.MODE_RK4)
+    c = twin.OsBatch(1, mode=_abi.MODE_RK4)
+    b.reset(g["influent"][:, None]); c.reset(g["influent"][:, None])
+    assert b.counters[0, 0] == 4 * 251
+    for k in range(463):
+        a = g["action"][k][:, None]
+        out_g, out_c = b.step(a), c.step(a)
+        assert b.counters[0, 0] == c.counters[0, 0], k
+        assert out_g[2][0, 0] == out_c[2][0, 0], k                    # t / 0.5: bit-identical running time
+        assert bool(out_g[4][0]) == bool(g["done"][k])
+    assert b.st[_abi.OS_STEPS, 0] == 463
+
+
+@pytest.mark.parametrize("mode,tol", [(_abi.MODE_RK4, 1e-9), (_abi.MODE_DP45, 2e-6)])
+def test_4096_envs_every_env_against_cpu_twin(built, cuda_device, mode, tol):
+    """BASELINE config 2 shape: 4096 envs, per-env influent and random per-step set-points, 60 steps across the
+    anoxic -> aerobic switch; every env against the g++ build of the same stepper."""
+    from gym_sbr2_b200 import influent
+    n = 4096
+    rng = np.random.RandomState(21)
+    infl = np.stack([influent.mix_numpy(6, rng.randn(48)) for _ in range(128)], axis=1)
+    infl = np.tile(infl, (1, n // 128)).copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    g, c = GpuOsBatch(n, cuda_device, mode=mode), twin.OsBatch(n, mode=mode)
+    og, oc = g.reset(infl), c.reset(infl)
+    assert np.allclose(og[0], oc[0], rtol=tol, atol=tol) and np.allclose(og[1], oc[1], rtol=tol, atol=tol)
+    for k in range(60):
+        act = np.stack([8 * rng.rand(n), 15 * rng.rand(n)])
+        rg, rc = g.step(act), c.step(act)
+        assert np.array_equal(rg[4], rc[4])
+        assert np.array_equal(g.status, c.status)
+        ok, worst = parity.os_close(rg[2], rc[2], rtol=tol, atol=tol * 1e-2)
+        assert ok, (k, worst)
+        assert np.allclose(rg[3], rc[3], rtol=max(tol, 1e-9) * 10, atol=1e-10), k
+        if mode == _abi.MODE_RK4:
+            assert np.array_equal(g.counters, c.counters)
+
+
+def test_vec_env_api_done_noop_and_autoreset(built, cuda_device):
+    g = load_episode("seed0_const")
+    n = 8
+    env = SbrOsVecEnv(n, device=cuda_device, seed=3, mode="dp45")
+    infl = torch.as_tensor(np.tile(g["influent"][:, None], (1, n))).to(cuda_device)
+    obs_do, obs_ec = env.reset(influent=infl)
+    assert obs_do.shape == (n, 9) and obs_ec.shape == (n, 9)
+    assert np.allclose(obs_do[0].cpu().numpy(), g["reset_obs_do"], rtol=1e-5, atol=1e-7)
+    total = torch.zeros(n, dtype=torch.float64, device=cuda_device)
+    for k in range(463):
+        a = torch.as_tensor(np.tile(g["action"][k][None, :], (n, 1))).to(cuda_device)
+        (o_do, o_ec), state, reward, done, info = env.step(a)
+        total += reward
+        assert bool(done.all()) == bool(g["done"][k]) and bool(done.any()) == bool(g["done"][k])
+    assert state.shape == (n, 15) and reward.shape == (n,)
+    assert abs(float(total[0]) - g["reward"].sum()) < 1e-5 * abs(g["reward"].sum())
+    assert torch.allclose(info["episode_return"], total, rtol=1e-12, atol=1e-14)
+    assert float(info["episode_steps"][0]) == 463
+    assert abs(float(info["Qw"][0]) - float(g["Qw"])) < 1e-5 * float(g["Qw"])
+    # stepping finished envs: no-op
+    (o_do, o_ec), state, reward, done, info = env.step(a)
+    assert bool(done.all()) and float(reward.abs().max()) == 0.0
+    assert int(info["status"].min()) == _abi.ST_DONE
+    # autoreset: the next step restarts every finished env and steps it once
+    env.autoreset = True
+    (o_do, o_ec), state, reward, done, info = env.step(torch.as_tensor(
+        np.tile(g["action"][0][None, :], (n, 1))).to(cuda_device))
+    assert not bool(done.any()) and bool(info["restarted"].all())
+    assert float(info["episode_steps"][0]) == 1
+    assert abs(float(state[0, 0]) * 0.5 - g["t"][0]) < 1e-15
+
+
+def test_argument_errors_do_not_launch(built, cuda_device):
+    lib = _abi.load()
+    p, s = _abi.default_params(), schedule.os_schedule()
+    import ctypes as C
+    rc = lib.sbr_os_step(0, 0, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, None, 0, None,
+                         None)
+    assert rc == -1 and b"n must be positive" in lib.sbr_last_error()
+    buf = core.OsBuffers(4, cuda_device)
+    s.fill_pts = 0
+    with pytest.raises(_abi.SbrLibraryError):
+        core.os_reset(buf, torch.zeros((14, 4), dtype=torch.float64, device=cuda_device), p, s)

@@ -1,0 +1,99 @@
+"""The drop-in boundary: the reference's ten env ids, class names, spaces and tuple shapes
+(gym_SBR/__init__.py:3-12, gym_SBR_env2.py:58-193, gym_SBR_oneshot.py:98-113,843-1273)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gym_sbr2_b200 as sbr
+from gym_sbr2_b200 import _abi
+
+REF_IDS = {"SBR-v0": "SbrEnv", "SBR-v1": "SbrEnv1", "SBR-v2": "SbrEnv2", "SBR-v4": "SbrEnv4",
+           "SBRCnt-v0": "SbrCnt0", "SBRCnt-v1": "SbrCnt1", "SBRCnt-v2": "SbrCnt2", "SBRCntMA-v1": "SbrCntMA1",
+           "SBROS-v1": "SbrOS", "SBROS-v2": "SbrOS1"}
+
+
+def test_all_ten_reference_ids_registered_under_reference_class_names():
+    assert set(sbr.spec_ids()) == set(REF_IDS)
+    import gym_sbr2_b200.envs as envs
+    for env_id, cls in REF_IDS.items():
+        assert sbr.registry[env_id]["entry_point"] == "gym_sbr2_b200.envs:" + cls
+        assert hasattr(envs, cls)
+
+
+def test_unsupported_ids_name_the_reference_failure():
+    for env_id in REF_IDS:
+        if env_id in ("SBR-v2", "SBROS-v1"):
+            continue
+        with pytest.raises(sbr.UnsupportedEnvError) as e:
+            sbr.make(env_id)
+        assert "reference step() raises" in str(e.value)
+
+
+def test_supported_ids_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    for env_id in ("SBR-v2", "SBROS-v1"):
+        with pytest.raises(_abi.SbrLibraryError):
+            sbr.make(env_id)
+
+
+def test_available_actions_mask_matches_reference_rule():
+    """gym_SBR_oneshot.py:440-459: +-0.1 on the DO set-point within [0,8], +-5 on the NO3 set-point within [0,15]."""
+    from gym_sbr2_b200.envs.single import SbrOS
+    masks = SbrOS.get_available_actions(None, [0.05, 12.0], 2, 3)
+    assert [list(m) for m in masks] == [[0, 1, 1], [1, 1, 0]]
+
+
+def test_product_never_imports_oracle_or_scipy():
+    pkg = os.path.dirname(sbr.__file__)
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(root, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|scipy)", src, flags=re.M), fn
+
+
+@pytest.mark.gpu
+def test_sbr_v2_known_answer_through_make(built, cuda_device, golden_v2):
+    """np.random.seed(0); reset(); step([.25,.25,.25]) -> reward 3.0758784413909894."""
+    env = sbr.make("SBR-v2")
+    assert env.action_space.shape == (3,) and env.observation_space.shape == (3,)
+    np.random.seed(0)
+    obs0 = env.reset()
+    assert isinstance(obs0, np.ndarray) and obs0.shape == (3,)
+    assert np.allclose(obs0, [1.27614847334958, 1.8235276185867406, 1.1067801724189357], rtol=1e-13)
+    assert np.array_equal(env.influent_mixed, golden_v2["influent"][0])           # same RNG consumption
+    obs, reward, done, info = env.step([0.25, 0.25, 0.25])
+    assert done is True and info == {} and isinstance(reward, float)
+    assert abs(reward - 3.0758784413909894) <= 1e-5 * 3.08
+    assert np.allclose(obs, [0.66, 262.1790959812511, 0.02970193763645346], rtol=1e-5)
+    # like the reference, a second step replays the cycle from x0_init (gym_SBR_env2.py:88-99)
+    obs2, reward2, _, _ = env.step([0.25, 0.25, 0.25])
+    assert reward2 == reward and np.array_equal(obs, obs2)
+
+
+@pytest.mark.gpu
+def test_sbros_v1_episode_through_make(built, cuda_device):
+    from test_oracle_golden_os import load_episode
+    g = load_episode("seed0_const")
+    env = sbr.make("SBROS-v1")
+    np.random.seed(0)
+    obs = env.reset()
+    assert isinstance(obs, tuple) and len(obs) == 2 and len(obs[0]) == 9 and len(obs[1]) == 9
+    assert np.array_equal(env.influent_mixed, g["influent"])
+    assert np.allclose(obs[0], g["reset_obs_do"], rtol=1e-5, atol=1e-7)
+    total, k = 0.0, 0
+    while True:
+        out = env.step([2.0, 5.0])
+        assert len(out) == 5                                   # (obs, state, reward, done, info)
+        obs, state, reward, done, info = out
+        assert len(state) == 15 and isinstance(done, bool) and info == {}
+        assert abs(reward - g["reward"][k]) <= 1e-5 * abs(g["reward"][k]) + 1e-9, k
+        total += reward
+        k += 1
+        if done:
+            break
+    assert k == 463 and abs(total - (-0.878967)) < 1e-5

@@ -72,6 +72,16 @@ def test_struct_layouts_match_header(built):
     assert fields == [f for f, _ in _abi.SbrParams._fields_]
     assert C.sizeof(_abi.SbrSchedule) == 8 * 4 + 8 * 4 + 8 * 8 + 8
     assert C.sizeof(_abi.SbrTol) == 24
+    body = re.search(r"typedef struct SbrOsSchedule \{(.*?)\} SbrOsSchedule;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"(?:double|int32_t)\s+([^;]+);", body):
+        fields += [f.strip() for f in decl.split(",")]
+    assert fields == [f for f, _ in _abi.SbrOsSchedule._fields_]
+    assert C.sizeof(_abi.SbrOsSchedule) == 10 * 8 + 4 * 4
+    rows = re.search(r"enum \{\s*SBR_OS_X = 0,(.*?)SBR_OS_ROWS", text, flags=re.S).group(1)
+    assert (_abi.OS_T, _abi.OS_KLA_RING, _abi.OS_RETURN, _abi.OS_QW, _abi.OS_ROWS) == (14, 22, 32, 34, 35)
+    assert rows.count("SBR_OS_") == 13
 
 
 def test_default_params_match_reference_constants(built):
