@@ -117,6 +117,102 @@ def measure_fp64_peak(core, torch, device):
     return best, sustained
 
 
+def cpu_baseline_leg(target_s):
+    """cpu_baseline: the oracle port of the reference's scipy-odeint path on every host core, on a bounded
+    sample of the same workload (independent seeded SBR-v2 cycle-steps) sized to ~target_s seconds."""
+    from oracle import cpu_baseline
+    cores = cpu_baseline.usable_cores()
+    probe = cpu_baseline.run(steps_per_proc=2, procs=cores, warmup=1)
+    per_proc_rate = probe["steps"] / cores / probe["wall_s"]
+    spp = max(2, min(400, int(round(target_s * per_proc_rate))))
+    r = cpu_baseline.run(steps_per_proc=spp, procs=cores, warmup=0)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "per_core": r["per_core"],
+            "sample": "%d SBR-v2 cycle-steps (%d procs x %d, reset influent draw + whole-cycle step each; oracle "
+                      "port of the reference's scipy LSODA path), %.1f s wall" % (r["steps"], r["cores"], spp, r["wall_s"])}
+
+
+# interval-per-step path: algorithmic flops (SURVEY.md 8d) and bytes per env per env.step
+F_EC = 94
+OS_BYTES_STEP = 2 * 35 * 8 + (9 + 9 + 15 + 1) * 8 + 2 * 8 + 1 + 4 + 8     # state in+out, obs/state/reward, action, done, status, counters
+
+
+def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
+    """SBROS-v1: whole episodes (reset = fill solve, 463 env.steps, the last one with settle + draw + idle) for
+    --interval-envs envs, one launch per env.step, state resident in HBM.  Reports interval-steps/s and, for the
+    plain react/dose steps (the dominant launch), FP64 and HBM fractions from the kernel's own RHS counters."""
+    from gym_sbr2_b200 import _abi
+    from gym_sbr2_b200.vec_env import SbrOsVecEnv
+    n = args.interval_envs
+    out = {}
+    for mode, kw in (("dp45", dict(rtol=1e-8, atol=1e-10)), ("rk4", dict(rk4_sub_interval=20))):
+        env = SbrOsVecEnv(n, device=device, seed=77, mode=mode, **kw)
+        gen = torch.Generator(device=device).manual_seed(5)
+        acts = [torch.stack([1 + 6 * torch.rand(n, dtype=torch.float64, device=device, generator=gen),
+                             2 + 10 * torch.rand(n, dtype=torch.float64, device=device, generator=gen)], dim=1)
+                for _ in range(8)]
+        infl = env._draw_influent()
+        env.reset(influent=infl)
+        for k in range(5):
+            env.step_async(acts[k % 8])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(464)]
+        rhs_sum = torch.zeros((), dtype=torch.float64, device=device)
+        rhs_mid = 0.0
+        e0.record()
+        env.reset(influent=infl)
+        for k in range(463):
+            ev[k].record()
+            env.step_async(acts[k % 8])
+            if k == 300:
+                rhs_mid = env.buf.counters[0].to(torch.float64).mean()
+        ev[463].record()
+        e1.record()
+        torch.cuda.synchronize()
+        assert bool(env.buf.done.all()), "episode did not end after 463 steps"
+        ms_episode = e0.elapsed_time(e1)
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(463)]
+        plain = sorted(per[60:270] + per[280:455])
+        ms_plain = plain[len(plain) // 2]
+        rhs = float(rhs_mid)
+        steps = rhs / 4.0 if mode == "rk4" else (rhs - 1) / 6.0
+        ovh = 196 if mode == "rk4" else 2 * 14 * (1 + 2 + 3 + 4 + 5 + 5 + 6) + 100
+        flops = rhs * F_EC + steps * ovh + 150
+        tf = n * flops / (ms_plain * 1e-3) / 1e12
+        out[mode] = {"envs": n, "ms_per_episode": ms_episode, "interval_steps_per_sec": n * 463 / (ms_episode * 1e-3),
+                     "ms_per_plain_step": ms_plain, "plain_interval_steps_per_sec": n / (ms_plain * 1e-3),
+                     "ms_terminal_step": per[462], "rhs_per_env_step": rhs,
+                     "roofline": {"bound": "fp64+hbm", "fp64_tflops": tf, "fp64_frac": tf / peak_burst,
+                                  "hbm_gbs": n * OS_BYTES_STEP / (ms_plain * 1e-3) / 1e9,
+                                  "hbm_frac": n * OS_BYTES_STEP / (ms_plain * 1e-3) / 1e9 / _hbm_peak(),
+                                  "flops_per_env_step": flops, "bytes_per_env_step": OS_BYTES_STEP},
+                     "config": dict(kw, integrator=mode), "bad_status": int((env.buf.status != 0).sum()),
+                     "gpu_launches": 464, "mean_episode_return": float(env.buf.st[_abi.OS_RETURN].mean())}
+        del env
+    return out
+
+
+def cycle_dp45_leg(torch, device, core, env, n):
+    """The same SBR-v2 batch through the adaptive Dormand-Prince mode (per-env step control)."""
+    from gym_sbr2_b200 import _abi
+    tol = _abi.make_tol(1e-7, 1e-9, 4000)
+    res = {}
+    core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=_abi.MODE_DP45, tol=tol)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    o = core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=_abi.MODE_DP45,
+                      tol=tol)
+    eb.record()
+    torch.cuda.synchronize()
+    ms = ea.elapsed_time(eb)
+    cnt = o.counters.to(torch.float64)
+    res = {"rtol": 1e-7, "atol": 1e-9, "kernel_ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
+           "rhs_per_env_mean": float(cnt[0].mean()), "rhs_per_env_max": float(cnt[0].max()),
+           "rejected_per_env_mean": float(cnt[1].mean()), "bad_status": int((o.status != 0).sum())}
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port of the scipy-odeint
     path, all host cores), same metric/unit/config.  Under torchrun only rank 0 works."""
@@ -162,6 +258,9 @@ def main():
     ap.add_argument("--atol", type=float, default=1e-10)
     ap.add_argument("--ref-steps-per-proc", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-interval-path", action="store_true", help="skip the SBROS-v1 (interval-per-step) leg")
+    ap.add_argument("--interval-envs", type=int, default=1 << 20)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -305,12 +404,13 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline
-        r = cpu_baseline.run(steps_per_proc=2, procs=cpu_baseline.usable_cores(), warmup=1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "per_core": r["per_core"],
-               "sample": "%d SBR-v2 cycle-steps (%d procs x 2, scipy LSODA oracle port), %.1f s wall"
-                         % (r["steps"], r["cores"], r["wall_s"])}
+        cpu = cpu_baseline_leg(args.cpu_seconds)
+
+    paths = None
+    if rank == 0 and world == 1 and not args.no_interval_path:
+        paths = {"sbros_v1": interval_path_leg(torch, device, args, peak_burst, peak_sustained)}
+        if args.mode == "rk4":
+            paths["sbr_v2_dp45"] = cycle_dp45_leg(torch, device, core, env, n)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -323,7 +423,7 @@ def main():
                 "interval_steps_per_sec": value * INTERVALS_PER_CYCLE,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
                 "gpu_launch_names": ["sbr_cycle_v2_kernel", "sbr_reward_stats_init_kernel", "sbr_reward_stats_kernel"],
-                "clocks": clocks, "reward_stats": reward_stats}
+                "clocks": clocks, "reward_stats": reward_stats, "paths": paths}
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()

@@ -61,7 +61,8 @@ LIB_NAME = "libsbr_b200.so"
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    """In-tree library; SBR_B200_LIB overrides it (A/B builds of the same ABI during kernel tuning)."""
+    return os.environ.get("SBR_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 _P = C.c_void_p

@@ -21,11 +21,6 @@ def _dev_ptr(t, rows, n, dtype=torch.float64, name="tensor"):
         return C.c_void_p(t.data_ptr()), n
     if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n or (n > 1 and t.stride(1) != 1):
         raise ValueError("%s must be SoA [%d, %d] with unit stride along envs, got %s" % (name, rows, n, tuple(t.shape)))
-    if n == 1:
-        # a [rows, 1] tensor may carry any stride on either axis; the ABI takes ONE row stride for all buffers
-        if t.stride(0) != 1:
-            raise ValueError("%s: [%d, 1] tensor must have row stride 1 (use core.soa1)" % (name, rows))
-        return C.c_void_p(t.data_ptr()), 1
     return C.c_void_p(t.data_ptr()), t.stride(0)
 
 

@@ -686,31 +686,45 @@ SBR_HD ObsRef obs_ref(const double (&x)[SBR_NX]) {
     return r;
 }
 
+// Observation scales are fixed API constants of the reference (gym_SBR_oneshot.py:150-156, 1069-1112); the
+// kernels multiply by their reciprocals (an IEEE double division is ~40 SASS instructions, and the epilogue has 42
+// of them) -- at most 1 ulp away from the reference's x / scale.
+#define SBR_INV(v) (1.0 / (v))
+
 // Clipped deltas shared by the reset and step observations (gym_SBR_oneshot.py:388-429, 1069-1112).
 SBR_HD void os_emit_deltas(const double (&x)[SBR_NX], const ObsRef& f, const Column& obs_do, const Column& obs_ec) {
-    const double dXbh = clip1((x[iXbh] - f.Xbh) / 4000), dSnh = clip1((x[iSnh] - f.Snh) / 50);
+    const double dXbh = clip1((x[iXbh] - f.Xbh) * SBR_INV(4000.0)), dSnh = clip1((x[iSnh] - f.Snh) * SBR_INV(50.0));
     obs_do.set(5, dXbh);
-    obs_do.set(6, clip1((x[iXba] - f.Xba) / 500));
-    obs_do.set(7, clip1((x[iSo] - f.So) / 8));
+    obs_do.set(6, clip1((x[iXba] - f.Xba) * SBR_INV(500.0)));
+    obs_do.set(7, clip1((x[iSo] - f.So) * SBR_INV(8.0)));
     obs_do.set(8, dSnh);
-    obs_ec.set(5, clip1((x[iSs] - f.Ss) / 50));
+    obs_ec.set(5, clip1((x[iSs] - f.Ss) * SBR_INV(50.0)));
     obs_ec.set(6, dXbh);
-    obs_ec.set(7, clip1((x[iSno] - f.Sno) / 50));
+    obs_ec.set(7, clip1((x[iSno] - f.Sno) * SBR_INV(50.0)));
     obs_ec.set(8, dSnh);
+}
+
+// 1 / x_1_state[1:] (gym_SBR_oneshot.py:153)
+SBR_HD constexpr double inv_state_scale(int i) {
+    return i == iV ? SBR_INV(1.32) : i == iSi ? SBR_INV(30.0) : i == iSs ? SBR_INV(30.0) : i == iXi ? SBR_INV(1500.0)
+         : i == iXs ? SBR_INV(150.0) : i == iXbh ? SBR_INV(3000.0) : i == iXba ? SBR_INV(2000.0)
+         : i == iXp ? SBR_INV(600.0) : i == iSo ? SBR_INV(8.0) : i == iSno ? SBR_INV(20.0) : i == iSnh ? SBR_INV(20.0)
+         : i == iSnd ? SBR_INV(10.0) : i == iXnd ? SBR_INV(10.0) : SBR_INV(10.0);
 }
 
 // Step observation epilogue (gym_SBR_oneshot.py:1015-1112): obs_DO = [t, Xbh, Xba, So, Snh] / x_1_DO,
 // obs_EC = [t, Ss, Xbh, Sno, Snh] / x_1_EC (:150-156), each followed by 4 clipped deltas; state = [t, x] / x_1_state.
 SBR_HD void os_emit_obs(double t, const double (&x)[SBR_NX], const ObsRef& first, const Column& obs_do,
                         const Column& obs_ec, const Column& state) {
-    obs_do.set(0, t / 0.5); obs_do.set(1, x[iXbh] / 2000); obs_do.set(2, x[iXba] / 500);
-    obs_do.set(3, x[iSo] / 8.0); obs_do.set(4, x[iSnh] / 10);
-    obs_ec.set(0, t / 0.5); obs_ec.set(1, x[iSs] / 30); obs_ec.set(2, x[iXbh] / 2000);
-    obs_ec.set(3, x[iSno] / 10); obs_ec.set(4, x[iSnh] / 10);
+    const double tn = t * 2.0, xbh = x[iXbh] * SBR_INV(2000.0), snh = x[iSnh] * SBR_INV(10.0);
+    obs_do.set(0, tn); obs_do.set(1, xbh); obs_do.set(2, x[iXba] * SBR_INV(500.0));
+    obs_do.set(3, x[iSo] * SBR_INV(8.0)); obs_do.set(4, snh);
+    obs_ec.set(0, tn); obs_ec.set(1, x[iSs] * SBR_INV(30.0)); obs_ec.set(2, xbh);
+    obs_ec.set(3, x[iSno] * SBR_INV(10.0)); obs_ec.set(4, snh);
     os_emit_deltas(x, first, obs_do, obs_ec);
-    state.set(0, t / 0.5);
+    state.set(0, tn);
 #pragma unroll
-    for (int i = 0; i < SBR_NX; ++i) state.set(i + 1, x[i] / tol_scale(i));   // tol_scale == x_1_state[1:]
+    for (int i = 0; i < SBR_NX; ++i) state.set(i + 1, x[i] * inv_state_scale(i));
 }
 
 // SbrOS.reset (gym_SBR_oneshot.py:168-438) + Sim_filling (:1585-1654).  x: in = x0, out = state after the fill.
@@ -740,17 +754,18 @@ SBR_HD int os_reset_env(double (&x)[SBR_NX], const Loading& load, const SbrParam
     for (int j = 0; j < 10; ++j) ring.set(j, (j & 1) ? kla : 0.0);
     // reset observation: flow-weighted mix of influent and reactor content (:347-364)
     const double Qin = p.Qin, IV = p.IV;
-    const double den = Qin + IV;
-    obs_do.set(0, c.t / 0.5);
-    obs_do.set(1, (Qin * load(iXbh) + x[iXbh] * IV) / den / 2000);
-    obs_do.set(2, (Qin * load(iXba) + x[iXba] * IV) / den / 500);
-    obs_do.set(3, (Qin * load(iSo) + x[iSo] * IV) / den / 8.0);
-    obs_do.set(4, (Qin * load(iSnh) + x[iSnh] * IV) / den / 10);
-    obs_ec.set(0, c.t / 0.5);
-    obs_ec.set(1, (Qin * load(iSs) + x[iSs] * IV) / den / 30);
-    obs_ec.set(2, (Qin * load(iXbh) + x[iXbh] * IV) / den / 2000);
-    obs_ec.set(3, (Qin * load(iSno) + x[iSno] * IV) / den / 10);
-    obs_ec.set(4, (Qin * load(iSnh) + x[iSnh] * IV) / den / 10);
+    const double iden = 1.0 / (Qin + IV);
+    const double mXbh = (Qin * load(iXbh) + x[iXbh] * IV) * iden, mSnh = (Qin * load(iSnh) + x[iSnh] * IV) * iden;
+    obs_do.set(0, c.t * 2.0);
+    obs_do.set(1, mXbh * SBR_INV(2000.0));
+    obs_do.set(2, (Qin * load(iXba) + x[iXba] * IV) * iden * SBR_INV(500.0));
+    obs_do.set(3, (Qin * load(iSo) + x[iSo] * IV) * iden * SBR_INV(8.0));
+    obs_do.set(4, mSnh * SBR_INV(10.0));
+    obs_ec.set(0, c.t * 2.0);
+    obs_ec.set(1, (Qin * load(iSs) + x[iSs] * IV) * iden * SBR_INV(30.0));
+    obs_ec.set(2, mXbh * SBR_INV(2000.0));
+    obs_ec.set(3, (Qin * load(iSno) + x[iSno] * IV) * iden * SBR_INV(10.0));
+    obs_ec.set(4, mSnh * SBR_INV(10.0));
     os_emit_deltas(x, x0r, obs_do, obs_ec);
     return status;
 }
@@ -763,7 +778,10 @@ struct OsStepOut {
 };
 
 // SbrOS.step (gym_SBR_oneshot.py:843-1273).  ring: the env's 10-entry Kla history (read after the integration,
-// so that it costs no registers while the stepper runs).
+// so that it costs no registers while the stepper runs).  Passes 0..3 are the reference's four NON-exclusive ifs on
+// the running time (:860,896,931,963: anoxic / aerobic / anoxic / aerobic -- a step that crosses a phase boundary
+// runs two intervals); pass 4 computes the reward and, at the end of the react phases, settle + draw + the idle
+// solve.  All five share ONE stepper call site per tail so the kernel stays inside the instruction cache.
 template <int MODE>
 SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, double a_do, double a_ec,
                         const SbrParams& p, const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol,
@@ -776,102 +794,109 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
     ObsRef first = obs_ref(x);
     TailArgs a;
     a.kla = 0.0; a.q = 0.0; a.ec_conc = p.ec_conc; a.load = Loading{nullptr, 0};
-    // four NON-exclusive ifs on the running time (:860,896,931,963): anoxic / aerobic / anoxic / aerobic
-    for (int pass = 0; pass < 4; ++pass) {
+    o.done = 0;
+    o.Qw = NAN;
+    o.reward = 0.0;
+    for (int pass = 0; pass < 5; ++pass) {
         const double t = c.t;
-        const bool cond = pass == 0 ? (t < s.tm3_0)
-                        : pass == 1 ? (t >= s.tm3_0 && t <= s.tm3_1)
-                        : pass == 2 ? (t > s.tm3_1 && t <= s.tm4_1)
-                                    : (t > s.tm4_1);
-        if (!cond) continue;
-        const bool aerobic = (pass & 1) != 0;
-        u_do = aerobic ? fmin(fmax(a_do, 0.0), p.do_sp_max) : 0.0;                  // :862-870, 898-906
-        const double u_ec = aerobic ? 0.0 : fmin(fmax(a_ec, 0.0), p.no_sp_max);
-        // run_aero_step / run_anaero_step (:1331-1419)
-        const double t_end = add_rn(t, s.t_delta);
-        span = sub_rn(t_end, t);
-        L = (int)div_rn(span, s.dt);
-        first = obs_ref(x);
-        const double so_start = x[iSo];
-        const double kla = os_pid_do(c, so_start, u_do, false, aerobic, pid);
-        ec_before = c.ec_last;
-        const double ec = os_pid_ec(c, u_ec, !aerobic, pid);
-        a.kla = kla; a.q = ec;
-        const int n_sub = s.rk4_sub_interval > 0 ? s.rk4_sub_interval : (L > 1 ? L - 1 : 1);
-        if (warp_any(ec != 0.0)) status |= integrate_interval<TAIL_EC, MODE>(x, span, n_sub, coef, a, tol, dp);
-        else status |= integrate_interval<TAIL_REACT, MODE>(x, span, n_sub, coef, a, tol, dp);
+        double T, so_start = x[iSo], t_next;
+        int n_sub;
+        if (pass < 4) {
+            const bool cond = pass == 0 ? (t < s.tm3_0)
+                            : pass == 1 ? (t >= s.tm3_0 && t <= s.tm3_1)
+                            : pass == 2 ? (t > s.tm3_1 && t <= s.tm4_1)
+                                        : (t > s.tm4_1);
+            if (!cond) continue;
+            const bool aerobic = (pass & 1) != 0;
+            u_do = aerobic ? fmin(fmax(a_do, 0.0), p.do_sp_max) : 0.0;                  // :862-870, 898-906
+            const double u_ec = aerobic ? 0.0 : fmin(fmax(a_ec, 0.0), p.no_sp_max);
+            // run_aero_step / run_anaero_step (:1331-1419)
+            t_next = add_rn(t, s.t_delta);
+            span = sub_rn(t_next, t);
+            L = (int)div_rn(span, s.dt);
+            first = obs_ref(x);
+            a.kla = os_pid_do(c, so_start, u_do, false, aerobic, pid);
+            ec_before = c.ec_last;
+            a.q = os_pid_ec(c, u_ec, !aerobic, pid);
+            T = span;
+            n_sub = s.rk4_sub_interval > 0 ? s.rk4_sub_interval : (L > 1 ? L - 1 : 1);
+        } else {
+            // reward = module_reward_EQIOCI.sbr_reward (module_reward_EQIOCI.py:4-115) on the post-interval state:
+            // `Kla` holds ONE entry per interval, so Kla[-L:-1] sums the previous L-1 intervals and leaves the
+            // current one out (:70-71); `EC` holds L-1 copies per interval, so EC[-L:-1] is the previous
+            // interval's flow once plus the current one L-2 times (:79).
+            double r[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) r[j] = ring.get(j);
+            if (n_run >= 1) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+                r[9] = kla_new0;
+            }
+            if (n_run >= 2) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+                r[9] = kla_new1;
+            }
+            double ksum = 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+                if (j >= 10 - L) ksum += r[j];
+            double esum = 0.0 + ec_before;
+            for (int j = 0; j < L - 2; ++j) esum += c.ec_last;
+            double eff[6];
+            const double EQI2 = effluent_quality(x, eff) * 0.1;
+            const double ispan = 1.0 / span;
+            const double AE = (8 / (1.8 * 1000)) * ispan * (1.32 * ksum * p.os_pid_dt);
+            const double ECO = p.ec_conc * esum * p.os_pid_dt * (ispan * 1e-3);
+            const double OCI = AE + ECO;
+            o.reward = (1 - (EQI2 * EQI2 + OCI * OCI)) * (1.0 / 473);
+            const bool terminal = c.t >= s.tm5_1;
+            // end of the react phases (:1122): Sim_Settling_Drawing (:2264-2420) + Sim_idle (:2554-2597) in this
+            // step; the reward stays the pre-settle one, obs/state are recomputed from the post-idle state with
+            // deltas taken against the end-of-react state (:1167-1261)
+            double kla_idle = 0.0;
+            T = s.t_delta; n_sub = 1; t_next = s.t_cycle;
+            if (terminal) {
+                o.done = 1;
+                first = obs_ref(x);
+                const double t_set_end = add_rn(c.t, s.settle_len);
+                const double T_set = sub_rn(t_set_end, c.t);
+                double sX[10], Xf;
+                settle_closed_form(x, T_set, p.settler_area, p.settler_vmax, sX, Xf);
+                DrawOut d;
+                draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+                status |= d.status;
+                o.Qw = d.Qw;
+                const double t_draw_end = add_rn(t_set_end, s.draw_len);
+                so_start = x[iSo];
+                c.so_prev = so_start;              // So padded with the frozen value over settle + draw (:2415-2416)
+                T = sub_rn(s.t_cycle, t_draw_end);
+                const int pts = (int)div_rn(T, s.dt);
+                n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
+                kla_idle = os_pid_do(c, so_start, u_do, false, true, pid);
+                a.kla = kla_idle; a.q = 0.0;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
+                r[9] = kla_idle;
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) ring.set(j, r[j]);
+            if (!terminal) break;
+        }
+        if (warp_any(a.q != 0.0)) status |= integrate_interval<TAIL_EC, MODE>(x, T, n_sub, coef, a, tol, dp);
+        else status |= integrate_interval<TAIL_REACT, MODE>(x, T, n_sub, coef, a, tol, dp);
         c.so_prev = so_start;
         c.sno_prev = c.sno_last;
         c.sno_last = x[iSno];
-        c.kla_last = kla;
-        c.ec_last = ec;
-        c.t = t_end;
-        if (n_run == 0) kla_new0 = kla; else kla_new1 = kla;
-        ++n_run;
+        c.kla_last = a.kla;
+        c.t = t_next;
+        if (pass < 4) {
+            c.ec_last = a.q;
+            if (n_run == 0) kla_new0 = a.kla; else kla_new1 = a.kla;
+            ++n_run;
+        }
     }
-    // push the new KLa entries into the history, then reward = module_reward_EQIOCI.sbr_reward
-    // (module_reward_EQIOCI.py:4-115): `Kla` holds ONE entry per interval, so Kla[-L:-1] sums the previous L-1
-    // intervals and leaves the current one out (:70-71); `EC` holds L-1 copies per interval, so EC[-L:-1] is the
-    // previous interval's flow once plus the current one L-2 times (:79).
-    double r[10];
-#pragma unroll
-    for (int j = 0; j < 10; ++j) r[j] = ring.get(j);
-    if (n_run >= 1) {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-        r[9] = kla_new0;
-    }
-    if (n_run >= 2) {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-        r[9] = kla_new1;
-    }
-    double ksum = 0.0;
-#pragma unroll
-    for (int j = 0; j < 9; ++j)
-        if (j >= 10 - L) ksum += r[j];
-    double esum = 0.0 + ec_before;
-    for (int j = 0; j < L - 2; ++j) esum += c.ec_last;
-    double eff[6];
-    const double EQI = effluent_quality(x, eff);
-    const double EQI2 = EQI / 10;
-    const double AE = 8 / (span * 1.8 * 1000) * (1.32 * ksum * p.os_pid_dt);
-    const double ECO = p.ec_conc * esum * p.os_pid_dt / (span * 1000);
-    const double OCI = AE + ECO;
-    o.reward = (1 - (EQI2 * EQI2 + OCI * OCI)) / 473;
-    o.done = 0;
-    o.Qw = NAN;
-    if (c.t >= s.tm5_1) {
-        // end of the react phases (:1122): Sim_Settling_Drawing (:2264-2420) + Sim_idle (:2554-2597) in this step;
-        // the reward stays the pre-settle one, obs/state are recomputed from the post-idle state with deltas
-        // taken against the end-of-react state (:1167-1261)
-        o.done = 1;
-        first = obs_ref(x);
-        const double t_set_end = add_rn(c.t, s.settle_len);
-        const double T_set = sub_rn(t_set_end, c.t);
-        double sX[10], Xf;
-        settle_closed_form(x, T_set, p.settler_area, p.settler_vmax, sX, Xf);
-        DrawOut d;
-        draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
-        status |= d.status;
-        o.Qw = d.Qw;
-        const double t_draw_end = add_rn(t_set_end, s.draw_len);
-        c.so_prev = x[iSo];                    // So padded with the frozen value over settle + draw (:2415-2416)
-        const double T_idle = sub_rn(s.t_cycle, t_draw_end);
-        const int pts = (int)div_rn(T_idle, s.dt);
-        const int n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
-        const double kla = os_pid_do(c, x[iSo], u_do, false, true, pid);
-        a.kla = kla; a.q = 0.0;
-        status |= integrate_interval<TAIL_REACT, MODE>(x, T_idle, n_sub, coef, a, tol, dp);
-        c.sno_prev = c.sno_last; c.sno_last = x[iSno];
-        c.kla_last = kla;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-        r[9] = kla;
-        c.t = s.t_cycle;
-    }
-#pragma unroll
-    for (int j = 0; j < 10; ++j) ring.set(j, r[j]);
     bool finite = fabs(o.reward) < 1e300;
 #pragma unroll
     for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);

@@ -30,6 +30,9 @@ int check_launch(const char* what) {
 }
 
 constexpr int kBlock = 64;   // 2 warps per CTA: fine-grained tail balancing across 148 SMs x 4 SMSPs
+#ifndef SBR_OS_STEP_MINBLOCKS
+#define SBR_OS_STEP_MINBLOCKS 6   // resident CTAs per SM the interval-step kernel is compiled for (168-register cap; measured best of 1/6)
+#endif
 
 struct CycleArgs {
     int64_t n, ld;
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kBlock) sbr_os_reset_kernel(OsArgs g, SbrParam
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+__global__ void __launch_bounds__(kBlock, SBR_OS_STEP_MINBLOCKS) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                              SbrTol tol) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= g.n) return;
