@@ -39,7 +39,7 @@ struct Coef {
     double c92, c93;      // Sno: -(1-Yh)/(2.86 Yh) , 1/Ya
     double n_ixb, c103;   // Snh: -ixb , -ixb - 1/Ya
     double c124;          // Xnd: ixb - fp*ixp
-    double c131, c132, c133, c136;  // Salk
+    double c136;          // Salk: 1/14 -- nu13_k == (nu10_k - nu9_k)/14 for every process k (charge balance)
     double so_sat;
 };
 
@@ -58,9 +58,6 @@ inline Coef make_coef(const SbrParams& p) {
     c.n_ixb = -p.ixb;
     c.c103 = -p.ixb - 1 / p.Ya;
     c.c124 = p.ixb - p.fp * p.ixp;
-    c.c131 = -p.ixb / 14;
-    c.c132 = (1 - p.Yh) / (14 * 2.86 * p.Yh) - p.ixb / 14;
-    c.c133 = -p.ixb / 14 - 1 / (7 * p.Ya);
     c.c136 = 1.0 / 14;
     c.so_sat = p.so_sat;
     return c;
@@ -70,23 +67,35 @@ inline Coef make_coef(const SbrParams& p) {
 // FP64 reciprocal: MUFU.RCP64H seed (>= 20 good bits) + one cubic Newton correction (3 DFMA) -> ~2^-60.
 // An IEEE divide costs ~10 FP64-pipe slots; the RHS has 6-7 of them per evaluation.
 // ---------------------------------------------------------------------------------------------------------
+#ifndef SBR_RCP_NEWTON
+#define SBR_RCP_NEWTON 3
+#endif
 SBR_HD double rcp(double d) {
 #ifdef __CUDA_ARCH__
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     double e = fma(-d, r, 1.0);
-    double t = fma(e, e, e);
+#if SBR_RCP_NEWTON >= 3
+    double t = fma(e, e, e);      // cubic: r (1 + e + e^2), error e^3
     return fma(r, t, r);
+#else
+    return fma(r, e, r);          // quadratic: r (1 + e), error e^2
+#endif
 #else
     return 1.0 / d;
 #endif
 }
 
-// Which components have a non-zero derivative / are read by the RHS, per tail.  React: V, Si, Xi are frozen
-// (sub_phases_FB.py:348,352,376); Xp and Salk are outputs that feed no rate.
-SBR_HD constexpr bool integ(int tail, int i) { return tail != TAIL_REACT || !(i == iV || i == iSi || i == iXi); }
+// Which components the stepper carries, per tail.  React: V, Si, Xi are frozen (sub_phases_FB.py:348,352,376);
+// Xp is an output that feeds no rate (integrated, but needs no stage value); Salk is not integrated at all:
+// every Salk stoichiometric coefficient is (nu_Snh - nu_Sno)/14 (sub_phases_FB.py:337-343 vs :329-336 -- the
+// charge balance of ASM1), so d(Salk)/dt == (d(Snh)/dt - d(Sno)/dt)/14 identically and, Runge-Kutta methods
+// being linear, Salk_end = Salk_0 + (dSnh - dSno)/14 is what integrating it would give (to rounding).
+SBR_HD constexpr bool integ(int tail, int i) {
+    return tail != TAIL_REACT || !(i == iV || i == iSi || i == iXi || i == iSalk);
+}
 SBR_HD constexpr bool staged(int tail, int i) {
-    return tail != TAIL_REACT || (integ(tail, i) && i != iXp && i != iSalk);
+    return tail != TAIL_REACT || (integ(tail, i) && i != iXp);
 }
 
 // Influent loading accessor: component i at p[i * stride] (shared memory column on the GPU).
@@ -98,6 +107,7 @@ struct Loading {
 
 struct TailArgs {
     double kla;        // oxygen transfer coefficient, constant over one PID interval
+    double kla_sat;    // kla * So_sat -- set by integrate_interval()
     double q;          // FILL: inflow m3/d ; EC: carbon dosing flow m3/d
     double ec_conc;    // EC: dosing concentration gCOD/m3
     Loading load;      // FILL: influent concentrations
@@ -129,25 +139,25 @@ SBR_HD void rhs(const double (&y)[SBR_NX], double (&k)[SBR_NX], const Coef& c, c
     const double rho1 = (c.muh * gh) * mOh;
     const double rho2 = (c.muh_etag * gh) * anox;
     const double rho3 = (c.mua * mNh) * (mOa * Xba);
-    const double rho4 = c.bh * Xbh;
-    const double rho5 = c.ba * Xba;
     const double rho6 = (c.ka * Snd) * Xbh;
     const double g = ((c.kh * Xbh) * r6) * fma(c.etah, anox, mOh);
     const double rho7 = Xs * g;
     const double rho8 = Xnd * g;
     const double s12 = rho1 + rho2;
-    const double s45 = rho4 + rho5;
+    const double s45 = fma(c.bh, Xbh, c.ba * Xba);          // rho4 + rho5 (decay of Xbh and Xba)
     k[iSs] = fma(c.n_invYh, s12, rho7);
     k[iXs] = fma(c.one_m_ixp, s45, -rho7);
-    k[iXbh] = s12 - rho4;
-    k[iXba] = rho3 - rho5;
+    k[iXbh] = fma(-c.bh, Xbh, s12);                         // rho1 + rho2 - rho4
+    k[iXba] = fma(-c.ba, Xba, rho3);                        // rho3 - rho5
     k[iXp] = c.ixp * s45;
-    k[iSo] = fma(a.kla, c.so_sat - So, fma(c.c81, rho1, c.c83 * rho3));
+    // aeration KLa (So_sat - So): KLa * So_sat is constant over the PID interval (a.kla_sat)
+    k[iSo] = fma(-a.kla, So, fma(c.c81, rho1, fma(c.c83, rho3, a.kla_sat)));
     k[iSno] = fma(c.c92, rho2, c.c93 * rho3);
     k[iSnh] = fma(c.n_ixb, s12, fma(c.c103, rho3, rho6));
     k[iSnd] = rho8 - rho6;
     k[iXnd] = fma(c.c124, s45, -rho8);
-    k[iSalk] = fma(c.c131, rho1, fma(c.c132, rho2, fma(c.c133, rho3, c.c136 * rho6)));
+    // kinetic part of d(Salk)/dt = (d(Snh)/dt - d(Sno)/dt)/14; the react tail reconstructs Salk after the step
+    if (TAIL != TAIL_REACT) k[iSalk] = (k[iSnh] - k[iSno]) * c.c136;
     if (TAIL == TAIL_FILL) {
         // dV/dt = q ; dx_i/dt = r_i + (q/V)(c_in,i - x_i)   (sub_phases_FB.py:146-176)
         const double qV = a.q * rcp(y[iV]);
@@ -329,14 +339,20 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Coef& c, const Tai
 // ---------------------------------------------------------------------------------------------------------
 template <int TAIL, int MODE>
 SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
-                              const TailArgs& a, const SbrTol& tol, Dp45State& st) {
+                              const TailArgs& a_in, const SbrTol& tol, Dp45State& st) {
+    TailArgs a = a_in;
+    a.kla_sat = a.kla * c.so_sat;
+    const double snh0 = x[iSnh], sno0 = x[iSno];
+    int status = 0;
     if (MODE == SBR_MODE_RK4) {
         const double h = T / (double)n_sub;
         for (int s = 0; s < n_sub; ++s) rk4_step<TAIL>(x, h, c, a);
         st.n_rhs += 4u * (uint32_t)n_sub;
-        return 0;
+    } else {
+        status = dp45_interval<TAIL>(x, T, c, a, tol, st);
     }
-    return dp45_interval<TAIL>(x, T, c, a, tol, st);
+    if (TAIL == TAIL_REACT) x[iSalk] = fma((x[iSnh] - snh0) - (x[iSno] - sno0), c.c136, x[iSalk]);
+    return status;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(kBlock) sbr_rhs_kernel(RhsArgs g, SbrParams p,
         a.q = a.load(0);
     }
     if (TAIL == sbr::TAIL_EC) a.q = g.ec[i];
+    a.kla_sat = a.kla * c.so_sat;
     sbr::rhs<TAIL>(x, k, c, a);
+    if (TAIL == sbr::TAIL_REACT) k[sbr::iSalk] = (k[sbr::iSnh] - k[sbr::iSno]) * c.c136;   // see sbr::integ()
 #pragma unroll
     for (int j = 0; j < SBR_NX; ++j) g.dx[j * g.ld + i] = k[j];
 }

@@ -89,7 +89,8 @@ int twin_rhs(int64_t n, int64_t ld, const double* x, const double* kla, const do
         a.kla = kla[i]; a.q = 0.0; a.ec_conc = p->ec_conc; a.load = Loading{load, 1};
         if (tail == TAIL_FILL) { for (int j = 0; j < SBR_NX; ++j) load[j] = loading[j * ld + i]; a.q = load[0]; }
         if (tail == TAIL_EC) a.q = ec[i];
-        if (tail == TAIL_REACT) rhs<TAIL_REACT>(xx, k, c, a);
+        a.kla_sat = a.kla * c.so_sat;
+        if (tail == TAIL_REACT) { rhs<TAIL_REACT>(xx, k, c, a); k[iSalk] = (k[iSnh] - k[iSno]) * c.c136; }
         else if (tail == TAIL_FILL) rhs<TAIL_FILL>(xx, k, c, a);
         else rhs<TAIL_EC>(xx, k, c, a);
         for (int j = 0; j < SBR_NX; ++j) dx[j * ld + i] = k[j];
