@@ -31,13 +31,14 @@ enum { iV = 0, iSi, iSs, iXi, iXs, iXbh, iXba, iXp, iSo, iSno, iSnh, iSnd, iXnd,
 // ---------------------------------------------------------------------------------------------------------
 struct Coef {
     double Ks, Koh, Kno, Knh, Koa, Kx;                 // half-saturation constants
-    double muh, muh_etag, mua, bh, ba, ka, kh, etah;   // rate constants
+    double muh, etag_Koh, etah_Koh, mua_Ya, bh, ba, ka, kh;   // rate constants (products folded on the host)
+    double Ya;            // rho3 = Ya * rho3s
     double n_invYh;       // nu2_1 = nu2_2 = -1/Yh
     double one_m_ixp;     // nu4_4 = nu4_5 = 1 - ixp   (sic: ixp where ASM1 has fp)
     double ixp;           // nu7_4 = nu7_5
-    double c81, c83;      // So:  -(1-Yh)/Yh , -(4.57-Ya)/Ya
-    double c92, c93;      // Sno: -(1-Yh)/(2.86 Yh) , 1/Ya
-    double n_ixb, c103;   // Snh: -ixb , -ixb - 1/Ya
+    double c81, c83_Ya;   // So:  -(1-Yh)/Yh , -(4.57-Ya)/Ya * Ya
+    double c92;           // Sno: -(1-Yh)/(2.86 Yh)   (nu9_3 = 1/Ya is folded into rho3s)
+    double n_ixb, c103_Ya;   // Snh: -ixb , (-ixb - 1/Ya) * Ya
     double c124;          // Xnd: ixb - fp*ixp
     double c136;          // Salk: 1/14 -- nu13_k == (nu10_k - nu9_k)/14 for every process k (charge balance)
     double so_sat;
@@ -46,17 +47,17 @@ struct Coef {
 inline Coef make_coef(const SbrParams& p) {
     Coef c;
     c.Ks = p.Ks; c.Koh = p.Koh; c.Kno = p.Kno; c.Knh = p.Knh; c.Koa = p.Koa; c.Kx = p.Kx;
-    c.muh = p.muh; c.muh_etag = p.muh * p.etag; c.mua = p.mua; c.bh = p.bh; c.ba = p.ba; c.ka = p.ka;
-    c.kh = p.kh; c.etah = p.etah;
+    c.muh = p.muh; c.etag_Koh = p.etag * p.Koh; c.etah_Koh = p.etah * p.Koh; c.mua_Ya = p.mua * (1 / p.Ya);
+    c.bh = p.bh; c.ba = p.ba; c.ka = p.ka; c.kh = p.kh;
+    c.Ya = p.Ya;
     c.n_invYh = -1 / p.Yh;
     c.one_m_ixp = 1 - p.ixp;
     c.ixp = p.ixp;
     c.c81 = -(1 - p.Yh) / p.Yh;
-    c.c83 = -(4.57 - p.Ya) / p.Ya;
+    c.c83_Ya = (-(4.57 - p.Ya) / p.Ya) * p.Ya;
     c.c92 = -((1 - p.Yh) / (2.86 * p.Yh));
-    c.c93 = 1 / p.Ya;
     c.n_ixb = -p.ixb;
-    c.c103 = -p.ixb - 1 / p.Ya;
+    c.c103_Ya = (-p.ixb - 1 / p.Ya) * p.Ya;
     c.c124 = p.ixb - p.fp * p.ixp;
     c.c136 = 1.0 / 14;
     c.so_sat = p.so_sat;
@@ -115,45 +116,45 @@ struct TailArgs {
 
 // ---------------------------------------------------------------------------------------------------------
 // Kinetic RHS (sub_phases_FB.py:278-404; tails :146-176 and gym_SBR_oneshot.py:1757-1787).
-// CSE-minimal form: 6 Monod denominators -> 6 reciprocals; hydrolysis written as Xs*g / Xnd*g so no divide
-// by Xs or Xbh is needed ((Xs/Xbh)/(Kx+Xs/Xbh) == Xs/(Kx*Xbh+Xs)).  Only masked components are written.
+// CSE-minimal form: 6 Monod denominators -> 4 reciprocals (two pairs are only needed as products); hydrolysis
+// written as Xs*g / Xnd*g so no divide by Xs or Xbh is needed ((Xs/Xbh)/(Kx+Xs/Xbh) == Xs/(Kx*Xbh+Xs)).
+// 57 FP64 instructions + 4 MUFU for the react tail.  Only masked components are written.
 // ---------------------------------------------------------------------------------------------------------
 template <int TAIL>
 SBR_HD void rhs(const double (&y)[SBR_NX], double (&k)[SBR_NX], const Coef& c, const TailArgs& a) {
     const double Ss = y[iSs], Xs = y[iXs], Xbh = y[iXbh], Xba = y[iXba], So = y[iSo], Sno = y[iSno],
                  Snh = y[iSnh], Snd = y[iSnd], Xnd = y[iXnd];
-    const double r1 = rcp(c.Ks + Ss);
-    const double r2 = rcp(c.Koh + So);
+    // Monod denominators.  Two pairs only ever appear as products, so each pair shares ONE reciprocal:
+    //   rho1, rho2 ~ 1/((Ks+Ss)(Koh+So))   and   rho3 ~ 1/((Knh+Snh)(Koa+So))
+    const double d1 = c.Ks + Ss, d2 = c.Koh + So, d4 = c.Knh + Snh, d5 = c.Koa + So;
+    const double r12 = rcp(d1 * d2);
+    const double r2 = r12 * d1;                              // 1/(Koh+So), needed on its own by hydrolysis
+    const double r45 = rcp(d4 * d5);
     const double r3 = rcp(c.Kno + Sno);
-    const double r4 = rcp(c.Knh + Snh);
-    const double r5 = rcp(c.Koa + So);
     const double r6 = rcp(fma(c.Kx, Xbh, Xs));
-    const double mSs = Ss * r1;
-    const double mOh = So * r2;      // So/(Koh+So)
-    const double iOh = c.Koh * r2;   // Koh/(Koh+So)
-    const double mNo = Sno * r3;
-    const double mNh = Snh * r4;
-    const double mOa = So * r5;
-    const double anox = iOh * mNo;
-    const double gh = mSs * Xbh;
-    const double rho1 = (c.muh * gh) * mOh;
-    const double rho2 = (c.muh_etag * gh) * anox;
-    const double rho3 = (c.mua * mNh) * (mOa * Xba);
+    const double mNo = Sno * r3;                             // Sno/(Kno+Sno)
+    const double C = c.muh * ((Ss * Xbh) * r12);
+    const double rho1 = C * So;                              // muh Ss/(Ks+Ss) So/(Koh+So) Xbh
+    const double rho2 = (C * c.etag_Koh) * mNo;              // muh Ss/(Ks+Ss) Koh/(Koh+So) Sno/(Kno+Sno) etag Xbh
+    // rho3 scaled by nu9_3 = 1/Ya on the host (mua_Ya = mua/Ya), so that d(Sno)/dt takes it without a multiply
+    const double rho3s = ((c.mua_Ya * Snh) * So) * (Xba * r45);
     const double rho6 = (c.ka * Snd) * Xbh;
-    const double g = ((c.kh * Xbh) * r6) * fma(c.etah, anox, mOh);
+    // hydrolysis: kh (Xs/Xbh)/(Kx+Xs/Xbh) [So/(Koh+So) + etah Koh/(Koh+So) Sno/(Kno+Sno)] Xbh  ==  Xs * g
+    const double g = ((c.kh * Xbh) * r6) * (r2 * fma(c.etah_Koh, mNo, So));
     const double rho7 = Xs * g;
     const double rho8 = Xnd * g;
     const double s12 = rho1 + rho2;
-    const double s45 = fma(c.bh, Xbh, c.ba * Xba);          // rho4 + rho5 (decay of Xbh and Xba)
+    const double dXba = c.ba * Xba;                          // rho5
+    const double s45 = fma(c.bh, Xbh, dXba);                 // rho4 + rho5 (decay of Xbh and Xba)
     k[iSs] = fma(c.n_invYh, s12, rho7);
     k[iXs] = fma(c.one_m_ixp, s45, -rho7);
-    k[iXbh] = fma(-c.bh, Xbh, s12);                         // rho1 + rho2 - rho4
-    k[iXba] = fma(-c.ba, Xba, rho3);                        // rho3 - rho5
+    k[iXbh] = fma(-c.bh, Xbh, s12);                          // rho1 + rho2 - rho4
+    k[iXba] = fma(c.Ya, rho3s, -dXba);                       // rho3 - rho5
     k[iXp] = c.ixp * s45;
     // aeration KLa (So_sat - So): KLa * So_sat is constant over the PID interval (a.kla_sat)
-    k[iSo] = fma(-a.kla, So, fma(c.c81, rho1, fma(c.c83, rho3, a.kla_sat)));
-    k[iSno] = fma(c.c92, rho2, c.c93 * rho3);
-    k[iSnh] = fma(c.n_ixb, s12, fma(c.c103, rho3, rho6));
+    k[iSo] = fma(-a.kla, So, fma(c.c81, rho1, fma(c.c83_Ya, rho3s, a.kla_sat)));
+    k[iSno] = fma(c.c92, rho2, rho3s);
+    k[iSnh] = fma(c.n_ixb, s12, fma(c.c103_Ya, rho3s, rho6));
     k[iSnd] = rho8 - rho6;
     k[iXnd] = fma(c.c124, s45, -rho8);
     // kinetic part of d(Salk)/dt = (d(Snh)/dt - d(Sno)/dt)/14; the react tail reconstructs Salk after the step
