@@ -127,5 +127,5 @@ def default_params():
     return p
 
 
-def make_tol(rtol=1e-8, atol=1e-10, max_steps=4000):
+def make_tol(rtol=1e-8, atol=1e-10, max_steps=200):
     return SbrTol(float(rtol), float(atol), int(max_steps), 0)

@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(kBlock) sbr_rhs_kernel(RhsArgs g, SbrParams p,
     if (TAIL == sbr::TAIL_EC) a.q = g.ec[i];
     a.kla_sat = a.kla * c.so_sat;
     sbr::rhs<TAIL>(x, k, c, a);
-    if (TAIL == sbr::TAIL_REACT) k[sbr::iSalk] = (k[sbr::iSnh] - k[sbr::iSno]) * c.c136;   // see sbr::integ()
 #pragma unroll
     for (int j = 0; j < SBR_NX; ++j) g.dx[j * g.ld + i] = k[j];
 }
@@ -344,7 +343,7 @@ int check_common(int64_t n, int64_t ld, const SbrParams* p) {
 
 SbrTol tol_or_default(const SbrTol* tol) {
     SbrTol t;
-    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 4000; t.reserved = 0;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.reserved = 0;
     if (tol) t = *tol;
     return t;
 }

@@ -34,7 +34,7 @@ class SbrV2VecEnv(object):
     num_obs = 3
     scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
 
-    def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=4000,
+    def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=200,
                  params=None, rng="torch"):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
@@ -129,7 +129,7 @@ class SbrOsVecEnv(object):
     scenario = 6                     # buffer_tank(6), gym_SBR_oneshot.py:180
     max_episode_steps = 463
 
-    def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=4000,
+    def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
                  params=None, rng="torch", autoreset=False, rk4_sub_interval=0):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)

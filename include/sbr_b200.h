@@ -126,7 +126,10 @@ typedef struct SbrOsSchedule {
 /* Adaptive-step controls (SBR_MODE_DP45). */
 typedef struct SbrTol {
     double rtol, atol;     /* mixed tolerance: err_i <= atol * scale_i + rtol * |x_i|          */
-    int32_t max_steps;     /* per PID interval, accepted + rejected                            */
+    int32_t max_steps;     /* accepted + rejected steps per 72-s PID interval (default 200; typical need: 1-5);
+                              the one-shot fill and idle solves of the interval-per-step path get max_steps x
+                              (their length / control interval).  Bounds the work of an env that has left the
+                              physical regime: one stuck env stalls its whole warp                       */
     int32_t reserved;
 } SbrTol;
 
