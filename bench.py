@@ -213,6 +213,37 @@ def cycle_dp45_leg(torch, device, core, env, n):
     return res
 
 
+def rollout_leg(torch, tdist, device, rank, world, args):
+    """BASELINE config 5: --rollout-envs SBROS-v1 envs in total, sharded over the ranks by contiguous index blocks,
+    one full episode (reset + 463 env.steps) driven by a small torch policy on the observation tensors, then an
+    NCCL all_gather of the per-env episode returns.  Strong scaling: total work is fixed as N grows."""
+    from gym_sbr2_b200 import dist, rollout
+    from gym_sbr2_b200.vec_env import SbrOsVecEnv
+    total = args.rollout_envs
+    lo, hi = dist.shard_range(total, rank, world)
+    env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
+    policy = rollout.TinyPolicy(device)
+    rollout.collect_episode(env, policy, max_steps=3)            # warm-up (allocations, policy kernels)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    ep = rollout.collect_episode(env, policy)
+    e1.record()
+    allr, stats = rollout.gather_episode_returns(ep["returns"], total)
+    e2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=device)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    ms_total, ms_gather = float(t[0]), float(t[1])
+    return {"total_envs": total, "envs_per_rank": hi - lo, "episode_steps": ep["steps"], "ms_episode": ms_total,
+            "interval_steps_per_sec": total * ep["steps"] / (ms_total * 1e-3), "ms_reward_gather": ms_gather,
+            "gathered_returns": int(allr.numel()), "all_done": bool(ep["all_done"]), "return_stats": stats,
+            "scaling": "strong", "collective": "all_gather of per-env returns (%d B per rank)" % ((hi - lo) * 8)}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port of the scipy-odeint
     path, all host cores), same metric/unit/config.  Under torchrun only rank 0 works."""
@@ -261,6 +292,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-interval-path", action="store_true", help="skip the SBROS-v1 (interval-per-step) leg")
     ap.add_argument("--interval-envs", type=int, default=1 << 20)
+    ap.add_argument("--no-rollout", action="store_true", help="skip the config-5 rollout leg")
+    ap.add_argument("--rollout-envs", type=int, default=1 << 20, help="TOTAL envs of the config-5 rollout (sharded)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -406,11 +439,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(args.cpu_seconds)
 
-    paths = None
+    paths = {}
     if rank == 0 and world == 1 and not args.no_interval_path:
-        paths = {"sbros_v1": interval_path_leg(torch, device, args, peak_burst, peak_sustained)}
+        paths["sbros_v1"] = interval_path_leg(torch, device, args, peak_burst, peak_sustained)
         if args.mode == "rk4":
             paths["sbr_v2_dp45"] = cycle_dp45_leg(torch, device, core, env, n)
+    if not args.no_rollout:
+        # every rank takes part: envs sharded over the ranks, NCCL gather of the episode returns
+        paths["config5_rollout"] = rollout_leg(torch, tdist, device, rank, world, args)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -80,6 +80,7 @@ _PROTOS = {
                                _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_os_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                               _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_influent_mix": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),

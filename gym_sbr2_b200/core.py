@@ -179,6 +179,34 @@ def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=No
     return buf
 
 
+_INFLUENT_TABLES = {}
+
+
+def influent_mix(switch, rnd, out=None, stream=None):
+    """influent_mixed [14,n] from rnd [48,n] (standard-normal draws) for scenario `switch` -- the device version of
+    buffer_tank3.influent.buffer_tank (buffer_tank3.py:18-108), bit-identical to numpy for the same rnd."""
+    from . import influent as influent_mod
+    lib = _abi.load()
+    n = rnd.shape[1]
+    key = (int(switch), rnd.device)
+    if key not in _INFLUENT_TABLES:
+        t = influent_mod.tables()
+        mean = torch.as_tensor(t["mean"][int(switch)], dtype=torch.float64).contiguous()
+        std = torch.as_tensor(t["std_frac"][int(switch)][:, None] * t["mean"][int(switch)], dtype=torch.float64).contiguous()
+        _INFLUENT_TABLES[key] = (mean.to(rnd.device), std.to(rnd.device))
+    mean, std = _INFLUENT_TABLES[key]
+    if out is None:
+        out = torch.empty((_abi.NX, n), dtype=torch.float64, device=rnd.device)
+    pr, l0 = _dev_ptr(rnd, influent_mod.N_POINTS, n, name="rnd")
+    po, l1 = _dev_ptr(out, _abi.NX, n, name="influent")
+    ld = _same_ld([l0, l1], "influent_mix")
+    with torch.cuda.device(rnd.device):
+        rc = lib.sbr_influent_mix(n, ld, pr, C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), po,
+                                  _stream_ptr(stream))
+    _abi.check(rc, "sbr_influent_mix")
+    return out
+
+
 def reward_stats(reward, status=None, out=None, stream=None):
     """[sum, sumsq, min, max, count] of the rewards of healthy envs, on the device (feeds the NCCL gather)."""
     lib = _abi.load()

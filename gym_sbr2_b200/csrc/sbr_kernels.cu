@@ -272,6 +272,34 @@ __global__ void __launch_bounds__(kBlock, SBR_OS_STEP_MINBLOCKS) sbr_os_step_ker
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
+// Influent mixing (buffer_tank3.py:50-107): one env per thread, tables staged in shared memory, 13 running sums in
+// registers, rnd read coalesced ([48][N]).  No FMA contraction and sequential sums => bit-identical to numpy.
+__global__ void __launch_bounds__(128) sbr_influent_mix_kernel(int64_t n, int64_t ld, const double* __restrict__ rnd,
+                                                               const double* __restrict__ mean,
+                                                               const double* __restrict__ stdv, double* influent) {
+    __shared__ double s_mean[SBR_NX * SBR_INFLUENT_POINTS], s_std[SBR_NX * SBR_INFLUENT_POINTS];
+    for (int k = threadIdx.x; k < SBR_NX * SBR_INFLUENT_POINTS; k += blockDim.x) { s_mean[k] = mean[k]; s_std[k] = stdv[k]; }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[SBR_NX];
+#pragma unroll
+    for (int j = 0; j < SBR_NX; ++j) acc[j] = 0.0;
+    for (int t = 0; t < SBR_INFLUENT_POINTS; ++t) {
+        const double z = rnd[t * ld + i];
+        const double q = __dadd_rn(s_mean[t], __dmul_rn(s_std[t], z));
+        acc[0] = __dadd_rn(acc[0], q);
+#pragma unroll
+        for (int j = 1; j < SBR_NX; ++j) {
+            const double cj = __dadd_rn(s_mean[j * SBR_INFLUENT_POINTS + t], __dmul_rn(s_std[j * SBR_INFLUENT_POINTS + t], z));
+            acc[j] = __dadd_rn(acc[j], __dmul_rn(cj, q));
+        }
+    }
+    influent[i] = 0.66;                                                    // buffer_tank3.py:92
+#pragma unroll
+    for (int j = 1; j < SBR_NX; ++j) influent[j * ld + i] = __ddiv_rn(acc[j], acc[0]);
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread, `iters` rounds of 8 DFMAs each.
 __global__ void sbr_fp64_probe_kernel(int iters, double* sink) {
     const double a = 1.0000001, b = 1e-9 * (double)(threadIdx.x + 1);
@@ -504,6 +532,16 @@ int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const S
     if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     return check_launch("sbr_os_step");
+}
+
+int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mean, const double* std,
+                     double* influent, void* stream) {
+    if (n <= 0) return fail(SBR_ERR_ARG, "n must be positive%s");
+    if (ld < n) return fail(SBR_ERR_ARG, "ld must be >= n%s");
+    if (!rnd || !mean || !std || !influent) return fail(SBR_ERR_ARG, "sbr_influent_mix: NULL buffer%s");
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    sbr_influent_mix_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, ld, rnd, mean, std, influent);
+    return check_launch("sbr_influent_mix");
 }
 
 int sbr_reward_stats_init(double* stats, void* stream) {

@@ -64,16 +64,17 @@ class SbrV2VecEnv(object):
 
     # -- influent ------------------------------------------------------------------------------------
     def _draw_influent(self):
+        """Per-env buffer_tank(scenario) draws: rnd ~ N(0,1)^48 per env, mixed on the device (sbr_influent_mix)."""
         n = self.num_envs
         if self.rng == "numpy":
-            # N sequential buffer_tank(0) calls on one numpy stream, as N reference resets would make
+            # N sequential buffer_tank(scenario) calls on one numpy stream, as N reference resets would make
             d = influent_mod.draws_per_reset(self.scenario)
             r = self._np_rng.randn(n, d, influent_mod.N_POINTS)[:, -1, :]
-            rnd = torch.as_tensor(r, dtype=torch.float64).to(self.device)
+            rnd = torch.as_tensor(np.ascontiguousarray(r.T), dtype=torch.float64).to(self.device)
         else:
-            rnd = torch.randn((n, influent_mod.N_POINTS), dtype=torch.float64, device=self.device,
+            rnd = torch.randn((influent_mod.N_POINTS, n), dtype=torch.float64, device=self.device,
                               generator=self._gen)
-        return influent_mod.mix_torch(self.scenario, rnd)
+        return core.influent_mix(self.scenario, core.soa1(rnd))
 
     def reset(self, influent=None, x0=None):
         """influent: optional [14,N] influent_mixed (row 0 ignored at step time); x0: optional [14,N]."""

@@ -207,6 +207,21 @@ int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const S
                 const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
 
+/*
+ * Influent generator, the step before the path = buffer_tank3.influent.buffer_tank (buffer_tank3.py:18-108): per env
+ * one shared rnd ~ N(0,1)^48 perturbs the 48-point mean profiles of the flow and the 13 concentrations
+ * (profile = mean + std * rnd, std = 0.1 * mean for Ss, Xi, Xs, Xbh, Snh, Snd, Xnd and the flow, 0 otherwise, :50-66) and
+ * the result is the flow-weighted mean influent_mixed = [0.66, sum(c q) / sum(q) ...] (:87-107).  Sums run
+ * sequentially over the 48 points with round-to-nearest mul/add and one IEEE division, i.e. bit-identical to the
+ * reference's numpy arithmetic for the same rnd.
+ *   rnd      [48][ld] in   standard-normal draws (the caller's RNG: torch Philox on the device, or numpy's stream)
+ *   mean,std [14][48] in   device copies of the scenario's tables (row 0 = flow), gym_sbr2_b200/data/influent_tables.npz
+ *   influent [14][ld] out  influent_mixed
+ */
+#define SBR_INFLUENT_POINTS 48
+int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mean, const double* std,
+                     double* influent, void* stream);
+
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the
  * envs whose status is 0 (all envs if status == NULL).  stats must be zero-initialised by the caller with
