@@ -223,7 +223,8 @@ def rollout_leg(torch, tdist, device, rank, world, args):
     lo, hi = dist.shard_range(total, rank, world)
     env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
     policy = rollout.TinyPolicy(device)
-    rollout.collect_episode(env, policy, max_steps=3)            # warm-up (allocations, policy kernels)
+    warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
+    dist.gather_rewards(warm["returns"], total)                  # ... and the NCCL channel set-up for this size
     torch.cuda.synchronize()
     if world > 1:
         tdist.barrier()
@@ -231,9 +232,10 @@ def rollout_leg(torch, tdist, device, rank, world, args):
     e0.record()
     ep = rollout.collect_episode(env, policy)
     e1.record()
-    allr, stats = rollout.gather_episode_returns(ep["returns"], total)
+    allr = dist.gather_rewards(ep["returns"], total)             # the only collective: all_gather over NVLink
     e2.record()
     torch.cuda.synchronize()
+    _, stats = rollout.gather_episode_returns(ep["returns"], total) if world == 1 else (None, rollout.return_stats(allr))
     t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=device)
     if world > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)

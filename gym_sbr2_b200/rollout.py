@@ -47,11 +47,14 @@ def collect_episode(env, policy, max_steps=None, store=False):
                 all_done=done.all(), status=info["status"])
 
 
+def return_stats(allr):
+    ok = torch.isfinite(allr)
+    r = allr[ok]
+    return dict(mean=float(r.mean()), std=float(r.std(unbiased=False)), min=float(r.min()), max=float(r.max()),
+                count=int(ok.sum()))
+
+
 def gather_episode_returns(local_returns, n_total):
     """NCCL all_gather of per-env episode returns across ranks (global env order), plus the 5 summary statistics."""
     allr = dist.gather_rewards(local_returns, n_total)
-    ok = torch.isfinite(allr)
-    r = allr[ok]
-    stats = dict(mean=float(r.mean()), std=float(r.std(unbiased=False)), min=float(r.min()), max=float(r.max()),
-                 count=int(ok.sum()))
-    return allr, stats
+    return allr, return_stats(allr)
