@@ -213,6 +213,36 @@ def cycle_dp45_leg(torch, device, core, env, n):
     return res
 
 
+def v4_path_leg(torch, device, args):
+    """SBR-v4 (fill phase stepped inside step(), 1-D delta-set-point action): one whole episode (493 launches)."""
+    from gym_sbr2_b200 import _abi
+    from gym_sbr2_b200.vec_env import SbrV4VecEnv
+    n = args.interval_envs
+    env = SbrV4VecEnv(n, device=device, seed=99, mode="dp45")
+    gen = torch.Generator(device=device).manual_seed(6)
+    acts = [0.2 * torch.randn(n, dtype=torch.float64, device=device, generator=gen) + 0.02 for _ in range(8)]
+    env.reset()
+    for k in range(3):
+        env.step_async(acts[k])
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(495)]
+    ev[0].record()
+    env.reset()
+    for k in range(493):
+        ev[k + 1].record()
+        env.step_async(acts[k % 8])
+    ev[494].record()
+    torch.cuda.synchronize()
+    per = [ev[k + 1].elapsed_time(ev[k + 2]) for k in range(493)]
+    ms_episode = ev[0].elapsed_time(ev[494])
+    fill, react = sorted(per[3:26]), sorted(per[40:490])
+    return {"envs": n, "ms_per_episode": ms_episode, "interval_steps_per_sec": n * 493 / (ms_episode * 1e-3),
+            "ms_per_fill_step": fill[len(fill) // 2], "ms_per_react_step": react[len(react) // 2],
+            "ms_terminal_step": per[492], "all_done": bool(env.buf.done.all()),
+            "bad_status": int((env.buf.status != 0).sum()), "config": {"integrator": "dp45", "rtol": 1e-8, "atol": 1e-10},
+            "gpu_launches": 494, "mean_episode_return": float(env.buf.st[_abi.V4_RETURN].mean())}
+
+
 def rollout_leg(torch, tdist, device, rank, world, args):
     """BASELINE config 5: --rollout-envs SBROS-v1 envs in total, sharded over the ranks by contiguous index blocks,
     one full episode (reset + 463 env.steps) driven by a small torch policy on the observation tensors, then an
@@ -446,6 +476,8 @@ def main():
         paths["sbros_v1"] = interval_path_leg(torch, device, args, peak_burst, peak_sustained)
         if args.mode == "rk4":
             paths["sbr_v2_dp45"] = cycle_dp45_leg(torch, device, core, env, n)
+    if rank == 0 and world == 1 and not args.no_interval_path:
+        paths["sbr_v4"] = v4_path_leg(torch, device, args)
     if not args.no_rollout:
         # every rank takes part: envs sharded over the ranks, NCCL gather of the episode returns
         paths["config5_rollout"] = rollout_leg(torch, tdist, device, rank, world, args)

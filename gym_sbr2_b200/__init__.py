@@ -13,7 +13,7 @@ from .registration import ENV_TABLE, UnsupportedEnvError, make, register, regist
 
 def __getattr__(name):
     # the vector envs import torch; keep `import gym_sbr2_b200` light
-    if name in ("SbrV2VecEnv", "SbrOsVecEnv"):
+    if name in ("SbrV2VecEnv", "SbrOsVecEnv", "SbrV4VecEnv"):
         from . import vec_env
         return getattr(vec_env, name)
     raise AttributeError(name)

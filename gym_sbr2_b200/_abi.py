@@ -20,6 +20,9 @@ OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
 OS_RETURN, OS_STEPS, OS_QW, OS_ROWS = 32, 33, 34, 35
 OS_NOBS, OS_NSTATE = 9, 15
+# rows of the persistent state of the SBR-v4 env (enum SBR_V4_*)
+V4_T, V4_U, V4_SO_PREV, V4_IE, V4_KLA_LAST, V4_KLA_SUM, V4_H, V4_RETURN, V4_STEPS, V4_QW, V4_ROWS = \
+    14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24
 
 _PARAM_FIELDS = [
     "muh", "Ks", "Koh", "Kno", "bh", "etag", "etah", "kh", "Kx", "mua", "Knh", "ba", "Koa", "ka",
@@ -80,6 +83,9 @@ _PROTOS = {
                                _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_os_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                               _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_v4_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), _P, _P, _P, _P]),
+    "sbr_v4_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
+                              _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_influent_mix": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),

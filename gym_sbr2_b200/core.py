@@ -179,6 +179,57 @@ def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=No
     return buf
 
 
+class V4Buffers(object):
+    """Device buffers of the SBR-v4 path: persistent state + per-step outputs (allocated once)."""
+
+    def __init__(self, n, device):
+        f = dict(dtype=torch.float64, device=device)
+        self.st = torch.zeros((_abi.V4_ROWS, n), **f)
+        self.obs = torch.empty((_abi.NX, n), **f)
+        self.reward = torch.zeros((n,), **f)
+        self.done = torch.ones((n,), dtype=torch.uint8, device=device)
+        self.status = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.counters = torch.zeros((2, n), dtype=torch.int32, device=device)
+
+
+def v4_reset(buf, influent, params, x0=None, mask=None, stream=None):
+    """SbrEnv4.reset for a batch (gym_SBR_env4.py:94-198).  influent [14,n] (row 0 = fill flow)."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    pst, l0 = _dev_ptr(buf.st, _abi.V4_ROWS, n, name="st")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    px0, l2 = _dev_ptr(x0, _abi.NX, n, name="x0")
+    pmk, _ = _dev_ptr(mask, 1, n, dtype=torch.uint8, name="mask")
+    pob, l3 = _dev_ptr(buf.obs, _abi.NX, n, name="obs")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    ld = _same_ld([l0, l1, l2 if x0 is not None else None, l3], "v4_reset")
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_v4_reset(n, ld, px0, pin, pmk, C.byref(params), pst, pob, pdn, _stream_ptr(stream))
+    _abi.check(rc, "sbr_v4_reset")
+    return buf
+
+
+def v4_step(buf, influent, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None):
+    """SbrEnv4.step for a batch (gym_SBR_env4.py:200-358).  action [n]: change of the DO set-point."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    pst, l0 = _dev_ptr(buf.st, _abi.V4_ROWS, n, name="st")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    pac, _ = _dev_ptr(action, 1, n, name="action")
+    pob, l2 = _dev_ptr(buf.obs, _abi.NX, n, name="obs")
+    prw, _ = _dev_ptr(buf.reward, 1, n, name="reward")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l3 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1, l2, l3], "v4_step")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_v4_step(n, ld, pst, pin, pac, C.byref(params), C.byref(sched), pob, prw, pdn, pss, pct,
+                             int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_v4_step")
+    return buf
+
+
 _INFLUENT_TABLES = {}
 
 

@@ -1012,4 +1012,122 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
     o.status = status;
 }
 
+// =========================================================================================================
+// SBR-v4 (SbrEnv4, gym_SBR_env4.py): interval-per-step env with the fill phase stepped inside step() and a 1-D
+// "change of DO set-point" action.  Same physics pieces as above; the controller is the incremental-bias DO-PID
+// with the cycle-per-step tuning (Kc 5, tauI 0.00035, tauD 0.005, :61-69) and PID dt = 0.002/24.
+// =========================================================================================================
+struct V4Ctrl {
+    double t, u, so_prev, ie, kla_last, kla_sum;
+};
+
+struct V4Out {
+    double reward, Qw;
+    int done, status;
+};
+
+// 1 / x_1 (gym_SBR_env4.py:91): the observation is x / x_1.
+SBR_HD constexpr double inv_x1_v4(int i) {
+    return i == 0 ? SBR_INV(1.32000000e+00) : i == 1 ? SBR_INV(3.00000000e+01) : i == 2 ? SBR_INV(3.81606587e+01)
+         : i == 3 ? SBR_INV(6.94658685e+02) : i == 4 ? SBR_INV(1.07772100e+02) : i == 5 ? SBR_INV(1.22613841e+03)
+         : i == 6 ? SBR_INV(7.88460027e+01) : i == 7 ? SBR_INV(2.57616136e+02) : i == 8 ? SBR_INV(1.01108024e+00)
+         : i == 9 ? SBR_INV(6.24510635e+00) : i == 10 ? SBR_INV(1.78877937e+01) : i == 11 ? SBR_INV(3.95743344e+00)
+         : i == 12 ? SBR_INV(5.70432163e+00) : SBR_INV(5.50185509e+00);
+}
+
+// Controller block shared by Sim_filling / Sim_rxn / Sim_idle (gym_SBR_env4.py:497-524, 667-697, 1202-1234).
+SBR_HD double v4_pid(V4Ctrl& c, double so_last, bool first, const SbrParams& p) {
+    const double dt = p.os_pid_dt;
+    const double e = c.u - so_last;
+    double dcv = 0.0;
+    if (!first) { dcv = (so_last - c.so_prev) / dt; c.ie = c.ie + e * dt; }
+    else c.ie = 0.0;
+    double kla = p.pid_Kc * e + p.pid_Kc / p.pid_tauI * c.ie + p.pid_Kc * p.pid_tauD * dcv + c.kla_last;
+    if (kla > p.kla_max) { kla = p.kla_max; c.ie = c.ie - e * dt; }
+    if (kla < p.kla_min) { kla = p.kla_min; c.ie = c.ie - e * dt; }
+    return kla;
+}
+
+// SbrEnv4.step + run_step (gym_SBR_env4.py:200-358).  load: the env's influent column (used in the fill phase).
+template <int MODE>
+SBR_HD void v4_step_env(double (&x)[SBR_NX], V4Ctrl& c, double action, const Loading& load, const SbrParams& p,
+                        const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol, Dp45State& dp,
+                        const Column& obs, V4Out& o) {
+    const bool first = c.t == 0.0;
+    if (first) { c.u = 0.0; c.kla_last = 0.0; c.kla_sum = 0.0; }       // u = 0 (:209); So = [x[8]], Kla = [0] (:272-277)
+    c.u = c.u + action;
+    c.u = c.u < 0.0 ? 0.0 : (c.u > p.do_sp_max ? p.do_sp_max : c.u);    // :213-218
+    const double t = c.t;
+    // batch type from the running time (:256-268): 0 fill, 1 react (phases 2-5), 2 settle + draw + idle
+    const int bt = (t >= 0.0 && t < s.t_fill) ? 0 : (t < s.tm5_1 ? 1 : 2);
+    TailArgs a;
+    a.kla = 0.0; a.q = 0.0; a.ec_conc = 0.0; a.load = load;
+    int status = 0;
+    double so_start = x[iSo], t_next, T;
+    int n_sub;
+    SbrTol tl = tol;
+    o.Qw = NAN;
+    double eff_snh = 0.0;
+    if (bt < 2) {
+        t_next = add_rn(t, s.t_delta);
+        T = sub_rn(t_next, t);
+        const int L = (int)div_rn(T, s.dt);                              // len(t_range) (:286)
+        n_sub = s.rk4_sub_interval > 0 ? s.rk4_sub_interval : (L > 1 ? L - 1 : 1);
+        a.kla = v4_pid(c, so_start, first, p);
+        if (bt == 0) a.q = load(0);
+    } else {
+        // Sim_Settling_Drawing (:919-1070; its `dt` argument is the control interval) then Sim_idle (:1202-1242)
+        const double t_set_end = add_rn(t, s.settle_len);
+        double sX[10], Xf;
+        settle_closed_form(x, sub_rn(t_set_end, t), p.settler_area, p.settler_vmax, sX, Xf);
+        DrawOut d;
+        draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+        status |= d.status;
+        o.Qw = d.Qw;
+        eff_snh = d.eff[3];
+        const double t_draw_end = add_rn(t_set_end, s.draw_len);
+        so_start = x[iSo];
+        c.so_prev = so_start;                                            // So extended with the frozen value (:1063-1064)
+        T = sub_rn(s.t_cycle, t_draw_end);
+        tl.max_steps = tol.max_steps * (int)ceil(T / s.t_delta);
+        const int pts = (int)div_rn(T, s.dt);
+        n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
+        a.kla = v4_pid(c, so_start, false, p);
+        t_next = s.t_cycle;
+    }
+    if (bt == 0) status |= integrate_interval<TAIL_FILL, MODE>(x, T, n_sub, coef, a, tl, dp);
+    else status |= integrate_interval<TAIL_REACT, MODE>(x, T, n_sub, coef, a, tl, dp);
+    c.so_prev = so_start;
+    c.kla_last = a.kla;
+    c.kla_sum += a.kla;
+    c.t = t_next;
+    // module_reward_continuous.sbr_reward (module_reward_continuous.py:4-65)
+    const double tdl = 0.002 / 24;
+    double PE, AE_dT, r_snh = 0.0;
+    if (bt == 0) { PE = 0.004 * p.Qin; AE_dT = 1.32 * a.kla * tdl; }
+    else if (bt == 1) { PE = 0.0; AE_dT = 1.32 * a.kla * tdl; }
+    else {
+        PE = 0.05 * o.Qw + 0.004 * p.Qeff;
+        AE_dT = 1.32 * c.kla_sum * tdl;
+        r_snh = eff_snh < 4 ? 0.0 : -246.0;
+    }
+    const double AE = p.so_sat / (1.8 * 1000) * AE_dT;
+    o.reward = (0.5 - (AE + PE)) + r_snh;
+    o.done = (bt == 2 && c.t >= s.t_cycle) ? 1 : 0;
+    bool finite = fabs(o.reward) < 1e300;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) { finite = finite && (fabs(x[i]) < 1e300); obs.set(i, x[i] * inv_x1_v4(i)); }
+    if (!finite) status |= SBR_ST_NONFINITE;
+    o.status = status;
+}
+
+// SbrEnv4.reset observation (gym_SBR_env4.py:185-191): x_2[0] = Qin + IV, x_2[i] = (Qin c_in,i + x0_i IV)/(Qin + IV).
+SBR_HD void v4_reset_obs(const double (&x0)[SBR_NX], const Loading& load, const SbrParams& p, const Column& obs) {
+    const double Qin = p.Qin, IV = p.IV;
+    const double iden = 1.0 / (Qin + IV);
+    obs.set(0, (Qin + IV) * inv_x1_v4(0));
+#pragma unroll
+    for (int i = 1; i < SBR_NX; ++i) obs.set(i, (Qin * load(i) + x0[i] * IV) * iden * inv_x1_v4(i));
+}
+
 }  // namespace sbr

@@ -272,6 +272,92 @@ __global__ void __launch_bounds__(kBlock, SBR_OS_STEP_MINBLOCKS) sbr_os_step_ker
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// SBR-v4 kernels: persistent per-env state st[SBR_V4_ROWS][ld] + the env's influent column [14][ld].
+// ---------------------------------------------------------------------------------------------------------
+struct V4Args {
+    int64_t n, ld;
+    double* st;
+    const double* x0;         // reset only (may be NULL)
+    const double* influent;
+    const uint8_t* mask;      // reset only (may be NULL)
+    const double* action;     // step only
+    double* obs;
+    double* reward;           // step only
+    uint8_t* done;
+    int32_t* status;
+    uint32_t* counters;
+};
+
+__global__ void __launch_bounds__(128) sbr_v4_reset_kernel(V4Args g, SbrParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    if (g.mask && g.mask[i] == 0) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) { x[k] = g.x0 ? g.x0[k * g.ld + i] : c_x0_init[k]; g.st[k * g.ld + i] = x[k]; }
+    const sbr::Loading load{g.influent + i, (int)g.ld};
+    sbr::v4_reset_obs(x, load, p, sbr::Column{g.obs + i, g.ld});
+#pragma unroll
+    for (int r = SBR_V4_T; r < SBR_V4_ROWS; ++r) g.st[r * g.ld + i] = 0.0;
+    g.st[SBR_V4_QW * g.ld + i] = NAN;
+    g.done[i] = 0;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, 6) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+                                                                SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
+    const sbr::Column ob{g.obs + i, g.ld};
+    if (g.done[i]) {
+        // stepping a finished episode is a no-op: same observation, reward 0
+#pragma unroll
+        for (int k = 0; k < SBR_NX; ++k) ob.set(k, x[k] * sbr::inv_x1_v4(k));
+        g.reward[i] = 0.0;
+        if (g.status) g.status[i] = SBR_ST_DONE;
+        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
+        return;
+    }
+    sbr::V4Ctrl ctl;
+    ctl.t = g.st[SBR_V4_T * g.ld + i];
+    ctl.u = g.st[SBR_V4_U * g.ld + i];
+    ctl.so_prev = g.st[SBR_V4_SO_PREV * g.ld + i];
+    ctl.ie = g.st[SBR_V4_IE * g.ld + i];
+    ctl.kla_last = g.st[SBR_V4_KLA_LAST * g.ld + i];
+    ctl.kla_sum = g.st[SBR_V4_KLA_SUM * g.ld + i];
+    sbr::Dp45State dp;
+    dp.h = g.st[SBR_V4_H * g.ld + i];
+    if (!(dp.h > 0.0)) dp.h = s.t_delta / 9.0;
+    dp.n_rhs = 0; dp.n_rej = 0;
+    if (ctl.t < s.t_fill) {          // the influent column is only read while the reactor fills (26 of 493 steps)
+#pragma unroll
+        for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+    }
+    const sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    sbr::V4Out o;
+    sbr::v4_step_env<MODE>(x, ctl, g.action[i], load, p, c, s, tol, dp, ob, o);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
+    g.st[SBR_V4_T * g.ld + i] = ctl.t;
+    g.st[SBR_V4_U * g.ld + i] = ctl.u;
+    g.st[SBR_V4_SO_PREV * g.ld + i] = ctl.so_prev;
+    g.st[SBR_V4_IE * g.ld + i] = ctl.ie;
+    g.st[SBR_V4_KLA_LAST * g.ld + i] = ctl.kla_last;
+    g.st[SBR_V4_KLA_SUM * g.ld + i] = ctl.kla_sum;
+    g.st[SBR_V4_H * g.ld + i] = dp.h;
+    g.st[SBR_V4_RETURN * g.ld + i] += o.reward;
+    g.st[SBR_V4_STEPS * g.ld + i] += 1.0;
+    if (o.done) { g.st[SBR_V4_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
+    g.reward[i] = o.reward;
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+}
+
 // Influent mixing (buffer_tank3.py:50-107): one env per thread, tables staged in shared memory, 13 running sums in
 // registers, rnd read coalesced ([48][N]).  No FMA contraction and sequential sums => bit-identical to numpy.
 __global__ void __launch_bounds__(128) sbr_influent_mix_kernel(int64_t n, int64_t ld, const double* __restrict__ rnd,
@@ -532,6 +618,36 @@ int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const S
     if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     return check_launch("sbr_os_step");
+}
+
+int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                 const SbrParams* p, double* st, double* obs, uint8_t* done, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!influent || !st || !obs || !done) return fail(SBR_ERR_ARG, "sbr_v4_reset: NULL buffer%s");
+    if (ld > 2147483647LL) return fail(SBR_ERR_ARG, "sbr_v4_reset: ld too large%s");
+    V4Args g{n, ld, st, x0, influent, mask, nullptr, obs, nullptr, done, nullptr, nullptr};
+    sbr_v4_reset_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, *p);
+    return check_launch("sbr_v4_reset");
+}
+
+int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
+                const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
+                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if ((rc = check_os_schedule(s))) return rc;
+    if (!st || !influent || !action || !obs || !reward || !done)
+        return fail(SBR_ERR_ARG, "sbr_v4_step: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_v4_step: bad mode%s");
+    V4Args g{n, ld, st, nullptr, influent, nullptr, action, obs, reward, done, status, counters};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    else sbr_v4_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    return check_launch("sbr_v4_step");
 }
 
 int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mean, const double* std,

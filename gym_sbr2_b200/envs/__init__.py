@@ -1,15 +1,14 @@
 """Single-environment Gym classes under the reference's class names (gym_SBR/envs/__init__.py:1-10).
 
-`SbrEnv2` and `SbrOS` are thin wrappers over a batch of ONE env of the CUDA vector envs, returning numpy / Python
+`SbrEnv2`, `SbrOS` and `SbrEnv4` are thin wrappers over a batch of ONE env of the CUDA vector envs, returning numpy / Python
 values exactly shaped like the reference's; "identical seeds" means `np.random.seed(s)` before `reset()` as in the
 reference (global numpy RNG, buffer_tank3.py:68) -- the influent draw consumes the same random numbers.
 The classes whose reference `step()` cannot run raise UnsupportedEnvError on construction.
 """
-from .single import SbrEnv2, SbrOS, unsupported_class
+from .single import SbrEnv2, SbrEnv4, SbrOS, unsupported_class
 
 SbrEnv = unsupported_class("SBR-v0")
 SbrEnv1 = unsupported_class("SBR-v1")
-SbrEnv4 = unsupported_class("SBR-v4")
 SbrCnt0 = unsupported_class("SBRCnt-v0")
 SbrCnt1 = unsupported_class("SBRCnt-v1")
 SbrCnt2 = unsupported_class("SBRCnt-v2")

@@ -5,7 +5,7 @@ import torch
 from .. import influent as influent_mod
 from ..registration import ENV_TABLE, UnsupportedEnvError
 from ..spaces import Box, env_base
-from ..vec_env import SbrOsVecEnv, SbrV2VecEnv
+from ..vec_env import SbrOsVecEnv, SbrV2VecEnv, SbrV4VecEnv
 
 _Base = env_base()
 
@@ -98,6 +98,37 @@ class SbrOS(_Base):
                 avail_u[i] = 1 if action_boundary[agent_i][0] <= v <= action_boundary[agent_i][1] else 0
             avail_us.append(avail_u)
         return avail_us
+
+    def render(self, mode="human", close=False):
+        print("Reward for this step: {}".format(self.reward))
+
+
+class SbrEnv4(_Base):
+    """`SBR-v4` (gym_SBR_env4.py:71-1294): one step = one 72-s PID interval incl. the fill phase; action = change of
+    the DO set-point in [-1, 1]; obs = x / x_1 (14 values); standard 4-tuple.  Parity is against the reference run
+    with numpy < 1.18 linspace semantics (its step() raises TypeError on current numpy) -- see SbrV4VecEnv."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device=None, mode="dp45", rtol=1e-8, atol=1e-10):
+        self.action_space = Box(np.array([-1.0]), np.array([1.0]), dtype=np.float32)                       # :77
+        self.observation_space = Box(low=0.9 * np.ones([14]), high=np.ones([14]), dtype=np.float32)        # :81
+        self._vec = SbrV4VecEnv(1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
+        self.influent_mixed = None
+        self.switch = None
+        self.reward = 0
+
+    def reset(self):
+        self.switch, self.influent_mixed = influent_mod.sample_numpy_random_scenario()                      # :104
+        obs = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
+        return obs.cpu().numpy()                                     # shape (1, 14) like the reference's x_2 / x_1
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1))
+        obs, reward, done, info = self._vec.step(a)
+        self.reward = float(reward[0])
+        return obs[0].cpu().numpy(), self.reward, bool(done[0]), {}
 
     def render(self, mode="human", close=False):
         print("Reward for this step: {}".format(self.reward))

@@ -61,6 +61,14 @@ def sample_numpy(switch, rng=None):
     return mix_numpy(switch, rnd)
 
 
+def sample_numpy_random_scenario(rng=None):
+    """SbrEnv4.reset's draw (gym_SBR_env4.py:104): buffer_tank(np.random.choice(8, 1)).  Consumes the RNG exactly like
+    the reference: one choice(8, 1), then the scenario's randn(48) draws.  Returns (switch, influent_mixed)."""
+    rng = np.random if rng is None else rng
+    switch = int(rng.choice(8, 1)[0])
+    return switch, sample_numpy(switch, rng)
+
+
 def mix_torch(switch, rnd):
     """Batched device version: rnd [n, 48] (torch, float64) -> influent_mixed SoA [14, n]."""
     import torch

@@ -3,8 +3,9 @@
 The reference registers ten ids with `gym.envs.registration.register(id=..., entry_point='gym_SBR.envs:<Class>')`
 and users call `gym.make(id)`.  The same ten ids are registered here, under the same class names:
   * `SBR-v2` (`SbrEnv2`) and `SBROS-v1` (`SbrOS`) -- the two ids whose `step()` runs in the reference on a current
-    toolchain (SURVEY.md 2.2) -- are served by the CUDA path;
-  * the other eight raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
+    toolchain -- and `SBR-v4` (`SbrEnv4`, whose reference `step()` only needs numpy < 1.18 `linspace`
+    semantics restored, SURVEY.md 8f rank 1) are served by the CUDA path;
+  * the other seven raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
     (they crash inside `step()` there), instead of pretending to work.
 `gym` / `gymnasium` are optional: when one is importable the ids are registered with it as well (so `gym.make`
 works unchanged); otherwise `gym_sbr2_b200.make(id)` is the equivalent.
@@ -20,8 +21,9 @@ ENV_TABLE = {
     "SBR-v1": ("SbrEnv1", "gym_SBR_env1.py", False,
                "reference step() raises TypeError: sbr_reward() arity mismatch (gym_SBR_env1.py:151 vs module_reward.py:4)"),
     "SBR-v2": ("SbrEnv2", "gym_SBR_env2.py", True, None),
-    "SBR-v4": ("SbrEnv4", "gym_SBR_env4.py", False,
-               "reference step() raises TypeError: float `num` in np.linspace (gym_SBR_env4.py:286)"),
+    # supported with a disclosure: the reference's step() raises TypeError on numpy >= 1.18 (float `num` in np.linspace,
+    # gym_SBR_env4.py:286); parity is against the unmodified source under numpy < 1.18 linspace semantics
+    "SBR-v4": ("SbrEnv4", "gym_SBR_env4.py", True, None),
     "SBRCnt-v0": ("SbrCnt0", "gym_SBR_continuous0.py", False,
                   "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
     "SBRCnt-v1": ("SbrCnt1", "gym_SBR_continuous1.py", False,

@@ -196,3 +196,93 @@ class SbrOsVecEnv(object):
 
     def render(self, mode="human", close=False):
         print("Reward for this step: {}".format(self.buf.reward))
+
+
+class SbrV4VecEnv(object):
+    """N x `SBR-v4` (the reference's `SbrEnv4`, gym_SBR_env4.py:71-1294): one `step` = one 72-s PID interval, the
+    FILL phase included (26 fill + 466 react steps, then one step that settles, draws and idles: 493 per episode).
+    action [N] or [N,1]: change of the DO set-point, accumulated into u and clipped to [0, 8] (:209-218).
+    reset() -> state [N,14] (flow-weighted mix of influent and reactor / x_1); step(a) -> (state [N,14] = x / x_1,
+    reward [N], done [N] bool, info) -- the standard Gym 4-tuple.  Every reset draws a scenario uniformly from the 8
+    influent scenarios per env (np.random.choice(8, 1), :104).
+
+    The reference's step() raises TypeError on numpy >= 1.18 (float `num` in np.linspace); parity is against the
+    unmodified source run with numpy < 1.18 linspace semantics (oracle/make_golden_v4.py)."""
+
+    num_actions = 1
+    max_episode_steps = 493
+
+    def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
+                 params=None, autoreset=False, rk4_sub_interval=0):
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _abi.SbrLibraryError("SbrV4VecEnv needs a CUDA device: there is no CPU fallback")
+        self.lib = _abi.load()
+        self.params = params if params is not None else _abi.default_params()
+        self.sched = schedule.os_schedule(rk4_sub_interval=rk4_sub_interval)
+        self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
+        self.tol = _abi.make_tol(rtol, atol, max_steps)
+        self.autoreset = bool(autoreset)
+        self._gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self._gen.manual_seed(int(seed))
+        n = self.num_envs
+        f = dict(dtype=torch.float64, device=self.device)
+        self.buf = core.V4Buffers(n, self.device)
+        self.influent = torch.zeros((_abi.NX, n), **f)          # influent_mixed with row 0 = 0.66
+        self.scenario = torch.zeros((n,), dtype=torch.int64, device=self.device)
+        self._loading = torch.zeros((_abi.NX, n), **f)          # ... with row 0 = the fill flow
+        self._action = torch.zeros((n,), **f)
+        self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_env4.py:193
+
+    def _draw_influent(self):
+        """Per env: scenario ~ U{0..7}, then one buffer_tank(scenario) draw (all eight mixes share the env's rnd)."""
+        n = self.num_envs
+        self.scenario = torch.randint(0, 8, (n,), device=self.device, generator=self._gen)
+        rnd = core.soa1(torch.randn((influent_mod.N_POINTS, n), dtype=torch.float64, device=self.device,
+                                    generator=self._gen))
+        out = torch.empty((_abi.NX, n), dtype=torch.float64, device=self.device)
+        for sw in range(8):
+            mix = core.influent_mix(sw, rnd)
+            sel = self.scenario == sw
+            out[:, sel] = mix[:, sel]
+        return out
+
+    def reset(self, influent=None, x0=None, mask=None):
+        if influent is None:
+            influent = self._draw_influent()
+        influent = influent.to(self.device, torch.float64)
+        if mask is None:
+            self.influent.copy_(influent)
+        else:
+            mask = mask.to(self.device).to(torch.uint8).contiguous()
+            self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
+        self._loading.copy_(self.influent)
+        self._loading[0] = self.fill_flow
+        if x0 is not None:
+            x0 = x0.to(self.device, torch.float64).contiguous()
+        core.v4_reset(self.buf, self._loading, self.params, x0=x0, mask=mask)
+        return self.buf.obs.t()
+
+    def step_async(self, action, stream=None):
+        action = action.reshape(-1)
+        if action.shape != (self.num_envs,):
+            raise ValueError("action must be [N] or [N,1], got %s" % (tuple(action.shape),))
+        self._action.copy_(action.to(self.device, torch.float64))
+        return core.v4_step(self.buf, self._loading, self._action, self.params, self.sched, mode=self.mode,
+                            tol=self.tol, stream=stream)
+
+    def step(self, action):
+        b = self.buf
+        restarted = None
+        if self.autoreset:
+            restarted = b.done.clone()
+            self.reset(mask=restarted)
+        self.step_async(action)
+        info = dict(status=b.status, counters=b.counters, t=b.st[_abi.V4_T], u=b.st[_abi.V4_U], Qw=b.st[_abi.V4_QW],
+                    episode_return=b.st[_abi.V4_RETURN], episode_steps=b.st[_abi.V4_STEPS], restarted=restarted)
+        return b.obs.t(), b.reward, b.done.bool(), info
+
+    def render(self, mode="human", close=False):
+        print("Reward for this step: {}".format(self.buf.reward))

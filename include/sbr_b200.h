@@ -123,6 +123,23 @@ typedef struct SbrOsSchedule {
     int32_t rk4_sub_idle;                /* RK4 sub-steps of the idle solve; 0 = int((t_cycle - t0)/dt) - 1    */
 } SbrOsSchedule;
 
+/* Rows of the persistent per-env state of the SBR-v4 env (st[r * ld + i]); the reference keeps these in module
+ * globals and growing lists (gym_SBR_env4.py:126-160, 205-222). */
+enum {
+    SBR_V4_X = 0,            /* rows 0..13: reactor state                                                      */
+    SBR_V4_T = 14,           /* running time `t` (days)                                                        */
+    SBR_V4_U,                /* DO set-point `u`, accumulated from the delta actions and clipped to [0, 8]      */
+    SBR_V4_SO_PREV,          /* So[-2] (So[-1] is x[8])                                                        */
+    SBR_V4_IE,               /* PID integral ie[-1]                                                            */
+    SBR_V4_KLA_LAST,         /* Kla[-1]                                                                        */
+    SBR_V4_KLA_SUM,          /* sum(Kla) over the episode (the terminal reward's aeration energy)              */
+    SBR_V4_H,                /* DP45 step-size proposal carried across intervals                               */
+    SBR_V4_RETURN,           /* sum of rewards since reset                                                     */
+    SBR_V4_STEPS,            /* env.step calls since reset                                                     */
+    SBR_V4_QW,               /* waste-sludge volume of the terminal draw; NaN before                           */
+    SBR_V4_ROWS
+};
+
 /* Adaptive-step controls (SBR_MODE_DP45). */
 typedef struct SbrTol {
     double rtol, atol;     /* mixed tolerance: err_i <= atol * scale_i + rtol * |x_i|          */
@@ -206,6 +223,28 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
 int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
                 const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+
+/*
+ * SBR-v4 (SbrEnv4, gym_SBR_env4.py:71-1294): interval-per-step env whose FILL phase is stepped inside step() too,
+ * with a 1-D action = change of the DO set-point.  NOTE: the reference's step() raises TypeError on numpy >= 1.18
+ * (float `num` in np.linspace, :286,921,982,1207); parity is against the unmodified source run with numpy < 1.18
+ * linspace semantics restored (oracle/make_golden_v4.py).
+ * sbr_v4_reset = SbrEnv4.reset (:94-198): no integration; state := x0 (NULL = x0_init), t := 0, and the reset
+ *   observation x_2 / x_1 with x_2 = flow-weighted mix of influent and reactor (:185-191).
+ *     influent [14][ld] in: row 0 = fill flow Qin / t_memory1[-1] (:193), rows 1..13 = influent concentrations
+ *     st [SBR_V4_ROWS][ld] out; obs [14][ld] out; done [n] out (cleared); mask [n] in (NULL = all)
+ * sbr_v4_step = SbrEnv4.step (:200-247) -> run_step (:250-358): u := clip(u + action, 0, 8); phase from the running
+ *   time (fill / react / settle+draw+idle); DO-PID with incremental bias (Sim_filling :497-534, Sim_rxn :667-707,
+ *   Sim_idle :1202-1242) -> one odeint interval; terminal step = Sim_Settling_Drawing (:919-1070) + Sim_idle; reward
+ *   module_reward_continuous.sbr_reward (module_reward_continuous.py:4-65); obs = x / x_1 (:236).
+ *     action [n] in; influent [14][ld] in (read during the fill phase only); the schedule is the SbrOsSchedule of the
+ *     SBROS-v1 path (same module_batch_time marks; t_fill doubles as t_memory1[-1])
+ */
+int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                 const SbrParams* p, double* st, double* obs, uint8_t* done, void* stream);
+int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
+                const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
+                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
 
 /*
  * Influent generator, the step before the path = buffer_tank3.influent.buffer_tank (buffer_tank3.py:18-108): per env

@@ -558,3 +558,129 @@ class SbrOsOracle(object):
             self.idle_pts = len(t_idle)
             o_do, o_ec, state = _obs_os(self.t, self.x, x_react_end, self.x)
         return (o_do, o_ec), state, reward, done
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SBR-v4 (SbrEnv4): interval-per-step env with the FILL phase stepped inside step(), 1-D delta-set-point action
+# ----------------------------------------------------------------------------------------------------------
+X1_V4 = np.array([1.32000000e+00, 3.00000000e+01, 3.81606587e+01, 6.94658685e+02, 1.07772100e+02, 1.22613841e+03,
+                  7.88460027e+01, 2.57616136e+02, 1.01108024e+00, 6.24510635e+00, 1.78877937e+01, 3.95743344e+00,
+                  5.70432163e+00, 5.50185509e+00])                                   # gym_SBR_env4.py:91
+V4_PID = dict(Kc=5, tauI=0.00035, tauD=0.005, lo=0, hi=240)                           # gym_SBR_env4.py:61-69
+
+
+def reward_v4(kla_list, batch_type, Qin, Qw, eff, so_sat=SO_SAT):
+    """module_reward_continuous.sbr_reward (module_reward_continuous.py:4-65)."""
+    t_delta = 0.002 / 24
+    r_snh = 0
+    if batch_type == 0:
+        PE = 0.004 * Qin
+        AE_dT = 1.32 * kla_list[-1] * t_delta
+    elif batch_type == 1:
+        AE_dT = 1.32 * kla_list[-1] * t_delta
+        PE = 0
+    else:
+        PE = 0.05 * Qw + 0.004 * eff[0]
+        AE_dT = 1.32 * sum(kla_list) * t_delta
+        r_snh = 0 if eff[3] < 4 else -246
+    AE = so_sat / (1.8 * 1000) * AE_dT
+    return (0.5 - (AE + PE)) + r_snh
+
+
+class SbrEnv4Oracle(object):
+    """Restatement of the reference's SbrEnv4 (gym_SBR_env4.py:71-1294), run with numpy < 1.18 linspace semantics
+    (float `num` truncated with int(); see oracle/make_golden_v4.py for the disclosure).
+    reset(influent_mixed) -> state[14]; step(action) -> (state[14], reward, done)."""
+
+    def __init__(self, ode_kw=None):
+        self.ode_kw = ode_kw or {}
+        self.marks = batch_time_marks()
+
+    def reset(self, influent_mixed, x0=X0_INIT):
+        self.infl = list(influent_mixed)
+        self.x0 = np.array(x0, dtype=float)
+        self.t = 0
+        self.batch_type = 0
+        self.dcv, self.ie, self.e, self.So, self.Kla = [], [], [], [], []
+        x_2 = np.zeros(14)
+        x_2[0] = QIN + IV
+        for i in range(1, 14):
+            x_2[i] = (QIN * self.infl[i] + self.x0[i] * IV) / (QIN + IV)               # :185-190
+        self.infl[0] = QIN / self.marks[0][1]                                          # :193
+        self.x = self.x0
+        self.Qw = 0
+        self.eff = []
+        return x_2 / X1_V4
+
+    def _pid(self, sp, t_start):
+        """Sim_filling / Sim_rxn / Sim_idle controller block (gym_SBR_env4.py:497-524, 667-697, 1202-1234):
+        incremental bias Kla[-1], PID dt = 0.002/24, two independent clamp checks with anti-windup."""
+        P = V4_PID
+        self.e.append(sp - self.So[-1])
+        if t_start > 0:
+            self.dcv.append((self.So[-1] - self.So[-2]) / OS_DT)
+            self.ie.append(self.ie[-1] + self.e[-1] * OS_DT)
+        else:
+            self.dcv.append(0)
+            self.ie.append(0)
+        kla = P['Kc'] * self.e[-1] + P['Kc'] / P['tauI'] * self.ie[-1] + P['Kc'] * P['tauD'] * self.dcv[-1] + self.Kla[-1]
+        self.Kla.append(kla)
+        if self.Kla[-1] > P['hi']:
+            self.Kla[-1] = P['hi']
+            self.ie[-1] = self.ie[-1] - self.e[-1] * OS_DT
+        if self.Kla[-1] < P['lo']:
+            self.Kla[-1] = P['lo']
+            self.ie[-1] = self.ie[-1] - self.e[-1] * OS_DT
+        return self.Kla[-1]
+
+    def step(self, action):
+        m = self.marks
+        if self.t == 0:
+            self.u = 0
+        self.u = self.u + action
+        self.u = 0 if self.u < 0 else (8 if self.u > 8 else self.u)                    # :213-218
+        x_in = self.x0 if self.t == 0 else self.x
+        t = self.t
+        if m[0][0] <= t < m[0][1]:
+            bt = 0
+        elif t < m[4][1]:
+            bt = 1
+        else:
+            bt = 2
+        if t == 0:
+            self.So.append(x_in[8])
+            self.Kla.append(0)
+        t_start, t_end = t, t + OS_T_DELTA
+        t_range = np.linspace(t_start, t_end, int((t_end - t_start) / OS_DT))
+        self.n_pts = len(t_range)
+        if bt == 0:
+            kla = self._pid(self.u, t_range[0])
+            x_out = odeint(rhs_fill, x_in, t_range, args=(kla, self.infl), **self.ode_kw)
+            self.So.append(x_out[-1][8])
+            self.Qw, self.eff = 0, []
+        elif bt == 1:
+            kla = self._pid(self.u, t_range[0])
+            x_out = odeint(rhs_react, x_in, t_range, args=(kla,), **self.ode_kw)
+            self.So.append(x_out[-1][8])
+            self.Qw, self.eff = 0, []
+        else:
+            # Sim_Settling_Drawing (:919-1070; called with dt := t_delta) then Sim_idle (:1202-1242)
+            t_set = np.linspace(t, t + T_RATIO[5] * T_CYCLE, int((T_RATIO[5] * T_CYCLE) / OS_T_DELTA))
+            Xf = 0.75 * (x_in[3] + x_in[4] + x_in[5] + x_in[6] + x_in[7])
+            z = x_in[0] / ((1.25 / 2) ** 2)
+            sX = odeint(settler_rhs, [Xf] * 10, t_set, args=(z, Xf), **self.ode_kw)[-1]
+            x_n, self.Qw, _, self.eff, self.draw_status = draw(x_in, sX, Xf)
+            t_draw = np.linspace(t_set[-1], t_set[-1] + T_RATIO[6] * T_CYCLE, int((T_RATIO[6] * T_CYCLE) / OS_T_DELTA))
+            self.So += [x_in[8]] * len(t_set) + [x_n[8]] * (len(t_draw) - 1)
+            t_idle = np.linspace(t_draw[-1], T_CYCLE, int((T_CYCLE - t_draw[-1]) / OS_DT))
+            kla = self._pid(self.u, t_draw[-1])
+            x_out = odeint(rhs_react, x_n, t_idle, args=(kla,), **self.ode_kw)
+            self.So.append(x_out[-1][8])
+            self.idle_pts = len(t_idle)
+            t_end = float(t_idle[-1])
+        self.t = t_end
+        self.batch_type = bt
+        self.x = x_out[-1]
+        reward = reward_v4(self.Kla, bt, QIN, self.Qw, self.eff)
+        done = (bt == 2) and (self.t >= T_CYCLE)
+        return self.x / X1_V4, reward, done

@@ -141,3 +141,42 @@ class OsBatch(object):
                               C.c_int(self.mode), C.byref(self.tol))
         assert rc == 0
         return self.obs_do.copy(), self.obs_ec.copy(), self.state.copy(), self.reward.copy(), self.done.copy()
+
+
+class V4Batch(object):
+    """Host-memory twin of the SBR-v4 path: same buffers and call sequence as sbr_v4_reset / sbr_v4_step."""
+
+    def __init__(self, n, params=None, sched=None, mode=0, tol=None):
+        from gym_sbr2_b200 import schedule
+        self.n = n
+        self.params = params or default_params()
+        self.sched = sched or schedule.os_schedule()
+        self.mode = mode
+        self.tol = tol or _abi.make_tol()
+        self.st = np.zeros((_abi.V4_ROWS, n))
+        self.obs = np.zeros((14, n)); self.reward = np.zeros(n); self.done = np.ones(n, dtype=np.uint8)
+        self.status = np.zeros(n, dtype=np.int32); self.counters = np.zeros((2, n), dtype=np.uint32)
+        self.influent = np.zeros((14, n))
+
+    def reset(self, influent, x0=None, mask=None):
+        lib = load()
+        self.influent = np.ascontiguousarray(influent, dtype=np.float64)
+        x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        n = self.n
+        rc = lib.twin_v4_reset(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(self.influent), _ptr(mask),
+                               C.byref(self.params), _ptr(self.st), _ptr(self.obs), _ptr(self.done))
+        assert rc == 0
+        return self.obs.copy()
+
+    def step(self, action):
+        lib = load()
+        action = np.ascontiguousarray(action, dtype=np.float64).reshape(-1)
+        n = self.n
+        assert action.shape == (n,)
+        rc = lib.twin_v4_step(C.c_int64(n), C.c_int64(n), _ptr(self.st), _ptr(self.influent), _ptr(action),
+                              C.byref(self.params), C.byref(self.sched), _ptr(self.obs), _ptr(self.reward),
+                              _ptr(self.done), _ptr(self.status), _ptr(self.counters), C.c_int(self.mode),
+                              C.byref(self.tol))
+        assert rc == 0
+        return self.obs.copy(), self.reward.copy(), self.done.copy()

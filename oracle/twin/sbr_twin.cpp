@@ -187,4 +187,61 @@ int twin_os_step(int64_t n, int64_t ld, double* st, const double* action, const 
     return 0;
 }
 
+int twin_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
+                  const SbrParams* p, double* st, double* obs, uint8_t* done) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && mask[i] == 0) continue;
+        double x[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) { x[k] = x0 ? x0[k * ld + i] : kX0Init[k]; st[k * ld + i] = x[k]; }
+        const Loading load{influent + i, (int)ld};
+        v4_reset_obs(x, load, *p, Column{obs + i, ld});
+        for (int r = SBR_V4_T; r < SBR_V4_ROWS; ++r) st[r * ld + i] = 0.0;
+        st[SBR_V4_QW * ld + i] = NAN;
+        done[i] = 0;
+    }
+    return 0;
+}
+
+int twin_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
+                 const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
+                 int32_t* status, uint32_t* counters, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        double x[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) x[k] = st[k * ld + i];
+        const Column ob{obs + i, ld};
+        if (done[i]) {
+            for (int k = 0; k < SBR_NX; ++k) ob.set(k, x[k] * inv_x1_v4(k));
+            reward[i] = 0.0;
+            if (status) status[i] = SBR_ST_DONE;
+            if (counters) { counters[i] = 0; counters[ld + i] = 0; }
+            continue;
+        }
+        V4Ctrl ctl;
+        ctl.t = st[SBR_V4_T * ld + i]; ctl.u = st[SBR_V4_U * ld + i]; ctl.so_prev = st[SBR_V4_SO_PREV * ld + i];
+        ctl.ie = st[SBR_V4_IE * ld + i]; ctl.kla_last = st[SBR_V4_KLA_LAST * ld + i];
+        ctl.kla_sum = st[SBR_V4_KLA_SUM * ld + i];
+        Dp45State dp;
+        dp.h = st[SBR_V4_H * ld + i];
+        if (!(dp.h > 0.0)) dp.h = s->t_delta / 9.0;
+        dp.n_rhs = 0; dp.n_rej = 0;
+        const Loading load{influent + i, (int)ld};
+        V4Out o;
+        if (mode == SBR_MODE_RK4) v4_step_env<SBR_MODE_RK4>(x, ctl, action[i], load, *p, c, *s, t, dp, ob, o);
+        else v4_step_env<SBR_MODE_DP45>(x, ctl, action[i], load, *p, c, *s, t, dp, ob, o);
+        for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
+        st[SBR_V4_T * ld + i] = ctl.t; st[SBR_V4_U * ld + i] = ctl.u; st[SBR_V4_SO_PREV * ld + i] = ctl.so_prev;
+        st[SBR_V4_IE * ld + i] = ctl.ie; st[SBR_V4_KLA_LAST * ld + i] = ctl.kla_last;
+        st[SBR_V4_KLA_SUM * ld + i] = ctl.kla_sum; st[SBR_V4_H * ld + i] = dp.h;
+        st[SBR_V4_RETURN * ld + i] += o.reward; st[SBR_V4_STEPS * ld + i] += 1.0;
+        if (o.done) { st[SBR_V4_QW * ld + i] = o.Qw; done[i] = 1; }
+        reward[i] = o.reward;
+        if (status) status[i] = o.status;
+        if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,91 @@
+"""GPU parity tests of the SBR-v4 path (sbr_v4_reset / sbr_v4_step through the C ABI): whole episodes of the
+reference `SbrEnv4` (numpy < 1.18 linspace semantics, see test_oracle_golden_v4.py), every env of a 4096 batch against
+the g++ twin, and the vector-env API."""
+import numpy as np
+import pytest
+import torch
+
+from gym_sbr2_b200 import _abi, core, schedule
+from gym_sbr2_b200.vec_env import SbrV4VecEnv
+from oracle.twin import binding as twin
+from test_oracle_golden_v4 import V4_EPISODES, load_v4
+from test_twin_parity_v4 import check_v4, run_v4
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuV4Batch(object):
+    """numpy-in / numpy-out adapter over the CUDA entry points with the interface of oracle.twin.binding.V4Batch."""
+
+    def __init__(self, n, device, mode=_abi.MODE_DP45):
+        self.n, self.device, self.mode = n, device, mode
+        self.params, self.sched, self.tol = _abi.default_params(), schedule.os_schedule(), _abi.make_tol()
+        self.buf = core.V4Buffers(n, device)
+
+    def _dev(self, a, dtype=torch.float64):
+        return None if a is None else core.soa1(torch.as_tensor(np.ascontiguousarray(a)).to(self.device, dtype))
+
+    def _sync(self):
+        torch.cuda.synchronize()
+        b = self.buf
+        self.st, self.status = b.st.cpu().numpy(), b.status.cpu().numpy()
+        self.counters, self.done = b.counters.cpu().numpy().astype(np.uint32), b.done.cpu().numpy()
+
+    def reset(self, influent, x0=None, mask=None):
+        self.influent = self._dev(influent)
+        core.v4_reset(self.buf, self.influent, self.params, x0=self._dev(x0), mask=self._dev(mask, torch.uint8))
+        self._sync()
+        return self.buf.obs.cpu().numpy()
+
+    def step(self, action):
+        a = torch.as_tensor(np.ascontiguousarray(action, dtype=np.float64).reshape(-1)).to(self.device)
+        b = core.v4_step(self.buf, self.influent, a, self.params, self.sched, mode=self.mode, tol=self.tol)
+        self._sync()
+        return b.obs.cpu().numpy(), b.reward.cpu().numpy(), self.done.copy()
+
+
+def test_dp45_episodes_match_reference(built, cuda_device):
+    G, b, ob0, rec = run_v4(lambda n: GpuV4Batch(n, cuda_device), V4_EPISODES)
+    check_v4(G, b, ob0, rec, V4_EPISODES)
+
+
+@pytest.mark.parametrize("mode,tol", [(_abi.MODE_RK4, 1e-9), (_abi.MODE_DP45, 2e-6)])
+def test_4096_envs_every_env_against_cpu_twin(built, cuda_device, mode, tol):
+    """4096 envs, per-env scenario and influent, random delta actions, 60 steps across the fill -> react switch."""
+    from gym_sbr2_b200 import influent
+    n = 4096
+    rng = np.random.RandomState(31)
+    infl = np.stack([influent.mix_numpy(rng.randint(8), rng.randn(48)) for _ in range(128)], axis=1)
+    infl = np.tile(infl, (1, n // 128)).copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    g, c = GpuV4Batch(n, cuda_device, mode=mode), twin.V4Batch(n, mode=mode)
+    og, oc = g.reset(infl), c.reset(infl)
+    assert np.array_equal(og, oc) or np.allclose(og, oc, rtol=1e-15, atol=0)
+    for k in range(60):
+        act = rng.uniform(-1, 1, n) * (0.3 if k > 5 else 1.0)
+        (sg, rg, dg), (sc, rc, dc) = g.step(act), c.step(act)
+        assert np.array_equal(dg, dc) and np.array_equal(g.status, c.status)
+        assert np.all(np.abs(sg - sc) <= tol * np.abs(sc) + tol * 1e-2), (k, np.abs(sg - sc).max())
+        assert np.allclose(rg, rc, rtol=max(tol, 1e-9) * 10, atol=1e-10), k
+        if mode == _abi.MODE_RK4:
+            assert np.array_equal(g.counters, c.counters)
+
+
+def test_vec_env_api_scenarios_autoreset(built, cuda_device):
+    n = 64
+    env = SbrV4VecEnv(n, device=cuda_device, seed=7)
+    obs = env.reset()
+    assert obs.shape == (n, 14) and bool(torch.isfinite(obs).all())
+    assert int(env.scenario.min()) >= 0 and int(env.scenario.max()) <= 7 and len(torch.unique(env.scenario)) > 3
+    assert float(obs[:, 0].min()) == 1.0 == float(obs[:, 0].max())          # (Qin + IV) / x_1[0] = 1.32 / 1.32
+    a = torch.full((n, 1), 0.05, dtype=torch.float64, device=cuda_device)
+    for k in range(493):
+        obs, reward, done, info = env.step(a if k < 60 else torch.zeros_like(a))
+        assert bool(done.all()) == (k == 492)
+    assert float(info["episode_steps"].min()) == 493 and float(info["u"].max()) <= 8.0
+    assert bool(torch.isfinite(info["Qw"]).all()) and int(info["status"].max()) == 0
+    obs2, reward, done, info = env.step(a)                                       # finished: no-op
+    assert torch.equal(obs2, obs) and float(reward.abs().max()) == 0.0
+    env.autoreset = True
+    obs3, reward, done, info = env.step(a)
+    assert not bool(done.any()) and float(info["episode_steps"].max()) == 1 and bool(info["restarted"].all())

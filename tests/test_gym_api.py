@@ -24,7 +24,7 @@ def test_all_ten_reference_ids_registered_under_reference_class_names():
 
 def test_unsupported_ids_name_the_reference_failure():
     for env_id in REF_IDS:
-        if env_id in ("SBR-v2", "SBROS-v1"):
+        if env_id in ("SBR-v2", "SBROS-v1", "SBR-v4"):
             continue
         with pytest.raises(sbr.UnsupportedEnvError) as e:
             sbr.make(env_id)
@@ -35,7 +35,7 @@ def test_supported_ids_fail_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
-    for env_id in ("SBR-v2", "SBROS-v1"):
+    for env_id in ("SBR-v2", "SBROS-v1", "SBR-v4"):
         with pytest.raises(_abi.SbrLibraryError):
             sbr.make(env_id)
 
@@ -97,3 +97,30 @@ def test_sbros_v1_episode_through_make(built, cuda_device):
         if done:
             break
     assert k == 463 and abs(total - (-0.878967)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_sbr_v4_episode_through_make(built, cuda_device):
+    """SBR-v4: standard 4-tuple, 14-dim obs = x / x_1, 493 steps per episode; same RNG consumption as the reference
+    (np.random.choice(8, 1) then the scenario's draws).  Reference run with numpy < 1.18 linspace semantics."""
+    from test_oracle_golden_v4 import load_v4
+    from test_twin_parity_v4 import V4_SO_SLACK, v4_state_close
+    g = load_v4("seed2_walk")
+    env = sbr.make("SBR-v4")
+    assert env.action_space.shape == (1,) and env.observation_space.shape == (14,)
+    np.random.seed(int(g["seed"]))
+    obs0 = env.reset()
+    assert obs0.shape == (1, 14) and np.allclose(obs0[0], g["reset_obs"], rtol=1e-13)
+    k = 0
+    while True:
+        out = env.step(g["action"][k])
+        assert len(out) == 4
+        obs, reward, done, info = out
+        assert obs.shape == (14,) and isinstance(done, bool) and info == {}
+        ok, worst = v4_state_close(obs, g["state"][k], so_slack=V4_SO_SLACK)
+        assert ok, (k, worst)
+        assert abs(reward - g["reward"][k]) <= 1e-5 * abs(g["reward"][k]) + 1e-9, k
+        k += 1
+        if done:
+            break
+    assert k == 493
