@@ -10,41 +10,50 @@ from . import dist
 
 
 class TinyPolicy(torch.nn.Module):
-    """obs_DO (9) ++ obs_EC (9) -> [DO set-point in (0.5, 7), NO3 set-point in (1, 14)] (float32 MLP, fixed seed)."""
+    """obs_DO (9) ++ obs_EC (9) -> [DO set-point in (0.5, 7), NO3 set-point in (1, 14)] (float32 MLP, fixed seed).
+    Works directly on the kernels' struct-of-arrays layout: input [18, N], output [2, N] -- no transposes."""
 
     def __init__(self, device, seed=0, hidden=32):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
-        self.w1 = (torch.randn(18, hidden, generator=g) * 0.3).to(device)
-        self.w2 = (torch.randn(hidden, 2, generator=g) * 0.3).to(device)
-        self.lo = torch.tensor([0.5, 1.0], device=device)
-        self.span = torch.tensor([6.5, 13.0], device=device)
+        self.w1t = (torch.randn(hidden, 18, generator=g) * 0.3).to(device)
+        self.w2t = (torch.randn(2, hidden, generator=g) * 0.3).to(device)
+        self.lo = torch.tensor([[0.5], [1.0]], device=device)
+        self.span = torch.tensor([[6.5], [13.0]], device=device)
 
     @torch.no_grad()
-    def forward(self, obs_do, obs_ec):
-        x = torch.cat([obs_do, obs_ec], dim=1).to(torch.float32)
-        y = torch.sigmoid(torch.tanh(x @ self.w1) @ self.w2)
+    def forward_soa(self, obs_do, obs_ec):
+        """obs_do, obs_ec: [9, N] float64 -> action [2, N] float64."""
+        x = torch.cat([obs_do, obs_ec], dim=0).to(torch.float32)
+        y = torch.sigmoid(self.w2t @ torch.tanh(self.w1t @ x))
         return (self.lo + self.span * y).to(torch.float64)
+
+    def forward(self, obs_do, obs_ec):
+        """Gym layout: obs [N, 9] each -> action [N, 2]."""
+        return self.forward_soa(obs_do.t(), obs_ec.t()).t()
 
 
 @torch.no_grad()
 def collect_episode(env, policy, max_steps=None, store=False):
-    """Run one SBROS-v1 episode for every env of `env` (a SbrOsVecEnv).  Returns dict(returns [N], steps, and, with
-    store=True, the [T,N] reward / done buffers a PPO update would consume)."""
-    obs_do, obs_ec = env.reset()
+    """Run one SBROS-v1 episode for every env of `env` (a SbrOsVecEnv), observations and actions staying in the
+    kernels' SoA layout.  Returns dict(returns [N], steps, and, with store=True, the [T,N] reward / done buffers a
+    PPO update would consume)."""
+    env.reset()
+    b = env.buf
     n = env.num_envs
     steps = max_steps or env.max_episode_steps
     rewards = torch.empty((steps, n), dtype=torch.float64, device=env.device) if store else None
     dones = torch.empty((steps, n), dtype=torch.bool, device=env.device) if store else None
     k = 0
     for k in range(steps):
-        action = policy(obs_do, obs_ec)
-        (obs_do, obs_ec), state, reward, done, info = env.step(action)
+        action = policy.forward_soa(b.obs_do, b.obs_ec)
+        env.step_soa(action.contiguous())
         if store:
-            rewards[k].copy_(reward)
-            dones[k].copy_(done)
-    return dict(returns=info["episode_return"].clone(), steps=k + 1, rewards=rewards, dones=dones,
-                all_done=done.all(), status=info["status"])
+            rewards[k].copy_(b.reward)
+            dones[k].copy_(b.done)
+    from . import _abi
+    return dict(returns=b.st[_abi.OS_RETURN].clone(), steps=k + 1, rewards=rewards, dones=dones,
+                all_done=b.done.bool().all(), status=b.status)
 
 
 def return_stats(allr):

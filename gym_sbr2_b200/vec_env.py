@@ -183,6 +183,15 @@ class SbrOsVecEnv(object):
         return core.os_step(self.buf, self._action, self.params, self.sched, mode=self.mode, tol=self.tol,
                             stream=stream)
 
+    def step_soa(self, action_soa, stream=None):
+        """Zero-copy variant for device-side policies: action_soa is the kernel's own layout [2,N] (float64, CUDA,
+        contiguous) and the observations are read from self.buf.obs_do / obs_ec / state ([9,N], [9,N], [15,N]),
+        reward from self.buf.reward, done from self.buf.done -- no transposes on either side of the launch."""
+        if action_soa.shape != (2, self.num_envs):
+            raise ValueError("action_soa must be [2,N], got %s" % (tuple(action_soa.shape),))
+        return core.os_step(self.buf, action_soa, self.params, self.sched, mode=self.mode, tol=self.tol,
+                            stream=stream)
+
     def step(self, action):
         b = self.buf
         restarted = None
