@@ -276,6 +276,33 @@ def rollout_leg(torch, tdist, device, rank, world, args):
             "scaling": "strong", "collective": "all_gather of per-env returns (%d B per rank)" % ((hi - lo) * 8)}
 
 
+def cycle_substeps_leg(torch, device, core, env, n, substeps):
+    """The headline batch with fewer RK4 sub-steps per PID interval than the reference's output grid (the grid is
+    a convention of the reference's trajectory logging, not of its integrator; accuracy table in
+    gym_sbr2_b200/schedule.py).  NOT the headline: reported beside it."""
+    from gym_sbr2_b200 import _abi, schedule
+    sched = schedule.cycle_schedule(substeps=substeps)
+    ref_x = env._out.x_last.clone()
+    core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=_abi.MODE_RK4)
+    torch.cuda.synchronize()
+    ref_x = env._out.x_last.clone()
+    core.cycle_v2(env.x0, env._loading, env._action, env.params, sched, out=env._out, mode=_abi.MODE_RK4)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    o = core.cycle_v2(env.x0, env._loading, env._action, env.params, sched, out=env._out, mode=_abi.MODE_RK4)
+    eb.record()
+    torch.cuda.synchronize()
+    ms = ea.elapsed_time(eb)
+    scale = torch.tensor([1.32, 30, 30, 1500, 150, 3000, 2000, 600, 8, 20, 20, 10, 10, 10], dtype=torch.float64,
+                         device=device)[:, None]
+    w = ((o.x_last - ref_x).abs() / (1e-5 * ref_x.abs() + 1e-9 * scale)).max(dim=0).values
+    return {"substeps": substeps, "kernel_ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
+            "vs_reference_grid_in_tolerance_units": {"median": float(w.median()),
+                                                     "p999": float(torch.quantile(w[:1 << 18], 0.999)),
+                                                     "frac_above_1": float((w > 1).double().mean())}}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port of the scipy-odeint
     path, all host cores), same metric/unit/config.  Under torchrun only rank 0 works."""
@@ -476,6 +503,7 @@ def main():
         paths["sbros_v1"] = interval_path_leg(torch, device, args, peak_burst, peak_sustained)
         if args.mode == "rk4":
             paths["sbr_v2_dp45"] = cycle_dp45_leg(torch, device, core, env, n)
+            paths["sbr_v2_rk4_7substeps"] = cycle_substeps_leg(torch, device, core, env, n, 7)
     if rank == 0 and world == 1 and not args.no_interval_path:
         paths["sbr_v4"] = v4_path_leg(torch, device, args)
     if not args.no_rollout:

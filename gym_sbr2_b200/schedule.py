@@ -35,8 +35,15 @@ def pid_grid(t_start, t_end, t_delta=T_DELTA):
     return t_save2, pts
 
 
-def cycle_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
-    """SbrSchedule for the cycle-per-step path (SBR-v2)."""
+def cycle_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA, substeps=None):
+    """SbrSchedule for the cycle-per-step path (SBR-v2).
+
+    substeps: RK4 sub-steps per PID interval.  None (default) = the reference's own output grid (9, phase 5: 10) --
+    the reference's LSODA does not step on that grid, it only interpolates onto it, so this is a convention, not a
+    requirement.  Measured on 4096 random envs against RK4 with 40 sub-steps, in units of the parity tolerance
+    (rtol 1e-5): reference grid median 0.004 / 99.9 % 0.056; 8 sub-steps 0.009 / 0.098; 7 sub-steps 0.015 / 0.17
+    (-22 % work); 5 in the anoxic phases only 0.005 / 0.41; 4 anywhere breaks the tolerance.  The reference's own
+    default-tolerance LSODA sits ~0.26 units from the converged solution."""
     s = _abi.SbrSchedule()
     bounds = phase_bounds(t_cycle, t_ratio, t_delta)
     for k in range(8):
@@ -51,7 +58,7 @@ def cycle_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
         if len(set(pts)) != 1:
             raise ValueError("phase %d: output points per interval are not uniform: %s" % (k + 1, sorted(set(pts))))
         s.n_int[k] = n_int
-        s.n_sub[k] = pts[0] - 1                    # RK4 sub-steps = gaps between the reference's output points
+        s.n_sub[k] = pts[0] - 1 if substeps is None else int(substeps)   # default: gaps between the reference's output points
         s.interval[k] = (t1 - t0) / n_int
     # the settler integrates over linspace(t0, t1, int((t1-t0)/t_delta)) -> total span t1 - t0
     s.settle_time = bounds[5][1] - bounds[5][0]

@@ -35,14 +35,14 @@ class SbrV2VecEnv(object):
     scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="torch"):
+                 params=None, rng="torch", substeps=None):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _abi.SbrLibraryError("SbrV2VecEnv needs a CUDA device: there is no CPU fallback")
         self.lib = _abi.load()
         self.params = params if params is not None else _abi.default_params()
-        self.sched = schedule.cycle_schedule()
+        self.sched = schedule.cycle_schedule(substeps=substeps)     # RK4 sub-steps per interval (None = reference grid)
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
         self.tol = _abi.make_tol(rtol, atol, max_steps)
         self.rng = rng
