@@ -193,23 +193,37 @@ def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
 
 
 def cycle_dp45_leg(torch, device, core, env, n):
-    """The same SBR-v2 batch through the adaptive Dormand-Prince mode (per-env step control)."""
+    """The same SBR-v2 batch through the adaptive Dormand-Prince mode (per-env step control): in the caller's env
+    order (random set-points side by side in a warp: the divergence case) and with the divergence-aware ordering
+    the vector env applies in this mode (envs assigned to warps by argsort of the first set-point; the argsort is
+    inside the timed region)."""
     from gym_sbr2_b200 import _abi
-    tol = _abi.make_tol(1e-7, 1e-9, 4000)
     res = {}
-    core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=_abi.MODE_DP45, tol=tol)
-    torch.cuda.synchronize()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    o = core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=_abi.MODE_DP45,
-                      tol=tol)
-    eb.record()
-    torch.cuda.synchronize()
-    ms = ea.elapsed_time(eb)
-    cnt = o.counters.to(torch.float64)
-    res = {"rtol": 1e-7, "atol": 1e-9, "kernel_ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
-           "rhs_per_env_mean": float(cnt[0].mean()), "rhs_per_env_max": float(cnt[0].max()),
-           "rejected_per_env_mean": float(cnt[1].mean()), "bad_status": int((o.status != 0).sum())}
+    for rtol, atol in ((1e-7, 1e-9), (1e-6, 1e-8)):
+        tol = _abi.make_tol(rtol, atol)
+        for ordered in (False, True):
+            def launch():
+                perm = torch.argsort(env._action[0]) if ordered else None
+                return core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out,
+                                     mode=_abi.MODE_DP45, tol=tol, perm=perm)
+            launch()
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            o = launch()
+            eb.record()
+            torch.cuda.synchronize()
+            ms = ea.elapsed_time(eb)
+            cnt = o.counters.to(torch.float64)
+            rhs = float(cnt[0].mean())
+            steps = (rhs - 528) / 6.0
+            flops = rhs * F_REACT + steps * (2 * 9 * 15 + 2 * 9 * 5 + 2 * 9 * 6 + 5 * 9) + F_EPILOGUE
+            res["rtol%g_%s" % (rtol, "ordered" if ordered else "env_order")] = {
+                "rtol": rtol, "atol": atol, "ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
+                "rhs_per_env_mean": rhs, "rhs_per_env_max": float(cnt[0].max()),
+                "warp_max_rhs_mean": float(cnt[0].view(-1, 32).max(dim=1).values.mean()) if not ordered else None,
+                "rejected_per_env_mean": float(cnt[1].mean()), "bad_status": int((o.status != 0).sum()),
+                "fp64_tflops": n * flops / (ms * 1e-3) / 1e12}
     return res
 
 

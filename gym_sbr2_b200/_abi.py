@@ -14,7 +14,7 @@ ST_NONFINITE, ST_WASTE, ST_STEPLIMIT, ST_LAYERS, ST_DONE = 1, 2, 4, 8, 16
 AUX_ROWS = 12
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 2
+ABI_VERSION = 3
 # rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
 OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
@@ -75,7 +75,7 @@ _PROTOS = {
     "sbr_device_count": (C.c_int, []),
     "sbr_params_default": (None, [C.POINTER(SbrParams)]),
     "sbr_cycle_v2": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrSchedule),
-                               _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+                               _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_integrate_interval": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int,
                                          C.c_double, C.c_int, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_rhs": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int, _P, _P]),

@@ -58,8 +58,9 @@ class CycleV2Out(object):
         self.counters = torch.empty((2, n), dtype=torch.int32, device=device)
 
 
-def cycle_v2(x0, influent, action, params, sched, out=None, mode=_abi.MODE_RK4, tol=None, stream=None):
-    """One whole cycle for a batch (SbrEnv2.step, gym_SBR_env2.py:131-171).  x0, influent [14,n]; action [3,n]."""
+def cycle_v2(x0, influent, action, params, sched, out=None, mode=_abi.MODE_RK4, tol=None, stream=None, perm=None):
+    """One whole cycle for a batch (SbrEnv2.step, gym_SBR_env2.py:131-171).  x0, influent [14,n]; action [3,n];
+    perm: optional int64 [n] permutation -- thread i works on env perm[i] (divergence-aware ordering for DP45)."""
     lib = _abi.load()
     n = x0.shape[1]
     if out is None:
@@ -75,9 +76,10 @@ def cycle_v2(x0, influent, action, params, sched, out=None, mode=_abi.MODE_RK4, 
     pct, l6 = _dev_ptr(out.counters, 2, n, dtype=torch.int32, name="counters")
     ld = _same_ld([l0, l1, l2, l3, l4, l5, l6], "cycle_v2")
     tol = tol or _abi.make_tol()
+    ppm, _ = _dev_ptr(perm, 1, n, dtype=torch.int64, name="perm")
     with torch.cuda.device(x0.device):
         rc = lib.sbr_cycle_v2(n, ld, px0, pin, pac, C.byref(params), C.byref(sched), pxl, pob, prw, pax, pst, pct,
-                              int(mode), C.byref(tol), _stream_ptr(stream))
+                              int(mode), C.byref(tol), ppm, _stream_ptr(stream))
     _abi.check(rc, "sbr_cycle_v2")
     return out
 

@@ -45,14 +45,19 @@ struct CycleArgs {
     double* aux;
     int32_t* status;
     uint32_t* counters;
+    const int64_t* perm;
 };
 
+#ifndef SBR_CYCLE_DP45_MINBLOCKS
+#define SBR_CYCLE_DP45_MINBLOCKS 1   // resident CTAs per SM the DP45 cycle kernel is compiled for
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
+__global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : 1) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
                                                               SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= g.n) return;
+    const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (slot >= g.n) return;
+    const int64_t i = g.perm ? g.perm[slot] : slot;      // divergence-aware ordering: see include/sbr_b200.h
     double x[SBR_NX], action[3];
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0[k * g.ld + i];
@@ -510,7 +515,8 @@ void sbr_params_default(SbrParams* p) {
 
 int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
                  const SbrParams* p, const SbrSchedule* s, double* x_last, double* obs, double* reward,
-                 double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+                 double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
+                 const int64_t* perm, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if (!x0 || !influent || !action || !s || !x_last || !obs || !reward)
@@ -521,7 +527,7 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
         if (s->n_int[k] < 1 || s->n_sub[k] < 1 || !(s->interval[k] > 0))
             return fail(SBR_ERR_ARG, "sbr_cycle_v2: schedule needs n_int, n_sub >= 1 and interval > 0%s");
     }
-    CycleArgs g{n, ld, x0, influent, action, x_last, obs, reward, aux, status, counters};
+    CycleArgs g{n, ld, x0, influent, action, x_last, obs, reward, aux, status, counters, perm};
     const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);

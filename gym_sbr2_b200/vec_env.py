@@ -35,7 +35,7 @@ class SbrV2VecEnv(object):
     scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="torch", substeps=None):
+                 params=None, rng="torch", substeps=None, order="auto"):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -46,6 +46,11 @@ class SbrV2VecEnv(object):
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
         self.tol = _abi.make_tol(rtol, atol, max_steps)
         self.rng = rng
+        # divergence-aware ordering: with adaptive steps, envs are assigned to warps in the order of their first DO
+        # set-point (one argsort per step, ~0.3 ms at 2^20 envs); results are unaffected, buffers keep env order
+        if order not in ("auto", "action", "none"):
+            raise ValueError("order must be 'auto', 'action' or 'none'")
+        self.order = ("action" if self.mode == _abi.MODE_DP45 else "none") if order == "auto" else order
         self._gen = torch.Generator(device=self.device)
         if seed is not None:
             self._gen.manual_seed(int(seed))
@@ -95,8 +100,9 @@ class SbrV2VecEnv(object):
         self._action.copy_(action.to(self.device, torch.float64).t())
         self._loading.copy_(self.influent)
         self._loading[0] = self.fill_flow
+        perm = torch.argsort(self._action[0]) if self.order == "action" and self.num_envs > 32 else None
         return core.cycle_v2(self.x0, self._loading, self._action, self.params, self.sched, out=self._out,
-                             mode=self.mode, tol=self.tol, stream=stream)
+                             mode=self.mode, tol=self.tol, stream=stream, perm=perm)
 
     def step(self, action):
         o = self.step_async(action)

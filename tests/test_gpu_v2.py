@@ -164,6 +164,29 @@ def test_ragged_sizes_strided_views_and_batch_invariance(built, cuda_device):
         assert torch.equal(out.reward, rw_full[lo:hi])
 
 
+@pytest.mark.parametrize("mode", [_abi.MODE_RK4, _abi.MODE_DP45])
+def test_env_ordering_does_not_change_results(built, cuda_device, mode):
+    """perm: thread i works on env perm[i] (divergence-aware ordering).  Every env's result is bit-identical to the
+    identity mapping, buffers keep the caller's env order; SbrV2VecEnv(order='action') sorts by the first set-point."""
+    n = 3000
+    x0, infl, act = _random_batch(n, 9, cuda_device)
+    p, s = _abi.default_params(), schedule.cycle_schedule()
+    X0, IN, AC = _dev(x0, cuda_device), _dev(infl, cuda_device), _dev(act, cuda_device)
+    base = core.cycle_v2(X0, IN, AC, p, s, mode=mode)
+    xl, rw, cn = base.x_last.clone(), base.reward.clone(), base.counters.clone()
+    for perm in (torch.argsort(AC[0]), torch.randperm(n, device=cuda_device), torch.arange(n - 1, -1, -1, device=cuda_device)):
+        out = core.cycle_v2(X0, IN, AC, p, s, mode=mode, perm=perm.to(torch.int64).contiguous())
+        assert torch.equal(out.x_last, xl) and torch.equal(out.reward, rw) and torch.equal(out.counters, cn)
+    env_a = SbrV2VecEnv(n, device=cuda_device, mode="dp45", order="action")
+    env_n = SbrV2VecEnv(n, device=cuda_device, mode="dp45", order="none")
+    assert env_a.order == "action" and SbrV2VecEnv(8, device=cuda_device, mode="rk4").order == "none"
+    infl_t = torch.as_tensor(infl).to(cuda_device)
+    env_a.reset(influent=infl_t); env_n.reset(influent=infl_t)
+    a = AC.t().contiguous()
+    ra, rn = env_a.step(a)[1].clone(), env_n.step(a)[1].clone()
+    assert torch.equal(ra, rn)
+
+
 def test_status_flags_and_error_returns(built, cuda_device):
     p, s = _abi.default_params(), schedule.cycle_schedule()
     x0, infl, act = _random_batch(64, 4, cuda_device)

@@ -104,13 +104,13 @@ def test_argument_errors_are_reported_without_gpu(built):
     p = _abi.default_params()
     s = schedule.cycle_schedule()
     rc = lib.sbr_cycle_v2(0, 0, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
-                          None, None)
+                          None, None, None)
     assert rc == -1 and b"n must be positive" in lib.sbr_last_error()
     rc = lib.sbr_cycle_v2(4, 2, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
-                          None, None)
+                          None, None, None)
     assert rc == -1 and b"ld" in lib.sbr_last_error()
     rc = lib.sbr_cycle_v2(4, 4, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, 0,
-                          None, None)
+                          None, None, None)
     assert rc == -1 and b"NULL" in lib.sbr_last_error()
     with pytest.raises(_abi.SbrLibraryError):
         _abi.check(rc, "sbr_cycle_v2")
