@@ -450,6 +450,11 @@ struct PidA {
     double Kc, Kc_tauI, Kc_tauD, dt, lo, hi;
 };
 
+// Clipping as the reference does it (np.clip / min(max(a, lo), hi) / if-elif chains): a NaN action is NOT
+// sanitised, it propagates into the state and ends up in status[i] (SBR_ST_NONFINITE), exactly as the reference's
+// outputs turn NaN; CUDA's fmin/fmax would silently turn it into a bound.
+SBR_HD double clip_keep_nan(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 SBR_HD PidA make_pid_a(const SbrParams& p) {
     PidA q;
     q.Kc = p.pid_Kc; q.Kc_tauI = p.pid_Kc / p.pid_tauI; q.Kc_tauD = p.pid_Kc * p.pid_tauD;
@@ -631,7 +636,7 @@ SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading loa
     const PidA pid = make_pid_a(p);
     double sp3[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sp3[j] = fmin(fmax(action[j], 0.0), 1.0) * p.action_scale;
+    for (int j = 0; j < 3; ++j) sp3[j] = clip_keep_nan(action[j], 0.0, 1.0) * p.action_scale;   // np.clip (:133)
     TailArgs a;
     a.kla = 0.0; a.q = q_fill; a.ec_conc = 0.0; a.load = load;
     int status = 0;
@@ -915,8 +920,8 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
                                         : (t > s.tm4_1);
             if (!cond) continue;
             const bool aerobic = (pass & 1) != 0;
-            u_do = aerobic ? fmin(fmax(a_do, 0.0), p.do_sp_max) : 0.0;                  // :862-870, 898-906
-            const double u_ec = aerobic ? 0.0 : fmin(fmax(a_ec, 0.0), p.no_sp_max);
+            u_do = aerobic ? clip_keep_nan(a_do, 0.0, p.do_sp_max) : 0.0;               // :862-870, 898-906
+            const double u_ec = aerobic ? 0.0 : clip_keep_nan(a_ec, 0.0, p.no_sp_max);
             // run_aero_step / run_anaero_step (:1331-1419)
             t_next = add_rn(t, s.t_delta);
             span = sub_rn(t_next, t);

@@ -145,3 +145,80 @@ def test_argument_errors_do_not_launch(built, cuda_device):
     s.fill_pts = 0
     with pytest.raises(_abi.SbrLibraryError):
         core.os_reset(buf, torch.zeros((14, 4), dtype=torch.float64, device=cuda_device), p, s)
+
+
+def test_full_size_properties_2p20(built, cuda_device):
+    """BASELINE full size (2^20 envs on one GPU), 56 env.steps across the anoxic -> aerobic switch: determinism,
+    batch-position invariance (the batch tiles 4096 distinct envs), agreement with the small batch, finite outputs."""
+    from gym_sbr2_b200 import influent
+    n, base = 1 << 20, 4096
+    rng = np.random.RandomState(41)
+    infl = np.stack([influent.mix_numpy(6, rng.randn(48)) for _ in range(64)], axis=1)
+    infl = np.tile(infl, (1, base // 64)).copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    acts = [np.stack([8 * rng.rand(base), 15 * rng.rand(base)]) for _ in range(56)]
+    rep = n // base
+    p, s, tol = _abi.default_params(), schedule.os_schedule(), _abi.make_tol()
+    dev = lambda a, r=1: torch.as_tensor(np.ascontiguousarray(np.tile(a, (1, r)))).to(cuda_device)
+
+    def run(r):
+        buf = core.OsBuffers(base * r, cuda_device)
+        core.os_reset(buf, dev(infl, r), p, s, mode=_abi.MODE_DP45, tol=tol)
+        for a in acts:
+            core.os_step(buf, dev(a, r), p, s, mode=_abi.MODE_DP45, tol=tol)
+        torch.cuda.synchronize()
+        return buf
+    big, small, again = run(rep), run(1), run(rep)
+    st = big.st.view(_abi.OS_ROWS, rep, base)
+    rows = [r for r in range(_abi.OS_ROWS) if r != _abi.OS_QW]                     # Qw is NaN until the episode ends
+    assert bool((st[rows] == st[rows][:, :1]).all())
+    assert torch.equal(big.st[rows][:, :base], small.st[rows]) and torch.equal(big.reward[:base], small.reward)
+    assert torch.equal(big.st[rows], again.st[rows]) and torch.equal(big.state, again.state)
+    assert bool(torch.isfinite(big.state).all()) and int(big.status.max()) == 0 and not bool(big.done.any())
+    assert float(big.st[_abi.OS_STEPS].min()) == 56 == float(big.st[_abi.OS_STEPS].max())
+
+
+def test_custom_start_state_against_oracle(built, cuda_device):
+    """reset(x0=...) with a perturbed start state: fill solve + 30 steps against the oracle with the same x0."""
+    from oracle import sbr_oracle as O
+    g = load_episode("seed2_walk")
+    rng = np.random.RandomState(6)
+    x0 = np.array(O.X0_INIT) * np.exp(0.05 * rng.randn(14))
+    x0[0] = O.X0_INIT[0]
+    b = GpuOsBatch(1, cuda_device)
+    od, oe = b.reset(g["influent"][:, None], x0=x0[:, None])
+    o = O.SbrOsOracle()
+    r_do, r_ec = o.reset(g["influent"], x0=x0)
+    assert np.allclose(od[:, 0], r_do, rtol=1e-5, atol=1e-7) and np.allclose(oe[:, 0], r_ec, rtol=1e-5, atol=1e-7)
+    for k in range(30):
+        o_do, o_ec, st, r, done = b.step(g["action"][k][:, None])
+        (_, _), r_st, r_r, _ = o.step(g["action"][k])
+        ok, worst = parity.os_close(st[:, 0], r_st)
+        assert ok, (k, worst)
+        assert abs(r[0] - r_r) <= 1e-5 * abs(r_r) + parity.OS_REWARD_ATOL, k
+
+
+def test_poisoned_actions_and_step_limit_are_flagged_not_fatal(built, cuda_device):
+    """NaN / absurd actions and a starved step budget: the launch terminates, the affected env is flagged in
+    `status`, its neighbours are untouched."""
+    g = load_episode("seed0_const")
+    n = 64
+    infl = np.tile(g["influent"][:, None], (1, n))
+    clean, dirty = GpuOsBatch(n, cuda_device), GpuOsBatch(n, cuda_device)
+    clean.reset(infl); dirty.reset(infl)
+    for k in range(60):
+        a = np.tile(g["action"][k][:, None], (1, n))
+        ref = clean.step(a)
+        a[0, 5] = np.nan if k == 55 else a[0, 5]              # NaN DO set-point once, in the aerobic phase
+        a[1, 9] = 1e300                                       # absurd NO3 set-point (clipped to 15 by the env)
+        out = dirty.step(a)
+    st = dirty.status
+    assert st[5] & _abi.ST_NONFINITE
+    keep = np.ones(n, dtype=bool); keep[[5, 9]] = False
+    assert (st[keep] == 0).all()
+    assert np.array_equal(out[2][:, keep], ref[2][:, keep]) and np.array_equal(out[3][keep], ref[3][keep])
+    assert np.isfinite(out[2][:, 9]).all()
+    starved = GpuOsBatch(4, cuda_device, tol=_abi.make_tol(1e-12, 1e-14, 1))
+    starved.reset(infl[:, :4])
+    starved.step(np.tile(g["action"][0][:, None], (1, 4)))
+    assert (starved.status & _abi.ST_STEPLIMIT).all()
