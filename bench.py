@@ -257,6 +257,48 @@ def v4_path_leg(torch, device, args):
             "gpu_launches": 494, "mean_episode_return": float(env.buf.st[_abi.V4_RETURN].mean())}
 
 
+def small_batch_leg(torch, device, n=4096):
+    """BASELINE config[1] size (4096 envs): one env.step is ~10 us of GPU work, so the Python loop and launches
+    dominate; reports the per-step WALL time of policy + step eagerly and through a CUDA graph (8 steps per replay),
+    and the SBR-v2 whole-cycle launch at this size (a single partial wave: latency-bound)."""
+    from gym_sbr2_b200 import rollout
+    from gym_sbr2_b200.vec_env import SbrOsVecEnv, SbrV2VecEnv
+    env = SbrOsVecEnv(n, device=device, seed=1, mode="dp45")
+    pol = rollout.TinyPolicy(device)
+    env.reset()
+    b = env.buf
+    for _ in range(5):
+        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+    torch.cuda.synchronize()
+    t_eager = (time.perf_counter() - t0) / 200
+    env.reset()
+    g8 = rollout.GraphedStepper(env, pol, 8)
+    env.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(25):
+        g8.replay()
+    torch.cuda.synchronize()
+    t_graph = (time.perf_counter() - t0) / 200
+    v2 = SbrV2VecEnv(n, device=device, seed=1)
+    v2.reset()
+    a3 = torch.rand((n, 3), dtype=torch.float64, device=device)
+    v2.step(a3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        v2.step(a3)
+    torch.cuda.synchronize()
+    t_cycle = (time.perf_counter() - t0) / 5
+    return {"envs": n, "sbros_v1_us_per_step_eager": t_eager * 1e6, "sbros_v1_us_per_step_cuda_graph": t_graph * 1e6,
+            "sbros_v1_interval_steps_per_sec_cuda_graph": n / t_graph,
+            "sbr_v2_ms_per_cycle_launch": t_cycle * 1e3, "sbr_v2_cycle_steps_per_sec": n / t_cycle}
+
+
 def rollout_leg(torch, tdist, device, rank, world, args):
     """BASELINE config 5: --rollout-envs SBROS-v1 envs in total, sharded over the ranks by contiguous index blocks,
     one full episode (reset + 463 env.steps) driven by a small torch policy on the observation tensors, then an
@@ -520,6 +562,8 @@ def main():
             paths["sbr_v2_rk4_7substeps"] = cycle_substeps_leg(torch, device, core, env, n, 7)
     if rank == 0 and world == 1 and not args.no_interval_path:
         paths["sbr_v4"] = v4_path_leg(torch, device, args)
+    if rank == 0 and world == 1 and not args.no_interval_path:
+        paths["config1_small_batch"] = small_batch_leg(torch, device)
     if not args.no_rollout:
         # every rank takes part: envs sharded over the ranks, NCCL gather of the episode returns
         paths["config5_rollout"] = rollout_leg(torch, tdist, device, rank, world, args)

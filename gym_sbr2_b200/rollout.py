@@ -56,6 +56,52 @@ def collect_episode(env, policy, max_steps=None, store=False):
                 all_done=b.done.bool().all(), status=b.status)
 
 
+class GraphedStepper(object):
+    """CUDA-graph version of the rollout inner loop for the launch-bound regime (BASELINE config[1]: 4096 envs, where
+    one env.step is ~10 us of GPU work behind ~160 us of Python + launches): `steps_per_replay` iterations of
+    [policy on the SoA observation buffers -> action, sbr_os_step] are captured once on the env's static buffers
+    and replayed with a single launch.  The C ABI launches on the stream it is given (torch's current stream), so
+    capture needs nothing special.  Episode ends are not handled inside the graph: replay whole episodes
+    (463 = 57 x 8 + 7 steps) and reset between them, or use steps_per_replay=1."""
+
+    def __init__(self, env, policy, steps_per_replay=8, warmup=3):
+        self.env, self.policy, self.k = env, policy, int(steps_per_replay)
+        self.action = torch.zeros((2, env.num_envs), dtype=torch.float64, device=env.device)
+        b = env.buf
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self._one(b)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            for _ in range(self.k):
+                self._one(b)
+
+    def _one(self, b):
+        self.action.copy_(self.policy.forward_soa(b.obs_do, b.obs_ec))
+        self.env.step_soa(self.action)
+
+    def replay(self):
+        """Advance every env by steps_per_replay env.steps."""
+        self.graph.replay()
+
+
+@torch.no_grad()
+def collect_episode_graphed(env, big, small):
+    """One whole episode through two captured graphs (`big`: k steps per replay, `small`: 1 step per replay)."""
+    env.reset()
+    steps = env.max_episode_steps
+    for _ in range(steps // big.k):
+        big.replay()
+    for _ in range(steps % big.k):
+        small.replay()
+    from . import _abi
+    b = env.buf
+    return dict(returns=b.st[_abi.OS_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status)
+
+
 def return_stats(allr):
     ok = torch.isfinite(allr)
     r = allr[ok]

@@ -60,3 +60,19 @@ def test_rollout_collects_full_episodes(built, cuda_device):
     allr, stats = rollout.gather_episode_returns(ep["returns"], n)           # world size 1: identity
     assert torch.equal(allr, ep["returns"]) and stats["count"] == n
     assert int(ep["status"].max()) == 0
+
+
+def test_graphed_rollout_matches_eager(built, cuda_device):
+    """The CUDA-graph inner loop (policy + step captured, 8 steps per replay) reproduces the eager rollout bit for bit."""
+    n = 256
+    policy = rollout.TinyPolicy(cuda_device)
+    env_e = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45")
+    eager = rollout.collect_episode(env_e, policy)
+    env_g = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45")
+    env_g.reset()
+    big, small = rollout.GraphedStepper(env_g, policy, 8), rollout.GraphedStepper(env_g, policy, 1)
+    env_g._gen.manual_seed(5)                                    # same influent draw as the eager env's first reset
+    ep = rollout.collect_episode_graphed(env_g, big, small)
+    assert bool(ep["all_done"]) and ep["steps"] == 463
+    assert torch.equal(ep["returns"], eager["returns"])
+    assert torch.equal(env_g.buf.st[:14], env_e.buf.st[:14])
