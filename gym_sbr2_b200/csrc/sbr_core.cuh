@@ -280,6 +280,16 @@ struct Dp45State {
     uint32_t n_rej;    // rejected steps
 };
 
+// First-same-as-last across PID intervals.  The last stage of an interval is f(x_end); the next interval starts
+// from the same state with only KLa changed by the PID, and KLa enters the right-hand side linearly and only in
+// d(So)/dt -- so its first stage is the carried one plus (KLa_new - KLa_old)(So_sat - So) in the So component.
+// Valid inside one phase (same tail, same flow); saves one of ~13 RHS evaluations per interval.
+struct Fsal {
+    double k[SBR_NX];
+    double g, kla;
+    bool valid;
+};
+
 // Per-component absolute-tolerance scale: atol_i = atol * scale_i, scale from the reference's own
 // normalisation vector x_1_state (gym_SBR_oneshot.py:153) so that So ~ 1e-15 in anoxic phases does not
 // drive the step to zero.
@@ -293,7 +303,7 @@ SBR_HD constexpr double tol_scale(int i) {
 // Returns status bits (0 or SBR_ST_STEPLIMIT).  The error norm is the RMS over the 9 active components.
 template <int TAIL>
 SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coef& c, const TailArgs& a,
-                         const SbrTol& tol, Dp45State& st, double& xpq) {
+                         const SbrTol& tol, Dp45State& st, double& xpq, Fsal& fs) {
     // Butcher tableau (Dormand & Prince 1980)
     const double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
     const double a21 = 1.0 / 5;
@@ -312,8 +322,17 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
     int steps = 0;
 #pragma unroll
     for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
-    double g1 = stage<TAIL>(y, k1, 0.0, f, c, a);   // the PID changes KLa at every interval start: FSAL restarts
-    st.n_rhs += 1;
+    double g1;
+    if (fs.valid) {
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i)) k1[i] = fs.k[i];
+        k1[iSo] = fma(a.kla - fs.kla, c.so_sat - x[iSo], k1[iSo]);
+        g1 = fs.g;
+    } else {
+        g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
+        st.n_rhs += 1;
+    }
     while (t < T) {
         if (steps >= tol.max_steps) { status = SBR_ST_STEPLIMIT; break; }
         ++steps;
@@ -398,6 +417,11 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         else h = fmax(h, hs * (double)fac);
     }
     st.h = h;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i)
+        if (active(i)) fs.k[i] = k1[i];
+    fs.g = g1; fs.kla = a.kla;
+    fs.valid = (status == 0) && (t >= T) && (fabs(g1) < 1e300);
     return status;
 }
 
@@ -407,7 +431,7 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
 // ---------------------------------------------------------------------------------------------------------
 template <int TAIL, int MODE>
 SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
-                              const TailArgs& a_in, const SbrTol& tol, Dp45State& st) {
+                              const TailArgs& a_in, const SbrTol& tol, Dp45State& st, Fsal& fs) {
     TailArgs a = a_in;
     a.kla_sat = a.kla * c.so_sat;
     const Flow f{x[iV], TAIL == TAIL_REACT ? 0.0 : a.q};
@@ -419,7 +443,7 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
         for (int s = 0; s < n_sub; ++s) rk4_step<TAIL>(x, (double)s * h, h, f, c, a, xpq);
         st.n_rhs += 4u * (uint32_t)n_sub;
     } else {
-        status = dp45_interval<TAIL>(x, T, f, c, a, tol, st, xpq);
+        status = dp45_interval<TAIL>(x, T, f, c, a, tol, st, xpq, fs);
     }
     const double dN = ((x[iSnh] - snh0) - (x[iSno] - sno0)) * c.c136;
     if (TAIL == TAIL_REACT) {
@@ -441,6 +465,14 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
         (void)dN;
     }
     return status;
+}
+
+template <int TAIL, int MODE>
+SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
+                              const TailArgs& a, const SbrTol& tol, Dp45State& st) {
+    Fsal fs;
+    fs.valid = false;
+    return integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -477,6 +509,8 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
     double bias = kla_in, ie = 0.0, so_prev = 0.0, so_i = x[iSo];
     double ksum = 0.0, kla = kla_in;
     int status = 0;
+    Fsal fs;
+    fs.valid = false;
     for (int i = 0; i < n_int; ++i) {
         const double e = sp - so_i;
         double dcv = 0.0;
@@ -489,7 +523,7 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
         if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
         if (i == 0) bias = kla;
         a.kla = kla;
-        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st);
+        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
         ksum += kla;
         so_prev = so_i;
         so_i = x[iSo];
