@@ -87,6 +87,17 @@ SBR_HD double rcp(double d) {
 #endif
 }
 
+// Raw MUFU.RCP64H reciprocal (~2^-20 relative): enough for ratios that only steer the step-size controller.
+SBR_HD double rcp_rough(double d) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+#else
+    return 1.0 / d;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // What the stepper carries.  Only NINE components are dynamically coupled ("active"):
 //     Ss, Xs, Xbh, Xba, So, Sno, Snh, Snd, Xnd
@@ -379,17 +390,19 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         const double g7 = stage<TAIL>(y, k2, t + hs, f, c, a);
         st.n_rhs += 6;
         // error estimate, RMS norm over the active components
+        // (h is factored out of the 9 error components; the per-component scale only steers the controller, so
+        // its reciprocal is the raw MUFU approximation: no FP64-pipe work)
         double en = 0.0;
 #pragma unroll
         for (int i = 0; i < SBR_NX; ++i)
             if (active(i)) {
-                const double err = hs * fma(e7, k2[i], fma(e6, k6[i], fma(e5, k5[i], fma(e4, k4[i],
+                const double err = fma(e7, k2[i], fma(e6, k6[i], fma(e5, k5[i], fma(e4, k4[i],
                                    fma(e3, k3[i], e1 * k1[i])))));
                 const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(y[i])), tol.atol * tol_scale(i));
-                const double q = err * rcp(sc);
+                const double q = err * rcp_rough(sc);
                 en = fma(q, q, en);
             }
-        en = en * (1.0 / 9);   // mean square
+        en = en * (hs * hs * (1.0 / 9));   // mean square
         const bool finite = en < 1e300;   // false for NaN/Inf
         if (en <= 1.0 || !finite) {
             // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
