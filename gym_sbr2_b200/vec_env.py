@@ -301,3 +301,41 @@ class SbrV4VecEnv(object):
 
     def render(self, mode="human", close=False):
         print("Reward for this step: {}".format(self.buf.reward))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# checkpoint / resume: the whole simulator state is a handful of torch tensors (the reference keeps it in module
+# globals and has no resume path); `torch.save(env.state_dict(), path)` is the checkpoint.
+# ---------------------------------------------------------------------------------------------------------
+def _state_dict_v2(self):
+    return dict(kind="SBR-v2", num_envs=self.num_envs, x0=self.x0.clone(), influent=self.influent.clone(),
+                gen=self._gen.get_state())
+
+
+def _load_state_dict_v2(self, sd):
+    if sd["kind"] != "SBR-v2" or sd["num_envs"] != self.num_envs:
+        raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
+    self.x0.copy_(sd["x0"]); self.influent.copy_(sd["influent"]); self._gen.set_state(sd["gen"].cpu())
+
+
+def _state_dict_buf(kind):
+    def state_dict(self):
+        b = self.buf
+        return dict(kind=kind, num_envs=self.num_envs, st=b.st.clone(), done=b.done.clone(),
+                    influent=self.influent.clone(), loading=self._loading.clone(), gen=self._gen.get_state(),
+                    scenario=self.scenario.clone() if torch.is_tensor(getattr(self, "scenario", None)) else None)
+
+    def load_state_dict(self, sd):
+        if sd["kind"] != kind or sd["num_envs"] != self.num_envs:
+            raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
+        b = self.buf
+        b.st.copy_(sd["st"]); b.done.copy_(sd["done"])
+        self.influent.copy_(sd["influent"]); self._loading.copy_(sd["loading"]); self._gen.set_state(sd["gen"].cpu())
+        if sd.get("scenario") is not None:
+            self.scenario = sd["scenario"].to(self.device)
+    return state_dict, load_state_dict
+
+
+SbrV2VecEnv.state_dict, SbrV2VecEnv.load_state_dict = _state_dict_v2, _load_state_dict_v2
+SbrOsVecEnv.state_dict, SbrOsVecEnv.load_state_dict = _state_dict_buf("SBROS-v1")
+SbrV4VecEnv.state_dict, SbrV4VecEnv.load_state_dict = _state_dict_buf("SBR-v4")

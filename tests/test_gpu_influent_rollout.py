@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from gym_sbr2_b200 import _abi, core, influent, rollout
-from gym_sbr2_b200.vec_env import SbrOsVecEnv, SbrV2VecEnv
+from gym_sbr2_b200.vec_env import SbrOsVecEnv, SbrV2VecEnv, SbrV4VecEnv
 
 pytestmark = pytest.mark.gpu
 
@@ -76,3 +76,29 @@ def test_graphed_rollout_matches_eager(built, cuda_device):
     assert bool(ep["all_done"]) and ep["steps"] == 463
     assert torch.equal(ep["returns"], eager["returns"])
     assert torch.equal(env_g.buf.st[:14], env_e.buf.st[:14])
+
+
+@pytest.mark.parametrize("cls,nact", [(SbrOsVecEnv, 2), (SbrV4VecEnv, 1)])
+def test_checkpoint_resume_mid_episode(built, cuda_device, tmp_path, cls, nact):
+    """torch.save(env.state_dict()) mid-episode, restore into a fresh env, continue: bit-identical to the
+    uninterrupted run (the reference has no resume path; its state lives in module globals)."""
+    n = 128
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    acts = [torch.rand((n, nact), dtype=torch.float64, device=cuda_device, generator=g) * (4 if nact == 2 else 0.1)
+            for _ in range(80)]
+    a = cls(n, device=cuda_device, seed=9)
+    a.reset()
+    for k in range(40):
+        a.step(acts[k])
+    path = str(tmp_path / "ckpt.pt")
+    torch.save(a.state_dict(), path)
+    for k in range(40, 80):
+        out_a = a.step(acts[k])
+    b = cls(n, device=cuda_device, seed=1234)                      # different seed: everything comes from the file
+    b.load_state_dict(torch.load(path))
+    for k in range(40, 80):
+        out_b = b.step(acts[k])
+    assert torch.equal(a.buf.st[:20], b.buf.st[:20])
+    ra, rb = (out_a[2], out_b[2]) if nact == 2 else (out_a[1], out_b[1])
+    assert torch.equal(ra, rb)
+    assert torch.equal(a.reset()[0] if nact == 2 else a.reset(), b.reset()[0] if nact == 2 else b.reset())   # RNG too
