@@ -551,13 +551,20 @@ def main():
            "d2h_bytes_per_step": world * ((obs_h.numel() + rew_h.numel()) * 8 + done_h.numel()),
            "api": "SbrV2VecEnv.reset(influent) + step(action), pinned host buffers, result read back every step"}
 
-    cpu = None
+    cpu, cpu_os = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(args.cpu_seconds)
+        from oracle import cpu_baseline as _cb
+        r = _cb.run_os(steps_per_proc=900)
+        cpu_os = {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"], "kind": "port",
+                  "per_core": r["per_core"],
+                  "sample": "%d SBROS-v1 env.steps (%d procs x 900; oracle port of the reference's scipy LSODA path), "
+                            "%.1f s wall" % (r["steps"], r["cores"], r["wall_s"])}
 
     paths = {}
     if rank == 0 and world == 1 and not args.no_interval_path:
         paths["sbros_v1"] = interval_path_leg(torch, device, args, peak_burst, peak_sustained)
+        paths["sbros_v1"]["cpu_baseline"] = cpu_os
         if args.mode == "rk4":
             paths["sbr_v2_dp45"] = cycle_dp45_leg(torch, device, core, env, n)
             paths["sbr_v2_rk4_7substeps"] = cycle_substeps_leg(torch, device, core, env, n, 7)

@@ -55,3 +55,41 @@ def run(steps_per_proc=3, procs=None, warmup=1):
     total = procs * steps_per_proc
     return dict(value=total / wall, cores=procs, steps=total, wall_s=wall,
                 per_core=total / sum(r[0] for r in res))
+
+
+def _worker_os(args):
+    seed, n_steps = args
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import warnings
+    import numpy as np
+    from gym_sbr2_b200 import influent
+    from oracle import sbr_oracle as O
+    rng = np.random.RandomState(seed)
+    env = O.SbrOsOracle()
+    env.reset(influent.sample_numpy(6, rng))
+    t0 = time.perf_counter()
+    acc = 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(n_steps):
+            (_, _), _, r, done = env.step([2.0 + rng.rand(), 4.0 + 2 * rng.rand()])
+            acc += r
+            if done:
+                env.reset(influent.sample_numpy(6, rng))
+    return time.perf_counter() - t0, acc
+
+
+def run_os(steps_per_proc=400, procs=None):
+    """SBROS-v1 interval-steps/s of the oracle port on the host cores (one env per process, 72-s PID intervals)."""
+    procs = procs or usable_cores()
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_worker_os, [(20_000 + i, 20) for i in range(procs)])
+        t0 = time.perf_counter()
+        res = pool.map(_worker_os, [(i, steps_per_proc) for i in range(procs)], chunksize=1)
+        wall = time.perf_counter() - t0
+    total = procs * steps_per_proc
+    return dict(value=total / wall, cores=procs, steps=total, wall_s=wall, per_core=total / sum(r[0] for r in res))
