@@ -555,10 +555,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(args.cpu_seconds)
         from oracle import cpu_baseline as _cb
-        r = _cb.run_os(steps_per_proc=900)
+        r = _cb.run_os(steps_per_proc=6000)
         cpu_os = {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"], "kind": "port",
                   "per_core": r["per_core"],
-                  "sample": "%d SBROS-v1 env.steps (%d procs x 900; oracle port of the reference's scipy LSODA path), "
+                  "sample": "%d SBROS-v1 env.steps (%d procs x 6000; oracle port of the reference's scipy LSODA path), "
                             "%.1f s wall" % (r["steps"], r["cores"], r["wall_s"])}
 
     paths = {}
