@@ -307,10 +307,20 @@ def rollout_leg(torch, tdist, device, rank, world, args):
     from gym_sbr2_b200.vec_env import SbrOsVecEnv
     total = args.rollout_envs
     lo, hi = dist.shard_range(total, rank, world)
-    env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
-    policy = rollout.TinyPolicy(device)
-    warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
-    dist.gather_rewards(warm["returns"], total)                  # ... and the NCCL channel set-up for this size
+    ok, err = 1.0, ""
+    try:                                                         # local set-up: no collectives in here
+        env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
+        policy = rollout.TinyPolicy(device)
+        warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
+        torch.cuda.synchronize()
+    except Exception as exc:                                     # noqa: BLE001
+        ok, err = 0.0, "%s: %s" % (type(exc).__name__, str(exc)[:300])
+    flag = torch.tensor([ok], dtype=torch.float64, device=device)
+    if world > 1:
+        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)            # every rank agrees before any data collective
+    if float(flag.item()) < 1.0:
+        return {"error": err or "set-up failed on another rank"}
+    dist.gather_rewards(warm["returns"], total)                  # the NCCL channel set-up for this size
     torch.cuda.synchronize()
     if world > 1:
         tdist.barrier()
