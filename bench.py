@@ -312,6 +312,10 @@ def rollout_leg(torch, tdist, device, rank, world, args):
         env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
         policy = rollout.TinyPolicy(device)
         warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
+        # the inner loop [policy -> action -> sbr_os_step] captured in CUDA graphs (8 steps and 1 step per replay):
+        # at 2^20 / 8 envs per rank the eager loop is bound by Python + launches, not by the GPU
+        big = rollout.GraphedStepper(env, policy, 8)
+        small = rollout.GraphedStepper(env, policy, 1)
         torch.cuda.synchronize()
     except Exception as exc:                                     # noqa: BLE001
         ok, err = 0.0, "%s: %s" % (type(exc).__name__, str(exc)[:300])
@@ -322,23 +326,35 @@ def rollout_leg(torch, tdist, device, rank, world, args):
         return {"error": err or "set-up failed on another rank"}
     dist.gather_rewards(warm["returns"], total)                  # the NCCL channel set-up for this size
     torch.cuda.synchronize()
-    if world > 1:
-        tdist.barrier()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record()
-    ep = rollout.collect_episode(env, policy)
-    e1.record()
-    allr = dist.gather_rewards(ep["returns"], total)             # the only collective: all_gather over NVLink
-    e2.record()
-    torch.cuda.synchronize()
+
+    def timed_episode(collect):
+        if world > 1:
+            tdist.barrier()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record()
+        ep = collect()
+        e1.record()
+        if world > 1:
+            tdist.barrier()                                      # absorbs the skew between ranks, so that ...
+        e2.record()
+        allr = dist.gather_rewards(ep["returns"], total)         # ... this times the only collective: all_gather over NVLink
+        e3.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e3), e2.elapsed_time(e3), e0.elapsed_time(e1)], dtype=torch.float64,
+                         device=device)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return ep, allr, float(t[0]), float(t[1]), float(t[2])
+
+    ep_e, _, ms_eager, _, _ = timed_episode(lambda: rollout.collect_episode(env, policy))
+    ep, allr, ms_total, ms_gather, ms_local = timed_episode(lambda: rollout.collect_episode_graphed(env, big, small))
     _, stats = rollout.gather_episode_returns(ep["returns"], total) if world == 1 else (None, rollout.return_stats(allr))
-    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=device)
-    if world > 1:
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    ms_total, ms_gather = float(t[0]), float(t[1])
     return {"total_envs": total, "envs_per_rank": hi - lo, "episode_steps": ep["steps"], "ms_episode": ms_total,
             "interval_steps_per_sec": total * ep["steps"] / (ms_total * 1e-3), "ms_reward_gather": ms_gather,
-            "gathered_returns": int(allr.numel()), "all_done": bool(ep["all_done"]), "return_stats": stats,
+            "ms_episode_slowest_rank_before_gather": ms_local, "ms_episode_eager_loop": ms_eager,
+            "stepper": "CUDA graphs (8 and 1 [policy, env.step] iterations per replay)",
+            "gathered_returns": int(allr.numel()), "all_done": bool(ep["all_done"]) and bool(ep_e["all_done"]),
+            "return_stats": stats,
             "scaling": "strong", "collective": "all_gather of per-env returns (%d B per rank)" % ((hi - lo) * 8)}
 
 

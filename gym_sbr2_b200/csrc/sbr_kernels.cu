@@ -30,9 +30,23 @@ int check_launch(const char* what) {
 }
 
 constexpr int kBlock = 64;   // 2 warps per CTA: fine-grained tail balancing across 148 SMs x 4 SMSPs
-#ifndef SBR_OS_STEP_MINBLOCKS
-#define SBR_OS_STEP_MINBLOCKS 6   // resident CTAs per SM the interval-step kernel is compiled for (168-register cap; measured best of 1/6)
+#ifndef SBR_OS_BLOCK
+#define SBR_OS_BLOCK 64      // threads per CTA of the interval-step kernel
 #endif
+constexpr int kOsBlock = SBR_OS_BLOCK;
+// Resident CTAs per SM the interval-step kernels are compiled for.  RK4 keeps ~41 doubles live and runs best at
+// 6 CTAs (168-register cap, 12 warps/SM); Dormand-Prince keeps six stage vectors live and spills 830 B per thread
+// under that cap -- at 4 CTAs (255 registers, 8 warps/SM) it spills nothing and one env.step of 2^20 envs takes
+// 0.237 ms instead of 0.268 ms (measured, gpurun_out/os_ab_r02a.log).
+#ifndef SBR_OS_STEP_MINBLOCKS_RK4
+#define SBR_OS_STEP_MINBLOCKS_RK4 6
+#endif
+#ifndef SBR_OS_STEP_MINBLOCKS_DP45
+#define SBR_OS_STEP_MINBLOCKS_DP45 4
+#endif
+constexpr int os_step_minblocks(int mode) {
+    return mode == SBR_MODE_DP45 ? SBR_OS_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
+}
 
 struct CycleArgs {
     int64_t n, ld;
@@ -233,25 +247,30 @@ __global__ void __launch_bounds__(kBlock) sbr_os_reset_kernel(OsArgs g, SbrParam
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
+// Touch the 128-byte lines of a row that this warp will read later (after the integration), so that the later read
+// is an L2 hit instead of a third exposed DRAM round trip.  No destination register, no scoreboard entry.
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
+#ifndef SBR_OS_STEP_HOIST
+#define SBR_OS_STEP_HOIST 1   // 1: every load of the launch is issued before the first use (one DRAM round trip)
+#endif
+
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, SBR_OS_STEP_MINBLOCKS) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+__global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                              SbrTol tol) {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kOsBlock + threadIdx.x;
     if (i >= g.n) return;
+    // All loads of the launch are issued back to back, before anything depends on them: the warp pays ONE DRAM
+    // round trip (state, controller scalars, action, done flag, episode counters), not one per dependent branch.
     double x[SBR_NX];
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
     sbr::OsCtrl ctl;
     ctl.t = g.st[SBR_OS_T * g.ld + i];
-    const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld}, os{g.state + i, g.ld};
-    if (g.done[i]) {
-        // stepping a finished episode is a no-op: same observation, zero deltas, reward 0
-        sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
-        g.reward[i] = 0.0;
-        if (g.status) g.status[i] = SBR_ST_DONE;
-        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
-        return;
-    }
+#if SBR_OS_STEP_HOIST
+    const uint8_t was_done = g.done[i];
     ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
     ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
     ctl.sno_prev = g.st[SBR_OS_SNO_PREV * g.ld + i];
@@ -261,16 +280,50 @@ __global__ void __launch_bounds__(kBlock, SBR_OS_STEP_MINBLOCKS) sbr_os_step_ker
     ctl.kla_last = g.st[(SBR_OS_KLA_RING + 9) * g.ld + i];
     sbr::Dp45State dp;
     dp.h = g.st[SBR_OS_H * g.ld + i];
-    dp.n_rhs = 0; dp.n_rej = 0;
     const double a_do = g.action[i], a_ec = g.action[g.ld + i];
+    const double ret0 = g.st[SBR_OS_RETURN * g.ld + i], steps0 = g.st[SBR_OS_STEPS * g.ld + i];
+    // the KLa history is read after the integration (it would cost 20 registers across the stepper): pull its
+    // lines into L2 now
+#pragma unroll
+    for (int j = 0; j < 9; ++j) prefetch_l2(g.st + (SBR_OS_KLA_RING + j) * g.ld + i);
+#else
+    const uint8_t was_done = g.done[i];
+#endif
+    const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld}, os{g.state + i, g.ld};
+    if (was_done) {
+        // stepping a finished episode is a no-op: same observation, zero deltas, reward 0
+        sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
+        g.reward[i] = 0.0;
+        if (g.status) g.status[i] = SBR_ST_DONE;
+        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
+        return;
+    }
+#if !SBR_OS_STEP_HOIST
+    ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
+    ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
+    ctl.sno_prev = g.st[SBR_OS_SNO_PREV * g.ld + i];
+    ctl.ie_do = g.st[SBR_OS_IE_DO * g.ld + i];
+    ctl.ie_ec = g.st[SBR_OS_IE_EC * g.ld + i];
+    ctl.ec_last = g.st[SBR_OS_EC_LAST * g.ld + i];
+    ctl.kla_last = g.st[(SBR_OS_KLA_RING + 9) * g.ld + i];
+    sbr::Dp45State dp;
+    dp.h = g.st[SBR_OS_H * g.ld + i];
+    const double a_do = g.action[i], a_ec = g.action[g.ld + i];
+#endif
+    dp.n_rhs = 0; dp.n_rej = 0;
     const sbr::Column ring{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld};
     sbr::OsStepOut o;
     sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, od, oe, os, o);
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
     os_store_ctrl(g.st, g.ld, i, ctl, dp.h);
+#if SBR_OS_STEP_HOIST
+    g.st[SBR_OS_RETURN * g.ld + i] = ret0 + o.reward;
+    g.st[SBR_OS_STEPS * g.ld + i] = steps0 + 1.0;
+#else
     g.st[SBR_OS_RETURN * g.ld + i] += o.reward;
     g.st[SBR_OS_STEPS * g.ld + i] += 1.0;
+#endif
     if (o.done) { g.st[SBR_OS_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
     g.reward[i] = o.reward;
     if (g.status) g.status[i] = o.status;
@@ -310,24 +363,16 @@ __global__ void __launch_bounds__(128) sbr_v4_reset_kernel(V4Args g, SbrParams p
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, 6) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+__global__ void __launch_bounds__(kBlock, os_step_minblocks(MODE)) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                                 SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= g.n) return;
+    // every load of the launch is issued before the first use (one DRAM round trip, as in sbr_os_step_kernel)
     double x[SBR_NX];
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
-    const sbr::Column ob{g.obs + i, g.ld};
-    if (g.done[i]) {
-        // stepping a finished episode is a no-op: same observation, reward 0
-#pragma unroll
-        for (int k = 0; k < SBR_NX; ++k) ob.set(k, x[k] * sbr::inv_x1_v4(k));
-        g.reward[i] = 0.0;
-        if (g.status) g.status[i] = SBR_ST_DONE;
-        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
-        return;
-    }
+    const uint8_t was_done = g.done[i];
     sbr::V4Ctrl ctl;
     ctl.t = g.st[SBR_V4_T * g.ld + i];
     ctl.u = g.st[SBR_V4_U * g.ld + i];
@@ -337,6 +382,18 @@ __global__ void __launch_bounds__(kBlock, 6) sbr_v4_step_kernel(V4Args g, SbrPar
     ctl.kla_sum = g.st[SBR_V4_KLA_SUM * g.ld + i];
     sbr::Dp45State dp;
     dp.h = g.st[SBR_V4_H * g.ld + i];
+    const double action = g.action[i];
+    const double ret0 = g.st[SBR_V4_RETURN * g.ld + i], steps0 = g.st[SBR_V4_STEPS * g.ld + i];
+    const sbr::Column ob{g.obs + i, g.ld};
+    if (was_done) {
+        // stepping a finished episode is a no-op: same observation, reward 0
+#pragma unroll
+        for (int k = 0; k < SBR_NX; ++k) ob.set(k, x[k] * sbr::inv_x1_v4(k));
+        g.reward[i] = 0.0;
+        if (g.status) g.status[i] = SBR_ST_DONE;
+        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
+        return;
+    }
     if (!(dp.h > 0.0)) dp.h = s.t_delta / 9.0;
     dp.n_rhs = 0; dp.n_rej = 0;
     if (ctl.t < s.t_fill) {          // the influent column is only read while the reactor fills (26 of 493 steps)
@@ -345,7 +402,7 @@ __global__ void __launch_bounds__(kBlock, 6) sbr_v4_step_kernel(V4Args g, SbrPar
     }
     const sbr::Loading load{&s_load[threadIdx.x], kBlock};
     sbr::V4Out o;
-    sbr::v4_step_env<MODE>(x, ctl, g.action[i], load, p, c, s, tol, dp, ob, o);
+    sbr::v4_step_env<MODE>(x, ctl, action, load, p, c, s, tol, dp, ob, o);
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
     g.st[SBR_V4_T * g.ld + i] = ctl.t;
@@ -355,8 +412,8 @@ __global__ void __launch_bounds__(kBlock, 6) sbr_v4_step_kernel(V4Args g, SbrPar
     g.st[SBR_V4_KLA_LAST * g.ld + i] = ctl.kla_last;
     g.st[SBR_V4_KLA_SUM * g.ld + i] = ctl.kla_sum;
     g.st[SBR_V4_H * g.ld + i] = dp.h;
-    g.st[SBR_V4_RETURN * g.ld + i] += o.reward;
-    g.st[SBR_V4_STEPS * g.ld + i] += 1.0;
+    g.st[SBR_V4_RETURN * g.ld + i] = ret0 + o.reward;
+    g.st[SBR_V4_STEPS * g.ld + i] = steps0 + 1.0;
     if (o.done) { g.st[SBR_V4_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
     g.reward[i] = o.reward;
     if (g.status) g.status[i] = o.status;
@@ -528,8 +585,8 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
             return fail(SBR_ERR_ARG, "sbr_cycle_v2: schedule needs n_int, n_sub >= 1 and interval > 0%s");
     }
     CycleArgs g{n, ld, x0, influent, action, x_last, obs, reward, aux, status, counters, perm};
-    const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == SBR_MODE_RK4)
@@ -549,8 +606,8 @@ int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, 
     if (tail == sbr::TAIL_EC && !ec) return fail(SBR_ERR_ARG, "sbr_integrate_interval: EC tail needs ec%s");
     if (!(T > 0) || n_sub < 1) return fail(SBR_ERR_ARG, "sbr_integrate_interval: T > 0 and n_sub >= 1 required%s");
     IntervalArgs g{n, ld, x, kla, ec, loading, counters, T, n_sub};
-    const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t st = (cudaStream_t)stream;
 #define SBR_LAUNCH(TAIL, MODE) sbr_interval_kernel<TAIL, MODE><<<grid, kBlock, 0, st>>>(g, *p, c, t)
@@ -598,8 +655,8 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
     if (!influent || !st || !obs_do || !obs_ec || !done) return fail(SBR_ERR_ARG, "sbr_os_reset: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_reset: bad mode%s");
     OsArgs g{n, ld, st, x0, influent, mask, nullptr, obs_do, obs_ec, nullptr, nullptr, done, status, counters};
-    const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t cs = (cudaStream_t)stream;
     if (mode == SBR_MODE_RK4) sbr_os_reset_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
@@ -617,12 +674,12 @@ int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const S
         return fail(SBR_ERR_ARG, "sbr_os_step: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_step: bad mode%s");
     OsArgs g{n, ld, st, nullptr, nullptr, nullptr, action, obs_do, obs_ec, state, reward, done, status, counters};
-    const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
-    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    const sbr::Coef c = sbr::make_coef(*p);
+    const unsigned grid = (unsigned)((n + kOsBlock - 1) / kOsBlock);
     cudaStream_t cs = (cudaStream_t)stream;
-    if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
-    else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kOsBlock, 0, cs>>>(g, *p, c, *s, t);
+    else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kOsBlock, 0, cs>>>(g, *p, c, *s, t);
     return check_launch("sbr_os_step");
 }
 
@@ -647,8 +704,8 @@ int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const
         return fail(SBR_ERR_ARG, "sbr_v4_step: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_v4_step: bad mode%s");
     V4Args g{n, ld, st, nullptr, influent, nullptr, action, obs, reward, done, status, counters};
-    const sbr::Coef c = sbr::make_coef(*p);
     const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t cs = (cudaStream_t)stream;
     if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
