@@ -619,22 +619,25 @@ def main():
                   "reads its results back; `value`: uploads of step k+1 overlap step k on a side stream, "
                   "`value_synchronous`: copy-in, step, copy-out, synchronize"}
 
-    cpu, cpu_os = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_leg(args.cpu_seconds)
-        from oracle import cpu_baseline as _cb
-        r = _cb.run_os(steps_per_proc=6000)
-        cpu_os = {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"], "kind": "port",
-                  "per_core": r["per_core"],
-                  "sample": "%d SBROS-v1 env.steps (%d procs x 6000; oracle port of the reference's scipy LSODA path), "
-                            "%.1f s wall" % (r["steps"], r["cores"], r["wall_s"])}
-
-    # optional legs: a failure in one of them must not cost the headline line
+    # legs beside the headline: a failure in one of them must not cost the headline line
     def leg(fn, *a):
         try:
             return fn(*a)
         except Exception as exc:          # noqa: BLE001 - reported, not swallowed
             return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+
+    def cpu_os_leg():
+        from oracle import cpu_baseline as _cb
+        r = _cb.run_os(steps_per_proc=6000)
+        return {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"], "kind": "port",
+                "per_core": r["per_core"],
+                "sample": "%d SBROS-v1 env.steps (%d procs x 6000; oracle port of the reference's scipy LSODA path), "
+                          "%.1f s wall" % (r["steps"], r["cores"], r["wall_s"])}
+
+    cpu, cpu_os = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = leg(cpu_baseline_leg, args.cpu_seconds)
+        cpu_os = leg(cpu_os_leg)
 
     paths = {}
     if rank == 0 and world == 1 and not args.no_interval_path:
@@ -647,7 +650,10 @@ def main():
         paths["config1_small_batch"] = leg(small_batch_leg, torch, device)
     if not args.no_rollout:
         # every rank takes part: envs sharded over the ranks, NCCL gather of the episode returns
-        paths["config5_rollout"] = rollout_leg(torch, tdist, device, rank, world, args)
+        # (guarded only on one GPU: with several ranks a swallowed exception on one of them would leave the others
+        # waiting in a collective -- there a failure must bring the job down)
+        paths["config5_rollout"] = (leg(rollout_leg, torch, tdist, device, rank, world, args) if world == 1
+                                    else rollout_leg(torch, tdist, device, rank, world, args))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -65,11 +65,19 @@ inline Coef make_coef(const SbrParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// FP64 reciprocal: MUFU.RCP64H seed (>= 20 good bits) + one cubic Newton correction (3 DFMA) -> ~2^-60.
+// FP64 reciprocal: MUFU.RCP64H seed (~2^-19) + one Newton step (2 DFMA) -> relative error <= ~2^-36.
 // An IEEE divide costs ~10 FP64-pipe slots; the RHS has 6-7 of them per evaluation.
+// SBR_RCP_NEWTON 2 (default): quadratic correction r (1 + e).  Measured on 2^20 whole cycles against the cubic
+//   variant (gpurun_out/ab_cycle_r02a.log): RHS relative error 2e-11, x_last moves by at most 2.4e-11 relative =
+//   2e-6 of ONE parity tolerance unit, 2500x below the RK4 truncation error on the reference grid (0.005 units) and
+//   below the rounding noise of the reference's own LSODA run -- for 4 % less kernel time (88.5 -> 85.0 ms).
+// SBR_RCP_NEWTON 3: cubic correction r (1 + e + e^2), 3 DFMA, ~2^-57.
+// Tried and rejected: a float seed built with integer instructions + MUFU.RCP (2^-22, then ONE Newton step reaches
+//   9e-13): FP64 instructions hold the issue port for two cycles, every other instruction for one, so the ~13 extra
+//   integer instructions per reciprocal cost more than the DFMA they save (88.5 -> 113.7 ms).
 // ---------------------------------------------------------------------------------------------------------
 #ifndef SBR_RCP_NEWTON
-#define SBR_RCP_NEWTON 3
+#define SBR_RCP_NEWTON 2
 #endif
 SBR_HD double rcp(double d) {
 #ifdef __CUDA_ARCH__

@@ -47,6 +47,12 @@ constexpr int kOsBlock = SBR_OS_BLOCK;
 constexpr int os_step_minblocks(int mode) {
     return mode == SBR_MODE_DP45 ? SBR_OS_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
 }
+#ifndef SBR_V4_STEP_MINBLOCKS_DP45
+#define SBR_V4_STEP_MINBLOCKS_DP45 6
+#endif
+constexpr int v4_step_minblocks(int mode) {
+    return mode == SBR_MODE_DP45 ? SBR_V4_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
+}
 
 struct CycleArgs {
     int64_t n, ld;
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(128) sbr_v4_reset_kernel(V4Args g, SbrParams p
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, os_step_minblocks(MODE)) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+__global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                                 SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;

@@ -30,6 +30,18 @@ for _ in range(3):
     e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 res["rk4_ms"] = min(ts)
 res["reward_mean"] = float(env._out.reward.mean()); res["x_last_sum"] = float(env._out.x_last.sum())
+import os
+from gym_sbr2_b200 import parity
+base = "/tmp/ab_xlast.pt"
+if not os.path.exists(base):
+    torch.save(dict(x=env._out.x_last.clone(), r=env._out.reward.clone()), base)
+else:
+    b = torch.load(base)
+    scale = torch.as_tensor(parity.STATE_SCALE, device=dev, dtype=torch.float64)[:, None] if hasattr(parity, "STATE_SCALE") else torch.ones((14, 1), device=dev, dtype=torch.float64)
+    u = (env._out.x_last - b["x"]).abs() / (1e-5 * b["x"].abs() + 1e-9 * scale)
+    res["vs_first_units_max"] = float(u.max()); res["vs_first_units_p999"] = float(u.flatten().kthvalue(int(0.999 * u.numel())).values)
+    res["vs_first_rel_max"] = float(((env._out.x_last - b["x"]).abs() / (b["x"].abs() + 1e-12)).max())
+    res["reward_absdiff_max"] = float((env._out.reward - b["r"]).abs().max())
 tol = _abi.make_tol(1e-7, 1e-9)
 core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=1, tol=tol); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
