@@ -286,6 +286,15 @@ SBR_HD void rk4_step(double (&x)[SBR_NX], double t, double h, const Flow& f, con
 #ifndef SBR_DP_FIRST
 #define SBR_DP_FIRST 0.7
 #endif
+// Step-size factor safety * en^(-1/10): it only steers the controller, so the device uses the MUFU lg2/ex2 pair
+// (2 instructions) instead of the ~30-instruction software log2f.
+SBR_HD float pow_m01(float en) {
+#ifdef __CUDA_ARCH__
+    return exp2f(-0.1f * __log2f(en));
+#else
+    return exp2f(-0.1f * log2f(en));
+#endif
+}
 SBR_HD float __frcp_rn_compat(float v) {
 #ifdef __CUDA_ARCH__
     return __frcp_rn(v);
@@ -293,6 +302,18 @@ SBR_HD float __frcp_rn_compat(float v) {
     return 1.0f / v;
 #endif
 }
+struct DpTab {
+    double c2, c3, c4, c5, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65;
+    double b1, b3, b4, b5, b6, e1, e3, e4, e5, e6, e7;
+};
+#define SBR_DP_TABLEAU                                                                                              \
+    {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0 / 5, 3.0 / 40, 9.0 / 40, 44.0 / 45, -56.0 / 15, 32.0 / 9,              \
+     19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 9017.0 / 3168, -355.0 / 33, 46732.0 / 5247,      \
+     49.0 / 176, -5103.0 / 18656, 35.0 / 384, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 71.0 / 57600,    \
+     -71.0 / 16695, 71.0 / 1920, -17253.0 / 339200, 22.0 / 525, -1.0 / 40}
+#ifdef __CUDACC__
+static __constant__ DpTab kDpTab = SBR_DP_TABLEAU;
+#endif
 struct Dp45State {
     double h;          // current step-size proposal, carried across PID intervals
     uint32_t n_rhs;    // RHS evaluations (accepted + rejected)
@@ -323,17 +344,21 @@ SBR_HD constexpr double tol_scale(int i) {
 template <int TAIL>
 SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coef& c, const TailArgs& a,
                          const SbrTol& tol, Dp45State& st, double& xpq, Fsal& fs) {
-    // Butcher tableau (Dormand & Prince 1980)
-    const double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
-    const double a21 = 1.0 / 5;
-    const double a31 = 3.0 / 40, a32 = 9.0 / 40;
-    const double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
-    const double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
-    const double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176,
-                 a65 = -5103.0 / 18656;
-    const double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
-    const double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200,
-                 e6 = 22.0 / 525, e7 = -1.0 / 40;
+    // Butcher tableau (Dormand & Prince 1980): on the device the coefficients are operands straight from the
+    // constant bank (kDpTab) -- as literals the compiler rebuilds 24 of them with two UMOVs each in every step
+#ifdef __CUDA_ARCH__
+    const DpTab& tb = kDpTab;
+#else
+    const DpTab tb = SBR_DP_TABLEAU;
+#endif
+    const double c2 = tb.c2, c3 = tb.c3, c4 = tb.c4, c5 = tb.c5;
+    const double a21 = tb.a21;
+    const double a31 = tb.a31, a32 = tb.a32;
+    const double a41 = tb.a41, a42 = tb.a42, a43 = tb.a43;
+    const double a51 = tb.a51, a52 = tb.a52, a53 = tb.a53, a54 = tb.a54;
+    const double a61 = tb.a61, a62 = tb.a62, a63 = tb.a63, a64 = tb.a64, a65 = tb.a65;
+    const double b1 = tb.b1, b3 = tb.b3, b4 = tb.b4, b5 = tb.b5, b6 = tb.b6;
+    const double e1 = tb.e1, e3 = tb.e3, e4 = tb.e4, e5 = tb.e5, e6 = tb.e6, e7 = tb.e7;
     double k1[SBR_NX], k2[SBR_NX], k3[SBR_NX], k4[SBR_NX], k5[SBR_NX], k6[SBR_NX], y[SBR_NX];
     double t = 0.0;
     double h = st.h * SBR_DP_FIRST;   // KLa has just jumped: the carried proposal is discounted for the first step
@@ -430,7 +455,7 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         // conservative: see DESIGN.md section 4 for the measured trade-off.
         float fac = SBR_DP_MAXGROW;
         if (en > 1e-20) {
-            fac = SBR_DP_SAFETY * exp2f(-0.1f * log2f((float)en));
+            fac = SBR_DP_SAFETY * pow_m01((float)en);
             fac = fminf(SBR_DP_MAXGROW, fmaxf(0.2f, fac));
         }
         if (en > 1.0) fac = fminf(fac, 1.0f);
