@@ -144,50 +144,69 @@ def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
     from gym_sbr2_b200.vec_env import SbrOsVecEnv
     n = args.interval_envs
     out = {}
+
+    def make_actions(gen, wide):
+        # per-step set-points; `moderate` is the distribution the CPU sample of this leg uses (oracle/cpu_baseline.py:
+        # DO set-point U(2,3), NO3 set-point U(4,6)); `wide` (DO U(1,7), NO3 U(2,12)) doses so much carbon that 30 % of
+        # the envs run into negative ammonia, where the adaptive stepper needs 5-20x more steps (a stress case)
+        lo_do, w_do, lo_no, w_no = (1.0, 6.0, 2.0, 10.0) if wide else (2.0, 1.0, 4.0, 2.0)
+        return [torch.stack([lo_do + w_do * torch.rand(n, dtype=torch.float64, device=device, generator=gen),
+                             lo_no + w_no * torch.rand(n, dtype=torch.float64, device=device, generator=gen)], dim=1)
+                for _ in range(8)]
+
+    def episode(env, infl, acts, per_step_events):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(464)] if per_step_events else None
+        rhs_mid = 0.0
+        e0.record()
+        env.reset(influent=infl)
+        for k in range(463):
+            if ev:
+                ev[k].record()
+            env.step_async(acts[k % 8])
+            if k == 300 and ev:
+                rhs_mid = env.buf.counters[0].to(torch.float64).mean()
+        if ev:
+            ev[463].record()
+        e1.record()
+        torch.cuda.synchronize()
+        assert bool(env.buf.done.all()), "episode did not end after 463 steps"
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(463)] if ev else None
+        return e0.elapsed_time(e1), per, float(rhs_mid)
+
     for mode, kw in (("dp45", dict(rtol=1e-8, atol=1e-10)), ("rk4", dict(rk4_sub_interval=20))):
         env = SbrOsVecEnv(n, device=device, seed=77, mode=mode, **kw)
         gen = torch.Generator(device=device).manual_seed(5)
-        acts = [torch.stack([1 + 6 * torch.rand(n, dtype=torch.float64, device=device, generator=gen),
-                             2 + 10 * torch.rand(n, dtype=torch.float64, device=device, generator=gen)], dim=1)
-                for _ in range(8)]
+        acts = make_actions(gen, wide=False)
         infl = env._draw_influent()
         env.reset(influent=infl)
         for k in range(5):
             env.step_async(acts[k % 8])
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(464)]
-        rhs_sum = torch.zeros((), dtype=torch.float64, device=device)
-        rhs_mid = 0.0
-        e0.record()
-        env.reset(influent=infl)
-        for k in range(463):
-            ev[k].record()
-            env.step_async(acts[k % 8])
-            if k == 300:
-                rhs_mid = env.buf.counters[0].to(torch.float64).mean()
-        ev[463].record()
-        e1.record()
-        torch.cuda.synchronize()
-        assert bool(env.buf.done.all()), "episode did not end after 463 steps"
-        ms_episode = e0.elapsed_time(e1)
-        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(463)]
+        ms_episode, per, rhs = episode(env, infl, acts, True)
+        bad = int((env.buf.status != 0).sum())
+        ret = float(env.buf.st[_abi.OS_RETURN].mean())
         plain = sorted(per[60:270] + per[280:455])
         ms_plain = plain[len(plain) // 2]
-        rhs = float(rhs_mid)
         steps = rhs / 4.0 if mode == "rk4" else (rhs - 1) / 6.0
         ovh = 196 if mode == "rk4" else 2 * 14 * (1 + 2 + 3 + 4 + 5 + 5 + 6) + 100
         flops = rhs * F_EC + steps * ovh + 150
         tf = n * flops / (ms_plain * 1e-3) / 1e12
+        ms_wide, _, _ = episode(env, infl, make_actions(gen, wide=True), False)
         out[mode] = {"envs": n, "ms_per_episode": ms_episode, "interval_steps_per_sec": n * 463 / (ms_episode * 1e-3),
+                     "actions": "per-step DO set-point U(2,3), NO3 set-point U(4,6): the distribution of the CPU sample",
                      "ms_per_plain_step": ms_plain, "plain_interval_steps_per_sec": n / (ms_plain * 1e-3),
                      "ms_terminal_step": per[462], "rhs_per_env_step": rhs,
                      "roofline": {"bound": "fp64+hbm", "fp64_tflops": tf, "fp64_frac": tf / peak_burst,
                                   "hbm_gbs": n * OS_BYTES_STEP / (ms_plain * 1e-3) / 1e9,
                                   "hbm_frac": n * OS_BYTES_STEP / (ms_plain * 1e-3) / 1e9 / _hbm_peak(),
                                   "flops_per_env_step": flops, "bytes_per_env_step": OS_BYTES_STEP},
-                     "config": dict(kw, integrator=mode), "bad_status": int((env.buf.status != 0).sum()),
-                     "gpu_launches": 464, "mean_episode_return": float(env.buf.st[_abi.OS_RETURN].mean())}
+                     "config": dict(kw, integrator=mode), "bad_status": bad,
+                     "gpu_launches": 464, "mean_episode_return": ret,
+                     "stress_wide_actions": {"actions": "DO set-point U(1,7), NO3 set-point U(2,12)",
+                                             "ms_per_episode": ms_wide,
+                                             "interval_steps_per_sec": n * 463 / (ms_wide * 1e-3),
+                                             "bad_status": int((env.buf.status != 0).sum())}}
         del env
     return out
 

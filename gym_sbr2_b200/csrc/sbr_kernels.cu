@@ -44,13 +44,13 @@ constexpr int kOsBlock = SBR_OS_BLOCK;
 #ifndef SBR_OS_STEP_MINBLOCKS_DP45
 #define SBR_OS_STEP_MINBLOCKS_DP45 4
 #endif
-constexpr int os_step_minblocks(int mode) {
+__host__ __device__ constexpr int os_step_minblocks(int mode) {
     return mode == SBR_MODE_DP45 ? SBR_OS_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
 }
 #ifndef SBR_V4_STEP_MINBLOCKS_DP45
 #define SBR_V4_STEP_MINBLOCKS_DP45 6
 #endif
-constexpr int v4_step_minblocks(int mode) {
+__host__ __device__ constexpr int v4_step_minblocks(int mode) {
     return mode == SBR_MODE_DP45 ? SBR_V4_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
 }
 

@@ -12,6 +12,8 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "dp45"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 70
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
 kw = dict(rk4_sub_interval=20) if mode == "rk4" else {}
+if mode == "rk4grid":
+    mode, kw = "rk4", {}
 env = SbrOsVecEnv(n, device="cuda:0", seed=1, mode=mode, **kw)
 env.reset()
 gen = torch.Generator(device="cuda:0").manual_seed(1)
