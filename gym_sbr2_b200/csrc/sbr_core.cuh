@@ -68,7 +68,7 @@ inline Coef make_coef(const SbrParams& p) {
 // FP64 reciprocal: MUFU.RCP64H seed (~2^-19) + one Newton step (2 DFMA) -> relative error <= ~2^-36.
 // An IEEE divide costs ~10 FP64-pipe slots; the RHS has 6-7 of them per evaluation.
 // SBR_RCP_NEWTON 2 (default): quadratic correction r (1 + e).  Measured on 2^20 whole cycles against the cubic
-//   variant (gpurun_out/ab_cycle_r02a.log): RHS relative error 2e-11, x_last moves by at most 2.4e-11 relative =
+//   variant (profiles/r01f_ab_cycle_rcp_variants.log): RHS relative error 2e-11, x_last moves by at most 2.4e-11 relative =
 //   2e-6 of ONE parity tolerance unit, 2500x below the RK4 truncation error on the reference grid (0.005 units) and
 //   below the rounding noise of the reference's own LSODA run -- for 4 % less kernel time (88.5 -> 85.0 ms).
 // SBR_RCP_NEWTON 3: cubic correction r (1 + e + e^2), 3 DFMA, ~2^-57.

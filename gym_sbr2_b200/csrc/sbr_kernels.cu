@@ -37,7 +37,7 @@ constexpr int kOsBlock = SBR_OS_BLOCK;
 // Resident CTAs per SM the interval-step kernels are compiled for.  RK4 keeps ~41 doubles live and runs best at
 // 6 CTAs (168-register cap, 12 warps/SM); Dormand-Prince keeps six stage vectors live and spills 830 B per thread
 // under that cap -- at 4 CTAs (255 registers, 8 warps/SM) it spills nothing and one env.step of 2^20 envs takes
-// 0.237 ms instead of 0.268 ms (measured, gpurun_out/os_ab_r02a.log).
+// 0.237 ms instead of 0.268 ms (measured, profiles/r01f_ab_os_step_hoist_minblocks.log).
 #ifndef SBR_OS_STEP_MINBLOCKS_RK4
 #define SBR_OS_STEP_MINBLOCKS_RK4 6
 #endif
