@@ -150,7 +150,7 @@ SBR_HD double cin(const TailArgs& a, int i) {
 // ---------------------------------------------------------------------------------------------------------
 // Kinetic rates of the active components (sub_phases_FB.py:278-372) + aeration.  CSE-minimal form: 6 Monod
 // denominators -> 3 reciprocals (they are only needed as products of two or three); hydrolysis written as
-// Xs*g / Xnd*g so no divide by Xs or Xbh is needed ((Xs/Xbh)/(Kx+Xs/Xbh) == Xs/(Kx*Xbh+Xs)).  55 FP64 + 3 MUFU.
+// Xs*g / Xnd*g so no divide by Xs or Xbh is needed ((Xs/Xbh)/(Kx+Xs/Xbh) == Xs/(Kx*Xbh+Xs)).  51 FP64 + 3 MUFU.
 // Returns s45 = rho4 + rho5 (the Xp production rate is ixp * s45).
 // ---------------------------------------------------------------------------------------------------------
 SBR_HD double kinetics(const double (&y)[SBR_NX], double (&k)[SBR_NX], const Coef& c, const TailArgs& a) {
@@ -161,19 +161,19 @@ SBR_HD double kinetics(const double (&y)[SBR_NX], double (&k)[SBR_NX], const Coe
     //   hydrolysis ~ 1/((Koh+So)(Kx Xbh+Xs)): folded into the first pair's reciprocal, R = 1/(d1 d2 d6)
     const double d1 = c.Ks + Ss, d2 = c.Koh + So, d4 = c.Knh + Snh, d5 = c.Koa + So, d6 = fma(c.Kx, Xbh, Xs);
     const double R = rcp((d1 * d2) * d6);
-    const double r12 = R * d6;                               // 1/((Ks+Ss)(Koh+So))
-    const double r26 = R * d1;                               // 1/((Koh+So)(Kx Xbh+Xs))
+    // both uses of R come with a factor Xbh: RX d6 = Xbh/((Ks+Ss)(Koh+So)), RX d1 = Xbh/((Koh+So)(Kx Xbh+Xs))
+    const double RX = R * Xbh;
     const double r45 = rcp(d4 * d5);
     const double r3 = rcp(c.Kno + Sno);
     const double mNo = Sno * r3;                             // Sno/(Kno+Sno)
-    const double C = c.muh * ((Ss * Xbh) * r12);
+    const double C = (c.muh * Ss) * (RX * d6);
     const double rho1 = C * So;                              // muh Ss/(Ks+Ss) So/(Koh+So) Xbh
     const double rho2 = (C * c.etag_Koh) * mNo;              // muh Ss/(Ks+Ss) Koh/(Koh+So) Sno/(Kno+Sno) etag Xbh
     // rho3 scaled by nu9_3 = 1/Ya on the host (mua_Ya = mua/Ya), so that d(Sno)/dt takes it without a multiply
     const double rho3s = ((c.mua_Ya * Snh) * So) * (Xba * r45);
     const double rho6 = (c.ka * Snd) * Xbh;
     // hydrolysis: kh (Xs/Xbh)/(Kx+Xs/Xbh) [So/(Koh+So) + etah Koh/(Koh+So) Sno/(Kno+Sno)] Xbh  ==  Xs * g
-    const double g = ((c.kh * Xbh) * r26) * fma(c.etah_Koh, mNo, So);
+    const double g = (c.kh * (RX * d1)) * fma(c.etah_Koh, mNo, So);
     const double rho7 = Xs * g;
     const double rho8 = Xnd * g;
     const double s12 = rho1 + rho2;
