@@ -1,8 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r01g.log 2>&1; tail -2 gpurun_out/pytest_gpu_r01g.log
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-interval-path --no-rollout > gpurun_out/bench_plain_r01g.log 2>&1; python - <<'PY'
-import json
-for l in open('gpurun_out/bench_plain_r01g.log'):
-    if l.startswith('{"metric"'):
-        d = json.loads(l); print(d['value'], d['roofline']['frac'], d['roofline']['kernel_ms'], d['e2e']['value'])
-PY
+python tools/ab_cycle.py gym_sbr2_b200/_variants/mb1.so gym_sbr2_b200/_variants/mb6.so gym_sbr2_b200/_variants/mb8.so > gpurun_out/ab_cycle_r01h.log 2>&1; cut -c1-400 gpurun_out/ab_cycle_r01h.log
