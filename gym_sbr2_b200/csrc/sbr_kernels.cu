@@ -71,13 +71,12 @@ struct CycleArgs {
 #ifndef SBR_CYCLE_DP45_MINBLOCKS
 #define SBR_CYCLE_DP45_MINBLOCKS 1   // resident CTAs per SM the DP45 cycle kernel is compiled for
 #endif
-#ifndef SBR_CYCLE_RK4_MINBLOCKS
-#define SBR_CYCLE_RK4_MINBLOCKS 8    // resident CTAs per SM the RK4 cycle kernel is compiled for: 128 registers, the 14 spilled
-                                     // words live outside the step loop (272 FP64 + 30 other instructions per RK4 step
-                                     // either way), 16 warps/SM: 84.1 -> 83.5 ms (profiles/r01f_ab_cycle_rk4_occupancy.log)
-#endif
+// RK4 runs without a register cap (184 registers, 10 warps/SM).  A 128-register build (16 warps/SM, spills outside
+// the step loop) is 0.7 % faster at 2^20 envs but 19 % slower at 4096 envs (one warp per sub-partition: latency is what
+// counts) and differs from this build in the last bits, which would make results depend on the batch size
+// (profiles/r01f_ab_cycle_rk4_occupancy.log) -- not taken.
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : SBR_CYCLE_RK4_MINBLOCKS) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
+__global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : 1) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
                                                               SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
