@@ -128,3 +128,28 @@ def test_no_cpu_fallback_in_product():
     from gym_sbr2_b200.vec_env import SbrV2VecEnv
     with pytest.raises(_abi.SbrLibraryError):
         SbrV2VecEnv(4, device="cpu")
+
+
+def test_cpu_baseline_workers_survive_the_reference_failure_regimes(monkeypatch):
+    """The reference's own failure regimes raise (round(inf) in the draw, gym_SBR_oneshot.py:2338); a CPU baseline
+    worker must count such a step and go on -- a crash there once cost the whole bench line."""
+    from oracle import cpu_baseline, sbr_oracle as O
+    calls = {"n": 0}
+    real_step = O.SbrOsOracle.step
+
+    def flaky_step(self, action):
+        calls["n"] += 1
+        if calls["n"] % 3 == 0:
+            raise OverflowError("cannot convert float infinity to integer")
+        return real_step(self, action)
+
+    monkeypatch.setattr(O.SbrOsOracle, "step", flaky_step)
+    dt, acc = cpu_baseline._worker_os((0, 7))
+    assert calls["n"] == 7 and dt > 0 and np.isfinite(acc)
+
+    def broken_cycle(action, infl):
+        raise ValueError("oracle left the physical regime")
+
+    monkeypatch.setattr(O, "sbr_v2_step", broken_cycle)
+    dt, acc = cpu_baseline._worker((0, 2))
+    assert dt >= 0 and acc == 0.0
