@@ -243,6 +243,15 @@ def cycle_dp45_leg(torch, device, core, env, n):
                 "warp_max_rhs_mean": float(cnt[0].view(-1, 32).max(dim=1).values.mean()) if not ordered else None,
                 "rejected_per_env_mean": float(cnt[1].mean()), "bad_status": int((o.status != 0).sum()),
                 "fp64_tflops": n * flops / (ms * 1e-3) / 1e12}
+            if not ordered:
+                # step-count histogram (BASELINE config 3: adaptive-step divergence): quantiles of the per-env RHS
+                # count, and what a warp pays for it -- the slowest of its 32 envs in env order vs in set-point order
+                q = torch.tensor([0.01, 0.1, 0.5, 0.9, 0.99], dtype=torch.float64, device=device)
+                sample = cnt[0][:1 << 18]
+                key = "rtol%g_%s" % (rtol, "env_order")
+                res[key]["rhs_per_env_quantiles_p1_p10_p50_p90_p99"] = [float(v) for v in torch.quantile(sample, q)]
+                by_sp = cnt[0][torch.argsort(env._action[0])]
+                res[key]["warp_max_rhs_mean_if_ordered_by_first_setpoint"] = float(by_sp.view(-1, 32).max(dim=1).values.mean())
     return res
 
 

@@ -263,23 +263,19 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-#ifndef SBR_OS_STEP_HOIST
-#define SBR_OS_STEP_HOIST 1   // 1: every load of the launch is issued before the first use (one DRAM round trip)
-#endif
-
 template <int MODE>
 __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                              SbrTol tol) {
     const int64_t i = (int64_t)blockIdx.x * kOsBlock + threadIdx.x;
     if (i >= g.n) return;
     // All loads of the launch are issued back to back, before anything depends on them: the warp pays ONE DRAM
-    // round trip (state, controller scalars, action, done flag, episode counters), not one per dependent branch.
+    // round trip (state, controller scalars, action, done flag, episode counters), not one per dependent branch
+    // (0.293 -> 0.268 ms per launch of 2^20 envs, profiles/r01f_ab_os_step_hoist_minblocks.log).
     double x[SBR_NX];
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
     sbr::OsCtrl ctl;
     ctl.t = g.st[SBR_OS_T * g.ld + i];
-#if SBR_OS_STEP_HOIST
     const uint8_t was_done = g.done[i];
     ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
     ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
@@ -296,9 +292,6 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
     // lines into L2 now
 #pragma unroll
     for (int j = 0; j < 9; ++j) prefetch_l2(g.st + (SBR_OS_KLA_RING + j) * g.ld + i);
-#else
-    const uint8_t was_done = g.done[i];
-#endif
     const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld}, os{g.state + i, g.ld};
     if (was_done) {
         // stepping a finished episode is a no-op: same observation, zero deltas, reward 0
@@ -308,18 +301,6 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
         if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
         return;
     }
-#if !SBR_OS_STEP_HOIST
-    ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
-    ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
-    ctl.sno_prev = g.st[SBR_OS_SNO_PREV * g.ld + i];
-    ctl.ie_do = g.st[SBR_OS_IE_DO * g.ld + i];
-    ctl.ie_ec = g.st[SBR_OS_IE_EC * g.ld + i];
-    ctl.ec_last = g.st[SBR_OS_EC_LAST * g.ld + i];
-    ctl.kla_last = g.st[(SBR_OS_KLA_RING + 9) * g.ld + i];
-    sbr::Dp45State dp;
-    dp.h = g.st[SBR_OS_H * g.ld + i];
-    const double a_do = g.action[i], a_ec = g.action[g.ld + i];
-#endif
     dp.n_rhs = 0; dp.n_rej = 0;
     const sbr::Column ring{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld};
     sbr::OsStepOut o;
@@ -327,13 +308,8 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
     os_store_ctrl(g.st, g.ld, i, ctl, dp.h);
-#if SBR_OS_STEP_HOIST
     g.st[SBR_OS_RETURN * g.ld + i] = ret0 + o.reward;
     g.st[SBR_OS_STEPS * g.ld + i] = steps0 + 1.0;
-#else
-    g.st[SBR_OS_RETURN * g.ld + i] += o.reward;
-    g.st[SBR_OS_STEPS * g.ld + i] += 1.0;
-#endif
     if (o.done) { g.st[SBR_OS_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
     g.reward[i] = o.reward;
     if (g.status) g.status[i] = o.status;
