@@ -1,5 +1,10 @@
 """Vectorised SBR environments: N independent reactors stepped by one CUDA launch.
 
+Buffer ownership: the tensors a `step` / `reset` returns (observations, state, reward, done, and the entries of
+`info`) are VIEWS of the env's own device buffers -- the kernels write straight into them and the next `step`
+overwrites them (zero copies on the step path).  A rollout that keeps them across steps must `.clone()` or copy
+them into its own storage, as `rollout.collect_episode(store=True)` does.
+
 `SbrV2VecEnv` is the batched drop-in for the reference's `SbrEnv2` (id `SBR-v2`, gym_SBR_env2.py:58-193):
 one `step` = one whole 12-h cycle (fill, 4 react phases, settle, draw, idle) with the DO->KLa PID inside.
 Observation / action / reward semantics are the reference's; tensors are torch CUDA float64.  The reference

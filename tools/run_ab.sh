@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; tail -2 gpurun_out/pytest_gpu_final.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err; echo rc=$?; python - <<'PY'
-import json
-for l in open('gpurun_out/bench_final.log'):
-    if l.startswith('{"metric"'):
-        d = json.loads(l); p = d['paths']
-        print(d['value'], d['roofline']['frac'], d['roofline']['kernel_ms'], d['e2e']['value'], d['cpu_baseline']['value'], d['clocks'])
-        print(json.dumps(p['sbr_v2_dp45']['rtol1e-06_env_order'])[:700])
-PY
+for v in d4 d6; do
+SBR_B200_LIB=$PWD/gym_sbr2_b200/_variants/$v.so python bench.py --mode dp45 --rtol 1e-6 --atol 1e-8 --steps 3 --warmup 3 --no-cpu-baseline --no-interval-path --no-rollout 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{\"metric\"'):
+        d = json.loads(l); print('$v', d['value'], d['roofline']['kernel_ms'], d['roofline'].get('rhs_per_env'))
+"
+done
