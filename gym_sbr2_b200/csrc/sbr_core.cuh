@@ -42,6 +42,10 @@ struct Coef {
     double c124;          // Xnd: ixb - fp*ixp
     double c136;          // Salk: 1/14 -- nu13_k == (nu10_k - nu9_k)/14 for every process k (charge balance)
     double so_sat;
+    // controller gains folded on the host (every env needs them in every launch; an IEEE divide is ~15 instructions
+    // and a ~150-cycle dependency chain on the device): Kc/tauI, Kc*tauD and 1/dt of the three PIDs
+    double pidA_KcI, pidA_KcD;                                 // cycle-per-step DO-PID (also SBR-v4's gains)
+    double os_KcI_DO, os_KcD_DO, os_KcI_EC, os_KcD_EC, os_inv_dt;   // SBROS-v1 DO- and NO3-PID; os_inv_dt also SBR-v4
 };
 
 inline Coef make_coef(const SbrParams& p) {
@@ -61,6 +65,10 @@ inline Coef make_coef(const SbrParams& p) {
     c.c124 = p.ixb - p.fp * p.ixp;
     c.c136 = 1.0 / 14;
     c.so_sat = p.so_sat;
+    c.pidA_KcI = p.pid_Kc / p.pid_tauI; c.pidA_KcD = p.pid_Kc * p.pid_tauD;
+    c.os_KcI_DO = p.os_Kc_DO / p.os_tauI_DO; c.os_KcD_DO = p.os_Kc_DO * p.os_tauD_DO;
+    c.os_KcI_EC = p.os_Kc_EC / p.os_tauI_EC; c.os_KcD_EC = p.os_Kc_EC * p.os_tauD_EC;
+    c.os_inv_dt = 1.0 / p.os_pid_dt;
     return c;
 }
 
@@ -533,9 +541,9 @@ struct PidA {
 // outputs turn NaN; CUDA's fmin/fmax would silently turn it into a bound.
 SBR_HD double clip_keep_nan(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-SBR_HD PidA make_pid_a(const SbrParams& p) {
+SBR_HD PidA make_pid_a(const SbrParams& p, const Coef& c) {
     PidA q;
-    q.Kc = p.pid_Kc; q.Kc_tauI = p.pid_Kc / p.pid_tauI; q.Kc_tauD = p.pid_Kc * p.pid_tauD;
+    q.Kc = p.pid_Kc; q.Kc_tauI = c.pidA_KcI; q.Kc_tauD = c.pidA_KcD;
     q.dt = p.pid_dt; q.lo = p.kla_min; q.hi = p.kla_max;
     return q;
 }
@@ -561,6 +569,11 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
         const double e = sp - so_i;
         double dcv = 0.0;
         if (i >= 1) {
+            // Kept as an IEEE division on purpose (528 per cycle: 0.4 % of the kernel).  With `* pid.inv_dt` the CUDA 12.9
+            // device front end at -O3 breaks the first-same-as-last carry of the adaptive cycle kernel: the carried
+            // stage no longer sees the KLa change, every other step is rejected (2766 instead of 49 per cycle) and
+            // x_last moves by 4e-5.  `-Xcicc -O1`, a volatile barrier here, or disabling the carry all restore the
+            // g++ twin's numbers to 2e-11; tests/test_gpu_v2.py (adaptive mode against the twin) is the tripwire.
             dcv = (so_i - so_prev) / pid.dt;
             ie = ie + e * pid.dt;
         }
@@ -713,7 +726,7 @@ template <int MODE>
 SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading load, double q_fill,
                      const SbrParams& p, const Coef& c, const SbrSchedule& s, const SbrTol& tol,
                      Dp45State& st, CycleOut& o) {
-    const PidA pid = make_pid_a(p);
+    const PidA pid = make_pid_a(p, c);
     double sp3[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sp3[j] = clip_keep_nan(action[j], 0.0, 1.0) * p.action_scale;   // np.clip (:133)
@@ -819,14 +832,14 @@ struct Column {
 };
 
 struct OsPid {
-    double Kc_DO, KcI_DO, KcD_DO, Kc_EC, KcI_EC, KcD_EC, dt, kla_lo, kla_hi, ec_lo, ec_hi;
+    double Kc_DO, KcI_DO, KcD_DO, Kc_EC, KcI_EC, KcD_EC, dt, inv_dt, kla_lo, kla_hi, ec_lo, ec_hi;
 };
 
-SBR_HD OsPid make_os_pid(const SbrParams& p) {
+SBR_HD OsPid make_os_pid(const SbrParams& p, const Coef& c) {
     OsPid q;
-    q.Kc_DO = p.os_Kc_DO; q.KcI_DO = p.os_Kc_DO / p.os_tauI_DO; q.KcD_DO = p.os_Kc_DO * p.os_tauD_DO;
-    q.Kc_EC = p.os_Kc_EC; q.KcI_EC = p.os_Kc_EC / p.os_tauI_EC; q.KcD_EC = p.os_Kc_EC * p.os_tauD_EC;
-    q.dt = p.os_pid_dt; q.kla_lo = p.kla_min; q.kla_hi = p.kla_max; q.ec_lo = p.ec_min; q.ec_hi = p.ec_max;
+    q.Kc_DO = p.os_Kc_DO; q.KcI_DO = c.os_KcI_DO; q.KcD_DO = c.os_KcD_DO;
+    q.Kc_EC = p.os_Kc_EC; q.KcI_EC = c.os_KcI_EC; q.KcD_EC = c.os_KcD_EC;
+    q.dt = p.os_pid_dt; q.inv_dt = c.os_inv_dt; q.kla_lo = p.kla_min; q.kla_hi = p.kla_max; q.ec_lo = p.ec_min; q.ec_hi = p.ec_max;
     return q;
 }
 
@@ -842,7 +855,7 @@ SBR_HD double os_pid_do(OsCtrl& c, double so_last, double sp, bool first, bool a
     const double e = sp - so_last;
     double dcv = 0.0;
     if (!first) {
-        dcv = (so_last - c.so_prev) / q.dt;
+        dcv = (so_last - c.so_prev) * q.inv_dt;      // the reference divides by dt: <= 1 ulp apart
         c.ie_do = c.ie_do + e * q.dt;
     } else {
         c.ie_do = 0.0;
@@ -857,7 +870,7 @@ SBR_HD double os_pid_do(OsCtrl& c, double so_last, double sp, bool first, bool a
 // Error sign reversed (Sno - sp); lower clamp first, `elif` upper.
 SBR_HD double os_pid_ec(OsCtrl& c, double sp, bool dosing, const OsPid& q) {
     const double e = c.sno_last - sp;
-    const double dcv = (c.sno_last - c.sno_prev) / q.dt;
+    const double dcv = (c.sno_last - c.sno_prev) * q.inv_dt;
     c.ie_ec = c.ie_ec + e * q.dt;
     double ec = dosing ? q.Kc_EC * e + q.KcI_EC * c.ie_ec + q.KcD_EC * dcv + c.ec_last : 0.0;
     if (ec < q.ec_lo) { ec = q.ec_lo; c.ie_ec = c.ie_ec - e * q.dt; }
@@ -921,7 +934,7 @@ template <int MODE>
 SBR_HD int os_reset_env(double (&x)[SBR_NX], const Loading& load, const SbrParams& p, const Coef& coef,
                         const SbrOsSchedule& s, const SbrTol& tol, Dp45State& dp, OsCtrl& c, const Column& ring,
                         const Column& obs_do, const Column& obs_ec) {
-    const OsPid pid = make_os_pid(p);
+    const OsPid pid = make_os_pid(p, coef);
     const ObsRef x0r = obs_ref(x);
     const double so0 = x[iSo], sno0 = x[iSno];
     c.so_prev = so0; c.sno_prev = sno0; c.sno_last = sno0;
@@ -978,7 +991,7 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
                         const SbrParams& p, const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol,
                         Dp45State& dp, const Column& obs_do, const Column& obs_ec, const Column& state,
                         OsStepOut& o) {
-    const OsPid pid = make_os_pid(p);
+    const OsPid pid = make_os_pid(p, coef);
     int status = 0, n_run = 0, L = 10;
     double span = s.t_delta, u_do = 0.0, ec_before = c.ec_last;
     double kla_new0 = 0.0, kla_new1 = 0.0;
@@ -1038,7 +1051,7 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
             for (int j = 0; j < L - 2; ++j) esum += c.ec_last;
             double eff[6];
             const double EQI2 = effluent_quality(x, eff) * 0.1;
-            const double ispan = 1.0 / span;
+            const double ispan = rcp(span);
             const double AE = (8 / (1.8 * 1000)) * ispan * (1.32 * ksum * p.os_pid_dt);
             const double ECO = p.ec_conc * esum * p.os_pid_dt * (ispan * 1e-3);
             const double OCI = AE + ECO;
@@ -1122,13 +1135,13 @@ SBR_HD constexpr double inv_x1_v4(int i) {
 }
 
 // Controller block shared by Sim_filling / Sim_rxn / Sim_idle (gym_SBR_env4.py:497-524, 667-697, 1202-1234).
-SBR_HD double v4_pid(V4Ctrl& c, double so_last, bool first, const SbrParams& p) {
+SBR_HD double v4_pid(V4Ctrl& c, double so_last, bool first, const SbrParams& p, const Coef& coef) {
     const double dt = p.os_pid_dt;
     const double e = c.u - so_last;
     double dcv = 0.0;
-    if (!first) { dcv = (so_last - c.so_prev) / dt; c.ie = c.ie + e * dt; }
+    if (!first) { dcv = (so_last - c.so_prev) * coef.os_inv_dt; c.ie = c.ie + e * dt; }
     else c.ie = 0.0;
-    double kla = p.pid_Kc * e + p.pid_Kc / p.pid_tauI * c.ie + p.pid_Kc * p.pid_tauD * dcv + c.kla_last;
+    double kla = p.pid_Kc * e + coef.pidA_KcI * c.ie + coef.pidA_KcD * dcv + c.kla_last;
     if (kla > p.kla_max) { kla = p.kla_max; c.ie = c.ie - e * dt; }
     if (kla < p.kla_min) { kla = p.kla_min; c.ie = c.ie - e * dt; }
     return kla;
@@ -1159,7 +1172,7 @@ SBR_HD void v4_step_env(double (&x)[SBR_NX], V4Ctrl& c, double action, const Loa
         T = sub_rn(t_next, t);
         const int L = (int)div_rn(T, s.dt);                              // len(t_range) (:286)
         n_sub = s.rk4_sub_interval > 0 ? s.rk4_sub_interval : (L > 1 ? L - 1 : 1);
-        a.kla = v4_pid(c, so_start, first, p);
+        a.kla = v4_pid(c, so_start, first, p, coef);
         if (bt == 0) a.q = load(0);
     } else {
         // Sim_Settling_Drawing (:919-1070; its `dt` argument is the control interval) then Sim_idle (:1202-1242)
@@ -1178,7 +1191,7 @@ SBR_HD void v4_step_env(double (&x)[SBR_NX], V4Ctrl& c, double action, const Loa
         tl.max_steps = tol.max_steps * (int)ceil(T / s.t_delta);
         const int pts = (int)div_rn(T, s.dt);
         n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
-        a.kla = v4_pid(c, so_start, false, p);
+        a.kla = v4_pid(c, so_start, false, p, coef);
         t_next = s.t_cycle;
     }
     if (bt == 0) status |= integrate_interval<TAIL_FILL, MODE>(x, T, n_sub, coef, a, tl, dp);
