@@ -81,8 +81,9 @@ inline Coef make_coef(const SbrParams& p) {
 //   below the rounding noise of the reference's own LSODA run -- for 4 % less kernel time (88.5 -> 85.0 ms).
 // SBR_RCP_NEWTON 3: cubic correction r (1 + e + e^2), 3 DFMA, ~2^-57.
 // Tried and rejected: a float seed built with integer instructions + MUFU.RCP (2^-22, then ONE Newton step reaches
-//   9e-13): FP64 instructions hold the issue port for two cycles, every other instruction for one, so the ~13 extra
-//   integer instructions per reciprocal cost more than the DFMA they save (88.5 -> 113.7 ms).
+//   9e-13): beside a saturated FP64 pipe every other instruction still costs ~half an issue cycle and lengthens
+//   the dependency chain, so the ~13 extra integer instructions per reciprocal cost more than the DFMA they save
+//   (88.5 -> 113.7 ms; tools/issue_probe.cu).
 // ---------------------------------------------------------------------------------------------------------
 #ifndef SBR_RCP_NEWTON
 #define SBR_RCP_NEWTON 2
