@@ -582,6 +582,12 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
         if (kla > pid.hi) { kla = pid.hi; ie = ie - e * pid.dt; }
         if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
         if (i == 0) bias = kla;
+#ifdef __CUDA_ARCH__
+        // opaque to the optimiser from here on (no instruction): the first-same-as-last carry below subtracts the
+        // previous interval's KLa from this one, and the device front end has been seen to reason that difference away
+        // (see the note at dcv above)
+        asm volatile("" : "+d"(kla));
+#endif
         a.kla = kla;
         status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
         ksum += kla;
