@@ -570,11 +570,13 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
         const double e = sp - so_i;
         double dcv = 0.0;
         if (i >= 1) {
-            // Kept as an IEEE division on purpose (528 per cycle: 0.4 % of the kernel).  With `* pid.inv_dt` the CUDA 12.9
-            // device front end at -O3 breaks the first-same-as-last carry of the adaptive cycle kernel: the carried
-            // stage no longer sees the KLa change, every other step is rejected (2766 instead of 49 per cycle) and
-            // x_last moves by 4e-5.  `-Xcicc -O1`, a volatile barrier here, or disabling the carry all restore the
-            // g++ twin's numbers to 2e-11; tests/test_gpu_v2.py (adaptive mode against the twin) is the tripwire.
+            // Kept as an IEEE division on purpose (528 per cycle: 0.4 % of the kernel).  With `* (1/dt)` instead, the
+            // adaptive cycle kernel built by CUDA 12.9 at -O3 rejects every other step (2766 instead of 49 per cycle,
+            // 3x the RHS evaluations) and x_last moves by 4e-5, while the g++ build of the same source, the RK4
+            // kernel, a build with `-Xcicc -O1`, one with a volatile copy of dcv, and one without the first-same-as-
+            // last carry all agree with each other to 2e-11.  An optimiser barrier on KLa does not help.  Cause not
+            // established (device front-end optimisation interacting with the FSAL carry); the adaptive-mode tests
+            // of tests/test_gpu_v2.py against the twin are the tripwire.
             dcv = (so_i - so_prev) / pid.dt;
             ie = ie + e * pid.dt;
         }
@@ -582,12 +584,6 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
         if (kla > pid.hi) { kla = pid.hi; ie = ie - e * pid.dt; }
         if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
         if (i == 0) bias = kla;
-#ifdef __CUDA_ARCH__
-        // opaque to the optimiser from here on (no instruction): the first-same-as-last carry below subtracts the
-        // previous interval's KLa from this one, and the device front end has been seen to reason that difference away
-        // (see the note at dcv above)
-        asm volatile("" : "+d"(kla));
-#endif
         a.kla = kla;
         status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
         ksum += kla;
