@@ -134,6 +134,37 @@ def test_vec_env_api_done_noop_and_autoreset(built, cuda_device):
     assert abs(float(state[0, 0]) * 0.5 - g["t"][0]) < 1e-15
 
 
+def test_autoreset_lockstep_path_draws_and_launches_nothing_between_episode_ends(built, cuda_device):
+    """Envs started by one full reset end together: with autoreset the env must not draw influent or reset anything
+    on the other steps (it did, every step, before), and must fall back to the masked path after a partial reset."""
+    n = 64
+    env = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45", autoreset=True)
+    env.reset()
+    a = torch.tensor([[2.0, 5.0]], dtype=torch.float64, device=cuda_device).repeat(n, 1)
+    gen0 = env._gen.get_state().clone()
+    for k in range(463):
+        _, _, _, done, info = env.step(a)
+        assert not bool(info["restarted"].any())
+        assert bool(done.all()) == (k == 462)
+    assert torch.equal(env._gen.get_state(), gen0)                       # nothing was drawn during the episode
+    ret1 = info["episode_return"].clone()
+    _, _, _, done, info = env.step(a)                                    # first step of the second episode
+    assert bool(info["restarted"].all()) and not bool(done.any()) and float(info["episode_steps"].max()) == 1
+    assert not torch.equal(env._gen.get_state(), gen0)                   # one influent draw per episode
+    for k in range(462):
+        _, _, _, done, info = env.step(a)
+    assert bool(done.all()) and float(info["episode_steps"].min()) == 463
+    assert bool(torch.isfinite(info["episode_return"]).all()) and not torch.equal(info["episode_return"], ret1)
+    # a partial reset leaves lock-step: the general (masked, every step) path takes over and still restarts envs
+    mask = torch.zeros(n, dtype=torch.bool, device=cuda_device)
+    mask[: n // 2] = True
+    env.reset(mask=mask)
+    assert env._lockstep is False
+    _, _, _, done, info = env.step(a)
+    assert bool(info["restarted"][n // 2:].all()) and not bool(info["restarted"][: n // 2].any())
+    assert float(info["episode_steps"].max()) == 1 and not bool(done.any())
+
+
 def test_argument_errors_do_not_launch(built, cuda_device):
     lib = _abi.load()
     p, s = _abi.default_params(), schedule.os_schedule()
