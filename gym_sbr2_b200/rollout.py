@@ -78,6 +78,10 @@ class GraphedStepper(object):
         with torch.cuda.graph(self.graph), torch.no_grad():
             for _ in range(self.k):
                 self._one(b)
+        # replays advance the envs without passing through the env's host-side episode clock: autoreset must not
+        # rely on it any more (it falls back to its masked, every-step path; a full reset() re-arms the clock, and
+        # replay() below takes it out again)
+        env._lockstep = False
 
     def _one(self, b):
         self.action.copy_(self.policy.forward_soa(b.obs_do, b.obs_ec))
@@ -85,6 +89,7 @@ class GraphedStepper(object):
 
     def replay(self):
         """Advance every env by steps_per_replay env.steps."""
+        self.env._lockstep = False
         self.graph.replay()
 
 
