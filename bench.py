@@ -118,17 +118,30 @@ def measure_fp64_peak(core, torch, device):
 
 
 def cpu_baseline_leg(target_s):
-    """cpu_baseline: the oracle port of the reference's scipy-odeint path on every host core, on a bounded
-    sample of the same workload (independent seeded SBR-v2 cycle-steps) sized to ~target_s seconds."""
+    """cpu_baseline: the UNMODIFIED reference (baseline/_ref, installed by oracle/install_ref.py) on every host core,
+    one process per core, on a bounded sample of the same workload (independent seeded SBR-v2 episodes: reset influent
+    draw + one whole-cycle step) sized to ~target_s seconds; the oracle port's number is reported beside it.  Falls
+    back to the port (kind "port") only when no reference install travelled with the snapshot."""
     from oracle import cpu_baseline
     cores = cpu_baseline.usable_cores()
-    probe = cpu_baseline.run(steps_per_proc=2, procs=cores, warmup=1)
+    have_ref = cpu_baseline.reference_root() is not None
+    runner = cpu_baseline.run_reference if have_ref else cpu_baseline.run
+    probe = runner(steps_per_proc=2, procs=cores, warmup=1)
     per_proc_rate = probe["steps"] / cores / probe["wall_s"]
     spp = max(2, min(400, int(round(target_s * per_proc_rate))))
-    r = cpu_baseline.run(steps_per_proc=spp, procs=cores, warmup=0)
-    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "per_core": r["per_core"],
-            "sample": "%d SBR-v2 cycle-steps (%d procs x %d, reset influent draw + whole-cycle step each; oracle "
-                      "port of the reference's scipy LSODA path), %.1f s wall" % (r["steps"], r["cores"], spp, r["wall_s"])}
+    r = runner(steps_per_proc=spp, procs=cores, warmup=0)
+    out = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference" if have_ref else "port",
+           "per_core": r["per_core"],
+           "sample": "%d SBR-v2 cycle-steps (%d procs x %d: np.random.seed, SbrEnv2.reset() influent draw + "
+                     "step(action) each; %s), %.1f s wall"
+                     % (r["steps"], r["cores"], spp,
+                        "unmodified reference from %s, scipy LSODA" % r.get("root") if have_ref
+                        else "oracle port of the reference's scipy LSODA path", r["wall_s"])}
+    if have_ref:
+        pr = cpu_baseline.run(steps_per_proc=max(2, spp // 2), procs=cores, warmup=1)
+        out["port"] = {"value": pr["value"], "per_core": pr["per_core"],
+                       "note": "oracle/sbr_oracle.py restatement (no trajectory appends, no prints)"}
+    return out
 
 
 # interval-per-step path: algorithmic flops (SURVEY.md 8d) and bytes per env per env.step
@@ -414,27 +427,32 @@ def cycle_substeps_leg(torch, device, core, env, n, substeps):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port of the scipy-odeint
-    path, all host cores), same metric/unit/config.  Under torchrun only rank 0 works."""
+    """--impl reference: the reference's own CPU implementation of the path -- the unmodified package from
+    baseline/_ref through its own SbrEnv2.reset()/step(), one process per host core -- same metric/unit/config.
+    Falls back to the oracle port when no reference install is present.  Under torchrun only rank 0 works."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from oracle import cpu_baseline
     cores = cpu_baseline.usable_cores()
+    have_ref = cpu_baseline.reference_root() is not None
+    runner = cpu_baseline.run_reference if have_ref else cpu_baseline.run
     per_proc = max(1, args.ref_steps_per_proc)
-    times, total = [], 0
+    total, t_all = 0, 0.0
     for _ in range(args.warmup):
-        cpu_baseline.run(steps_per_proc=1, procs=cores, warmup=0)
-    t_all = 0.0
+        runner(steps_per_proc=1, procs=cores, warmup=0)
     for _ in range(args.steps):
-        r = cpu_baseline.run(steps_per_proc=per_proc, procs=cores, warmup=1)
-        times.append(r["wall_s"]); total += r["steps"]; t_all += r["wall_s"]
+        r = runner(steps_per_proc=per_proc, procs=cores, warmup=1)
+        total += r["steps"]; t_all += r["wall_s"]
     value = total / t_all
-    sample = "%d procs x %d SBR-v2 cycle-steps per bench step (reset influent draw + step), scipy LSODA" % (cores, per_proc)
+    kind = "reference" if have_ref else "port"
+    sample = ("%d procs x %d SBR-v2 cycle-steps per bench step (np.random.seed, reset influent draw + step); %s"
+              % (cores, per_proc, "unmodified reference (baseline/_ref) SbrEnv2, scipy LSODA" if have_ref
+                 else "oracle port, scipy LSODA"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "envs_per_gpu": args.envs_per_gpu, "integrator": "lsoda"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "interval_steps_per_sec": value * INTERVALS_PER_CYCLE, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -656,11 +674,13 @@ def main():
 
     def cpu_os_leg():
         from oracle import cpu_baseline as _cb
-        r = _cb.run_os(steps_per_proc=6000)
-        return {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"], "kind": "port",
-                "per_core": r["per_core"],
-                "sample": "%d SBROS-v1 env.steps (%d procs x 6000; oracle port of the reference's scipy LSODA path), "
-                          "%.1f s wall" % (r["steps"], r["cores"], r["wall_s"])}
+        have_ref = _cb.reference_root() is not None
+        r = _cb.run_reference(steps_per_proc=6000, warmup=20, path="os") if have_ref else _cb.run_os(steps_per_proc=6000)
+        return {"value": r["value"], "unit": "interval-steps/s", "cores": r["cores"],
+                "kind": "reference" if have_ref else "port", "per_core": r["per_core"],
+                "sample": "%d SBROS-v1 env.steps (%d procs x 6000; %s), %.1f s wall"
+                          % (r["steps"], r["cores"], "unmodified reference SbrOS, scipy LSODA" if have_ref
+                             else "oracle port of the reference's scipy LSODA path", r["wall_s"])}
 
     cpu, cpu_os = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -44,7 +44,7 @@ struct Coef {
     double so_sat;
     // controller gains folded on the host (every env needs them in every launch; an IEEE divide is ~15 instructions
     // and a ~150-cycle dependency chain on the device): Kc/tauI, Kc*tauD and 1/dt of the three PIDs
-    double pidA_KcI, pidA_KcD;                                 // cycle-per-step DO-PID (also SBR-v4's gains)
+    double pidA_KcI, pidA_KcD, pidA_inv_dt;                    // cycle-per-step DO-PID (also SBR-v4's gains)
     double os_KcI_DO, os_KcD_DO, os_KcI_EC, os_KcD_EC, os_inv_dt;   // SBROS-v1 DO- and NO3-PID; os_inv_dt also SBR-v4
 };
 
@@ -65,7 +65,7 @@ inline Coef make_coef(const SbrParams& p) {
     c.c124 = p.ixb - p.fp * p.ixp;
     c.c136 = 1.0 / 14;
     c.so_sat = p.so_sat;
-    c.pidA_KcI = p.pid_Kc / p.pid_tauI; c.pidA_KcD = p.pid_Kc * p.pid_tauD;
+    c.pidA_KcI = p.pid_Kc / p.pid_tauI; c.pidA_KcD = p.pid_Kc * p.pid_tauD; c.pidA_inv_dt = 1.0 / p.pid_dt;
     c.os_KcI_DO = p.os_Kc_DO / p.os_tauI_DO; c.os_KcD_DO = p.os_Kc_DO * p.os_tauD_DO;
     c.os_KcI_EC = p.os_Kc_EC / p.os_tauI_EC; c.os_KcD_EC = p.os_Kc_EC * p.os_tauD_EC;
     c.os_inv_dt = 1.0 / p.os_pid_dt;
@@ -329,16 +329,6 @@ struct Dp45State {
     uint32_t n_rej;    // rejected steps
 };
 
-// First-same-as-last across PID intervals.  The last stage of an interval is f(x_end); the next interval starts
-// from the same state with only KLa changed by the PID, and KLa enters the right-hand side linearly and only in
-// d(So)/dt -- so its first stage is the carried one plus (KLa_new - KLa_old)(So_sat - So) in the So component.
-// Valid inside one phase (same tail, same flow); saves one of ~13 RHS evaluations per interval.
-struct Fsal {
-    double k[SBR_NX];
-    double g, kla;
-    bool valid;
-};
-
 // Per-component absolute-tolerance scale: atol_i = atol * scale_i, scale from the reference's own
 // normalisation vector x_1_state (gym_SBR_oneshot.py:153) so that So ~ 1e-15 in anoxic phases does not
 // drive the step to zero.
@@ -352,7 +342,7 @@ SBR_HD constexpr double tol_scale(int i) {
 // Returns status bits (0 or SBR_ST_STEPLIMIT).  The error norm is the RMS over the 9 active components.
 template <int TAIL>
 SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coef& c, const TailArgs& a,
-                         const SbrTol& tol, Dp45State& st, double& xpq, Fsal& fs) {
+                         const SbrTol& tol, Dp45State& st, double& xpq) {
     // Butcher tableau (Dormand & Prince 1980): on the device the coefficients are operands straight from the
     // constant bank (kDpTab) -- as literals the compiler rebuilds 24 of them with two UMOVs each in every step
 #ifdef __CUDA_ARCH__
@@ -375,17 +365,8 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
     int steps = 0;
 #pragma unroll
     for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
-    double g1;
-    if (fs.valid) {
-#pragma unroll
-        for (int i = 0; i < SBR_NX; ++i)
-            if (active(i)) k1[i] = fs.k[i];
-        k1[iSo] = fma(a.kla - fs.kla, c.so_sat - x[iSo], k1[iSo]);
-        g1 = fs.g;
-    } else {
-        g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
-        st.n_rhs += 1;
-    }
+    double g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
+    st.n_rhs += 1;
     while (t < T) {
         if (steps >= tol.max_steps) { status = SBR_ST_STEPLIMIT; break; }
         ++steps;
@@ -472,11 +453,6 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         else h = fmax(h, hs * (double)fac);
     }
     st.h = h;
-#pragma unroll
-    for (int i = 0; i < SBR_NX; ++i)
-        if (active(i)) fs.k[i] = k1[i];
-    fs.g = g1; fs.kla = a.kla;
-    fs.valid = (status == 0) && (t >= T) && (fabs(g1) < 1e300);
     return status;
 }
 
@@ -486,7 +462,7 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
 // ---------------------------------------------------------------------------------------------------------
 template <int TAIL, int MODE>
 SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
-                              const TailArgs& a_in, const SbrTol& tol, Dp45State& st, Fsal& fs) {
+                              const TailArgs& a_in, const SbrTol& tol, Dp45State& st) {
     TailArgs a = a_in;
     a.kla_sat = a.kla * c.so_sat;
     const Flow f{x[iV], TAIL == TAIL_REACT ? 0.0 : a.q};
@@ -498,7 +474,7 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
         for (int s = 0; s < n_sub; ++s) rk4_step<TAIL>(x, (double)s * h, h, f, c, a, xpq);
         st.n_rhs += 4u * (uint32_t)n_sub;
     } else {
-        status = dp45_interval<TAIL>(x, T, f, c, a, tol, st, xpq, fs);
+        status = dp45_interval<TAIL>(x, T, f, c, a, tol, st, xpq);
     }
     const double dN = ((x[iSnh] - snh0) - (x[iSno] - sno0)) * c.c136;
     if (TAIL == TAIL_REACT) {
@@ -522,19 +498,11 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
     return status;
 }
 
-template <int TAIL, int MODE>
-SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Coef& c,
-                              const TailArgs& a, const SbrTol& tol, Dp45State& st) {
-    Fsal fs;
-    fs.valid = false;
-    return integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // DO -> KLa positional PID of the cycle-per-step path (sub_phases_FB.py:233-250).
 // ---------------------------------------------------------------------------------------------------------
 struct PidA {
-    double Kc, Kc_tauI, Kc_tauD, dt, lo, hi;
+    double Kc, Kc_tauI, Kc_tauD, dt, inv_dt, lo, hi;
 };
 
 // Clipping as the reference does it (np.clip / min(max(a, lo), hi) / if-elif chains): a NaN action is NOT
@@ -545,8 +513,27 @@ SBR_HD double clip_keep_nan(double v, double lo, double hi) { return v < lo ? lo
 SBR_HD PidA make_pid_a(const SbrParams& p, const Coef& c) {
     PidA q;
     q.Kc = p.pid_Kc; q.Kc_tauI = c.pidA_KcI; q.Kc_tauD = c.pidA_KcD;
-    q.dt = p.pid_dt; q.lo = p.kla_min; q.hi = p.kla_max;
+    q.dt = p.pid_dt; q.inv_dt = c.pidA_inv_dt; q.lo = p.kla_min; q.hi = p.kla_max;
     return q;
+}
+
+// One update of the positional DO->KLa PID (sub_phases_FB.py:233-250).  `first` = interval 0 of a phase: no
+// derivative / integral update, and the clamped output becomes the bias of the phase's later intervals (:218,243).
+// Two independent clamp checks, each undoing the integral update (:245-250).  The derivative uses the gain folded
+// on the host (1/dt, at most 1 ulp from the reference's division), like the interval-per-step PIDs.
+SBR_HD double pid_a_update(const PidA& pid, double sp, double so_i, double so_prev, bool first, double& ie,
+                           double& bias) {
+    const double e = sp - so_i;
+    double dcv = 0.0;
+    if (!first) {
+        dcv = (so_i - so_prev) * pid.inv_dt;
+        ie = ie + e * pid.dt;
+    }
+    double kla = pid.Kc * e + pid.Kc_tauI * ie + pid.Kc_tauD * dcv + bias;
+    if (kla > pid.hi) { kla = pid.hi; ie = ie - e * pid.dt; }
+    if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
+    if (first) bias = kla;
+    return kla;
 }
 
 struct PhaseOut {
@@ -554,9 +541,8 @@ struct PhaseOut {
     double kla_last;
 };
 
-// One PID-controlled phase = filling.sim_rxn / rxn.sim_rxn (sub_phases_FB.py:178-271, 406-500).
-// The bias of intervals i >= 1 is the clamped output of interval 0 (:218,243); So is sampled at interval
-// starts; two independent clamp checks each undo the integral update (:245-250).
+// One PID-controlled phase = filling.sim_rxn / rxn.sim_rxn (sub_phases_FB.py:178-271, 406-500), interval by
+// interval: the fixed-step (RK4) form of the cycle path.  So is sampled at interval starts.
 template <int TAIL, int MODE>
 SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double sp, double kla_in,
                      const Coef& c, TailArgs a, const PidA& pid, const SbrTol& tol, Dp45State& st,
@@ -564,34 +550,248 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
     double bias = kla_in, ie = 0.0, so_prev = 0.0, so_i = x[iSo];
     double ksum = 0.0, kla = kla_in;
     int status = 0;
-    Fsal fs;
-    fs.valid = false;
     for (int i = 0; i < n_int; ++i) {
-        const double e = sp - so_i;
-        double dcv = 0.0;
-        if (i >= 1) {
-            // Kept as an IEEE division on purpose (528 per cycle: 0.4 % of the kernel).  With `* (1/dt)` instead, the
-            // adaptive cycle kernel built by CUDA 12.9 at -O3 rejects every other step (2766 instead of 49 per cycle,
-            // 3x the RHS evaluations) and x_last moves by 4e-5, while the g++ build of the same source, the RK4
-            // kernel, a build with `-Xcicc -O1`, one with a volatile copy of dcv, and one without the first-same-as-
-            // last carry all agree with each other to 2e-11.  An optimiser barrier on KLa does not help.  Cause not
-            // established (device front-end optimisation interacting with the FSAL carry); the adaptive-mode tests
-            // of tests/test_gpu_v2.py against the twin are the tripwire.
-            dcv = (so_i - so_prev) / pid.dt;
-            ie = ie + e * pid.dt;
-        }
-        kla = pid.Kc * e + pid.Kc_tauI * ie + pid.Kc_tauD * dcv + bias;
-        if (kla > pid.hi) { kla = pid.hi; ie = ie - e * pid.dt; }
-        if (kla < pid.lo) { kla = pid.lo; ie = ie - e * pid.dt; }
-        if (i == 0) bias = kla;
+        kla = pid_a_update(pid, sp, so_i, so_prev, i == 0, ie, bias);
         a.kla = kla;
-        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st, fs);
+        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st);
         ksum += kla;
         so_prev = so_i;
         so_i = x[iSo];
     }
     out.kla_sum = ksum;
     out.kla_last = kla;
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adaptive (Dormand-Prince) form of the cycle path: one SEGMENT = a run of consecutive PID-controlled phases that
+// share a tail (fill | react phases 2-5 | idle), integrated by ONE loop whose body is "one step attempt".
+//
+// Why not interval by interval (as pid_phase does for RK4): with per-env step sizes the envs of a warp need
+// different numbers of steps in every 72-s interval, and a loop nest "for interval: while (t < T)" re-converges
+// the warp at the end of every interval -- the warp pays the slowest env 528 times per cycle (measured in round 1:
+// 29.6 of 32 lanes active even with envs sorted by set-point, 19 in env order).  Here the interval / phase
+// bookkeeping (PID update, KLa jump, phase switch) is a short predicated block INSIDE the step loop, so every lane
+// runs through its own intervals at its own pace and the warp only re-converges at the end of the segment: it
+// pays max_lane(sum of steps), not sum_interval(max_lane steps).
+//
+// First-same-as-last is kept across PID intervals and phase switches of a segment: the last stage of an interval
+// is f(x_end); the next interval starts from the same state with only KLa changed by the PID, and KLa enters the
+// right-hand side linearly and only in d(So)/dt -- so the carried stage is corrected by dKLa (So_sat - So).  dKLa
+// is formed from the PID output and the KLa still held in `kla` BEFORE `kla` is overwritten: round 1 kept a
+// second loop-carried copy (Fsal::kla) and ptxas 12.9 coalesced that copy with the new value ("lost copy":
+// `DADD R12, R74, -R74` -- the correction compiled to zero, profiles/r02_fsal_lost_copy_sass.txt).
+//
+// Register budget (this is what bounds occupancy): the classical formulation keeps x, y and six stage vectors
+// live (72 doubles).  Here the 5th-order solution and the error estimate are accumulated as soon as their
+// inputs exist, so that k2..k5 die when the input of stage 6 is formed, and (SBR_DP_PARK) k3 and k4 wait in a
+// shared-memory column while they are not needed (45 LDS/STS per step against 620 FP64 instructions): at most
+// five vectors are live inside any kinetics evaluation.  The passive components (V, Si, Xi, Xp, Salk) leave the
+// loop entirely: closed forms / one quadrature over the whole segment (see the table above `active`).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef SBR_DP_PARK
+#define SBR_DP_PARK 1
+#endif
+
+// Packed index of an active component (0..8).
+SBR_HD constexpr int aidx(int i) {
+    return i == iSs ? 0 : i == iXs ? 1 : i == iXbh ? 2 : i == iXba ? 3 : i == iSo ? 4 : i == iSno ? 5
+         : i == iSnh ? 6 : i == iSnd ? 7 : 8;
+}
+
+// Scratch column of one env outside the register file: slot j at p[j * stride] (shared memory on the device,
+// conflict-free for consecutive threads; a local array in the CPU twin).  Accesses are volatile so that the
+// compiler neither forwards a parked value through a register nor reorders the accesses.
+enum { PARK_K3 = 0, PARK_K4 = 9, PARK_KSUM = 18, PARK_SLOTS = 22 };
+struct Park {
+    double* p;
+    int stride;
+    SBR_HD void put(int j, double v) const { ((volatile double*)p)[j * stride] = v; }
+    SBR_HD double get(int j) const { return ((volatile double*)p)[j * stride]; }
+};
+
+// ph0: schedule index of the segment's first phase; NPH phases follow each other in the schedule; sp[]: this env's
+// DO set-point per phase.  On return: x = state at the end of the segment (all 14 components), kla_last = KLa of the
+// last interval, park slots PARK_KSUM + j = sum of the per-interval KLa of phase j.  Returns status bits.
+template <int TAIL, int NPH>
+SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, const double (&sp)[NPH], double kla_in,
+                        const Coef& c, TailArgs a, const PidA& pid, const SbrTol& tol, Dp45State& st,
+                        const Park& park, double& kla_last) {
+#ifdef __CUDA_ARCH__
+    const DpTab& tb = kDpTab;
+#else
+    const DpTab tb = SBR_DP_TABLEAU;
+#endif
+    const double V_start = x[iV], snh0 = x[iSnh], sno0 = x[iSno];
+    Flow f{V_start, TAIL == TAIL_REACT ? 0.0 : a.q};      // f.V0 = volume at the start of the current interval
+    double xpq = 0.0;                                      // Xp quadrature over the whole segment
+    // controller state of the current phase
+    int ph = 0, i_int = 0, n_int = s.n_int[ph0];
+    double T = s.interval[ph0], spc = sp[0];
+    double bias = kla_in, ie = 0.0, so_prev = 0.0, so_i = x[iSo], ksum = 0.0;
+    double kla = pid_a_update(pid, spc, so_i, so_prev, true, ie, bias);
+    a.kla = kla;
+    a.kla_sat = kla * c.so_sat;
+    double k1[SBR_NX], k2[SBR_NX], k3[SBR_NX], k4[SBR_NX], k5[SBR_NX], y[SBR_NX], sol[SBR_NX], err[SBR_NX];
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
+    double g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
+    st.n_rhs += 1;
+    double t = 0.0;
+    double h = st.h * SBR_DP_FIRST;   // KLa has just jumped: the carried proposal is discounted for the first step
+    int status = 0, steps = 0;
+    for (;;) {
+        bool end_interval = false;
+        if (steps >= tol.max_steps) {
+            // work bound of an env that has left the physical regime: give the interval up (state flagged)
+            status |= SBR_ST_STEPLIMIT;
+            end_interval = true;
+        } else {
+            ++steps;
+            // spread what is left of the interval over equal steps no longer than the controller's proposal: a
+            // proposal that does not divide the interval would otherwise end it with a sliver step (6 RHS for nothing)
+            const double rem = T - t;
+            const float n_f = ceilf((float)rem * __frcp_rn_compat((float)h) * 0.99999f);   // float is plenty for a count
+            const bool last = !(n_f > 1.0f);
+            const double hs = last ? rem : rem * (double)__frcp_rn_compat(n_f);
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) y[i] = fma(hs * tb.a21, k1[i], x[i]);
+            stage<TAIL>(y, k2, fma(tb.c2, hs, t), f, c, a);   // b2 = 0: no quadrature contribution
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) y[i] = fma(hs * tb.a32, k2[i], fma(hs * tb.a31, k1[i], x[i]));
+            const double g3 = stage<TAIL>(y, k3, fma(tb.c3, hs, t), f, c, a);
+            double gq = fma(tb.b3, g3, tb.b1 * g1);
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) {
+                    y[i] = fma(hs * tb.a43, k3[i], fma(hs * tb.a42, k2[i], fma(hs * tb.a41, k1[i], x[i])));
+                    if (SBR_DP_PARK) park.put(PARK_K3 + aidx(i), k3[i]);
+                }
+            const double g4 = stage<TAIL>(y, k4, fma(tb.c4, hs, t), f, c, a);
+            gq = fma(tb.b4, g4, gq);
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) {
+                    const double k3i = SBR_DP_PARK ? park.get(PARK_K3 + aidx(i)) : k3[i];
+                    y[i] = fma(hs * tb.a54, k4[i], fma(hs * tb.a53, k3i, fma(hs * tb.a52, k2[i],
+                           fma(hs * tb.a51, k1[i], x[i]))));
+                    if (SBR_DP_PARK) park.put(PARK_K4 + aidx(i), k4[i]);
+                }
+            const double g5 = stage<TAIL>(y, k5, fma(tb.c5, hs, t), f, c, a);
+            gq = fma(tb.b5, g5, gq);
+            // input of stage 6, and everything of the 5th-order solution and of the error estimate that k1..k5
+            // contribute: k2..k5 are dead after this block
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) {
+                    const double k3i = SBR_DP_PARK ? park.get(PARK_K3 + aidx(i)) : k3[i];
+                    const double k4i = SBR_DP_PARK ? park.get(PARK_K4 + aidx(i)) : k4[i];
+                    y[i] = fma(hs * tb.a65, k5[i], fma(hs * tb.a64, k4i, fma(hs * tb.a63, k3i,
+                           fma(hs * tb.a62, k2[i], fma(hs * tb.a61, k1[i], x[i])))));
+                    sol[i] = fma(hs * tb.b5, k5[i], fma(hs * tb.b4, k4i, fma(hs * tb.b3, k3i,
+                             fma(hs * tb.b1, k1[i], x[i]))));
+                    err[i] = fma(tb.e5, k5[i], fma(tb.e4, k4i, fma(tb.e3, k3i, tb.e1 * k1[i])));
+                }
+            const double g6 = stage<TAIL>(y, k2, t + hs, f, c, a);       // k6 lands in k2's registers
+            gq = fma(tb.b6, g6, gq);
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) {
+                    sol[i] = fma(hs * tb.b6, k2[i], sol[i]);
+                    err[i] = fma(tb.e6, k2[i], err[i]);
+                }
+            const double g7 = stage<TAIL>(sol, k2, t + hs, f, c, a);     // k7 = f(5th-order solution)
+            st.n_rhs += 6;
+            // error estimate, RMS norm over the active components (h is factored out of the 9 components; the
+            // per-component scale only steers the controller, so its reciprocal is the raw MUFU approximation)
+            double en = 0.0;
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) {
+                    const double e_i = fma(tb.e7, k2[i], err[i]);
+                    const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(sol[i])), tol.atol * tol_scale(i));
+                    const double q = e_i * rcp_rough(sc);
+                    en = fma(q, q, en);
+                }
+            en = en * (hs * hs * (1.0 / 9));   // mean square
+            const bool finite = en < 1e300;   // false for NaN/Inf
+            if (en <= 1.0 || !finite) {
+                // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
+                t = (last || !finite) ? T : t + hs;
+                xpq = fma(hs, gq, xpq);
+                g1 = g7;
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) { x[i] = sol[i]; k1[i] = k2[i]; }
+                end_interval = t >= T;
+            } else {
+                st.n_rej += 1;
+            }
+            // step-size controller: h *= clamp(safety * en^(-1/10), 0.2, max growth)  (en is the SQUARED norm).  A
+            // rejected step costs 6 RHS evaluations, so the constants lean conservative.
+            float fac = SBR_DP_MAXGROW;
+            if (en > 1e-20) {
+                fac = SBR_DP_SAFETY * pow_m01((float)en);
+                fac = fminf(SBR_DP_MAXGROW, fmaxf(0.2f, fac));
+            }
+            if (en > 1.0) fac = fminf(fac, 1.0f);
+            if (!(last && en <= 1.0)) h = hs * (double)fac;   // a truncated final step does not shrink the carry
+            else h = fmax(h, hs * (double)fac);
+        }
+        if (end_interval) {
+            // ---- end of a PID interval (sub_phases_FB.py:226-265): sample So, next PID output, KLa jump ----
+            ksum += kla;
+            so_prev = so_i;
+            so_i = x[iSo];
+            if (TAIL != TAIL_REACT) f.V0 = f.V(T);
+            ++i_int;
+            bool first = false;
+            if (i_int == n_int) {
+                // ---- end of a phase (SBR_model_FB.py:88-172): the next one starts from this phase's last KLa ----
+                park.put(PARK_KSUM + ph, ksum);
+                ksum = 0.0;
+                ++ph;
+                if (ph == NPH) break;
+                i_int = 0;
+                n_int = s.n_int[ph0 + ph];
+                T = s.interval[ph0 + ph];
+#pragma unroll
+                for (int j = 1; j < NPH; ++j)
+                    if (ph == j) spc = sp[j];
+                ie = 0.0; bias = kla; first = true;
+            }
+            const double kla_new = pid_a_update(pid, spc, so_i, so_prev, first, ie, bias);
+            // first-same-as-last across the KLa jump: dKLa from the OLD kla, then overwrite it (see the header)
+            k1[iSo] = fma(kla_new - kla, c.so_sat - x[iSo], k1[iSo]);
+            kla = kla_new;
+            a.kla = kla_new;
+            a.kla_sat = kla_new * c.so_sat;
+            t = 0.0;
+            steps = 0;
+            h = h * SBR_DP_FIRST;
+        }
+    }
+    st.h = h;
+    kla_last = kla;
+    // ---- passive components over the whole segment (closed forms; see the table above `active`) ----
+    if (TAIL == TAIL_REACT) {
+        x[iXp] = fma(c.ixp, xpq, x[iXp]);
+        x[iSalk] += ((x[iSnh] - snh0) - (x[iSno] - sno0)) * c.c136;
+    } else {
+        const double V_end = f.V0;
+        const double w = V_start / V_end, u = (V_end - V_start) / V_end;   // x_end = x_start V_start/V_end + c_in dV/V_end
+        x[iV] = V_end;
+        x[iSi] = fma(x[iSi], w, cin<TAIL>(a, iSi) * u);
+        x[iXi] = fma(x[iXi], w, cin<TAIL>(a, iXi) * u);
+        x[iXp] = fma(x[iXp], w, fma(cin<TAIL>(a, iXp), u, c.ixp * xpq / V_end));
+        // D = Salk - (Snh - Sno)/14 is a pure dilution variable (charge balance): closed form, nitrogen part added back
+        const double n0 = (snh0 - sno0) * c.c136;
+        const double n_in = (cin<TAIL>(a, iSnh) - cin<TAIL>(a, iSno)) * c.c136;
+        const double D1 = fma(x[iSalk] - n0, w, (cin<TAIL>(a, iSalk) - n_in) * u);
+        x[iSalk] = D1 + (x[iSnh] - x[iSno]) * c.c136;
+    }
     return status;
 }
 
@@ -723,12 +923,33 @@ struct CycleOut {
     int status;
 };
 
+// Epilogue shared by both integrator forms: reward (module_reward.py:4-51), observation and aux rows
+// (gym_SBR_env2.py:156-171).
+SBR_HD void cycle_epilogue(const double (&x)[SBR_NX], const SbrParams& p, const DrawOut& d, const double (&kla_mean)[3],
+                           int status, CycleOut& o) {
+    double reward, OCI;
+    reward_v2(p, kla_mean[0], kla_mean[1], kla_mean[2], d.Qw, d.eff[3], reward, OCI);
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);
+    if (!finite || !(fabs(reward) < 1e300)) status |= SBR_ST_NONFINITE;
+    o.obs[0] = p.Qeff; o.obs[1] = d.eff[2]; o.obs[2] = d.eff[3] / 30;
+    o.reward = reward;
+    o.aux[SBR_AUX_OCI] = OCI; o.aux[SBR_AUX_QW] = d.Qw; o.aux[SBR_AUX_EQI] = d.EQI;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o.aux[SBR_AUX_EFF_Q + j] = d.eff[j];
+    o.aux[SBR_AUX_KLA3_MEAN] = kla_mean[0]; o.aux[SBR_AUX_KLA5_MEAN] = kla_mean[1];
+    o.aux[SBR_AUX_KLA8_MEAN] = kla_mean[2];
+    o.status = status;
+}
+
 // Whole cycle = SBR_model_FB.run (SBR_model_FB.py:8-295) + SbrEnv2.step epilogue (gym_SBR_env2.py:131-171).
 // x: in = start state, out = state after the idle phase.  action: raw, clipped here.
+// MODE RK4: interval by interval (pid_phase); MODE DP45: three segments (dp45_segment), `park` required.
 template <int MODE>
 SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading load, double q_fill,
                      const SbrParams& p, const Coef& c, const SbrSchedule& s, const SbrTol& tol,
-                     Dp45State& st, CycleOut& o) {
+                     Dp45State& st, CycleOut& o, const Park& park) {
     const PidA pid = make_pid_a(p, c);
     double sp3[3];
 #pragma unroll
@@ -736,13 +957,36 @@ SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading loa
     TailArgs a;
     a.kla = 0.0; a.q = q_fill; a.ec_conc = 0.0; a.load = load;
     int status = 0;
-    PhaseOut po;
     double kla_mean[3] = {0.0, 0.0, 0.0};
+    DrawOut d;
+    if (MODE == SBR_MODE_DP45) {
+        double kla = 0.0;
+        // phase 1: fill, set-point 0 (gym_SBR_env2.py:54)
+        const double sp_fill[1] = {0.0};
+        status |= dp45_segment<TAIL_FILL, 1>(x, s, 0, sp_fill, p.kla0, c, a, pid, tol, st, park, kla);
+        a.q = 0.0;
+        // phases 2..5 react with set-points [0, sp3[0], 0, sp3[1]], each biased by the previous phase's last KLa
+        // (SBR_model_FB.py:94,120,146,172)
+        const double sp_react[4] = {0.0, sp3[0], 0.0, sp3[1]};
+        status |= dp45_segment<TAIL_REACT, 4>(x, s, 1, sp_react, kla, c, a, pid, tol, st, park, kla);
+        kla_mean[0] = park.get(PARK_KSUM + 1) / (double)s.n_int[2];
+        kla_mean[1] = park.get(PARK_KSUM + 3) / (double)s.n_int[4];
+        double sX[10], Xf;
+        settle_closed_form(x, s.settle_time, p.settler_area, p.settler_vmax, sX, Xf);
+        draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+        status |= d.status;
+        // phase 8 idle with set-point sp3[2], biased by phase 5's last KLa (:266)
+        const double sp_idle[1] = {sp3[2]};
+        status |= dp45_segment<TAIL_REACT, 1>(x, s, 7, sp_idle, kla, c, a, pid, tol, st, park, kla);
+        kla_mean[2] = park.get(PARK_KSUM + 0) / (double)s.n_int[7];
+        cycle_epilogue(x, p, d, kla_mean, status, o);
+        return;
+    }
+    PhaseOut po;
     // phase 1: fill, set-point 0 (gym_SBR_env2.py:54)
     status |= pid_phase<TAIL_FILL, MODE>(x, s.n_int[0], s.n_sub[0], s.interval[0], 0.0, p.kla0, c, a, pid, tol, st, po);
     double kla = po.kla_last;
     a.q = 0.0;
-    DrawOut d;
     // phases 2..5 react with set-points [0, sp3[0], 0, sp3[1]], each biased by the previous phase's last KLa
     // (SBR_model_FB.py:94,120,146,172); then settle + draw; then phase 8 idle with set-point sp3[2], biased
     // by phase 5's last KLa (:266).  One loop so that the react stepper is instantiated once.
@@ -763,20 +1007,7 @@ SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading loa
         if (j == 3) kla_mean[1] = mean;
         if (j == 4) kla_mean[2] = mean;
     }
-    double reward, OCI;
-    reward_v2(p, kla_mean[0], kla_mean[1], kla_mean[2], d.Qw, d.eff[3], reward, OCI);
-    bool finite = true;
-#pragma unroll
-    for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);
-    if (!finite || !(fabs(reward) < 1e300)) status |= SBR_ST_NONFINITE;
-    o.obs[0] = p.Qeff; o.obs[1] = d.eff[2]; o.obs[2] = d.eff[3] / 30;
-    o.reward = reward;
-    o.aux[SBR_AUX_OCI] = OCI; o.aux[SBR_AUX_QW] = d.Qw; o.aux[SBR_AUX_EQI] = d.EQI;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) o.aux[SBR_AUX_EFF_Q + j] = d.eff[j];
-    o.aux[SBR_AUX_KLA3_MEAN] = kla_mean[0]; o.aux[SBR_AUX_KLA5_MEAN] = kla_mean[1];
-    o.aux[SBR_AUX_KLA8_MEAN] = kla_mean[2];
-    o.status = status;
+    cycle_epilogue(x, p, d, kla_mean, status, o);
 }
 
 

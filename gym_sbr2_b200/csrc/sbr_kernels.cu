@@ -79,6 +79,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : 1) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
                                                               SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
+    // adaptive mode: per-env scratch column for parked stage vectors and per-phase KLa sums (sbr::Park)
+    __shared__ double s_park[(MODE == SBR_MODE_DP45 ? sbr::PARK_SLOTS : 1) * kBlock];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (slot >= g.n) return;
     const int64_t i = g.perm ? g.perm[slot] : slot;      // divergence-aware ordering: see include/sbr_b200.h
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45
     st.n_rhs = 0;
     st.n_rej = 0;
     sbr::CycleOut o;
-    sbr::cycle_v2<MODE>(x, action, load, load(0), p, c, s, tol, st, o);
+    sbr::cycle_v2<MODE>(x, action, load, load(0), p, c, s, tol, st, o, sbr::Park{&s_park[threadIdx.x], kBlock});
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.x_last[k * g.ld + i] = x[k];
 #pragma unroll

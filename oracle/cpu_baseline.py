@@ -1,11 +1,14 @@
-"""CPU baseline = the oracle port of the reference's scipy-odeint path, timed on the host cores.
-TEST / MEASUREMENT INFRASTRUCTURE ONLY: imported by bench.py's `cpu_baseline` leg and `--impl reference` arm.
+"""CPU baseline, timed on the host cores.  TEST / MEASUREMENT INFRASTRUCTURE ONLY: imported by bench.py's
+`cpu_baseline` leg and `--impl reference` arm.
 
-One Python process per core (BLAS/OpenMP threads pinned to 1), each stepping independent seeded SBR-v2 episodes
-(reset influent draw + one whole-cycle step) exactly as N reference processes would.
-The unmodified reference cannot travel to the GPU box (/root/reference is absent there), so kind = "port": the
-port reproduces the reference bit for bit on this path (tests/test_oracle_golden.py) and has the same cost
-structure (530 odeint calls, ~13.6k Python RHS callbacks per cycle).
+kind = "reference": the UNMODIFIED reference package, installed by oracle/install_ref.py into baseline/_ref/
+(git-ignored, travels to the GPU box with the snapshot) and imported through oracle/ref_shim.py (only `gym` and
+`matplotlib` are stubbed; numpy and scipy.integrate.odeint are the real ones; the envs' per-step prints are swallowed).
+One Python process per core (BLAS/OpenMP threads pinned to 1), each running independent seeded episodes --
+`np.random.seed(s)`, `SbrEnv2().reset()`, `step(action)` -- exactly as N reference processes would (BASELINE.md
+section 3).  kind = "port" (`run`, `run_os`): the oracle restatement (oracle/sbr_oracle.py), which reproduces the
+reference bit for bit on this path (tests/test_oracle_golden.py) but skips its trajectory appends and prints; it is
+reported beside the reference's number and is the fallback when baseline/_ref is missing.
 """
 import multiprocessing as mp
 import os
@@ -35,6 +38,102 @@ def _worker(args):
         except (OverflowError, ValueError, ZeroDivisionError, FloatingPointError):
             pass        # the reference's own failure regimes: the step was paid for, count it
     return time.perf_counter() - t0, acc
+
+
+def reference_root():
+    """Where the unmodified reference can be imported from: baseline/_ref (installed copy), else the authoring
+    container's read-only checkout, else None."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(root, "gym_SBR", "envs", "gym_SBR_env2.py")):
+            return root
+    return None
+
+
+def _load_reference(root):
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    os.environ["SBR_REFERENCE_ROOT"] = root
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    ref_shim.REFERENCE_ROOT = root
+    ref_shim.load_reference()
+    return ref_shim
+
+
+def _worker_ref(args):
+    """SBR-v2 through the reference's own class: reset (influent draw) + one whole-cycle step per episode."""
+    seed, n_steps, root = args
+    ref_shim = _load_reference(root)
+    import numpy as np
+    from gym_SBR.envs.gym_SBR_env2 import SbrEnv2
+    acc = 0.0
+    with ref_shim.quiet():
+        env = SbrEnv2()
+        np.random.seed(seed)
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            try:
+                env.reset()
+                _, reward, _, _ = env.step(np.random.rand(3))
+                acc += reward
+            except (OverflowError, ValueError, ZeroDivisionError, FloatingPointError, NameError):
+                pass    # the reference's own failure regimes (SURVEY.md 8c): the step was paid for, count it
+        dt = time.perf_counter() - t0
+    return dt, acc
+
+
+def _worker_ref_os(args):
+    """SBROS-v1 through the reference's own class: one 72-s PID interval per step, 463 steps per episode."""
+    seed, n_steps, root = args
+    ref_shim = _load_reference(root)
+    import warnings
+    import numpy as np
+    from gym_SBR.envs.gym_SBR_oneshot import SbrOS
+    acc = 0.0
+    with ref_shim.quiet(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = SbrOS()
+        np.random.seed(seed)
+        env.reset()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            try:
+                out = env.step([2.0 + np.random.rand(), 4.0 + 2 * np.random.rand()])
+                acc += out[2]
+                done = out[3]
+            except (OverflowError, ValueError, ZeroDivisionError, FloatingPointError, NameError):
+                done = True     # e.g. round(inf) in the draw (gym_SBR_oneshot.py:2338): an RL loop would reset
+            if done:
+                env.reset()
+        dt = time.perf_counter() - t0
+    return dt, acc
+
+
+def _run_pool(worker, jobs_warm, jobs, procs):
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        if jobs_warm:
+            pool.map(worker, jobs_warm)
+        t0 = time.perf_counter()
+        res = pool.map(worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    return res, wall
+
+
+def run_reference(steps_per_proc=3, procs=None, warmup=1, path="v2"):
+    """The unmodified reference on every host core.  path "v2": SBR-v2 cycle-steps/s; "os": SBROS-v1
+    interval-steps/s.  Returns None when no reference install is available."""
+    root = reference_root()
+    if root is None:
+        return None
+    procs = procs or usable_cores()
+    worker = _worker_ref if path == "v2" else _worker_ref_os
+    warm = [(10_000 + i, warmup, root) for i in range(procs)] if warmup else None
+    res, wall = _run_pool(worker, warm, [(i, steps_per_proc, root) for i in range(procs)], procs)
+    total = procs * steps_per_proc
+    return dict(value=total / wall, cores=procs, steps=total, wall_s=wall, per_core=total / sum(r[0] for r in res),
+                root=os.path.relpath(root, ROOT) if root.startswith(ROOT) else root)
 
 
 def usable_cores():

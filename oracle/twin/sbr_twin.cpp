@@ -33,8 +33,10 @@ int twin_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influen
         st.n_rhs = 0; st.n_rej = 0;
         CycleOut o;
         Loading L{load, 1};
-        if (mode == SBR_MODE_RK4) cycle_v2<SBR_MODE_RK4>(x, a, L, load[0], *p, c, *s, t, st, o);
-        else cycle_v2<SBR_MODE_DP45>(x, a, L, load[0], *p, c, *s, t, st, o);
+        double parkbuf[PARK_SLOTS];
+        const Park park{parkbuf, 1};
+        if (mode == SBR_MODE_RK4) cycle_v2<SBR_MODE_RK4>(x, a, L, load[0], *p, c, *s, t, st, o, park);
+        else cycle_v2<SBR_MODE_DP45>(x, a, L, load[0], *p, c, *s, t, st, o, park);
         for (int k = 0; k < SBR_NX; ++k) x_last[k * ld + i] = x[k];
         for (int k = 0; k < 3; ++k) obs[k * ld + i] = o.obs[k];
         reward[i] = o.reward;
