@@ -227,17 +227,21 @@ def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
 def cycle_dp45_leg(torch, device, core, env, n):
     """The same SBR-v2 batch through the adaptive Dormand-Prince mode (per-env step control): in the caller's env
     order (random set-points side by side in a warp: the divergence case) and with the divergence-aware ordering
-    the vector env applies in this mode (envs assigned to warps by argsort of the first set-point; the argsort is
-    inside the timed region)."""
+    the vector env applies in this mode: argsort of the first set-point, one gather launch (inputs), the cycle
+    kernel on unit-stride sorted buffers, one scatter launch (outputs) -- all four inside the timed region."""
     from gym_sbr2_b200 import _abi
+    from gym_sbr2_b200.vec_env import SbrV2VecEnv
     res = {}
     for rtol, atol in ((1e-7, 1e-9), (1e-6, 1e-8)):
         tol = _abi.make_tol(rtol, atol)
+        env_o = SbrV2VecEnv(n, device=device, seed=env.seed, mode="dp45", rtol=rtol, atol=atol, order="action")
+        env_o.reset(influent=env.influent)
         for ordered in (False, True):
             def launch():
-                perm = torch.argsort(env._action[0]) if ordered else None
+                if ordered:
+                    return env_o.step_soa(env._action)
                 return core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out,
-                                     mode=_abi.MODE_DP45, tol=tol, perm=perm)
+                                     mode=_abi.MODE_DP45, tol=tol)
             launch()
             torch.cuda.synchronize()
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,21 +254,33 @@ def cycle_dp45_leg(torch, device, core, env, n):
             rhs = float(cnt[0].mean())
             steps = (rhs - 6) / 6.0
             flops = rhs * F_REACT + steps * (2 * 9 * 15 + 2 * 9 * 5 + 2 * 9 * 6 + 5 * 9) + F_EPILOGUE
-            res["rtol%g_%s" % (rtol, "ordered" if ordered else "env_order")] = {
+            key = "rtol%g_%s" % (rtol, "ordered" if ordered else "env_order")
+            res[key] = {
                 "rtol": rtol, "atol": atol, "ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
                 "rhs_per_env_mean": rhs, "rhs_per_env_max": float(cnt[0].max()),
                 "warp_max_rhs_mean": float(cnt[0].view(-1, 32).max(dim=1).values.mean()) if not ordered else None,
                 "rejected_per_env_mean": float(cnt[1].mean()), "bad_status": int((o.status != 0).sum()),
                 "fp64_tflops": n * flops / (ms * 1e-3) / 1e12}
-            if not ordered:
+            if ordered:
+                # the cycle kernel alone on the already sorted buffers (what the roofline fraction is quoted on)
+                z = env_o._sorted
+                ea.record()
+                core.cycle_v2(z["x0"], z["loading"], z["action"], env_o.params, env_o.sched, out=z["out"],
+                              mode=_abi.MODE_DP45, tol=tol)
+                eb.record()
+                torch.cuda.synchronize()
+                res[key]["kernel_ms"] = ea.elapsed_time(eb)
+                res[key]["kernel_fp64_tflops"] = n * flops / (res[key]["kernel_ms"] * 1e-3) / 1e12
+                res[key]["launches"] = "argsort + sbr_permute_rows (gather) + sbr_cycle_v2 + sbr_permute_rows (scatter)"
+            else:
                 # step-count histogram (BASELINE config 3: adaptive-step divergence): quantiles of the per-env RHS
                 # count, and what a warp pays for it -- the slowest of its 32 envs in env order vs in set-point order
                 q = torch.tensor([0.01, 0.1, 0.5, 0.9, 0.99], dtype=torch.float64, device=device)
                 sample = cnt[0][:1 << 18]
-                key = "rtol%g_%s" % (rtol, "env_order")
                 res[key]["rhs_per_env_quantiles_p1_p10_p50_p90_p99"] = [float(v) for v in torch.quantile(sample, q)]
                 by_sp = cnt[0][torch.argsort(env._action[0])]
                 res[key]["warp_max_rhs_mean_if_ordered_by_first_setpoint"] = float(by_sp.view(-1, 32).max(dim=1).values.mean())
+        del env_o
     return res
 
 
@@ -350,7 +366,7 @@ def rollout_leg(torch, tdist, device, rank, world, args):
     lo, hi = dist.shard_range(total, rank, world)
     ok, err = 1.0, ""
     try:                                                         # local set-up: no collectives in here
-        env = SbrOsVecEnv(hi - lo, device=device, seed=4242 + rank, mode="dp45")
+        env = SbrOsVecEnv(hi - lo, device=device, seed=4242, mode="dp45", env_offset=lo)   # draws keyed by GLOBAL env index
         policy = rollout.TinyPolicy(device)
         warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
         # the inner loop [policy -> action -> sbr_os_step] captured in CUDA graphs (8 steps and 1 step per replay):
@@ -502,7 +518,7 @@ def main():
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
 
-    env = SbrV2VecEnv(n, device=device, seed=1234 + rank, mode=args.mode, rtol=args.rtol, atol=args.atol)
+    env = SbrV2VecEnv(n, device=device, seed=1234, mode=args.mode, rtol=args.rtol, atol=args.atol, env_offset=rank * n)
     env.reset()
     gen = torch.Generator(device=device).manual_seed(99 + rank)
     action = torch.rand((n, 3), dtype=torch.float64, device=device, generator=gen)
@@ -550,12 +566,15 @@ def main():
 
     # ---- dominant kernel alone: per-launch CUDA-event time of sbr_cycle_v2 on its launching stream ----------
     kern_ms = []
-    perm = torch.argsort(env._action[0]) if env.order == "action" else None     # as SbrV2VecEnv.step_async does
+    # (adaptive mode: on the sorted, unit-stride buffers SbrV2VecEnv.step_soa hands it -- the argsort and the two
+    # sbr_permute_rows launches around it are inside `value`, not inside this per-kernel time)
+    kb = env._sorted if env.order == "action" and env._sorted is not None else None
+    kx0, kload, kact, kout = (kb["x0"], kb["loading"], kb["action"], kb["out"]) if kb else \
+        (env.x0, env._loading, env._action, env._out)
     for _ in range(K):
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
-        o = core.cycle_v2(env.x0, env._loading, env._action, env.params, env.sched, out=env._out, mode=env.mode,
-                          tol=env.tol, perm=perm)
+        o = core.cycle_v2(kx0, kload, kact, env.params, env.sched, out=kout, mode=env.mode, tol=env.tol)
         eb.record()
         torch.cuda.synchronize()
         kern_ms.append(ea.elapsed_time(eb))
@@ -712,8 +731,9 @@ def main():
                            "l2": "inputs %d MB per step > 126 MB L2" % (n * 31 * 8 >> 20),
                            "parallelism": "env-sharded x%d, no step-path collective" % world},
                 "interval_steps_per_sec": value * INTERVALS_PER_CYCLE,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * K,
-                "gpu_launch_names": ["sbr_cycle_v2_kernel", "sbr_reward_stats_init_kernel", "sbr_reward_stats_kernel"],
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (5 if kb else 3) * K,
+                "gpu_launch_names": ["sbr_cycle_v2_kernel", "sbr_reward_stats_init_kernel", "sbr_reward_stats_kernel"]
+                + (["sbr_permute_rows_kernel (gather)", "sbr_permute_rows_kernel (scatter)"] if kb else []),
                 "clocks": clocks, "reward_stats": reward_stats, "paths": paths}
         print(json.dumps(line), flush=True)
     if world > 1:

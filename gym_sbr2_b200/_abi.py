@@ -12,9 +12,10 @@ MODE_RK4, MODE_DP45 = 0, 1
 TAIL_REACT, TAIL_FILL, TAIL_EC = 0, 1, 2
 ST_NONFINITE, ST_WASTE, ST_STEPLIMIT, ST_LAYERS, ST_DONE = 1, 2, 4, 8, 16
 AUX_ROWS = 12
+PERMUTE_MAX = 8
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 3
+ABI_VERSION = 4
 # rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
 OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
@@ -87,6 +88,12 @@ _PROTOS = {
     "sbr_v4_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                               _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_influent_mix": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "sbr_influent_sample": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P,
+                                      _P, _P, _P, _P]),
+    "sbr_philox_normals": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
+    "sbr_permute_rows": (C.c_int, [C.c_int64, _P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.c_int, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),

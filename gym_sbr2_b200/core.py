@@ -260,6 +260,85 @@ def influent_mix(switch, rnd, out=None, stream=None):
     return out
 
 
+_ALL_TABLES = {}
+
+
+def _all_tables(device):
+    """Device copies of all 8 scenario tables: mean, std [8,14,48]."""
+    from . import influent as influent_mod
+    key = torch.device(device)
+    if key not in _ALL_TABLES:
+        t = influent_mod.tables()
+        mean = torch.as_tensor(t["mean"], dtype=torch.float64).contiguous()
+        std = torch.as_tensor(t["std_frac"][:, :, None] * t["mean"], dtype=torch.float64).contiguous()
+        _ALL_TABLES[key] = (mean.to(key), std.to(key))
+    return _ALL_TABLES[key]
+
+
+def influent_sample(n, device, seed, env_offset=0, scenario=0, epoch=None, epoch0=0, mask=None, out=None,
+                    scenario_out=None, stream=None):
+    """N independent buffer_tank(scenario) calls (buffer_tank3.py:18-108) with counter-based randomness: the draws
+    of env i depend only on (seed, env_offset + i, its episode number) -- see sbr_influent_sample in the header.
+    scenario: 0..7 or -1 (drawn per env, SbrEnv4.reset); epoch: optional int64 [n], incremented for drawing envs."""
+    lib = _abi.load()
+    mean, std = _all_tables(device)
+    if out is None:
+        out = torch.zeros((_abi.NX, n), dtype=torch.float64, device=device)
+    po, ld = _dev_ptr(out, _abi.NX, n, name="influent")
+    pe, _ = _dev_ptr(epoch, 1, n, dtype=torch.int64, name="epoch")
+    pm, _ = _dev_ptr(mask, 1, n, dtype=torch.uint8, name="mask")
+    ps, _ = _dev_ptr(scenario_out, 1, n, dtype=torch.int32, name="scenario_out")
+    with torch.cuda.device(device):
+        rc = lib.sbr_influent_sample(n, ld, int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), pe, int(epoch0),
+                                     int(scenario), C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), pm, po,
+                                     ps, _stream_ptr(stream))
+    _abi.check(rc, "sbr_influent_sample")
+    return out
+
+
+def philox_normals(n, device, seed, env_offset=0, epoch0=0, stream=None):
+    """The 48 standard normals per env that influent_sample draws for episode `epoch0`: z [48,n]."""
+    from . import influent as influent_mod
+    lib = _abi.load()
+    z = torch.empty((influent_mod.N_POINTS, n), dtype=torch.float64, device=device)
+    pz, ld = _dev_ptr(z, influent_mod.N_POINTS, n, name="z")
+    with torch.cuda.device(device):
+        rc = lib.sbr_philox_normals(n, ld, int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), int(epoch0), pz,
+                                    _stream_ptr(stream))
+    _abi.check(rc, "sbr_philox_normals")
+    return z
+
+
+def permute_rows(perm, pairs, scatter=False, stream=None):
+    """Row permutation of SoA buffers in one launch: for every (src, dst) pair of [rows, n] (or [n]) tensors,
+    dst[r, i] = src[r, perm[i]] (gather) or dst[r, perm[i]] = src[r, i] (scatter).  float64 / int32 / uint32."""
+    lib = _abi.load()
+    n = perm.shape[0]
+    if not (0 < len(pairs) <= _abi.PERMUTE_MAX):
+        raise ValueError("permute_rows: 1..%d buffers per launch" % _abi.PERMUTE_MAX)
+    pp, _ = _dev_ptr(perm, 1, n, dtype=torch.int64, name="perm")
+    k = len(pairs)
+    src, dst = (C.c_void_p * k)(), (C.c_void_p * k)()
+    lds, ldd = (C.c_int64 * k)(), (C.c_int64 * k)()
+    rows, elem = (C.c_int32 * k)(), (C.c_int32 * k)()
+    for j, (s, d) in enumerate(pairs):
+        if s.dtype != d.dtype or s.shape != d.shape or not (s.is_cuda and d.is_cuda):
+            raise ValueError("permute_rows: src/dst of pair %d differ in dtype, shape or device" % j)
+        if s.element_size() not in (4, 8):
+            raise TypeError("permute_rows: 4- or 8-byte elements only")
+        if s.dim() == 1:
+            s, d = s[None, :], d[None, :]
+        if s.shape[1] != n or s.stride(1) != 1 or d.stride(1) != 1:
+            raise ValueError("permute_rows: buffers must be [rows, %d] with unit stride along envs" % n)
+        src[j], dst[j] = s.data_ptr(), d.data_ptr()
+        lds[j] = s.stride(0) if s.shape[0] > 1 else n
+        ldd[j] = d.stride(0) if d.shape[0] > 1 else n
+        rows[j], elem[j] = s.shape[0], s.element_size()
+    with torch.cuda.device(perm.device):
+        rc = lib.sbr_permute_rows(n, pp, k, src, dst, lds, ldd, rows, elem, 1 if scatter else 0, _stream_ptr(stream))
+    _abi.check(rc, "sbr_permute_rows")
+
+
 def reward_stats(reward, status=None, out=None, stream=None):
     """[sum, sumsq, min, max, count] of the rewards of healthy envs, on the device (feeds the NCCL gather)."""
     lib = _abi.load()

@@ -224,6 +224,10 @@ SBR_HD double stage(const double (&y)[SBR_NX], double (&k)[SBR_NX], double t, co
             else k[i] = fma(-dil, y[i], k[i]);
         }
     if (TAIL == TAIL_EC) k[iSs] = fma(dil, a.ec_conc, k[iSs]);
+    // an env that does not dose (q == 0) inside a warp that runs the dosing tail must get the react tail's result
+    // bit for bit (its trajectory must not depend on its 31 neighbours): every dilution FMA above is exact for
+    // dil == 0, and the quadrature integrand stays s45 as in the react tail (see integrate_interval's epilogue)
+    if (TAIL == TAIL_EC && f.q == 0.0) return s45;
     return s45 * Vt;
 }
 
@@ -307,6 +311,17 @@ SBR_HD float pow_m01(float en) {
 SBR_HD float __frcp_rn_compat(float v) {
 #ifdef __CUDA_ARCH__
     return __frcp_rn(v);
+#else
+    return 1.0f / v;
+#endif
+}
+// 1/v for a step COUNT: the raw MUFU.RCP approximation (1 instruction; __frcp_rn is MUFU + two FFMA + a slow-path
+// call).  The 0.99999 factor at the call site absorbs its 1-ulp error.
+SBR_HD float frcp_fast(float v) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 #else
     return 1.0f / v;
 #endif
@@ -477,7 +492,7 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
         status = dp45_interval<TAIL>(x, T, f, c, a, tol, st, xpq);
     }
     const double dN = ((x[iSnh] - snh0) - (x[iSno] - sno0)) * c.c136;
-    if (TAIL == TAIL_REACT) {
+    if (TAIL == TAIL_REACT || (TAIL == TAIL_EC && f.q == 0.0)) {
         x[iXp] = fma(c.ixp, xpq, x[iXp]);
         x[iSalk] += dN;
     } else {
@@ -565,15 +580,7 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
 
 // ---------------------------------------------------------------------------------------------------------
 // Adaptive (Dormand-Prince) form of the cycle path: one SEGMENT = a run of consecutive PID-controlled phases that
-// share a tail (fill | react phases 2-5 | idle), integrated by ONE loop whose body is "one step attempt".
-//
-// Why not interval by interval (as pid_phase does for RK4): with per-env step sizes the envs of a warp need
-// different numbers of steps in every 72-s interval, and a loop nest "for interval: while (t < T)" re-converges
-// the warp at the end of every interval -- the warp pays the slowest env 528 times per cycle (measured in round 1:
-// 29.6 of 32 lanes active even with envs sorted by set-point, 19 in env order).  Here the interval / phase
-// bookkeeping (PID update, KLa jump, phase switch) is a short predicated block INSIDE the step loop, so every lane
-// runs through its own intervals at its own pace and the warp only re-converges at the end of the segment: it
-// pays max_lane(sum of steps), not sum_interval(max_lane steps).
+// share a tail (fill | react phases 2-5 | idle), integrated by one loop nest "for interval: while (t < T) step".
 //
 // First-same-as-last is kept across PID intervals and phase switches of a segment: the last stage of an interval
 // is f(x_end); the next interval starts from the same state with only KLa changed by the PID, and KLa enters the
@@ -583,15 +590,26 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
 // `DADD R12, R74, -R74` -- the correction compiled to zero, profiles/r02_fsal_lost_copy_sass.txt).
 //
 // Register budget (this is what bounds occupancy): the classical formulation keeps x, y and six stage vectors
-// live (72 doubles).  Here the 5th-order solution and the error estimate are accumulated as soon as their
-// inputs exist, so that k2..k5 die when the input of stage 6 is formed, and (SBR_DP_PARK) k3 and k4 wait in a
-// shared-memory column while they are not needed (45 LDS/STS per step against 620 FP64 instructions): at most
-// five vectors are live inside any kinetics evaluation.  The passive components (V, Si, Xi, Xp, Salk) leave the
-// loop entirely: closed forms / one quadrature over the whole segment (see the table above `active`).
+// live (72 doubles).  Here the 5th-order solution and the error estimate are accumulated as soon as their inputs
+// exist, so that k2..k5 die when the input of stage 6 is formed; the passive components (V, Si, Xi, Xp, Salk) leave
+// the loop entirely: closed forms / one quadrature over the whole segment (see the table above `active`).  The step
+// loop of the react segment then runs in 254 registers without spills (8 warps/SM).
+//
+// Tried and rejected, each measured on 2^20 envs at rtol 1e-7, envs sorted by first set-point (profiles/r02*_ab_*):
+//  * k3 and k4 parked in a shared-memory column between their uses (45 LDS/STS per step; 168 registers, 12 warps/SM,
+//    no spills): 105.6 ms against 76.6 ms -- beside the FP64 pipe every LSU instruction costs far more than its
+//    issue slot, and the third warp per sub-partition does not buy it back (compiler spills at 168 registers: 86.1 ms).
+//  * a single flat loop whose body is "one step attempt" with the interval / phase bookkeeping as a predicated block
+//    inside it, so that the lanes of a warp run through their intervals at their own pace and only re-converge at the
+//    end of the segment.  The per-env step count is a property of the env (its first DO set-point: corr -0.96 below
+//    1 g/m3), not of the interval, so max_lane(sum of steps) is no better than sum_interval(max_lane steps) in env
+//    order (13.8k vs 14.3k RHS per warp against a mean of 8.4k), and with envs sorted by set-point the 3 % it gains
+//    (30.6 instead of 29.6 of 32 lanes) is eaten by the bookkeeping block running in every iteration.
+//  * the step-size controller run once per planned run of equal steps instead of once per step (it is ~300 cycles of
+//    dependent latency per step: the same body without any controller takes 1300 cycles per warp-step, with it 1860):
+//    the graded steps after each KLa jump are lost and the RHS count rises 37 %.
+// Kept: the error norm as three partial sums and the raw MUFU reciprocal for the step count (-4 %).
 // ---------------------------------------------------------------------------------------------------------
-#ifndef SBR_DP_PARK
-#define SBR_DP_PARK 1
-#endif
 
 // Packed index of an active component (0..8).
 SBR_HD constexpr int aidx(int i) {
@@ -600,14 +618,14 @@ SBR_HD constexpr int aidx(int i) {
 }
 
 // Scratch column of one env outside the register file: slot j at p[j * stride] (shared memory on the device,
-// conflict-free for consecutive threads; a local array in the CPU twin).  Accesses are volatile so that the
-// compiler neither forwards a parked value through a register nor reorders the accesses.
-enum { PARK_K3 = 0, PARK_K4 = 9, PARK_KSUM = 18, PARK_SLOTS = 22 };
+// conflict-free for consecutive threads; a local array in the CPU twin).  Holds what is written once per phase and
+// read once per cycle (the per-phase KLa sums), so that it costs no registers inside the step loop.
+enum { PARK_KSUM = 0, PARK_SLOTS = 4 };
 struct Park {
     double* p;
     int stride;
-    SBR_HD void put(int j, double v) const { ((volatile double*)p)[j * stride] = v; }
-    SBR_HD double get(int j) const { return ((volatile double*)p)[j * stride]; }
+    SBR_HD void put(int j, double v) const { p[j * stride] = v; }
+    SBR_HD double get(int j) const { return p[j * stride]; }
 };
 
 // ph0: schedule index of the segment's first phase; NPH phases follow each other in the schedule; sp[]: this env's
@@ -637,141 +655,132 @@ SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, cons
     for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
     double g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
     st.n_rhs += 1;
-    double t = 0.0;
-    double h = st.h * SBR_DP_FIRST;   // KLa has just jumped: the carried proposal is discounted for the first step
-    int status = 0, steps = 0;
+    double h = st.h;
+    int status = 0;
     for (;;) {
-        bool end_interval = false;
-        if (steps >= tol.max_steps) {
+        // ---- one PID interval: step attempts until t reaches T ----
+        double t = 0.0;
+        int steps = 0;
+        h = h * SBR_DP_FIRST;          // KLa has just jumped: the carried proposal is discounted for the first step
+        while (t < T) {
             // work bound of an env that has left the physical regime: give the interval up (state flagged)
-            status |= SBR_ST_STEPLIMIT;
-            end_interval = true;
-        } else {
+            if (steps >= tol.max_steps) { status |= SBR_ST_STEPLIMIT; break; }
             ++steps;
             // spread what is left of the interval over equal steps no longer than the controller's proposal: a
             // proposal that does not divide the interval would otherwise end it with a sliver step (6 RHS for nothing)
             const double rem = T - t;
-            const float n_f = ceilf((float)rem * __frcp_rn_compat((float)h) * 0.99999f);   // float is plenty for a count
+            const float n_f = ceilf((float)rem * frcp_fast((float)h) * 0.99999f);   // float is plenty for a count
             const bool last = !(n_f > 1.0f);
-            const double hs = last ? rem : rem * (double)__frcp_rn_compat(n_f);
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) y[i] = fma(hs * tb.a21, k1[i], x[i]);
-            stage<TAIL>(y, k2, fma(tb.c2, hs, t), f, c, a);   // b2 = 0: no quadrature contribution
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) y[i] = fma(hs * tb.a32, k2[i], fma(hs * tb.a31, k1[i], x[i]));
-            const double g3 = stage<TAIL>(y, k3, fma(tb.c3, hs, t), f, c, a);
-            double gq = fma(tb.b3, g3, tb.b1 * g1);
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) {
-                    y[i] = fma(hs * tb.a43, k3[i], fma(hs * tb.a42, k2[i], fma(hs * tb.a41, k1[i], x[i])));
-                    if (SBR_DP_PARK) park.put(PARK_K3 + aidx(i), k3[i]);
-                }
-            const double g4 = stage<TAIL>(y, k4, fma(tb.c4, hs, t), f, c, a);
-            gq = fma(tb.b4, g4, gq);
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) {
-                    const double k3i = SBR_DP_PARK ? park.get(PARK_K3 + aidx(i)) : k3[i];
-                    y[i] = fma(hs * tb.a54, k4[i], fma(hs * tb.a53, k3i, fma(hs * tb.a52, k2[i],
-                           fma(hs * tb.a51, k1[i], x[i]))));
-                    if (SBR_DP_PARK) park.put(PARK_K4 + aidx(i), k4[i]);
-                }
-            const double g5 = stage<TAIL>(y, k5, fma(tb.c5, hs, t), f, c, a);
-            gq = fma(tb.b5, g5, gq);
-            // input of stage 6, and everything of the 5th-order solution and of the error estimate that k1..k5
-            // contribute: k2..k5 are dead after this block
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) {
-                    const double k3i = SBR_DP_PARK ? park.get(PARK_K3 + aidx(i)) : k3[i];
-                    const double k4i = SBR_DP_PARK ? park.get(PARK_K4 + aidx(i)) : k4[i];
-                    y[i] = fma(hs * tb.a65, k5[i], fma(hs * tb.a64, k4i, fma(hs * tb.a63, k3i,
-                           fma(hs * tb.a62, k2[i], fma(hs * tb.a61, k1[i], x[i])))));
-                    sol[i] = fma(hs * tb.b5, k5[i], fma(hs * tb.b4, k4i, fma(hs * tb.b3, k3i,
-                             fma(hs * tb.b1, k1[i], x[i]))));
-                    err[i] = fma(tb.e5, k5[i], fma(tb.e4, k4i, fma(tb.e3, k3i, tb.e1 * k1[i])));
-                }
-            const double g6 = stage<TAIL>(y, k2, t + hs, f, c, a);       // k6 lands in k2's registers
-            gq = fma(tb.b6, g6, gq);
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) {
-                    sol[i] = fma(hs * tb.b6, k2[i], sol[i]);
-                    err[i] = fma(tb.e6, k2[i], err[i]);
-                }
-            const double g7 = stage<TAIL>(sol, k2, t + hs, f, c, a);     // k7 = f(5th-order solution)
-            st.n_rhs += 6;
-            // error estimate, RMS norm over the active components (h is factored out of the 9 components; the
-            // per-component scale only steers the controller, so its reciprocal is the raw MUFU approximation)
-            double en = 0.0;
-#pragma unroll
-            for (int i = 0; i < SBR_NX; ++i)
-                if (active(i)) {
-                    const double e_i = fma(tb.e7, k2[i], err[i]);
-                    const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(sol[i])), tol.atol * tol_scale(i));
-                    const double q = e_i * rcp_rough(sc);
-                    en = fma(q, q, en);
-                }
-            en = en * (hs * hs * (1.0 / 9));   // mean square
-            const bool finite = en < 1e300;   // false for NaN/Inf
-            if (en <= 1.0 || !finite) {
-                // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
-                t = (last || !finite) ? T : t + hs;
-                xpq = fma(hs, gq, xpq);
-                g1 = g7;
+            const double hs = last ? rem : rem * (double)frcp_fast(n_f);
+            {
 #pragma unroll
                 for (int i = 0; i < SBR_NX; ++i)
-                    if (active(i)) { x[i] = sol[i]; k1[i] = k2[i]; }
-                end_interval = t >= T;
-            } else {
-                st.n_rej += 1;
-            }
-            // step-size controller: h *= clamp(safety * en^(-1/10), 0.2, max growth)  (en is the SQUARED norm).  A
-            // rejected step costs 6 RHS evaluations, so the constants lean conservative.
-            float fac = SBR_DP_MAXGROW;
-            if (en > 1e-20) {
-                fac = SBR_DP_SAFETY * pow_m01((float)en);
-                fac = fminf(SBR_DP_MAXGROW, fmaxf(0.2f, fac));
-            }
-            if (en > 1.0) fac = fminf(fac, 1.0f);
-            if (!(last && en <= 1.0)) h = hs * (double)fac;   // a truncated final step does not shrink the carry
-            else h = fmax(h, hs * (double)fac);
-        }
-        if (end_interval) {
-            // ---- end of a PID interval (sub_phases_FB.py:226-265): sample So, next PID output, KLa jump ----
-            ksum += kla;
-            so_prev = so_i;
-            so_i = x[iSo];
-            if (TAIL != TAIL_REACT) f.V0 = f.V(T);
-            ++i_int;
-            bool first = false;
-            if (i_int == n_int) {
-                // ---- end of a phase (SBR_model_FB.py:88-172): the next one starts from this phase's last KLa ----
-                park.put(PARK_KSUM + ph, ksum);
-                ksum = 0.0;
-                ++ph;
-                if (ph == NPH) break;
-                i_int = 0;
-                n_int = s.n_int[ph0 + ph];
-                T = s.interval[ph0 + ph];
+                    if (active(i)) y[i] = fma(hs * tb.a21, k1[i], x[i]);
+                stage<TAIL>(y, k2, fma(tb.c2, hs, t), f, c, a);   // b2 = 0: no quadrature contribution
 #pragma unroll
-                for (int j = 1; j < NPH; ++j)
-                    if (ph == j) spc = sp[j];
-                ie = 0.0; bias = kla; first = true;
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) y[i] = fma(hs * tb.a32, k2[i], fma(hs * tb.a31, k1[i], x[i]));
+                const double g3 = stage<TAIL>(y, k3, fma(tb.c3, hs, t), f, c, a);
+                double gq = fma(tb.b3, g3, tb.b1 * g1);
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) y[i] = fma(hs * tb.a43, k3[i], fma(hs * tb.a42, k2[i], fma(hs * tb.a41, k1[i], x[i])));
+                const double g4 = stage<TAIL>(y, k4, fma(tb.c4, hs, t), f, c, a);
+                gq = fma(tb.b4, g4, gq);
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i))
+                        y[i] = fma(hs * tb.a54, k4[i], fma(hs * tb.a53, k3[i], fma(hs * tb.a52, k2[i],
+                               fma(hs * tb.a51, k1[i], x[i]))));
+                const double g5 = stage<TAIL>(y, k5, fma(tb.c5, hs, t), f, c, a);
+                gq = fma(tb.b5, g5, gq);
+                // input of stage 6, and everything of the 5th-order solution and of the error estimate that k1..k5
+                // contribute: k2..k5 are dead after this block
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) {
+                        y[i] = fma(hs * tb.a65, k5[i], fma(hs * tb.a64, k4[i], fma(hs * tb.a63, k3[i],
+                               fma(hs * tb.a62, k2[i], fma(hs * tb.a61, k1[i], x[i])))));
+                        sol[i] = fma(hs * tb.b5, k5[i], fma(hs * tb.b4, k4[i], fma(hs * tb.b3, k3[i],
+                                 fma(hs * tb.b1, k1[i], x[i]))));
+                        err[i] = fma(tb.e5, k5[i], fma(tb.e4, k4[i], fma(tb.e3, k3[i], tb.e1 * k1[i])));
+                    }
+                const double g6 = stage<TAIL>(y, k2, t + hs, f, c, a);       // k6 lands in k2's registers
+                gq = fma(tb.b6, g6, gq);
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) {
+                        sol[i] = fma(hs * tb.b6, k2[i], sol[i]);
+                        err[i] = fma(tb.e6, k2[i], err[i]);
+                    }
+                const double g7 = stage<TAIL>(sol, k2, t + hs, f, c, a);     // k7 = f(5th-order solution)
+                st.n_rhs += 6;
+                // error estimate, RMS norm over the active components (h is factored out of the 9 components; the
+                // per-component scale only steers the controller, so its reciprocal is the raw MUFU approximation).
+                // Three partial sums: the 9 squares would otherwise be one serial DFMA chain at the very point
+                // where the step has no other work left to overlap with it.
+                double en3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < SBR_NX; ++i)
+                    if (active(i)) {
+                        const double e_i = fma(tb.e7, k2[i], err[i]);
+                        const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(sol[i])), tol.atol * tol_scale(i));
+                        const double q = e_i * rcp_rough(sc);
+                        en3[aidx(i) % 3] = fma(q, q, en3[aidx(i) % 3]);
+                    }
+                const double en = ((en3[0] + en3[1]) + en3[2]) * (hs * hs * (1.0 / 9));   // mean square
+                const bool finite = en < 1e300;   // false for NaN/Inf
+                if (en <= 1.0 || !finite) {
+                    // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
+                    t = (last || !finite) ? T : t + hs;
+                    xpq = fma(hs, gq, xpq);
+                    g1 = g7;
+#pragma unroll
+                    for (int i = 0; i < SBR_NX; ++i)
+                        if (active(i)) { x[i] = sol[i]; k1[i] = k2[i]; }
+                } else {
+                    st.n_rej += 1;
+                }
+                // step-size controller: h *= clamp(safety * en^(-1/10), 0.2, max growth)  (en is the SQUARED norm).
+                // A rejected step costs the whole warp 6 RHS evaluations (the other 31 envs wait), so the constants
+                // lean conservative: see DESIGN.md section 4 for the measured trade-off.
+                float fac = SBR_DP_MAXGROW;
+                if (en > 1e-20) {
+                    fac = SBR_DP_SAFETY * pow_m01((float)en);
+                    fac = fminf(SBR_DP_MAXGROW, fmaxf(0.2f, fac));
+                }
+                if (en > 1.0) fac = fminf(fac, 1.0f);
+                if (!(last && en <= 1.0)) h = hs * (double)fac;   // a truncated final step does not shrink the carry
+                else h = fmax(h, hs * (double)fac);
             }
-            const double kla_new = pid_a_update(pid, spc, so_i, so_prev, first, ie, bias);
-            // first-same-as-last across the KLa jump: dKLa from the OLD kla, then overwrite it (see the header)
-            k1[iSo] = fma(kla_new - kla, c.so_sat - x[iSo], k1[iSo]);
-            kla = kla_new;
-            a.kla = kla_new;
-            a.kla_sat = kla_new * c.so_sat;
-            t = 0.0;
-            steps = 0;
-            h = h * SBR_DP_FIRST;
         }
+        // ---- end of a PID interval (sub_phases_FB.py:226-265): sample So, next PID output, KLa jump ----
+        ksum += kla;
+        so_prev = so_i;
+        so_i = x[iSo];
+        if (TAIL != TAIL_REACT) f.V0 = f.V(T);
+        ++i_int;
+        bool first = false;
+        if (i_int == n_int) {
+            // ---- end of a phase (SBR_model_FB.py:88-172): the next one starts from this phase's last KLa ----
+            park.put(PARK_KSUM + ph, ksum);
+            ksum = 0.0;
+            ++ph;
+            if (ph == NPH) break;
+            i_int = 0;
+            n_int = s.n_int[ph0 + ph];
+            T = s.interval[ph0 + ph];
+#pragma unroll
+            for (int j = 1; j < NPH; ++j)
+                if (ph == j) spc = sp[j];
+            ie = 0.0; bias = kla; first = true;
+        }
+        const double kla_new = pid_a_update(pid, spc, so_i, so_prev, first, ie, bias);
+        // first-same-as-last across the KLa jump: dKLa from the OLD kla, then overwrite it (see the header)
+        k1[iSo] = fma(kla_new - kla, c.so_sat - x[iSo], k1[iSo]);
+        kla = kla_new;
+        a.kla = kla_new;
+        a.kla_sat = kla_new * c.so_sat;
     }
     st.h = h;
     kla_last = kla;

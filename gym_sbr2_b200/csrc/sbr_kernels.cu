@@ -436,6 +436,139 @@ __global__ void __launch_bounds__(128) sbr_influent_mix_kernel(int64_t n, int64_
     for (int j = 1; j < SBR_NX; ++j) influent[j * ld + i] = __ddiv_rn(acc[j], acc[0]);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Counter-based influent draws: Philox4x32-10 keyed by the run's seed, counter = (GLOBAL env index, episode number,
+// block).  An env's draws depend on nothing but (seed, its global index, its episode number): not on the batch
+// size, the rank that owns it, the world size or the order of resets -- which is what makes results invariant
+// to the sharding.  Normals by Box-Muller from two 53-bit uniforms; 24 Philox blocks give the 48
+// draws of one buffer_tank call, block 24 the scenario of SbrEnv4's np.random.choice(8, 1).
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct SampleArgs {
+    int64_t n, ld, env_offset, epoch0;
+    uint64_t seed;
+    int64_t* epoch;            // [n] in/out (may be NULL: every env uses epoch0)
+    const uint8_t* mask;       // [n] (may be NULL)
+    const double* mean;        // [8][14][48]
+    const double* stdv;        // [8][14][48]
+    double* influent;          // [14][ld]
+    int32_t* scenario_out;     // [n] (may be NULL)
+    int scenario;              // 0..7, or -1: drawn per env
+};
+
+__global__ void __launch_bounds__(128) sbr_influent_sample_kernel(SampleArgs g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    if (g.mask && g.mask[i] == 0) return;
+    const uint64_t env = (uint64_t)(g.env_offset + i);
+    const int64_t ep = g.epoch ? g.epoch[i] : g.epoch0;
+    const uint32_t k0 = (uint32_t)g.seed, k1 = (uint32_t)(g.seed >> 32);
+    int scn = g.scenario;
+    if (scn < 0) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)ep, 24u};
+        philox4x32_10(c, k0, k1);
+        scn = (int)(c[0] >> 29);                                            // uniform on 0..7
+    }
+    const double* __restrict__ mean = g.mean + (size_t)scn * SBR_NX * SBR_INFLUENT_POINTS;
+    const double* __restrict__ stdv = g.stdv + (size_t)scn * SBR_NX * SBR_INFLUENT_POINTS;
+    double acc[SBR_NX];
+#pragma unroll
+    for (int j = 0; j < SBR_NX; ++j) acc[j] = 0.0;
+    for (int b = 0; b < SBR_INFLUENT_POINTS / 2; ++b) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)ep, (uint32_t)b};
+        philox4x32_10(c, k0, k1);
+        // two uniforms in (0, 1): 53 random bits + half an ulp
+        const double u1 = ((double)((((uint64_t)c[1] << 32) | c[0]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)((((uint64_t)c[3] << 32) | c[2]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        const double zz[2] = {r * cs, r * sn};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * b + h;
+            const double z = zz[h];
+            // same arithmetic as sbr_influent_mix_kernel (bit-identical to numpy for the same z)
+            const double q = __dadd_rn(__ldg(mean + t), __dmul_rn(__ldg(stdv + t), z));
+            acc[0] = __dadd_rn(acc[0], q);
+#pragma unroll
+            for (int j = 1; j < SBR_NX; ++j) {
+                const double cj = __dadd_rn(__ldg(mean + j * SBR_INFLUENT_POINTS + t),
+                                            __dmul_rn(__ldg(stdv + j * SBR_INFLUENT_POINTS + t), z));
+                acc[j] = __dadd_rn(acc[j], __dmul_rn(cj, q));
+            }
+        }
+    }
+    g.influent[i] = 0.66;                                                   // buffer_tank3.py:92
+#pragma unroll
+    for (int j = 1; j < SBR_NX; ++j) g.influent[j * g.ld + i] = __ddiv_rn(acc[j], acc[0]);
+    if (g.scenario_out) g.scenario_out[i] = scn;
+    if (g.epoch) g.epoch[i] = ep + 1;
+}
+
+// Standard normals of one env's episode, as the sampler draws them: z [48][ld] (tests, and the parity story of the
+// generator: mixing these with sbr_influent_mix reproduces sbr_influent_sample bit for bit).
+__global__ void __launch_bounds__(128) sbr_philox_normals_kernel(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset,
+                                                                 int64_t epoch0, double* z) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t env = (uint64_t)(env_offset + i);
+    for (int b = 0; b < SBR_INFLUENT_POINTS / 2; ++b) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)epoch0, (uint32_t)b};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double u1 = ((double)((((uint64_t)c[1] << 32) | c[0]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)((((uint64_t)c[3] << 32) | c[2]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[(2 * b) * ld + i] = r * cs;
+        z[(2 * b + 1) * ld + i] = r * sn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row permutation of SoA buffers: dst[r][i] = src[r][perm[i]] (gather) or dst[r][perm[i]] = src[r][i] (scatter), for
+// up to SBR_PERMUTE_MAX buffers per launch.  Used to hand the adaptive cycle kernel its envs in divergence-aware
+// order with unit-stride loads and stores.  blockIdx.y = (buffer, row): the blocks of one row run together, so the
+// row's 8 n bytes and perm stay in L2 while the random side touches each 32-B sector four times -- DRAM traffic
+// stays at the algorithmic bytes.
+// ---------------------------------------------------------------------------------------------------------
+struct PermuteArgs {
+    int64_t n;
+    const int64_t* perm;
+    const void* src[SBR_PERMUTE_MAX];
+    void* dst[SBR_PERMUTE_MAX];
+    int64_t ld_src[SBR_PERMUTE_MAX], ld_dst[SBR_PERMUTE_MAX];
+    int32_t row0[SBR_PERMUTE_MAX + 1];      // first blockIdx.y of each buffer
+    int32_t elem[SBR_PERMUTE_MAX];          // element size: 4 or 8 bytes
+    int32_t nbuf, scatter;
+};
+
+__global__ void __launch_bounds__(256) sbr_permute_rows_kernel(PermuteArgs g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < SBR_PERMUTE_MAX; ++k)
+        if (k < g.nbuf && (int)blockIdx.y >= g.row0[k]) b = k;
+    const int64_t r = (int64_t)blockIdx.y - g.row0[b];
+    const int64_t j = g.perm[i];
+    const int64_t is = g.scatter ? i : j, id = g.scatter ? j : i;
+    if (g.elem[b] == 8)
+        ((double*)g.dst[b])[r * g.ld_dst[b] + id] = ((const double*)g.src[b])[r * g.ld_src[b] + is];
+    else
+        ((int32_t*)g.dst[b])[r * g.ld_dst[b] + id] = ((const int32_t*)g.src[b])[r * g.ld_src[b] + is];
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread, `iters` rounds of 8 DFMAs each.
 __global__ void sbr_fp64_probe_kernel(int iters, double* sink) {
     const double a = 1.0000001, b = 1e-9 * (double)(threadIdx.x + 1);
@@ -709,6 +842,51 @@ int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mea
     const unsigned grid = (unsigned)((n + 127) / 128);
     sbr_influent_mix_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, ld, rnd, mean, std, influent);
     return check_launch("sbr_influent_mix");
+}
+
+int sbr_influent_sample(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset, int64_t* epoch, int64_t epoch0,
+                        int scenario, const double* mean, const double* std, const uint8_t* mask, double* influent,
+                        int32_t* scenario_out, void* stream) {
+    if (n <= 0) return fail(SBR_ERR_ARG, "n must be positive%s");
+    if (ld < n) return fail(SBR_ERR_ARG, "ld must be >= n%s");
+    if (!mean || !std || !influent) return fail(SBR_ERR_ARG, "sbr_influent_sample: NULL buffer%s");
+    if (scenario < -1 || scenario > 7) return fail(SBR_ERR_ARG, "sbr_influent_sample: scenario must be -1..7%s");
+    if (env_offset < 0) return fail(SBR_ERR_ARG, "sbr_influent_sample: env_offset must be >= 0%s");
+    SampleArgs g{n, ld, env_offset, epoch0, seed, epoch, mask, mean, std, influent, scenario_out, scenario};
+    sbr_influent_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g);
+    return check_launch("sbr_influent_sample");
+}
+
+int sbr_philox_normals(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset, int64_t epoch0, double* z,
+                       void* stream) {
+    if (n <= 0 || ld < n || !z || env_offset < 0) return fail(SBR_ERR_ARG, "sbr_philox_normals: bad arguments%s");
+    sbr_philox_normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, ld, seed, env_offset,
+                                                                                               epoch0, z);
+    return check_launch("sbr_philox_normals");
+}
+
+int sbr_permute_rows(int64_t n, const int64_t* perm, int nbuf, const void* const* src, void* const* dst,
+                     const int64_t* ld_src, const int64_t* ld_dst, const int32_t* rows, const int32_t* elem_bytes,
+                     int scatter, void* stream) {
+    if (n <= 0 || !perm || !src || !dst || !ld_src || !ld_dst || !rows || !elem_bytes)
+        return fail(SBR_ERR_ARG, "sbr_permute_rows: bad arguments%s");
+    if (nbuf < 1 || nbuf > SBR_PERMUTE_MAX) return fail(SBR_ERR_ARG, "sbr_permute_rows: 1..SBR_PERMUTE_MAX buffers%s");
+    PermuteArgs g;
+    memset(&g, 0, sizeof(g));
+    g.n = n; g.perm = perm; g.nbuf = nbuf; g.scatter = scatter ? 1 : 0;
+    int total = 0;
+    for (int k = 0; k < nbuf; ++k) {
+        if (!src[k] || !dst[k] || rows[k] < 1 || ld_src[k] < n || ld_dst[k] < n || (elem_bytes[k] != 4 && elem_bytes[k] != 8))
+            return fail(SBR_ERR_ARG, "sbr_permute_rows: bad buffer descriptor%s");
+        g.src[k] = src[k]; g.dst[k] = dst[k]; g.ld_src[k] = ld_src[k]; g.ld_dst[k] = ld_dst[k];
+        g.elem[k] = elem_bytes[k]; g.row0[k] = total;
+        total += rows[k];
+    }
+    g.row0[nbuf] = total;
+    if (total > 65535) return fail(SBR_ERR_ARG, "sbr_permute_rows: too many rows%s");
+    const dim3 grid((unsigned)((n + 255) / 256), (unsigned)total);
+    sbr_permute_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+    return check_launch("sbr_permute_rows");
 }
 
 int sbr_reward_stats_init(double* stats, void* stream) {

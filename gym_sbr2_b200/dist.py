@@ -61,8 +61,10 @@ def gather_rewards(local_rewards, n_total):
         return local_rewards.clone()
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
-    pad = torch.full((width,), float("nan"), dtype=local_rewards.dtype, device=local_rewards.device)
+    # gloo (CPU tests, or two ranks sharing one GPU) gathers host tensors; NCCL gathers in place on the device
+    dev = local_rewards.device if dist.get_backend() == "nccl" else torch.device("cpu")
+    pad = torch.full((width,), float("nan"), dtype=local_rewards.dtype, device=dev)
     pad[: local_rewards.shape[0]] = local_rewards
-    out = torch.empty((world, width), dtype=local_rewards.dtype, device=local_rewards.device)
-    dist.all_gather_into_tensor(out, pad.reshape(1, width))
-    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)])
+    out = [torch.empty((width,), dtype=local_rewards.dtype, device=dev) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([out[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)]).to(local_rewards.device)

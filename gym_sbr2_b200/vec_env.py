@@ -11,6 +11,9 @@ Observation / action / reward semantics are the reference's; tensors are torch C
 keeps its state in module globals, so two reference envs in one process share state (SURVEY.md section 1);
 the semantics here are "N fresh processes each running one env".
 """
+import contextlib
+import os
+
 import numpy as np
 import torch
 
@@ -21,6 +24,62 @@ X0_INIT = (0.6161484733495801, 30, 0.571098000538576, 1440.01157895393, 31.25422
            0.35996687629947, 1.86916737961228, 3.790463057094611)        # gym_SBR_env2.py:78-80
 WV = 1.32                                                                  # gym_SBR_env2.py:33
 IV = 0.6161484733495801                                                    # gym_SBR_env2.py:85
+
+
+def _on(stream):
+    """Context that makes `stream` torch's current stream (so that the staging copies are ordered with the kernel
+    launched on it); a no-op for stream=None."""
+    return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+
+def _init_rng(self, seed, rng, env_offset):
+    """Influent randomness.  rng="philox" (default): counter-based draws inside sbr_influent_sample keyed by
+    (seed, GLOBAL env index = env_offset + i, episode number of that env) -- an env's influent sequence does not
+    depend on the batch size, the rank that owns it or the order of resets, so a sharded run reproduces the
+    single-GPU run env for env.  rng="torch": one torch Philox stream per env object (draws depend
+    on the batch).  rng="numpy": the reference's own numpy stream, consumed like N sequential reference resets."""
+    if rng not in ("philox", "torch", "numpy"):
+        raise ValueError("rng must be 'philox', 'torch' or 'numpy'")
+    self.rng = rng
+    self.env_offset = int(env_offset)
+    self.seed = int(seed) if seed is not None else int.from_bytes(os.urandom(8), "little")
+    self.epoch = torch.zeros((self.num_envs,), dtype=torch.int64, device=self.device)   # episodes started per env
+    self._gen = torch.Generator(device=self.device)
+    if seed is not None:
+        self._gen.manual_seed(int(seed))
+    self._np_rng = np.random.RandomState(seed) if seed is not None else np.random
+
+
+def _draw_influent(self, mask=None, out=None):
+    """Per-env buffer_tank(scenario) draws -> influent_mixed [14,N].  mask (philox only): draw for these envs only,
+    the other columns of `out` are left as they are."""
+    n = self.num_envs
+    scn = getattr(self, "_scenario_arg", None)
+    scn = self.scenario if scn is None else scn
+    if self.rng == "philox":
+        return core.influent_sample(n, self.device, self.seed, env_offset=self.env_offset, scenario=scn,
+                                    epoch=self.epoch, mask=mask, out=out,
+                                    scenario_out=getattr(self, "_scenario_i32", None))
+    if scn < 0:
+        raise ValueError("per-env scenario draws need rng='philox'")
+    if self.rng == "numpy":
+        # N sequential buffer_tank(scenario) calls on one numpy stream, as N reference resets would make
+        d = influent_mod.draws_per_reset(scn)
+        r = self._np_rng.randn(n, d, influent_mod.N_POINTS)[:, -1, :]
+        rnd = torch.as_tensor(np.ascontiguousarray(r.T), dtype=torch.float64).to(self.device)
+    else:
+        rnd = torch.randn((influent_mod.N_POINTS, n), dtype=torch.float64, device=self.device, generator=self._gen)
+    drawn = core.influent_mix(scn, core.soa1(rnd))
+    if mask is not None:
+        self.epoch += mask.to(torch.int64)
+        if out is not None:
+            drawn = torch.where(mask.bool()[None, :], drawn, out)
+    else:
+        self.epoch += 1
+    if out is not None:
+        out.copy_(drawn)
+        return out
+    return drawn
 
 
 class SbrV2VecEnv(object):
@@ -40,7 +99,7 @@ class SbrV2VecEnv(object):
     scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="torch", substeps=None, order="auto"):
+                 params=None, rng="philox", substeps=None, order="auto", env_offset=0):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -50,16 +109,14 @@ class SbrV2VecEnv(object):
         self.sched = schedule.cycle_schedule(substeps=substeps)     # RK4 sub-steps per interval (None = reference grid)
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
         self.tol = _abi.make_tol(rtol, atol, max_steps)
-        self.rng = rng
-        # divergence-aware ordering: with adaptive steps, envs are assigned to warps in the order of their first DO
-        # set-point (one argsort per step, ~0.3 ms at 2^20 envs); results are unaffected, buffers keep env order
+        # divergence-aware ordering: with adaptive steps, envs are handed to the kernel in the order of their first DO
+        # set-point (the per-env step count is a function of it), physically reordered by one gather launch before
+        # and one scatter launch after the cycle kernel so that its loads and stores stay unit-stride; results are
+        # unaffected and the caller's buffers keep env order
         if order not in ("auto", "action", "none"):
             raise ValueError("order must be 'auto', 'action' or 'none'")
         self.order = ("action" if self.mode == _abi.MODE_DP45 else "none") if order == "auto" else order
-        self._gen = torch.Generator(device=self.device)
-        if seed is not None:
-            self._gen.manual_seed(int(seed))
-        self._np_rng = np.random.RandomState(seed) if seed is not None else np.random
+        self._init_rng(seed, rng, env_offset)
         n = self.num_envs
         f = dict(dtype=torch.float64, device=self.device)
         self.x0 = torch.tensor(X0_INIT, **f)[:, None].repeat(1, n).contiguous()
@@ -71,28 +128,22 @@ class SbrV2VecEnv(object):
         self._action = torch.zeros((3, n), **f)
         self._out = core.CycleV2Out(n, self.device)
         self._done = torch.ones((n,), dtype=torch.bool, device=self.device)
+        self._sorted = None                  # gather targets of the ordered launch, allocated on first use
 
-    # -- influent ------------------------------------------------------------------------------------
-    def _draw_influent(self):
-        """Per-env buffer_tank(scenario) draws: rnd ~ N(0,1)^48 per env, mixed on the device (sbr_influent_mix)."""
-        n = self.num_envs
-        if self.rng == "numpy":
-            # N sequential buffer_tank(scenario) calls on one numpy stream, as N reference resets would make
-            d = influent_mod.draws_per_reset(self.scenario)
-            r = self._np_rng.randn(n, d, influent_mod.N_POINTS)[:, -1, :]
-            rnd = torch.as_tensor(np.ascontiguousarray(r.T), dtype=torch.float64).to(self.device)
-        else:
-            rnd = torch.randn((influent_mod.N_POINTS, n), dtype=torch.float64, device=self.device,
-                              generator=self._gen)
-        return core.influent_mix(self.scenario, core.soa1(rnd))
+    _init_rng, _draw_influent = _init_rng, _draw_influent
 
     def reset(self, influent=None, x0=None):
         """influent: optional [14,N] influent_mixed (row 0 ignored at step time); x0: optional [14,N]."""
         if influent is None:
-            influent = self._draw_influent()
-        self.influent.copy_(influent.to(self.device, torch.float64))
+            self._draw_influent(out=self.influent)
+        else:
+            self.influent.copy_(influent.to(self.device, torch.float64))
         if x0 is not None:
             self.x0.copy_(x0.to(self.device, torch.float64))
+        # what the fill phase loads: the influent concentrations with row 0 = the fill flow (gym_SBR_env2.py:144);
+        # staged here, once per reset, not per step
+        self._loading.copy_(self.influent)
+        self._loading[0] = self.fill_flow
         s = self.x0 + self.influent
         cod = s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7]
         return torch.stack([s[0], (cod - 5145) / 10, s[10] / 30], dim=1)
@@ -102,12 +153,31 @@ class SbrV2VecEnv(object):
         """Launch one cycle for every env; returns the SoA output buffers without synchronising."""
         if action.shape != (self.num_envs, 3):
             raise ValueError("action must be [N,3], got %s" % (tuple(action.shape),))
-        self._action.copy_(action.to(self.device, torch.float64).t())
-        self._loading.copy_(self.influent)
-        self._loading[0] = self.fill_flow
-        perm = torch.argsort(self._action[0]) if self.order == "action" and self.num_envs > 32 else None
-        return core.cycle_v2(self.x0, self._loading, self._action, self.params, self.sched, out=self._out,
-                             mode=self.mode, tol=self.tol, stream=stream, perm=perm)
+        with _on(stream):
+            self._action.copy_(action.to(self.device, torch.float64).t())
+        return self.step_soa(self._action, stream=stream)
+
+    def step_soa(self, action_soa, stream=None):
+        """Zero-copy variant: action_soa is the kernel's own layout [3,N] (float64, CUDA, contiguous)."""
+        if action_soa.shape != (3, self.num_envs):
+            raise ValueError("action_soa must be [3,N], got %s" % (tuple(action_soa.shape),))
+        n = self.num_envs
+        if self.order != "action" or n <= 32:
+            return core.cycle_v2(self.x0, self._loading, action_soa, self.params, self.sched, out=self._out,
+                                 mode=self.mode, tol=self.tol, stream=stream)
+        if self._sorted is None:
+            f = dict(dtype=torch.float64, device=self.device)
+            self._sorted = dict(x0=torch.empty((_abi.NX, n), **f), loading=torch.empty((_abi.NX, n), **f),
+                                action=torch.empty((3, n), **f), out=core.CycleV2Out(n, self.device))
+        z, o = self._sorted, self._out
+        with _on(stream):
+            perm = torch.argsort(action_soa[0])
+            core.permute_rows(perm, [(self.x0, z["x0"]), (self._loading, z["loading"]), (action_soa, z["action"])])
+            zo = core.cycle_v2(z["x0"], z["loading"], z["action"], self.params, self.sched, out=z["out"],
+                               mode=self.mode, tol=self.tol)
+            core.permute_rows(perm, [(zo.x_last, o.x_last), (zo.obs, o.obs), (zo.reward, o.reward), (zo.aux, o.aux),
+                                     (zo.status, o.status), (zo.counters, o.counters)], scatter=True)
+        return o
 
     def step(self, action):
         o = self.step_async(action)
@@ -133,10 +203,13 @@ class SbrOsVecEnv(object):
                 (clipped to [0,15], used in anoxic phases) (:862-906).  The declared action_space Box([-1],[1]) of
                 the reference does not describe what `step` consumes; neither is enforced.
     autoreset: envs whose episode has ended are restarted (new influent draw, reset kernel) at the start of the next
-               `step` and then take that step like every other env; info["restarted"] marks them.  While all envs
-               stem from one full reset they end together and nothing is drawn or launched in between (one
-               `done.all()` per episode); after a masked reset the general path runs a masked reset kernel before
-               every step with the next influent drawn ahead (0.22 / 0.43 ms per step at 2^20 envs).
+               `step` and then take that step like every other env.  Convention: info["restarted"] marks them and
+               info["reset_obs"] holds the observations the reset produced (copies, valid for the marked envs; None
+               when nothing restarted) -- the action an on-policy caller passed for a marked env was computed from
+               the previous episode's terminal observation, so the first transition of the new episode should be
+               formed from reset_obs (or dropped).  While all envs stem from one full reset they end together and
+               nothing is drawn or launched in between (one `done.all()` per episode); after a masked reset the
+               general path runs a masked influent draw and a masked reset kernel before every step.
                Without autoreset, stepping a finished env is a no-op (reward 0, status SBR_ST_DONE).
     """
 
@@ -145,7 +218,7 @@ class SbrOsVecEnv(object):
     max_episode_steps = 463
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="torch", autoreset=False, rk4_sub_interval=0):
+                 params=None, rng="philox", autoreset=False, rk4_sub_interval=0, env_offset=0):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -155,12 +228,8 @@ class SbrOsVecEnv(object):
         self.sched = schedule.os_schedule(rk4_sub_interval=rk4_sub_interval)
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
         self.tol = _abi.make_tol(rtol, atol, max_steps)
-        self.rng = rng
         self.autoreset = bool(autoreset)
-        self._gen = torch.Generator(device=self.device)
-        if seed is not None:
-            self._gen.manual_seed(int(seed))
-        self._np_rng = np.random.RandomState(seed) if seed is not None else np.random
+        self._init_rng(seed, rng, env_offset)
         n = self.num_envs
         f = dict(dtype=torch.float64, device=self.device)
         self.buf = core.OsBuffers(n, self.device)
@@ -170,19 +239,21 @@ class SbrOsVecEnv(object):
         self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_oneshot.py:287
         self._init_lockstep()
 
-    _draw_influent = SbrV2VecEnv._draw_influent
+    _init_rng, _draw_influent = _init_rng, _draw_influent
 
     def reset(self, influent=None, x0=None, mask=None):
         """influent: optional [14,N] influent_mixed (row 0 is replaced by the fill flow); x0: optional [14,N];
         mask: optional [N] bool/uint8 -- restart only these envs."""
-        if influent is None:
-            influent = self._draw_influent()
-        influent = influent.to(self.device, torch.float64)
-        if mask is None:
-            self.influent.copy_(influent)
-        else:
+        if mask is not None:
             mask = mask.to(self.device).to(torch.uint8).contiguous()
-            self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
+        if influent is None:
+            self._draw_influent(mask=mask, out=self.influent)
+        else:
+            influent = influent.to(self.device, torch.float64)
+            if mask is None:
+                self.influent.copy_(influent)
+            else:
+                self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
         self._note_reset(mask)
         self._loading.copy_(self.influent)
         self._loading[0] = self.fill_flow
@@ -195,7 +266,8 @@ class SbrOsVecEnv(object):
     def step_async(self, action, stream=None):
         if action.shape != (self.num_envs, 2):
             raise ValueError("action must be [N,2], got %s" % (tuple(action.shape),))
-        self._action.copy_(action.to(self.device, torch.float64).t())
+        with _on(stream):
+            self._action.copy_(action.to(self.device, torch.float64).t())
         self._host_steps += 1
         return core.os_step(self.buf, self._action, self.params, self.sched, mode=self.mode, tol=self.tol,
                             stream=stream)
@@ -212,12 +284,15 @@ class SbrOsVecEnv(object):
 
     def step(self, action):
         b = self.buf
-        restarted = None
+        restarted = reset_obs = None
         if self.autoreset:
             restarted = self._autoreset()
+            if restarted is not self._no_restart:
+                reset_obs = (b.obs_do.t().clone(), b.obs_ec.t().clone())
         self.step_async(action)
         info = dict(status=b.status, counters=b.counters, t=b.st[_abi.OS_T], Qw=b.st[_abi.OS_QW],
-                    episode_return=b.st[_abi.OS_RETURN], episode_steps=b.st[_abi.OS_STEPS], restarted=restarted)
+                    episode_return=b.st[_abi.OS_RETURN], episode_steps=b.st[_abi.OS_STEPS], restarted=restarted,
+                    reset_obs=reset_obs)
         return (b.obs_do.t(), b.obs_ec.t()), b.state.t(), b.reward, b.done.bool(), info
 
     def render(self, mode="human", close=False):
@@ -239,7 +314,7 @@ class SbrV4VecEnv(object):
     max_episode_steps = 493
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, autoreset=False, rk4_sub_interval=0):
+                 params=None, autoreset=False, rk4_sub_interval=0, env_offset=0):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -250,50 +325,43 @@ class SbrV4VecEnv(object):
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
         self.tol = _abi.make_tol(rtol, atol, max_steps)
         self.autoreset = bool(autoreset)
-        self._gen = torch.Generator(device=self.device)
-        if seed is not None:
-            self._gen.manual_seed(int(seed))
+        self._init_rng(seed, "philox", env_offset)
         n = self.num_envs
         f = dict(dtype=torch.float64, device=self.device)
         self.buf = core.V4Buffers(n, self.device)
         self.influent = torch.zeros((_abi.NX, n), **f)          # influent_mixed with row 0 = 0.66
-        self.scenario = torch.zeros((n,), dtype=torch.int64, device=self.device)
+        self._scenario_i32 = torch.zeros((n,), dtype=torch.int32, device=self.device)   # written by the sampler
         self._loading = torch.zeros((_abi.NX, n), **f)          # ... with row 0 = the fill flow
         self._action = torch.zeros((n,), **f)
         self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_env4.py:193
         self._init_lockstep()
 
-    def _draw_influent(self):
-        """Per env: scenario ~ U{0..7}, then one buffer_tank(scenario) draw (all eight mixes share the env's rnd).
-        Returns the [14,N] influent; the scenarios drawn with it are left in `self._drawn_scenario` (`reset` copies
-        them into `self.scenario` for the envs it restarts).  No host synchronisation."""
-        n = self.num_envs
-        scn = torch.randint(0, 8, (n,), device=self.device, generator=self._gen)
-        rnd = core.soa1(torch.randn((influent_mod.N_POINTS, n), dtype=torch.float64, device=self.device,
-                                    generator=self._gen))
-        out = torch.zeros((_abi.NX, n), dtype=torch.float64, device=self.device)
-        for sw in range(8):
-            out = torch.where((scn == sw)[None, :], core.influent_mix(sw, rnd), out)
-        self._drawn_scenario = scn
-        return out
+    _scenario_arg = -1               # np.random.choice(8, 1) per reset, gym_SBR_env4.py:104: drawn by the sampler
+    _init_rng, _draw_influent = _init_rng, _draw_influent
 
-    def reset(self, influent=None, x0=None, mask=None):
-        drawn = None
-        if influent is None:
-            influent = self._draw_influent()
-            drawn = self._drawn_scenario
-        elif influent is getattr(self, "_next_influent", None):
-            drawn = self._next_scenario
-        influent = influent.to(self.device, torch.float64)
-        if mask is None:
-            self.influent.copy_(influent)
-            if drawn is not None:
-                self.scenario = drawn.clone()
-        else:
+    @property
+    def scenario(self):
+        """[N] influent scenario (0..7) of every env's current episode."""
+        return self._scenario_i32
+
+    def reset(self, influent=None, x0=None, mask=None, scenario=None):
+        """influent: optional [14,N] (then `scenario`, optional [N], only labels it); default: per env a scenario
+        ~ U{0..7} and one buffer_tank(scenario) draw, both inside one sbr_influent_sample launch (masked envs only)."""
+        if mask is not None:
             mask = mask.to(self.device).to(torch.uint8).contiguous()
-            self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
-            if drawn is not None:
-                self.scenario = torch.where(mask.bool(), drawn, self.scenario)
+        if influent is None:
+            self._draw_influent(mask=mask, out=self.influent)
+        else:
+            influent = influent.to(self.device, torch.float64)
+            scn = None if scenario is None else scenario.to(self.device, torch.int32)
+            if mask is None:
+                self.influent.copy_(influent)
+                if scn is not None:
+                    self._scenario_i32.copy_(scn)
+            else:
+                self.influent.copy_(torch.where(mask.bool()[None, :], influent, self.influent))
+                if scn is not None:
+                    self._scenario_i32.copy_(torch.where(mask.bool(), scn, self._scenario_i32))
         self._note_reset(mask)
         self._loading.copy_(self.influent)
         self._loading[0] = self.fill_flow
@@ -306,19 +374,23 @@ class SbrV4VecEnv(object):
         action = action.reshape(-1)
         if action.shape != (self.num_envs,):
             raise ValueError("action must be [N] or [N,1], got %s" % (tuple(action.shape),))
-        self._action.copy_(action.to(self.device, torch.float64))
+        with _on(stream):
+            self._action.copy_(action.to(self.device, torch.float64))
         self._host_steps += 1
         return core.v4_step(self.buf, self._loading, self._action, self.params, self.sched, mode=self.mode,
                             tol=self.tol, stream=stream)
 
     def step(self, action):
         b = self.buf
-        restarted = None
+        restarted = reset_obs = None
         if self.autoreset:
             restarted = self._autoreset()
+            if restarted is not self._no_restart:
+                reset_obs = b.obs.t().clone()
         self.step_async(action)
         info = dict(status=b.status, counters=b.counters, t=b.st[_abi.V4_T], u=b.st[_abi.V4_U], Qw=b.st[_abi.V4_QW],
-                    episode_return=b.st[_abi.V4_RETURN], episode_steps=b.st[_abi.V4_STEPS], restarted=restarted)
+                    episode_return=b.st[_abi.V4_RETURN], episode_steps=b.st[_abi.V4_STEPS], restarted=restarted,
+                    reset_obs=reset_obs)
         return b.obs.t(), b.reward, b.done.bool(), info
 
     def render(self, mode="human", close=False):
@@ -335,7 +407,6 @@ def _init_lockstep(self):
     self._lockstep = False
     self._host_steps = 0
     self._no_restart = torch.zeros((self.num_envs,), dtype=torch.uint8, device=self.device)
-    self._next_influent, self._next_scenario, self._next_age = None, None, 0
 
 
 def _note_reset(self, mask):
@@ -355,20 +426,10 @@ def _autoreset(self):
             self.reset()
             return restarted
         self._lockstep = False
+    # general path: masked influent draw + masked reset kernel before every step (both return at once for running
+    # envs).  Every restart draws afresh: the sampler's counter is (global env index, that env's episode number).
     restarted = b.done.clone()
-    # general path: masked reset kernel before every step (a no-op for running envs).  The influent of the NEXT
-    # episode of every env is drawn ahead and refreshed every 128 steps -- an env restarts at most once per 463, so
-    # no column is used twice -- instead of drawing [48,N] normals per step (1.16 -> 0.3 ms per step at 2^20 envs).
-    # With rng="numpy" (reference-identical streams) the draw stays where the reference makes it: at the reset.
-    if getattr(self, "rng", "torch") != "torch":
-        self.reset(mask=restarted)
-        return restarted
-    if self._next_influent is None or self._next_age >= 128:
-        self._next_influent = self._draw_influent()
-        self._next_scenario = getattr(self, "_drawn_scenario", None)
-        self._next_age = 0
-    self._next_age += 1
-    self.reset(influent=self._next_influent, mask=restarted)
+    self.reset(mask=restarted)
     return restarted
 
 
@@ -380,33 +441,59 @@ for _cls in (SbrOsVecEnv, SbrV4VecEnv):
 # checkpoint / resume: the whole simulator state is a handful of torch tensors (the reference keeps it in module
 # globals and has no resume path); `torch.save(env.state_dict(), path)` is the checkpoint.
 # ---------------------------------------------------------------------------------------------------------
+def _rng_state(self):
+    np_state = self._np_rng.get_state() if isinstance(self._np_rng, np.random.RandomState) else None
+    return dict(rng=self.rng, seed=self.seed, env_offset=self.env_offset, epoch=self.epoch.clone(),
+                gen=self._gen.get_state(), np_state=np_state)
+
+
+def _load_rng_state(self, sd):
+    self.rng, self.seed, self.env_offset = sd["rng"], int(sd["seed"]), int(sd["env_offset"])
+    self.epoch.copy_(sd["epoch"])
+    self._gen.set_state(sd["gen"].cpu())
+    if sd.get("np_state") is not None:
+        if not isinstance(self._np_rng, np.random.RandomState):
+            self._np_rng = np.random.RandomState()
+        self._np_rng.set_state(sd["np_state"])
+
+
 def _state_dict_v2(self):
     return dict(kind="SBR-v2", num_envs=self.num_envs, x0=self.x0.clone(), influent=self.influent.clone(),
-                gen=self._gen.get_state())
+                loading=self._loading.clone(), rng_state=_rng_state(self))
 
 
 def _load_state_dict_v2(self, sd):
     if sd["kind"] != "SBR-v2" or sd["num_envs"] != self.num_envs:
         raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
-    self.x0.copy_(sd["x0"]); self.influent.copy_(sd["influent"]); self._gen.set_state(sd["gen"].cpu())
+    self.x0.copy_(sd["x0"]); self.influent.copy_(sd["influent"]); self._loading.copy_(sd["loading"])
+    _load_rng_state(self, sd["rng_state"])
+
+
+# every device buffer a policy-driven rollout reads before the next step writes it (observations, reward, done,
+# status, counters) is part of the checkpoint, not only the integrator state
+_BUF_FIELDS = ("st", "done", "obs_do", "obs_ec", "state", "obs", "reward", "status", "counters")
 
 
 def _state_dict_buf(kind):
     def state_dict(self):
         b = self.buf
-        return dict(kind=kind, num_envs=self.num_envs, st=b.st.clone(), done=b.done.clone(),
-                    influent=self.influent.clone(), loading=self._loading.clone(), gen=self._gen.get_state(),
-                    scenario=self.scenario.clone() if torch.is_tensor(getattr(self, "scenario", None)) else None)
+        sd = dict(kind=kind, num_envs=self.num_envs, influent=self.influent.clone(), loading=self._loading.clone(),
+                  rng_state=_rng_state(self), lockstep=self._lockstep, host_steps=self._host_steps,
+                  buf={k: getattr(b, k).clone() for k in _BUF_FIELDS if hasattr(b, k)})
+        if hasattr(self, "_scenario_i32"):
+            sd["scenario"] = self._scenario_i32.clone()
+        return sd
 
     def load_state_dict(self, sd):
         if sd["kind"] != kind or sd["num_envs"] != self.num_envs:
             raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
-        b = self.buf
-        b.st.copy_(sd["st"]); b.done.copy_(sd["done"])
-        self._lockstep, self._next_influent = False, None
-        self.influent.copy_(sd["influent"]); self._loading.copy_(sd["loading"]); self._gen.set_state(sd["gen"].cpu())
+        for k, v in sd["buf"].items():
+            getattr(self.buf, k).copy_(v)
+        self._lockstep, self._host_steps = bool(sd["lockstep"]), int(sd["host_steps"])
+        self.influent.copy_(sd["influent"]); self._loading.copy_(sd["loading"])
+        _load_rng_state(self, sd["rng_state"])
         if sd.get("scenario") is not None:
-            self.scenario = sd["scenario"].to(self.device)
+            self._scenario_i32.copy_(sd["scenario"])
     return state_dict, load_state_dict
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 3
+#define SBR_ABI_VERSION 4
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -266,6 +266,43 @@ int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const
 #define SBR_INFLUENT_POINTS 48
 int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mean, const double* std,
                      double* influent, void* stream);
+
+/*
+ * Influent generator with its own counter-based randomness = N independent `buffer_tank(scenario)` calls
+ * (buffer_tank3.py:18-108; SbrEnv4.reset draws the scenario too: np.random.choice(8, 1), gym_SBR_env4.py:104).
+ * The 48 standard normals of env i come from Philox4x32-10 keyed by `seed` with counter (env_offset + i, episode
+ * number, block): they depend only on the run's seed, the env's GLOBAL index and how many episodes that env has
+ * started -- not on n, the rank that owns the env, the world size or the order of resets, so results are invariant
+ * to the sharding.  Mixing arithmetic = sbr_influent_mix (bit-identical for the same normals).
+ *   seed        the run's seed (same on every rank)
+ *   env_offset  global index of this shard's env 0
+ *   epoch       [n] in/out (may be NULL): episode number per env; used for the draw and incremented for every env
+ *               that draws.  NULL: every env uses epoch0.
+ *   scenario    0..7, or -1 = drawn per env (uniform on 0..7); scenario_out [n] (may be NULL) receives it
+ *   mean, std   [8][14][48] device copies of ALL scenario tables (row 0 = flow)
+ *   mask        [n] (may be NULL): only envs with mask[i] != 0 draw (their influent column, epoch and scenario_out
+ *               are updated; every other env is left untouched)
+ *   influent    [14][ld] out
+ * sbr_philox_normals writes the same normals z [48][ld] for epoch0 (tests; the RNG half of the parity story).
+ */
+int sbr_influent_sample(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset, int64_t* epoch, int64_t epoch0,
+                        int scenario, const double* mean, const double* std, const uint8_t* mask, double* influent,
+                        int32_t* scenario_out, void* stream);
+int sbr_philox_normals(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset, int64_t epoch0, double* z,
+                       void* stream);
+
+/*
+ * Row permutation of SoA buffers, up to SBR_PERMUTE_MAX buffers in one launch:
+ *   gather  (scatter == 0): dst[k][r][i]       = src[k][r][perm[i]]
+ *   scatter (scatter != 0): dst[k][r][perm[i]] = src[k][r][i]          r < rows[k], i < n
+ * elem_bytes[k] is 8 (double) or 4 (int32 / uint32).  The vector env uses it to hand sbr_cycle_v2 (adaptive mode)
+ * its envs in divergence-aware order -- sorted by the first DO set-point -- with unit-stride loads and stores, and to
+ * put the results back into the caller's env order (no reference counterpart: the reference steps one env).
+ */
+#define SBR_PERMUTE_MAX 8
+int sbr_permute_rows(int64_t n, const int64_t* perm, int nbuf, const void* const* src, void* const* dst,
+                     const int64_t* ld_src, const int64_t* ld_dst, const int32_t* rows, const int32_t* elem_bytes,
+                     int scatter, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

@@ -71,7 +71,7 @@ def test_graphed_rollout_matches_eager(built, cuda_device):
     env_g = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45")
     env_g.reset()
     big, small = rollout.GraphedStepper(env_g, policy, 8), rollout.GraphedStepper(env_g, policy, 1)
-    env_g._gen.manual_seed(5)                                    # same influent draw as the eager env's first reset
+    env_g.epoch.zero_()                                          # same influent draw as the eager env's first reset
     ep = rollout.collect_episode_graphed(env_g, big, small)
     assert bool(ep["all_done"]) and ep["steps"] == 463
     assert torch.equal(ep["returns"], eager["returns"])
@@ -95,10 +95,38 @@ def test_checkpoint_resume_mid_episode(built, cuda_device, tmp_path, cls, nact):
     for k in range(40, 80):
         out_a = a.step(acts[k])
     b = cls(n, device=cuda_device, seed=1234)                      # different seed: everything comes from the file
-    b.load_state_dict(torch.load(path))
+    b.load_state_dict(torch.load(path, weights_only=False))
     for k in range(40, 80):
         out_b = b.step(acts[k])
     assert torch.equal(a.buf.st[:20], b.buf.st[:20])
     ra, rb = (out_a[2], out_b[2]) if nact == 2 else (out_a[1], out_b[1])
     assert torch.equal(ra, rb)
     assert torch.equal(a.reset()[0] if nact == 2 else a.reset(), b.reset()[0] if nact == 2 else b.reset())   # RNG too
+
+
+@pytest.mark.parametrize("rng", ["philox", "numpy"])
+def test_checkpoint_resume_policy_driven(built, cuda_device, tmp_path, rng):
+    """Resume with the policy computing its first action from the RESTORED observation buffers (they are part of the
+    checkpoint, not torch.empty of a fresh env), across an autoreset so that the restored RNG state is used too."""
+    n = 96
+    policy = rollout.TinyPolicy(cuda_device)
+
+    def advance(env, k):
+        for _ in range(k):
+            b = env.buf
+            out = env.step(policy.forward(b.obs_do.t(), b.obs_ec.t()))
+        return out
+
+    a = SbrOsVecEnv(n, device=cuda_device, seed=21, rng=rng, autoreset=True)
+    a.reset()
+    advance(a, 430)
+    path = str(tmp_path / "ckpt.pt")
+    torch.save(a.state_dict(), path)
+    out_a = advance(a, 60)                                                   # crosses the episode end at step 463
+    b = SbrOsVecEnv(n, device=cuda_device, seed=5, rng="philox", autoreset=True)
+    b.load_state_dict(torch.load(path, weights_only=False))
+    out_b = advance(b, 60)
+    assert torch.equal(a.buf.st.view(torch.int64), b.buf.st.view(torch.int64))      # bit patterns: Qw is NaN mid-episode
+    assert torch.equal(a.influent, b.influent)
+    assert torch.equal(out_a[2], out_b[2]) and torch.equal(out_a[0][0], out_b[0][0])
+    assert float(out_a[4]["episode_steps"].max()) == 27

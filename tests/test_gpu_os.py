@@ -141,16 +141,18 @@ def test_autoreset_lockstep_path_draws_and_launches_nothing_between_episode_ends
     env = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45", autoreset=True)
     env.reset()
     a = torch.tensor([[2.0, 5.0]], dtype=torch.float64, device=cuda_device).repeat(n, 1)
-    gen0 = env._gen.get_state().clone()
+    assert int(env.epoch.min()) == 1 == int(env.epoch.max())             # one influent draw so far
     for k in range(463):
         _, _, _, done, info = env.step(a)
         assert not bool(info["restarted"].any())
         assert bool(done.all()) == (k == 462)
-    assert torch.equal(env._gen.get_state(), gen0)                       # nothing was drawn during the episode
+        assert info["reset_obs"] is None
+    assert int(env.epoch.max()) == 1                                     # nothing was drawn during the episode
     ret1 = info["episode_return"].clone()
     _, _, _, done, info = env.step(a)                                    # first step of the second episode
     assert bool(info["restarted"].all()) and not bool(done.any()) and float(info["episode_steps"].max()) == 1
-    assert not torch.equal(env._gen.get_state(), gen0)                   # one influent draw per episode
+    assert int(env.epoch.min()) == 2 == int(env.epoch.max())             # one influent draw per episode
+    assert info["reset_obs"][0].shape == (n, 9) and bool(torch.isfinite(info["reset_obs"][0]).all())
     for k in range(462):
         _, _, _, done, info = env.step(a)
     assert bool(done.all()) and float(info["episode_steps"].min()) == 463
