@@ -146,7 +146,16 @@ def cpu_baseline_leg(target_s):
 
 # interval-per-step path: algorithmic flops and bytes per env per env.step
 F_EC = 94
-OS_BYTES_STEP = 2 * 35 * 8 + (9 + 9 + 15 + 1) * 8 + 2 * 8 + 1 + 4 + 8     # state in+out, obs/state/reward, action, done, status, counters
+# read: st rows 0..33 (x, controller scalars, 10-entry circular KLa history, return, steps), action, done flag;
+# write: x + controller scalars + return + steps (24 rows), one KLa slot, reward, status, counters, obs_DO, obs_EC, state
+OS_BYTES_STEP = 34 * 8 + 2 * 8 + 1 + 24 * 8 + 8 + 8 + 4 + 8 + (9 + 9 + 15) * 8
+OS_BYTES_STEP_LEAN = OS_BYTES_STEP - 15 * 8          # emit=("obs_do", "obs_ec"): the 15-dim `state` is not written
+
+
+def status_bits(torch, status):
+    """How many envs carry each per-env status bit (include/sbr_b200.h SBR_ST_*)."""
+    names = (("nonfinite", 1), ("waste_unassigned", 2), ("steplimit", 4), ("layers", 8))
+    return {nm: int(((status & bit) != 0).sum()) for nm, bit in names}
 
 
 def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
@@ -206,6 +215,25 @@ def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
         flops = rhs * F_EC + steps * ovh + 150
         tf = n * flops / (ms_plain * 1e-3) / 1e12
         ms_wide, _, _ = episode(env, infl, make_actions(gen, wide=True), False)
+        wide_bits = status_bits(torch, env.buf.status)
+        wide_bad = int((env.buf.status != 0).sum())
+        # the same plain step without the `state` output (a policy that reads obs_DO / obs_EC only), and K = 8 steps
+        # per launch (frame-skip: the state stays in registers between the 8 intervals)
+        env.emit = ("obs_do", "obs_ec")
+        ms_lean = sorted(episode(env, infl, acts, True)[1][60:270])[105]
+        env.emit = ("obs_do", "obs_ec", "state")
+        env.reset(influent=infl)
+        a8 = torch.stack([a.t().contiguous() for a in acts])                 # [8, 2, n]
+        r8 = torch.empty((8, n), dtype=torch.float64, device=device)
+        for _ in range(8):
+            env.step_k(a8, r8)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            env.step_k(a8, r8)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_k8 = e0.elapsed_time(e1) / 160
         out[mode] = {"envs": n, "ms_per_episode": ms_episode, "interval_steps_per_sec": n * 463 / (ms_episode * 1e-3),
                      "actions": "per-step DO set-point U(2,3), NO3 set-point U(4,6): the distribution of the CPU sample",
                      "ms_per_plain_step": ms_plain, "plain_interval_steps_per_sec": n / (ms_plain * 1e-3),
@@ -219,7 +247,12 @@ def interval_path_leg(torch, device, args, peak_burst, peak_sustained):
                      "stress_wide_actions": {"actions": "DO set-point U(1,7), NO3 set-point U(2,12)",
                                              "ms_per_episode": ms_wide,
                                              "interval_steps_per_sec": n * 463 / (ms_wide * 1e-3),
-                                             "bad_status": int((env.buf.status != 0).sum())}}
+                                             "bad_status": wide_bad, "status_bits": wide_bits},
+                     "lean_outputs": {"emit": "obs_do, obs_ec (no 15-dim state)", "ms_per_plain_step": ms_lean,
+                                      "bytes_per_env_step": OS_BYTES_STEP_LEAN,
+                                      "hbm_frac": n * OS_BYTES_STEP_LEAN / (ms_lean * 1e-3) / 1e9 / _hbm_peak()},
+                     "k8_launch": {"what": "sbr_os_step_k, K = 8 env.steps per launch (steps 64..231 of the episode)",
+                                   "ms_per_env_step": ms_k8, "interval_steps_per_sec": n / (ms_k8 * 1e-3)}}
         del env
     return out
 
@@ -366,7 +399,8 @@ def rollout_leg(torch, tdist, device, rank, world, args):
     lo, hi = dist.shard_range(total, rank, world)
     ok, err = 1.0, ""
     try:                                                         # local set-up: no collectives in here
-        env = SbrOsVecEnv(hi - lo, device=device, seed=4242, mode="dp45", env_offset=lo)   # draws keyed by GLOBAL env index
+        env = SbrOsVecEnv(hi - lo, device=device, seed=4242, mode="dp45", env_offset=lo,    # draws keyed by GLOBAL env index
+                          emit=("obs_do", "obs_ec"))                                        # all the policy reads
         policy = rollout.TinyPolicy(device)
         warm = rollout.collect_episode(env, policy, max_steps=3)     # warm-up (allocations, policy kernels)
         # the inner loop [policy -> action -> sbr_os_step] captured in CUDA graphs (8 steps and 1 step per replay):
@@ -413,6 +447,53 @@ def rollout_leg(torch, tdist, device, rank, world, args):
             "gathered_returns": int(allr.numel()), "all_done": bool(ep["all_done"]) and bool(ep_e["all_done"]),
             "return_stats": stats,
             "scaling": "strong", "collective": "all_gather of per-env returns (%d B per rank)" % ((hi - lo) * 8)}
+
+
+def headline_strong_leg(torch, tdist, device, rank, world, args, core, peak):
+    """What north_star literally asks: --strong-envs (2^20) SBR-v2 envs IN TOTAL, sharded over the ranks by contiguous
+    global index blocks (influent keyed by global index: the same 2^20 envs at every N), one whole cycle each; the
+    cycle kernel's CUDA-event time (max over ranks) and its FP64 roofline fraction at this per-GPU batch."""
+    from gym_sbr2_b200 import dist
+    from gym_sbr2_b200.vec_env import SbrV2VecEnv
+    total = args.strong_envs
+    lo, hi = dist.shard_range(total, rank, world)
+    n = hi - lo
+    env = SbrV2VecEnv(n, device=device, seed=1234, mode=args.mode, rtol=args.rtol, atol=args.atol, env_offset=lo)
+    env.reset()
+    # the action of env i is a function of its GLOBAL index too
+    gen = torch.Generator(device=device).manual_seed(99)
+    action = torch.rand((total, 3), dtype=torch.float64, device=device, generator=gen)[lo:hi].contiguous()
+    for _ in range(2):
+        o = env.step_async(action)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    ea.record()
+    for _ in range(reps):
+        o = env.step_async(action)
+    eb.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ea.elapsed_time(eb) / reps], dtype=torch.float64, device=device)
+    chk = torch.stack([o.reward.sum(), (o.status != 0).sum().to(torch.float64)])
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(chk, op=tdist.ReduceOp.SUM)
+    ms = float(t.item())
+    if args.mode == "rk4":
+        flops_env, _ = cycle_flops_rk4(env.sched)
+    else:
+        cnt = o.counters.to(torch.float64)
+        rhs = float(cnt[0].mean())
+        flops_env = rhs * F_REACT + (rhs - 6) / 6.0 * (2 * 9 * 15 + 2 * 11 * 5 + 2 * 11 * 6 + 5 * 11) + F_EPILOGUE
+    tf = n * flops_env / (ms * 1e-3) / 1e12
+    ctas = (n + 63) // 64
+    return {"total_envs": total, "envs_per_gpu": n, "ms_per_cycle_step": ms, "cycle_steps_per_sec": total / (ms * 1e-3),
+            "scaling": "strong", "integrator": args.mode,
+            "roofline": {"bound": "fp64", "achieved_per_gpu": tf, "peak": peak, "frac": tf / peak, "unit": "TFLOP/s"},
+            "grid": "%d CTAs of 64 threads per GPU over 148 SMs" % ctas,
+            "reward_sum_all_ranks": float(chk[0]), "bad_status": int(chk[1])}
 
 
 def cycle_substeps_leg(torch, device, core, env, n, substeps):
@@ -497,6 +578,8 @@ def main():
     ap.add_argument("--interval-envs", type=int, default=1 << 20)
     ap.add_argument("--no-rollout", action="store_true", help="skip the config-5 rollout leg")
     ap.add_argument("--rollout-envs", type=int, default=1 << 20, help="TOTAL envs of the config-5 rollout (sharded)")
+    ap.add_argument("--strong-envs", type=int, default=1 << 20,
+                    help="TOTAL SBR-v2 envs of the strong-scaling headline leg (sharded over the ranks)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -592,6 +675,14 @@ def main():
     achieved_tf = n * flops_env / (kern_avg * 1e-3) / 1e12
     peak_burst, peak_sustained = measure_fp64_peak(core, torch, device)
     peak = peak_sustained if kern_avg * K > 500 else peak_burst
+    sm_mhz = torch.cuda.get_device_properties(device).clock_rate / 1e3 if hasattr(
+        torch.cuda.get_device_properties(device), "clock_rate") else None
+    try:
+        sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        pass
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+    peak_theory = n_sm * 64 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12       # SMs x 64 DFMA/clk x 2 flop x max SM clock
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -604,6 +695,9 @@ def main():
                 "flops_per_env": flops_env, "rhs_per_env": rhs_mean, "rejected_per_env": rej_mean,
                 "peak_source": "in-run DFMA probe (MEASURED_PEAKS.json has no FP64 entry); burst %.2f, sustained %.2f"
                                % (peak_burst, peak_sustained),
+                "peak_theoretical": peak_theory, "frac_of_theoretical": achieved_tf / peak_theory,
+                "peak_theoretical_source": "%d SMs x 64 DFMA/clk x 2 flop x %.0f MHz (max SM clock)"
+                                           % (n_sm, sm_mhz or 1965.0),
                 "hbm": {"bytes_per_env": BYTES_PER_ENV, "achieved_gbs": n * BYTES_PER_ENV / (kern_avg * 1e-3) / 1e9,
                         "peak_gbs": _hbm_peak()}}
 
@@ -716,6 +810,9 @@ def main():
         paths["sbr_v4"] = leg(v4_path_leg, torch, device, args)
         paths["config1_small_batch"] = leg(small_batch_leg, torch, device)
     if not args.no_rollout:
+        paths["headline_strong_scaling"] = (leg(headline_strong_leg, torch, tdist, device, rank, world, args, core, peak)
+                                            if world == 1 else
+                                            headline_strong_leg(torch, tdist, device, rank, world, args, core, peak))
         # every rank takes part: envs sharded over the ranks, NCCL gather of the episode returns
         # (guarded only on one GPU: with several ranks a swallowed exception on one of them would leave the others
         # waiting in a collective -- there a failure must bring the job down)

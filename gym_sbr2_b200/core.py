@@ -159,24 +159,40 @@ def os_reset(buf, influent, params, sched, x0=None, mask=None, mode=_abi.MODE_DP
     return buf
 
 
-def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None):
-    """One env.step for a batch (SbrOS.step, gym_SBR_oneshot.py:843-1273).  action [2,n]: DO and NO3 set-points."""
+def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None, emit=("obs_do", "obs_ec", "state"),
+            rewards=None):
+    """One env.step for a batch (SbrOS.step, gym_SBR_oneshot.py:843-1273).  action [2,n]: DO and NO3 set-points --
+    or [K,2,n] with rewards [K,n]: K consecutive steps in one launch (sbr_os_step_k).  emit: which of the
+    observation outputs are written (the others cost no memory traffic and keep their old contents)."""
     lib = _abi.load()
     n = buf.st.shape[1]
     pst, l0 = _dev_ptr(buf.st, _abi.OS_ROWS, n, name="st")
-    pac, l1 = _dev_ptr(action, 2, n, name="action")
-    pod, l2 = _dev_ptr(buf.obs_do, _abi.OS_NOBS, n, name="obs_do")
-    poe, l3 = _dev_ptr(buf.obs_ec, _abi.OS_NOBS, n, name="obs_ec")
-    pse, l4 = _dev_ptr(buf.state, _abi.OS_NSTATE, n, name="state")
-    prw, _ = _dev_ptr(buf.reward, 1, n, name="reward")
+    if action.dim() == 3:
+        K = action.shape[0]
+        if rewards is None or rewards.shape != (K, n):
+            raise ValueError("K-step launch: rewards must be [K, n]")
+        if action.shape[1:] != (2, n) or not action.is_contiguous() or not rewards.is_contiguous():
+            raise ValueError("K-step launch: action must be contiguous [K, 2, n], rewards contiguous [K, n]")
+        pac, l1 = _dev_ptr(action.view(2 * K, n), 2 * K, n, name="action")
+        prw, l6 = _dev_ptr(rewards, K, n, name="rewards") if K > 1 else (C.c_void_p(rewards.data_ptr()), n)
+        if K == 1:
+            l1 = n
+    else:
+        K = 1
+        pac, l1 = _dev_ptr(action, 2, n, name="action")
+        prw, _ = _dev_ptr(buf.reward, 1, n, name="reward")
+        l6 = None
+    pod, l2 = _dev_ptr(buf.obs_do if "obs_do" in emit else None, _abi.OS_NOBS, n, name="obs_do")
+    poe, l3 = _dev_ptr(buf.obs_ec if "obs_ec" in emit else None, _abi.OS_NOBS, n, name="obs_ec")
+    pse, l4 = _dev_ptr(buf.state if "state" in emit else None, _abi.OS_NSTATE, n, name="state")
     pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
     pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
     pct, l5 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
-    ld = _same_ld([l0, l1, l2, l3, l4, l5], "os_step")
+    ld = _same_ld([l0, l1, l2 if pod else None, l3 if poe else None, l4 if pse else None, l5, l6], "os_step")
     tol = tol or _abi.make_tol()
     with torch.cuda.device(buf.st.device):
-        rc = lib.sbr_os_step(n, ld, pst, pac, C.byref(params), C.byref(sched), pod, poe, pse, prw, pdn, pss, pct,
-                             int(mode), C.byref(tol), _stream_ptr(stream))
+        rc = lib.sbr_os_step_k(n, ld, K, pst, pac, C.byref(params), C.byref(sched), pod, poe, pse, prw, pdn, pss, pct,
+                               int(mode), C.byref(tol), _stream_ptr(stream))
     _abi.check(rc, "sbr_os_step")
     return buf
 

@@ -135,6 +135,12 @@ SBR_HD constexpr bool active(int i) {
         || i == iXnd;
 }
 
+// Packed index of an active component (0..8).
+SBR_HD constexpr int aidx(int i) {
+    return i == iSs ? 0 : i == iXs ? 1 : i == iXbh ? 2 : i == iXba ? 3 : i == iSo ? 4 : i == iSno ? 5
+         : i == iSnh ? 6 : i == iSnd ? 7 : 8;
+}
+
 // Influent loading accessor: component i at p[i * stride] (shared memory column on the GPU).
 struct Loading {
     const double* p;
@@ -388,9 +394,9 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         // spread what is left of the interval over equal steps no longer than the controller's proposal: a
         // proposal that does not divide the interval would otherwise end it with a sliver step (6 RHS for nothing)
         const double rem = T - t;
-        const float n_f = ceilf((float)rem * __frcp_rn_compat((float)h) * 0.99999f);   // float is plenty for a count
+        const float n_f = ceilf((float)rem * frcp_fast((float)h) * 0.99999f);   // float is plenty for a count
         const bool last = !(n_f > 1.0f);
-        const double hs = last ? rem : rem * (double)__frcp_rn_compat(n_f);
+        const double hs = last ? rem : rem * (double)frcp_fast(n_f);
 #pragma unroll
         for (int i = 0; i < SBR_NX; ++i)
             if (active(i)) y[i] = fma(hs * a21, k1[i], x[i]);
@@ -428,19 +434,21 @@ SBR_HD int dp45_interval(double (&x)[SBR_NX], double T, const Flow& f, const Coe
         const double g7 = stage<TAIL>(y, k2, t + hs, f, c, a);
         st.n_rhs += 6;
         // error estimate, RMS norm over the active components
-        // (h is factored out of the 9 error components; the per-component scale only steers the controller, so
-        // its reciprocal is the raw MUFU approximation: no FP64-pipe work)
-        double en = 0.0;
+        // (h is factored out of the 9 error components; the per-component scale only steers the controller: it is
+        // taken from the new solution alone -- |y| is an operand modifier, where max(|x|, |y|) costs ten integer
+        // instructions per component -- and its reciprocal is the raw MUFU approximation; three partial sums instead
+        // of one serial DFMA chain)
+        double en3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < SBR_NX; ++i)
             if (active(i)) {
                 const double err = fma(e7, k2[i], fma(e6, k6[i], fma(e5, k5[i], fma(e4, k4[i],
                                    fma(e3, k3[i], e1 * k1[i])))));
-                const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(y[i])), tol.atol * tol_scale(i));
+                const double sc = fma(tol.rtol, fabs(y[i]), tol.atol * tol_scale(i));
                 const double q = err * rcp_rough(sc);
-                en = fma(q, q, en);
+                en3[aidx(i) % 3] = fma(q, q, en3[aidx(i) % 3]);
             }
-        en = en * (hs * hs * (1.0 / 9));   // mean square
+        const double en = ((en3[0] + en3[1]) + en3[2]) * (hs * hs * (1.0 / 9));   // mean square
         const bool finite = en < 1e300;   // false for NaN/Inf
         if (en <= 1.0 || !finite) {
             // accept (a non-finite state is accepted so that the loop terminates; flagged by the caller)
@@ -611,11 +619,6 @@ SBR_HD int pid_phase(double (&x)[SBR_NX], int n_int, int n_sub, double T, double
 // Kept: the error norm as three partial sums and the raw MUFU reciprocal for the step count (-4 %).
 // ---------------------------------------------------------------------------------------------------------
 
-// Packed index of an active component (0..8).
-SBR_HD constexpr int aidx(int i) {
-    return i == iSs ? 0 : i == iXs ? 1 : i == iXbh ? 2 : i == iXba ? 3 : i == iSo ? 4 : i == iSno ? 5
-         : i == iSnh ? 6 : i == iSnd ? 7 : 8;
-}
 
 // Scratch column of one env outside the register file: slot j at p[j * stride] (shared memory on the device,
 // conflict-free for consecutive threads; a local array in the CPU twin).  Holds what is written once per phase and
@@ -724,7 +727,7 @@ SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, cons
                 for (int i = 0; i < SBR_NX; ++i)
                     if (active(i)) {
                         const double e_i = fma(tb.e7, k2[i], err[i]);
-                        const double sc = fma(tol.rtol, fmax(fabs(x[i]), fabs(sol[i])), tol.atol * tol_scale(i));
+                        const double sc = fma(tol.rtol, fabs(sol[i]), tol.atol * tol_scale(i));
                         const double q = e_i * rcp_rough(sc);
                         en3[aidx(i) % 3] = fma(q, q, en3[aidx(i) % 3]);
                     }
@@ -1068,11 +1071,36 @@ SBR_HD bool warp_any(bool pred) {
 
 // One SoA column of an env: element j at p[j * stride].
 struct Column {
-    double* p;
+    double* p;           // NULL: an output the caller did not ask for (set() is then a no-op)
     int64_t stride;
     SBR_HD double get(int j) const { return p[(int64_t)j * stride]; }
-    SBR_HD void set(int j, double v) const { p[(int64_t)j * stride] = v; }
+    SBR_HD void set(int j, double v) const { if (p) p[(int64_t)j * stride] = v; }
 };
+
+// The env's KLa history (the last 10 entries of the reference's ever-growing `Kla` list) as a CIRCULAR buffer: the
+// entry of the k-th interval since the reset sits in slot k % 10, so that a step writes one slot (two at a phase
+// switch) instead of shifting ten.  The slot of the next push follows from the running time (every interval advances
+// it by t_delta and pushes exactly one entry), so no head pointer is stored.  `in`: where the entries are read from
+// (the state rows in global memory, or their staged copy in shared memory); `out`: the state rows in global memory.
+// A push goes to both, so that later steps of the same launch see it.
+struct KlaRing {
+    Column in, out;
+    int head;                                                          // slot of the next push = oldest entry
+    SBR_HD double back(int m) const {                                  // m = 1: newest ... m = 10: oldest
+        int j = head - m;
+        j += j < 0 ? 10 : 0;
+        return in.get(j);
+    }
+    SBR_HD void push(double v) {
+        out.set(head, v);
+        if (in.p != out.p) in.set(head, v);
+        head = head == 9 ? 0 : head + 1;
+    }
+};
+SBR_HD int os_ring_head(double t, const SbrOsSchedule& s) {
+    const int k = (int)((t - s.t_fill) / s.t_delta + 0.5);             // intervals run since the reset
+    return k > 0 ? k % 10 : 0;
+}
 
 struct OsPid {
     double Kc_DO, KcI_DO, KcD_DO, Kc_EC, KcI_EC, KcD_EC, dt, inv_dt, kla_lo, kla_hi, ec_lo, ec_hi;
@@ -1220,24 +1248,24 @@ SBR_HD int os_reset_env(double (&x)[SBR_NX], const Loading& load, const SbrParam
 struct OsStepOut {
     double reward;
     double Qw;       // only meaningful when done
+    ObsRef first;    // reference state of the observation deltas (start of the step's last interval)
     int done;
     int status;
 };
 
-// SbrOS.step (gym_SBR_oneshot.py:843-1273).  ring: the env's 10-entry Kla history (read after the integration,
-// so that it costs no registers while the stepper runs).  Passes 0..3 are the reference's four NON-exclusive ifs on
+// SbrOS.step (gym_SBR_oneshot.py:843-1273) without the observation epilogue (the caller emits it with os_emit_obs
+// from o.first: a launch that advances K steps stores only the last one's).  ring: the env's 10-entry Kla history
+// (read after the integration, so that it costs no registers while the stepper runs).  Passes 0..3 are the reference's four NON-exclusive ifs on
 // the running time (:860,896,931,963: anoxic / aerobic / anoxic / aerobic -- a step that crosses a phase boundary
 // runs two intervals); pass 4 computes the reward and, at the end of the react phases, settle + draw + the idle
 // solve.  All five share ONE stepper call site per tail so the kernel stays inside the instruction cache.
 template <int MODE>
-SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, double a_do, double a_ec,
+SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_do, double a_ec,
                         const SbrParams& p, const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol,
-                        Dp45State& dp, const Column& obs_do, const Column& obs_ec, const Column& state,
-                        OsStepOut& o) {
+                        Dp45State& dp, OsStepOut& o) {
     const OsPid pid = make_os_pid(p, coef);
-    int status = 0, n_run = 0, L = 10;
+    int status = 0, L = 10;
     double span = s.t_delta, u_do = 0.0, ec_before = c.ec_last;
-    double kla_new0 = 0.0, kla_new1 = 0.0;
     ObsRef first = obs_ref(x);
     TailArgs a;
     a.kla = 0.0; a.q = 0.0; a.ec_conc = p.ec_conc; a.load = Loading{nullptr, 0};
@@ -1272,24 +1300,9 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
             // reward = module_reward_EQIOCI.sbr_reward (module_reward_EQIOCI.py:4-115) on the post-interval state:
             // `Kla` holds ONE entry per interval, so Kla[-L:-1] sums the previous L-1 intervals and leaves the
             // current one out (:70-71); `EC` holds L-1 copies per interval, so EC[-L:-1] is the previous
-            // interval's flow once plus the current one L-2 times (:79).
-            double r[10];
-#pragma unroll
-            for (int j = 0; j < 10; ++j) r[j] = ring.get(j);
-            if (n_run >= 1) {
-#pragma unroll
-                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-                r[9] = kla_new0;
-            }
-            if (n_run >= 2) {
-#pragma unroll
-                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-                r[9] = kla_new1;
-            }
+            // interval's flow once plus the current one L-2 times (:79).  Summed oldest first, like sum() does.
             double ksum = 0.0;
-#pragma unroll
-            for (int j = 0; j < 9; ++j)
-                if (j >= 10 - L) ksum += r[j];
+            for (int j = L; j >= 2; --j) ksum += ring.back(j);
             double esum = 0.0 + ec_before;
             for (int j = 0; j < L - 2; ++j) esum += c.ec_last;
             double eff[6];
@@ -1325,12 +1338,8 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
                 n_sub = s.rk4_sub_idle > 0 ? s.rk4_sub_idle : (pts > 1 ? pts - 1 : 1);
                 kla_idle = os_pid_do(c, so_start, u_do, false, true, pid);
                 a.kla = kla_idle; a.q = 0.0;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) r[j] = r[j + 1];
-                r[9] = kla_idle;
+                ring.push(kla_idle);
             }
-#pragma unroll
-            for (int j = 0; j < 10; ++j) ring.set(j, r[j]);
             if (!terminal) break;
         }
         if (warp_any(a.q != 0.0)) status |= integrate_interval<TAIL_EC, MODE>(x, T, n_sub, coef, a, tl, dp);
@@ -1342,15 +1351,14 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, const Column& ring, doub
         c.t = t_next;
         if (pass < 4) {
             c.ec_last = a.q;
-            if (n_run == 0) kla_new0 = a.kla; else kla_new1 = a.kla;
-            ++n_run;
+            ring.push(a.kla);
         }
     }
     bool finite = fabs(o.reward) < 1e300;
 #pragma unroll
     for (int i = 0; i < SBR_NX; ++i) finite = finite && (fabs(x[i]) < 1e300);
     if (!finite) status |= SBR_ST_NONFINITE;
-    os_emit_obs(c.t, x, first, obs_do, obs_ec, state);
+    o.first = first;
     o.status = status;
 }
 

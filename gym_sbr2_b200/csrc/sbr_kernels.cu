@@ -5,6 +5,7 @@
 // (component c of env i at base[c*ld + i]).  The path is FP64-FMA-pipe bound (no contraction => no tensor
 // cores); see DESIGN.md for the roofline arithmetic.  Per-env influent concentrations sit in a shared-memory
 // column (conflict-free: consecutive threads -> consecutive 8-byte words) so the fill tail costs no registers.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -200,11 +201,8 @@ struct OsArgs {
     const double* x0;         // reset only (may be NULL)
     const double* influent;   // reset only
     const uint8_t* mask;      // reset only (may be NULL)
-    const double* action;     // step only
     double* obs_do;
     double* obs_ec;
-    double* state;            // step only
-    double* reward;           // step only
     uint8_t* done;
     int32_t* status;
     uint32_t* counters;
@@ -259,63 +257,239 @@ __global__ void __launch_bounds__(kBlock) sbr_os_reset_kernel(OsArgs g, SbrParam
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
-// Touch the 128-byte lines of a row that this warp will read later (after the integration), so that the later read
-// is an L2 hit instead of a third exposed DRAM round trip.  No destination register, no scoreboard entry.
+// Touch the 128-byte lines of a row that this warp will read later, so that the later read is an L2 hit instead of
+// an exposed DRAM round trip.  No destination register, no scoreboard entry.
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
+// ---- TMA tile loads global -> shared completing on an mbarrier ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const CUtensorMap* tm, int c0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
+                 ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sbr_os_step / sbr_os_step_k: persistent warps, one tile of 32 consecutive envs at a time.
+//
+// One env.step is ~1.5 k FP64 instructions on ~0.65 kB of state: arithmetic intensity sits at the ridge, and with
+// 254 registers per thread only two warps per scheduler are resident -- too few to hide a DRAM round trip behind
+// another warp's arithmetic (round 1: 58 % of HBM peak, 41 % of the FP64 pipe, stalled on long_scoreboard).  So the
+// loads are taken off the warps: while a warp computes tile k, the TMA unit copies the rows of its NEXT tile -- a
+// [34 rows x 32 envs] box of st, the step's [2 x 32] action box and the 32 done flags: three tensor-map copies issued
+// by one lane, completing on the warp's own mbarrier -- into the other half of the warp's double buffer.  Every warp
+// runs its own pipeline (no CTA-wide barrier couples the two warps of a CTA); the lanes read their state from shared
+// memory (conflict-free: consecutive lanes, consecutive words) and write results straight to global memory
+// (coalesced stores do not stall a warp).  TMA zero-fills the ragged last tile.  Buffers that are not 16-byte aligned
+// (or an odd ld) take a plain-load fill of the stage instead.
+// ---------------------------------------------------------------------------------------------------------
+struct OsStepArgs {
+    int64_t n, ld, num_tiles;
+    double* st;
+    const double* action;     // [K][2][ld]
+    double* obs_do;           // may be NULL
+    double* obs_ec;           // may be NULL
+    double* state;            // may be NULL
+    double* reward;           // [K][ld]
+    uint8_t* done;
+    int32_t* status;          // may be NULL
+    uint32_t* counters;       // may be NULL
+    int K, tma;
+};
+
+constexpr int kOsTile = 32;                        // envs per tile = one warp
+constexpr int kOsWarps = kOsBlock / 32;
+constexpr int kOsStageRows = SBR_OS_QW + 2;        // st rows 0..SBR_OS_QW-1, then the first step's two action rows
+constexpr int kOsRowAct = SBR_OS_QW;
+constexpr uint32_t kOsStageBytes = kOsStageRows * kOsTile * sizeof(double) + kOsTile;
+
 template <int MODE>
-__global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step_kernel(OsArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
-                                                             SbrTol tol) {
-    const int64_t i = (int64_t)blockIdx.x * kOsBlock + threadIdx.x;
-    if (i >= g.n) return;
-    // All loads of the launch are issued back to back, before anything depends on them: the warp pays ONE DRAM
-    // round trip (state, controller scalars, action, done flag, episode counters), not one per dependent branch
-    // (0.293 -> 0.268 ms per launch of 2^20 envs, profiles/r01f_ab_os_step_hoist_minblocks.log).
-    double x[SBR_NX];
-#pragma unroll
-    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
-    sbr::OsCtrl ctl;
-    ctl.t = g.st[SBR_OS_T * g.ld + i];
-    const uint8_t was_done = g.done[i];
-    ctl.so_prev = g.st[SBR_OS_SO_PREV * g.ld + i];
-    ctl.sno_last = g.st[SBR_OS_SNO_LAST * g.ld + i];
-    ctl.sno_prev = g.st[SBR_OS_SNO_PREV * g.ld + i];
-    ctl.ie_do = g.st[SBR_OS_IE_DO * g.ld + i];
-    ctl.ie_ec = g.st[SBR_OS_IE_EC * g.ld + i];
-    ctl.ec_last = g.st[SBR_OS_EC_LAST * g.ld + i];
-    ctl.kla_last = g.st[(SBR_OS_KLA_RING + 9) * g.ld + i];
-    sbr::Dp45State dp;
-    dp.h = g.st[SBR_OS_H * g.ld + i];
-    const double a_do = g.action[i], a_ec = g.action[g.ld + i];
-    const double ret0 = g.st[SBR_OS_RETURN * g.ld + i], steps0 = g.st[SBR_OS_STEPS * g.ld + i];
-    // the KLa history is read after the integration (it would cost 20 registers across the stepper): pull its
-    // lines into L2 now
-#pragma unroll
-    for (int j = 0; j < 9; ++j) prefetch_l2(g.st + (SBR_OS_KLA_RING + j) * g.ld + i);
-    const sbr::Column od{g.obs_do + i, g.ld}, oe{g.obs_ec + i, g.ld}, os{g.state + i, g.ld};
-    if (was_done) {
-        // stepping a finished episode is a no-op: same observation, zero deltas, reward 0
-        sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
-        g.reward[i] = 0.0;
-        if (g.status) g.status[i] = SBR_ST_DONE;
-        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
-        return;
+__global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step_kernel(
+        OsStepArgs g, SbrParams p, sbr::Coef c, SbrOsSchedule s, SbrTol tol, const __grid_constant__ CUtensorMap tm_st,
+        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_done) {
+    __shared__ __align__(128) double s_stage[kOsWarps][2][kOsStageRows * kOsTile];
+    __shared__ __align__(128) uint8_t s_done[kOsWarps][2][128];
+    __shared__ __align__(8) uint64_t s_bar[kOsWarps][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    dp.n_rhs = 0; dp.n_rej = 0;
-    const sbr::Column ring{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld};
-    sbr::OsStepOut o;
-    sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, od, oe, os, o);
+    __syncwarp();
+    const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
+
+    // fill the warp's stage `stg` with tile `tile`: three TMA box copies, or plain loads of the lane's own column
+    auto fill = [&](int64_t tile, int stg) {
+        const int64_t i0 = tile * kOsTile;
+        double* sg = s_stage[warp][stg];
+        if (g.tma) {
+            if (lane == 0) {
+                const uint32_t bar = bar0 + 8u * stg;
+                mbar_expect_tx(bar, kOsStageBytes);
+                tma_load_2d(smem_u32(sg), &tm_st, (int)i0, 0, bar);
+                tma_load_2d(smem_u32(sg + kOsRowAct * kOsTile), &tm_act, (int)i0, 0, bar);
+                tma_load_1d(smem_u32(s_done[warp][stg]), &tm_done, (int)i0, bar);
+            }
+        } else if (i0 + lane < g.n) {
+            const int64_t i = i0 + lane;
 #pragma unroll
-    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
-    os_store_ctrl(g.st, g.ld, i, ctl, dp.h);
-    g.st[SBR_OS_RETURN * g.ld + i] = ret0 + o.reward;
-    g.st[SBR_OS_STEPS * g.ld + i] = steps0 + 1.0;
-    if (o.done) { g.st[SBR_OS_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
-    g.reward[i] = o.reward;
-    if (g.status) g.status[i] = o.status;
-    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+            for (int r = 0; r < SBR_OS_QW; ++r) sg[r * kOsTile + lane] = g.st[r * g.ld + i];
+            sg[kOsRowAct * kOsTile + lane] = g.action[i];
+            sg[(kOsRowAct + 1) * kOsTile + lane] = g.action[g.ld + i];
+            s_done[warp][stg][lane] = g.done[i];
+        }
+    };
+
+    const int64_t stride = (int64_t)gridDim.x * kOsWarps;
+    int64_t tile = (int64_t)blockIdx.x * kOsWarps + warp;
+    uint32_t parity = 0u;                            // bit stg = phase parity the warp waits for next on that stage
+    int stg = 0;
+    if (tile < g.num_tiles) fill(tile, 0);
+    for (; tile < g.num_tiles; tile += stride, stg ^= 1) {
+        // the other stage was released at the end of the previous iteration: prefetch the next tile into it
+        if (tile + stride < g.num_tiles) fill(tile + stride, stg ^ 1);
+        if (g.tma) {
+            mbar_wait(bar0 + 8u * stg, (parity >> stg) & 1u);
+            parity ^= 1u << stg;
+        }
+        const int64_t i = tile * kOsTile + lane;
+        if (i < g.n) {
+            double* sg = s_stage[warp][stg] + lane;
+            double x[SBR_NX];
+#pragma unroll
+            for (int k = 0; k < SBR_NX; ++k) x[k] = sg[k * kOsTile];
+            sbr::OsCtrl ctl;
+            ctl.t = sg[SBR_OS_T * kOsTile];
+            ctl.so_prev = sg[SBR_OS_SO_PREV * kOsTile];
+            ctl.sno_last = sg[SBR_OS_SNO_LAST * kOsTile];
+            ctl.sno_prev = sg[SBR_OS_SNO_PREV * kOsTile];
+            ctl.ie_do = sg[SBR_OS_IE_DO * kOsTile];
+            ctl.ie_ec = sg[SBR_OS_IE_EC * kOsTile];
+            ctl.ec_last = sg[SBR_OS_EC_LAST * kOsTile];
+            sbr::Dp45State dp;
+            dp.h = sg[SBR_OS_H * kOsTile];
+            dp.n_rhs = 0; dp.n_rej = 0;
+            sbr::KlaRing ring{sbr::Column{sg + SBR_OS_KLA_RING * kOsTile, kOsTile},
+                              sbr::Column{g.st + SBR_OS_KLA_RING * g.ld + i, g.ld}, sbr::os_ring_head(ctl.t, s)};
+            ctl.kla_last = ring.back(1);
+            bool is_done = s_done[warp][stg][lane] != 0;
+            const bool was_done = is_done;
+            int status = was_done ? SBR_ST_DONE : 0;
+            double qw = NAN;
+            const sbr::Column od{g.obs_do ? g.obs_do + i : nullptr, g.ld}, oe{g.obs_ec ? g.obs_ec + i : nullptr, g.ld},
+                os{g.state ? g.state + i : nullptr, g.ld};
+            if (g.K > 1) {
+                for (int k = 1; k < g.K; ++k) {
+                    prefetch_l2(g.action + (int64_t)(2 * k) * g.ld + i);
+                    prefetch_l2(g.action + (int64_t)(2 * k + 1) * g.ld + i);
+                }
+            }
+            for (int k = 0; k < g.K; ++k) {
+                if (is_done) {
+                    // stepping a finished episode is a no-op: reward 0 (and, if the launch starts on a finished env,
+                    // the same observation with zero deltas and status SBR_ST_DONE)
+                    g.reward[(int64_t)k * g.ld + i] = 0.0;
+                    continue;
+                }
+                const double a_do = k == 0 ? sg[kOsRowAct * kOsTile] : g.action[(int64_t)(2 * k) * g.ld + i];
+                const double a_ec = k == 0 ? sg[(kOsRowAct + 1) * kOsTile] : g.action[(int64_t)(2 * k + 1) * g.ld + i];
+                sbr::OsStepOut o;
+                sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, o);
+                g.reward[(int64_t)k * g.ld + i] = o.reward;
+                // episode return and step count accumulate in their staged slots (no registers across the stepper),
+                // step by step, so that K steps in one launch round exactly like K launches
+                sg[SBR_OS_RETURN * kOsTile] += o.reward;
+                sg[SBR_OS_STEPS * kOsTile] += 1.0;
+                status |= o.status;
+                if (o.done) { is_done = true; qw = o.Qw; }
+                // the observation of the last step that ran (the terminal one if the episode ends inside the launch)
+                if (k == g.K - 1 || o.done) sbr::os_emit_obs(ctl.t, x, o.first, od, oe, os);
+            }
+            if (was_done) {
+                sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
+                os_store_ctrl(g.st, g.ld, i, ctl, dp.h);
+                g.st[SBR_OS_RETURN * g.ld + i] = sg[SBR_OS_RETURN * kOsTile];
+                g.st[SBR_OS_STEPS * g.ld + i] = sg[SBR_OS_STEPS * kOsTile];
+                if (is_done) { g.st[SBR_OS_QW * g.ld + i] = qw; g.done[i] = 1; }
+            }
+            if (g.status) g.status[i] = status;
+            if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+        }
+        __syncwarp();             // every lane is done with stage `stg`: the next iteration refills it
+    }
+}
+
+// Persistent grid of the interval-step kernel: resident CTAs per SM (occupancy query, cached per device) x SMs.
+template <int MODE>
+static int os_step_grid(int64_t num_tiles) {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int per_sm = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_os_step_kernel<MODE>, kOsBlock, 0);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    const int64_t ctas = (num_tiles + kOsWarps - 1) / kOsWarps;
+    return (int)(ctas < (int64_t)cached[dev] ? ctas : (int64_t)cached[dev]);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map of a row-major [rows][ld] array seen as {inner = n envs, outer = rows}, box = {box_cols, box_rows}.
+static bool make_map_2d(CUtensorMap* tm, CUtensorMapDataType dt, size_t elem, const void* base, int64_t n, int64_t rows,
+                        int64_t ld, int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    return fn(tm, dt, rows > 1 ? 2 : 1, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -775,7 +949,7 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
     if ((rc = check_os_schedule(s))) return rc;
     if (!influent || !st || !obs_do || !obs_ec || !done) return fail(SBR_ERR_ARG, "sbr_os_reset: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_reset: bad mode%s");
-    OsArgs g{n, ld, st, x0, influent, mask, nullptr, obs_do, obs_ec, nullptr, nullptr, done, status, counters};
+    OsArgs g{n, ld, st, x0, influent, mask, obs_do, obs_ec, done, status, counters};
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
@@ -785,23 +959,45 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
     return check_launch("sbr_os_reset");
 }
 
-int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
-                const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
-                uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
+                  const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                  uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
-    if (!st || !action || !obs_do || !obs_ec || !state || !reward || !done)
-        return fail(SBR_ERR_ARG, "sbr_os_step: NULL buffer%s");
+    if (K < 1 || K > 4096) return fail(SBR_ERR_ARG, "sbr_os_step_k: K must be in 1..4096%s");
+    if (!st || !action || !reward || !done) return fail(SBR_ERR_ARG, "sbr_os_step: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_step: bad mode%s");
-    OsArgs g{n, ld, st, nullptr, nullptr, nullptr, action, obs_do, obs_ec, state, reward, done, status, counters};
+    OsStepArgs g;
+    g.n = n; g.ld = ld; g.num_tiles = (n + kOsTile - 1) / kOsTile;
+    g.st = st; g.action = action; g.obs_do = obs_do; g.obs_ec = obs_ec; g.state = state; g.reward = reward;
+    g.done = done; g.status = status; g.counters = counters; g.K = K;
+    // TMA needs 16-byte aligned bases and row pitches (and 32-bit coordinates); anything else takes the plain-load fill
+    CUtensorMap tm_st, tm_act, tm_done;
+    memset(&tm_st, 0, sizeof(tm_st)); memset(&tm_act, 0, sizeof(tm_act)); memset(&tm_done, 0, sizeof(tm_done));
+    g.tma = ((uintptr_t)st % 16 == 0 && (uintptr_t)action % 16 == 0 && (uintptr_t)done % 16 == 0 && ld % 2 == 0 &&
+             n < (int64_t)1 << 31) ? 1 : 0;
+    if (g.tma)
+        g.tma = make_map_2d(&tm_st, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st, n, SBR_OS_QW, ld, kOsTile, SBR_OS_QW) &&
+                make_map_2d(&tm_act, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, action, n, 2, ld, kOsTile, 2) &&
+                make_map_2d(&tm_done, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, done, n, 1, n, kOsTile, 1) ? 1 : 0;
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
-    const unsigned grid = (unsigned)((n + kOsBlock - 1) / kOsBlock);
     cudaStream_t cs = (cudaStream_t)stream;
-    if (mode == SBR_MODE_RK4) sbr_os_step_kernel<SBR_MODE_RK4><<<grid, kOsBlock, 0, cs>>>(g, *p, c, *s, t);
-    else sbr_os_step_kernel<SBR_MODE_DP45><<<grid, kOsBlock, 0, cs>>>(g, *p, c, *s, t);
+    if (mode == SBR_MODE_RK4)
+        sbr_os_step_kernel<SBR_MODE_RK4><<<os_step_grid<SBR_MODE_RK4>(g.num_tiles), kOsBlock, 0, cs>>>(
+            g, *p, c, *s, t, tm_st, tm_act, tm_done);
+    else
+        sbr_os_step_kernel<SBR_MODE_DP45><<<os_step_grid<SBR_MODE_DP45>(g.num_tiles), kOsBlock, 0, cs>>>(
+            g, *p, c, *s, t, tm_st, tm_act, tm_done);
     return check_launch("sbr_os_step");
+}
+
+int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
+                const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    return sbr_os_step_k(n, ld, 1, st, action, p, s, obs_do, obs_ec, state, reward, done, status, counters, mode, tol,
+                         stream);
 }
 
 int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,

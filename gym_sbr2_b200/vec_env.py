@@ -218,11 +218,15 @@ class SbrOsVecEnv(object):
     max_episode_steps = 463
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="philox", autoreset=False, rk4_sub_interval=0, env_offset=0):
+                 params=None, rng="philox", autoreset=False, rk4_sub_interval=0, env_offset=0,
+                 emit=("obs_do", "obs_ec", "state")):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _abi.SbrLibraryError("SbrOsVecEnv needs a CUDA device: there is no CPU fallback")
+        # which observation outputs the step kernel writes: a rollout whose policy reads only obs_DO / obs_EC passes
+        # emit=("obs_do", "obs_ec") and saves the 120 B per env-step of the 15-dim `state` (it then keeps its reset value)
+        self.emit = tuple(emit)
         self.lib = _abi.load()
         self.params = params if params is not None else _abi.default_params()
         self.sched = schedule.os_schedule(rk4_sub_interval=rk4_sub_interval)
@@ -270,7 +274,18 @@ class SbrOsVecEnv(object):
             self._action.copy_(action.to(self.device, torch.float64).t())
         self._host_steps += 1
         return core.os_step(self.buf, self._action, self.params, self.sched, mode=self.mode, tol=self.tol,
-                            stream=stream)
+                            stream=stream, emit=self.emit)
+
+    def step_k(self, actions_soa, rewards, stream=None):
+        """K consecutive env.steps in ONE launch (sbr_os_step_k): actions_soa [K,2,N], rewards [K,N] (out, row k = the
+        reward of step k; 0 after the episode has ended).  The observation buffers hold the observation after the last
+        step that ran.  Frame-skip / open-loop set-point sequences: the state never leaves the registers in between."""
+        if actions_soa.dim() != 3 or actions_soa.shape[1:] != (2, self.num_envs):
+            raise ValueError("actions_soa must be [K,2,N], got %s" % (tuple(actions_soa.shape),))
+        self._host_steps += int(actions_soa.shape[0])
+        self._lockstep = self._lockstep and not self.autoreset
+        return core.os_step(self.buf, actions_soa, self.params, self.sched, mode=self.mode, tol=self.tol,
+                            stream=stream, emit=self.emit, rewards=rewards)
 
     def step_soa(self, action_soa, stream=None):
         """Zero-copy variant for device-side policies: action_soa is the kernel's own layout [2,N] (float64, CUDA,
@@ -280,7 +295,7 @@ class SbrOsVecEnv(object):
             raise ValueError("action_soa must be [2,N], got %s" % (tuple(action_soa.shape),))
         self._host_steps += 1
         return core.os_step(self.buf, action_soa, self.params, self.sched, mode=self.mode, tol=self.tol,
-                            stream=stream)
+                            stream=stream, emit=self.emit)
 
     def step(self, action):
         b = self.buf

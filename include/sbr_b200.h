@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 4
+#define SBR_ABI_VERSION 5
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -222,13 +222,27 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
  *   st      [SBR_OS_ROWS][ld] in/out
  *   action  [2][ld] in   row 0 = DO set-point (clipped to [0, do_sp_max], aerobic phases), row 1 = NO3 set-point
  *                        (clipped to [0, no_sp_max], anoxic phases) (:862-906)
- *   obs_do, obs_ec [9][ld] out; state [15][ld] out; reward [n] out; done [n] in/out
+ *   obs_do, obs_ec [9][ld] out, state [15][ld] out: each may be NULL (an output the caller does not consume costs
+ *                        no memory traffic); reward [n] out; done [n] in/out
  *   status [n] out (may be NULL); counters [2][ld] out (may be NULL)
  * An env whose done flag is already set is left untouched (reward 0, status SBR_ST_DONE).
+ * Rows SBR_OS_KLA_RING.. of st are a CIRCULAR buffer: the KLa of the k-th interval since the reset sits in row
+ * SBR_OS_KLA_RING + k % 10 (k follows from st[SBR_OS_T]); a step writes one row (two at a phase switch).
+ * For full speed st, action and done should be 16-byte aligned and ld even (rows are then staged by bulk copies).
+ *
+ * sbr_os_step_k = K consecutive env.steps in ONE launch, the state staying in registers in between (frame-skip /
+ * open-loop set-point sequences, e.g. a policy evaluated every K-th interval):
+ *   action [K][2][ld] in: the set-points of step k in rows 2k, 2k+1; reward [K][ld] out: row k = reward of step k
+ *   (0 for steps after the episode has ended); obs_do / obs_ec / state: the observation after the last step that
+ *   ran (the terminal one if the episode ends inside the launch); status = OR, counters = sum over the K steps.
+ * K = 1 is sbr_os_step; K steps of sbr_os_step give bit-identical st, rewards and final observation.
  */
 int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,
                 const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
                 uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
+                  const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                  uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
 
 /*
  * SBR-v4 (SbrEnv4, gym_SBR_env4.py:71-1294): interval-per-step env whose FILL phase is stepped inside step() too,

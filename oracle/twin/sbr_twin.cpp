@@ -168,15 +168,17 @@ int twin_os_step(int64_t n, int64_t ld, double* st, const double* action, const 
         ctl.so_prev = st[SBR_OS_SO_PREV * ld + i]; ctl.sno_last = st[SBR_OS_SNO_LAST * ld + i];
         ctl.sno_prev = st[SBR_OS_SNO_PREV * ld + i]; ctl.ie_do = st[SBR_OS_IE_DO * ld + i];
         ctl.ie_ec = st[SBR_OS_IE_EC * ld + i]; ctl.ec_last = st[SBR_OS_EC_LAST * ld + i];
-        ctl.kla_last = st[(SBR_OS_KLA_RING + 9) * ld + i];
         Dp45State dp;
         dp.h = st[SBR_OS_H * ld + i]; dp.n_rhs = 0; dp.n_rej = 0;
-        const Column ring{st + SBR_OS_KLA_RING * ld + i, ld};
+        const Column rcol{st + SBR_OS_KLA_RING * ld + i, ld};
+        KlaRing ring{rcol, rcol, os_ring_head(ctl.t, *s)};
+        ctl.kla_last = ring.back(1);
         OsStepOut o;
         if (mode == SBR_MODE_RK4)
-            os_step_env<SBR_MODE_RK4>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, od, oe, os, o);
+            os_step_env<SBR_MODE_RK4>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o);
         else
-            os_step_env<SBR_MODE_DP45>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, od, oe, os, o);
+            os_step_env<SBR_MODE_DP45>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o);
+        os_emit_obs(ctl.t, x, o.first, od, oe, os);
         for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
         store_ctrl(st, ld, i, ctl, dp.h);
         st[SBR_OS_RETURN * ld + i] += o.reward;

@@ -255,3 +255,92 @@ def test_poisoned_actions_and_step_limit_are_flagged_not_fatal(built, cuda_devic
     starved.reset(infl[:, :4])
     starved.step(np.tile(g["action"][0][:, None], (1, 4)))
     assert (starved.status & _abi.ST_STEPLIMIT).all()
+
+
+def _random_os_batch(n, device, seed):
+    from gym_sbr2_b200 import influent
+    rng = np.random.RandomState(seed)
+    infl = np.stack([influent.mix_numpy(6, rng.randn(48)) for _ in range(64)], axis=1)
+    infl = np.tile(infl, (1, (n + 63) // 64))[:, :n].copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    return torch.as_tensor(infl).to(device), rng
+
+
+@pytest.mark.parametrize("mode", [_abi.MODE_RK4, _abi.MODE_DP45])
+def test_k_step_launch_equals_k_single_steps(built, cuda_device, mode):
+    """sbr_os_step_k: K consecutive env.steps in one launch (state in registers in between) == K launches of
+    sbr_os_step, bit for bit: state rows (incl. the circular KLa history), rewards, final observation, counters summed.
+    Covers blocks that cross the double-interval step 51, ragged batch sizes and the end of the episode."""
+    n = 1000                                                       # 15 full tiles + a partial one
+    infl, rng = _random_os_batch(n, cuda_device, 3)
+    p, s, tol = _abi.default_params(), schedule.os_schedule(), _abi.make_tol()
+    acts = torch.as_tensor(np.stack([np.stack([1 + 6 * rng.rand(n), 2 + 10 * rng.rand(n)]) for _ in range(463)])
+                           ).to(cuda_device)
+    one, blk = core.OsBuffers(n, cuda_device), core.OsBuffers(n, cuda_device)
+    core.os_reset(one, infl, p, s, mode=mode, tol=tol)
+    core.os_reset(blk, infl, p, s, mode=mode, tol=tol)
+    k0 = 0
+    for K in (1, 7, 16, 40, 200, 250):                             # 514 > 463: the last block runs past the episode end
+        a = torch.zeros((K, 2, n), dtype=torch.float64, device=cuda_device)
+        a[: min(K, 463 - k0)] = acts[k0:k0 + K]
+        rew1 = torch.zeros((K, n), dtype=torch.float64, device=cuda_device)
+        cnt = torch.zeros((2, n), dtype=torch.int64, device=cuda_device)
+        stat = torch.zeros((n,), dtype=torch.int32, device=cuda_device)
+        for k in range(K):
+            was_done = one.done.clone().bool()
+            core.os_step(one, a[k].contiguous(), p, s, mode=mode, tol=tol)
+            rew1[k] = one.reward
+            cnt += one.counters.to(torch.int64)
+            stat |= torch.where(was_done & (k > 0), torch.zeros_like(stat), one.status)
+            if k == 0:
+                last = [one.obs_do.clone(), one.obs_ec.clone(), one.state.clone()]
+            else:
+                for dst, src in zip(last, (one.obs_do, one.obs_ec, one.state)):
+                    dst.copy_(torch.where(was_done[None, :], dst, src))
+        rewK = torch.full((K, n), 7.0, dtype=torch.float64, device=cuda_device)
+        core.os_step(blk, a, p, s, mode=mode, tol=tol, rewards=rewK)
+        rows = [r for r in range(_abi.OS_ROWS) if r != _abi.OS_QW]
+        assert torch.equal(blk.st[rows].view(torch.int64), one.st[rows].view(torch.int64)), K
+        assert torch.equal(rewK, rew1) and torch.equal(blk.done, one.done), K
+        assert torch.equal(blk.obs_do, last[0]) and torch.equal(blk.obs_ec, last[1]) and torch.equal(blk.state, last[2]), K
+        assert torch.equal(blk.counters.to(torch.int64), cnt) and torch.equal(blk.status, stat), K
+        k0 += K
+    assert bool(one.done.all()) and torch.equal(blk.st[_abi.OS_QW], one.st[_abi.OS_QW])
+    assert float(one.st[_abi.OS_STEPS].min()) == 463 == float(blk.st[_abi.OS_STEPS].max())
+
+
+def test_optional_outputs_and_unaligned_buffers(built, cuda_device):
+    """obs_do / obs_ec / state may be NULL (not written, everything else identical); row strides and bases that rule
+    out the 16-byte aligned bulk-copy staging take the plain-load path with identical results."""
+    n = 200
+    infl, rng = _random_os_batch(n, cuda_device, 8)
+    p, s, tol = _abi.default_params(), schedule.os_schedule(), _abi.make_tol()
+    acts = [torch.as_tensor(np.stack([1 + 6 * rng.rand(n), 2 + 10 * rng.rand(n)])).to(cuda_device) for _ in range(30)]
+    full, lean = core.OsBuffers(n, cuda_device), core.OsBuffers(n, cuda_device)
+    core.os_reset(full, infl, p, s, tol=tol); core.os_reset(lean, infl, p, s, tol=tol)
+    lean.state.fill_(-5.0); lean.obs_ec.fill_(-6.0)
+    for a in acts:
+        core.os_step(full, a, p, s, tol=tol)
+        core.os_step(lean, a, p, s, tol=tol, emit=("obs_do",))
+    rows = [r for r in range(_abi.OS_ROWS) if r != _abi.OS_QW]
+    assert torch.equal(lean.st[rows], full.st[rows]) and torch.equal(lean.obs_do, full.obs_do)
+    assert torch.equal(lean.reward, full.reward)
+    assert bool((lean.state == -5.0).all()) and bool((lean.obs_ec == -6.0).all())
+    # odd row stride + bases offset by 8 bytes: strided views of wider buffers
+    ld = n + 7
+    odd = core.OsBuffers(ld + 1, cuda_device)
+    view = core.OsBuffers.__new__(core.OsBuffers)
+    for name in ("st", "obs_do", "obs_ec", "state", "counters"):
+        setattr(view, name, getattr(odd, name)[:, 1:1 + n])
+    view.st = odd.st[:, 1:1 + n]
+    for name in ("reward", "done", "status"):
+        setattr(view, name, torch.empty_like(getattr(full, name)))
+    wide_infl = torch.zeros((14, ld + 1), dtype=torch.float64, device=cuda_device)
+    wide_infl[:, 1:1 + n] = infl
+    core.os_reset(view, wide_infl[:, 1:1 + n], p, s, tol=tol)
+    wide_act = torch.zeros((2, ld + 1), dtype=torch.float64, device=cuda_device)
+    for a in acts:
+        wide_act[:, 1:1 + n] = a
+        core.os_step(view, wide_act[:, 1:1 + n], p, s, tol=tol)
+    assert torch.equal(view.st[rows], full.st[rows]) and torch.equal(view.state, full.state)
+    assert torch.equal(view.reward, full.reward)
