@@ -21,6 +21,9 @@ OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
 OS_RETURN, OS_STEPS, OS_QW, OS_ROWS = 32, 33, 34, 35
 OS_NOBS, OS_NSTATE = 9, 15
+# rows of one trajectory record (enum SBR_TRAJ_*)
+TRAJ_T, TRAJ_X, TRAJ_KLA, TRAJ_EC, TRAJ_U_DO, TRAJ_U_EC, TRAJ_REWARD, TRAJ_EQI, TRAJ_OCI, TRAJ_AE, TRAJ_ECO, TRAJ_ROWS = \
+    0, 1, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24
 # rows of the persistent state of the SBR-v4 env (enum SBR_V4_*)
 V4_T, V4_U, V4_SO_PREV, V4_IE, V4_KLA_LAST, V4_KLA_SUM, V4_H, V4_RETURN, V4_STEPS, V4_QW, V4_ROWS = \
     14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24
@@ -86,6 +89,9 @@ _PROTOS = {
                               _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_os_step_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                                 _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_os_step_traj": (C.c_int, [C.c_int64, C.c_int64, C.c_int, _P, _P, C.POINTER(SbrParams),
+                                   C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P,
+                                   C.c_int, _P]),
     "sbr_v4_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), _P, _P, _P, _P]),
     "sbr_v4_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                               _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),

@@ -160,13 +160,20 @@ def os_reset(buf, influent, params, sched, x0=None, mask=None, mode=_abi.MODE_DP
 
 
 def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None, emit=("obs_do", "obs_ec", "state"),
-            rewards=None):
+            rewards=None, traj=None):
     """One env.step for a batch (SbrOS.step, gym_SBR_oneshot.py:843-1273).  action [2,n]: DO and NO3 set-points --
     or [K,2,n] with rewards [K,n]: K consecutive steps in one launch (sbr_os_step_k).  emit: which of the
-    observation outputs are written (the others cost no memory traffic and keep their old contents)."""
+    observation outputs are written (the others cost no memory traffic and keep their old contents).
+    traj: optional [cap, TRAJ_ROWS, n] float64 buffer receiving one record per PID interval (sbr_os_step_traj)."""
     lib = _abi.load()
     n = buf.st.shape[1]
     pst, l0 = _dev_ptr(buf.st, _abi.OS_ROWS, n, name="st")
+    ptj, cap, l7 = None, 0, None
+    if traj is not None:
+        if traj.dim() != 3 or traj.shape[1] != _abi.TRAJ_ROWS or traj.shape[2] != n or not traj.is_contiguous():
+            raise ValueError("traj must be contiguous [cap, %d, n]" % _abi.TRAJ_ROWS)
+        cap = traj.shape[0]
+        ptj, l7 = _dev_ptr(traj.view(cap * _abi.TRAJ_ROWS, n), cap * _abi.TRAJ_ROWS, n, name="traj")
     if action.dim() == 3:
         K = action.shape[0]
         if rewards is None or rewards.shape != (K, n):
@@ -188,11 +195,11 @@ def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=No
     pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
     pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
     pct, l5 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
-    ld = _same_ld([l0, l1, l2 if pod else None, l3 if poe else None, l4 if pse else None, l5, l6], "os_step")
+    ld = _same_ld([l0, l1, l2 if pod else None, l3 if poe else None, l4 if pse else None, l5, l6, l7], "os_step")
     tol = tol or _abi.make_tol()
     with torch.cuda.device(buf.st.device):
-        rc = lib.sbr_os_step_k(n, ld, K, pst, pac, C.byref(params), C.byref(sched), pod, poe, pse, prw, pdn, pss, pct,
-                               int(mode), C.byref(tol), _stream_ptr(stream))
+        rc = lib.sbr_os_step_traj(n, ld, K, pst, pac, C.byref(params), C.byref(sched), pod, poe, pse, prw, pdn, pss,
+                                  pct, int(mode), C.byref(tol), ptj, int(cap), _stream_ptr(stream))
     _abi.check(rc, "sbr_os_step")
     return buf
 

@@ -1097,10 +1097,32 @@ struct KlaRing {
         head = head == 9 ? 0 : head + 1;
     }
 };
-SBR_HD int os_ring_head(double t, const SbrOsSchedule& s) {
-    const int k = (int)((t - s.t_fill) / s.t_delta + 0.5);             // intervals run since the reset
-    return k > 0 ? k % 10 : 0;
+SBR_HD int os_interval_count(double t, const SbrOsSchedule& s) {       // intervals run since the reset
+    const int k = (int)((t - s.t_fill) / s.t_delta + 0.5);
+    return k > 0 ? k : 0;
 }
+SBR_HD int os_ring_head(double t, const SbrOsSchedule& s) { return os_interval_count(t, s) % 10; }
+
+// Optional trajectory dump (the reference's trajectory(), gym_SBR_oneshot.py:1275-1288, sampled at the ENDS of the
+// PID intervals): record k = the state after the k-th interval since the reset, rows SBR_TRAJ_* of include/sbr_b200.h;
+// the terminal step appends two more records (after settle + draw, after the idle phase).  p == NULL: off (the timed
+// path).  Records beyond `cap` are dropped.
+struct OsTraj {
+    double* p;           // this env's column of traj[cap][SBR_TRAJ_ROWS][ld]
+    int64_t ld;
+    int cap;
+    SBR_HD bool on(int k) const { return p != nullptr && k >= 0 && k < cap; }
+    SBR_HD void put(int k, int row, double v) const { p[((int64_t)k * SBR_TRAJ_ROWS + row) * ld] = v; }
+    SBR_HD void state(int k, double t, const double (&x)[SBR_NX], double kla, double ec, double u_do, double u_ec) const {
+        if (!on(k)) return;
+        put(k, SBR_TRAJ_T, t);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i) put(k, SBR_TRAJ_X + i, x[i]);
+        put(k, SBR_TRAJ_KLA, kla); put(k, SBR_TRAJ_EC, ec); put(k, SBR_TRAJ_U_DO, u_do); put(k, SBR_TRAJ_U_EC, u_ec);
+        put(k, SBR_TRAJ_REWARD, NAN); put(k, SBR_TRAJ_EQI, NAN); put(k, SBR_TRAJ_OCI, NAN);
+        put(k, SBR_TRAJ_AE, NAN); put(k, SBR_TRAJ_ECO, NAN);
+    }
+};
 
 struct OsPid {
     double Kc_DO, KcI_DO, KcD_DO, Kc_EC, KcI_EC, KcD_EC, dt, inv_dt, kla_lo, kla_hi, ec_lo, ec_hi;
@@ -1262,10 +1284,10 @@ struct OsStepOut {
 template <int MODE>
 SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_do, double a_ec,
                         const SbrParams& p, const Coef& coef, const SbrOsSchedule& s, const SbrTol& tol,
-                        Dp45State& dp, OsStepOut& o) {
+                        Dp45State& dp, OsStepOut& o, const OsTraj& traj) {
     const OsPid pid = make_os_pid(p, coef);
     int status = 0, L = 10;
-    double span = s.t_delta, u_do = 0.0, ec_before = c.ec_last;
+    double span = s.t_delta, u_do = 0.0, u_ec_rec = 0.0, ec_before = c.ec_last;
     ObsRef first = obs_ref(x);
     TailArgs a;
     a.kla = 0.0; a.q = 0.0; a.ec_conc = p.ec_conc; a.load = Loading{nullptr, 0};
@@ -1286,6 +1308,7 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_
             const bool aerobic = (pass & 1) != 0;
             u_do = aerobic ? clip_keep_nan(a_do, 0.0, p.do_sp_max) : 0.0;               // :862-870, 898-906
             const double u_ec = aerobic ? 0.0 : clip_keep_nan(a_ec, 0.0, p.no_sp_max);
+            u_ec_rec = u_ec;
             // run_aero_step / run_anaero_step (:1331-1419)
             t_next = add_rn(t, s.t_delta);
             span = sub_rn(t_next, t);
@@ -1312,6 +1335,19 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_
             const double ECO = p.ec_conc * esum * p.os_pid_dt * (ispan * 1e-3);
             const double OCI = AE + ECO;
             o.reward = (1 - (EQI2 * EQI2 + OCI * OCI)) * (1.0 / 473);
+            if (traj.p) {
+                const int k = os_interval_count(c.t, s) - 1;
+                if (traj.on(k)) {
+                    // the diagnostics the reference appends to reward_EQI_t / reward_OCI_t / reward_AE_t / reward_EC_t:
+                    // EQI / 10 and the two cost terms normalised by their maxima (module_reward_EQIOCI.py:72,80,96,109-112)
+                    const double dt = p.os_pid_dt;
+                    const double AE_max = 1.32 * (240 * 11) * dt * (8 / ((dt * 11) * 1.8 * 1000));
+                    const double EC_max = p.ec_conc * (0.0005 * 11) * dt / ((dt * 11) * 1000);
+                    traj.put(k, SBR_TRAJ_REWARD, o.reward); traj.put(k, SBR_TRAJ_EQI, EQI2);
+                    traj.put(k, SBR_TRAJ_OCI, AE / AE_max + ECO / EC_max);
+                    traj.put(k, SBR_TRAJ_AE, AE / AE_max); traj.put(k, SBR_TRAJ_ECO, ECO / EC_max);
+                }
+            }
             const bool terminal = c.t >= s.tm5_1;
             // end of the react phases (:1122): Sim_Settling_Drawing (:2264-2420) + Sim_idle (:2554-2597) in this
             // step; the reward stays the pre-settle one, obs/state are recomputed from the post-idle state with
@@ -1330,6 +1366,7 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_
                 status |= d.status;
                 o.Qw = d.Qw;
                 const double t_draw_end = add_rn(t_set_end, s.draw_len);
+                if (traj.p) traj.state(os_interval_count(c.t, s), t_draw_end, x, 0.0, 0.0, u_do, 0.0);
                 so_start = x[iSo];
                 c.so_prev = so_start;              // So padded with the frozen value over settle + draw (:2415-2416)
                 T = sub_rn(s.t_cycle, t_draw_end);
@@ -1348,6 +1385,11 @@ SBR_HD void os_step_env(double (&x)[SBR_NX], OsCtrl& c, KlaRing& ring, double a_
         c.sno_prev = c.sno_last;
         c.sno_last = x[iSno];
         c.kla_last = a.kla;
+        if (traj.p) {
+            // interval k ends here; the idle solve of the terminal step is the record after the post-draw one
+            const int k = pass < 4 ? os_interval_count(t_next, s) - 1 : os_interval_count(c.t, s) + 1;
+            traj.state(k, t_next, x, a.kla, a.q, u_do, pass < 4 ? u_ec_rec : 0.0);
+        }
         c.t = t_next;
         if (pass < 4) {
             c.ec_last = a.q;

@@ -313,7 +313,8 @@ struct OsStepArgs {
     uint8_t* done;
     int32_t* status;          // may be NULL
     uint32_t* counters;       // may be NULL
-    int K, tma;
+    double* traj;             // may be NULL: [traj_cap][SBR_TRAJ_ROWS][ld]
+    int K, tma, traj_cap;
 };
 
 constexpr int kOsTile = 32;                        // envs per tile = one warp
@@ -414,7 +415,8 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
                 const double a_do = k == 0 ? sg[kOsRowAct * kOsTile] : g.action[(int64_t)(2 * k) * g.ld + i];
                 const double a_ec = k == 0 ? sg[(kOsRowAct + 1) * kOsTile] : g.action[(int64_t)(2 * k + 1) * g.ld + i];
                 sbr::OsStepOut o;
-                sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, o);
+                sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, o,
+                                       sbr::OsTraj{g.traj ? g.traj + i : nullptr, g.ld, g.traj_cap});
                 g.reward[(int64_t)k * g.ld + i] = o.reward;
                 // episode return and step count accumulate in their staged slots (no registers across the stepper),
                 // step by step, so that K steps in one launch round exactly like K launches
@@ -962,6 +964,14 @@ int sbr_os_reset(int64_t n, int64_t ld, const double* x0, const double* influent
 int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
                   const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
                   uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    return sbr_os_step_traj(n, ld, K, st, action, p, s, obs_do, obs_ec, state, reward, done, status, counters, mode, tol,
+                            nullptr, 0, stream);
+}
+
+int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
+                     const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                     uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
+                     double* traj, int traj_cap, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
@@ -972,6 +982,8 @@ int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action
     g.n = n; g.ld = ld; g.num_tiles = (n + kOsTile - 1) / kOsTile;
     g.st = st; g.action = action; g.obs_do = obs_do; g.obs_ec = obs_ec; g.state = state; g.reward = reward;
     g.done = done; g.status = status; g.counters = counters; g.K = K;
+    if (traj && traj_cap < 1) return fail(SBR_ERR_ARG, "sbr_os_step_traj: traj_cap must be positive%s");
+    g.traj = traj; g.traj_cap = traj ? traj_cap : 0;
     // TMA needs 16-byte aligned bases and row pitches (and 32-bit coordinates); anything else takes the plain-load fill
     CUtensorMap tm_st, tm_act, tm_done;
     memset(&tm_st, 0, sizeof(tm_st)); memset(&tm_act, 0, sizeof(tm_act)); memset(&tm_done, 0, sizeof(tm_done));

@@ -68,13 +68,30 @@ class SbrOS(_Base):
     def __init__(self, device=None, mode="dp45", rtol=1e-8, atol=1e-10):
         self.action_space = Box(np.array([-1]), np.array([1]), dtype=np.float32)                           # :106
         self.observation_space = Box(low=np.array([0, 0, 0, -1, -1]), high=np.ones([5]) * 1.0, dtype=np.float32)
-        self._vec = SbrOsVecEnv(1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
+        self._vec = SbrOsVecEnv(1, device=_device(device), mode=mode, rtol=rtol, atol=atol, record_trajectory=True)
         self.influent_mixed = None
         self.reward = 0
+        self._states = []
+
+    def trajectory(self):
+        """The reference's 18-tuple (gym_SBR_oneshot.py:1275-1288), same order:
+        (t_t, x_t, u_DO_t, u_EC_t, state_t, So_t, Ss_t, EC, Sno_t, dcv_EC, ie_EC, e_EC, reward_t, reward_EQI_t,
+        reward_OCI_t, reward_AE_t, reward_EC_t, Snh_t).  Time-resolved entries (t_t, x_t, So_t, Ss_t, EC, Sno_t,
+        Snh_t) are sampled at the ENDS of the PID intervals (the reference also lists the 8-9 interior output points of
+        every interval), starting with the state after the fill phase; u_DO_t / u_EC_t hold the clipped set-point in
+        force in each interval; state_t and the reward lists have one entry per step().  The NO3-controller
+        internals dcv_EC, ie_EC, e_EC are not recorded (None)."""
+        tr = self._vec.trajectory(0)
+        x = tr["x"]
+        return (tr["t"].tolist(), x, tr["u_do"].tolist(), tr["u_ec"].tolist(), list(self._states), x[:, 8].tolist(),
+                x[:, 2].tolist(), tr["ec"].tolist(), x[:, 9].tolist(), None, None, None, tr["reward"].tolist(),
+                tr["reward_EQI"].tolist(), tr["reward_OCI"].tolist(), tr["reward_AE"].tolist(),
+                tr["reward_EC"].tolist(), x[:, 10].tolist())
 
     def reset(self):
         self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)       # buffer_tank(6), :180
         obs_do, obs_ec = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
+        self._states = []
         return (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
 
     def step(self, action):
@@ -84,7 +101,9 @@ class SbrOS(_Base):
         (obs_do, obs_ec), state, reward, done, info = self._vec.step(a)
         self.reward = float(reward[0])
         obs = (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
-        return obs, state[0].cpu().numpy().tolist(), self.reward, bool(done[0]), {}
+        state = state[0].cpu().numpy()
+        self._states.append(state)
+        return obs, state.tolist(), self.reward, bool(done[0]), {}
 
     def get_available_actions(self, pre_action, n_agents, n_action):
         """Action masks of the reference's discrete multi-agent wrapper (gym_SBR_oneshot.py:440-459)."""

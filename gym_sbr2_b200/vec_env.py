@@ -219,7 +219,7 @@ class SbrOsVecEnv(object):
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
                  params=None, rng="philox", autoreset=False, rk4_sub_interval=0, env_offset=0,
-                 emit=("obs_do", "obs_ec", "state")):
+                 emit=("obs_do", "obs_ec", "state"), record_trajectory=False):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -241,9 +241,35 @@ class SbrOsVecEnv(object):
         self._loading = torch.zeros((_abi.NX, n), **f)
         self._action = torch.zeros((2, n), **f)
         self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_oneshot.py:287
+        # optional trajectory dump (the reference's trajectory(), gym_SBR_oneshot.py:1275-1288): one record per PID
+        # interval, written by the step kernel (sbr_os_step_traj).  184 B per env and interval: for analysis and
+        # plotting of small batches, not for the timed path.
+        self.traj_cap = (470 if record_trajectory is True else int(record_trajectory)) if record_trajectory else 0
+        self.traj = torch.full((self.traj_cap, _abi.TRAJ_ROWS, n), float("nan"), **f) if self.traj_cap else None
+        self.traj0 = torch.zeros((1 + _abi.NX, n), **f) if self.traj_cap else None      # [t, x] after the fill
         self._init_lockstep()
 
     _init_rng, _draw_influent = _init_rng, _draw_influent
+
+    def trajectory(self, env=0):
+        """Trajectory of env `env` since its last reset, sampled at the ends of the PID intervals (needs
+        record_trajectory=...).  dict of numpy arrays: t [M+1], x [M+1,14] (entry 0 = state after the fill phase),
+        and per interval kla, ec, u_do, u_ec [M]; per env.step reward, reward_EQI, reward_OCI, reward_AE, reward_EC and
+        step_end (index into t / x of the step's last interval)."""
+        if self.traj is None:
+            raise RuntimeError("construct the env with record_trajectory=True (or a record capacity)")
+        T = _abi
+        rec = self.traj[:, :, env].cpu().numpy()
+        m = int(np.isfinite(rec[:, T.TRAJ_T]).sum())
+        rec = rec[:m]
+        first = self.traj0[:, env].cpu().numpy()
+        has_r = np.isfinite(rec[:, T.TRAJ_REWARD])
+        return dict(t=np.concatenate([first[:1], rec[:, T.TRAJ_T]]),
+                    x=np.concatenate([first[None, 1:], rec[:, T.TRAJ_X:T.TRAJ_X + T.NX]], axis=0),
+                    kla=rec[:, T.TRAJ_KLA], ec=rec[:, T.TRAJ_EC], u_do=rec[:, T.TRAJ_U_DO], u_ec=rec[:, T.TRAJ_U_EC],
+                    reward=rec[has_r, T.TRAJ_REWARD], reward_EQI=rec[has_r, T.TRAJ_EQI], reward_OCI=rec[has_r, T.TRAJ_OCI],
+                    reward_AE=rec[has_r, T.TRAJ_AE], reward_EC=rec[has_r, T.TRAJ_ECO],
+                    step_end=np.nonzero(has_r)[0] + 1)
 
     def reset(self, influent=None, x0=None, mask=None):
         """influent: optional [14,N] influent_mixed (row 0 is replaced by the fill flow); x0: optional [14,N];
@@ -265,6 +291,15 @@ class SbrOsVecEnv(object):
             x0 = x0.to(self.device, torch.float64).contiguous()
         core.os_reset(self.buf, self._loading, self.params, self.sched, x0=x0, mask=mask, mode=self.mode,
                       tol=self.tol)
+        if self.traj is not None:
+            first = torch.cat([self.buf.st[_abi.OS_T:_abi.OS_T + 1], self.buf.st[:_abi.NX]], dim=0)
+            if mask is None:
+                self.traj.fill_(float("nan"))
+                self.traj0.copy_(first)
+            else:
+                m = mask.bool()
+                self.traj[:, :, m] = float("nan")
+                self.traj0.copy_(torch.where(m[None, :], first, self.traj0))
         return self.buf.obs_do.t(), self.buf.obs_ec.t()
 
     def step_async(self, action, stream=None):
@@ -274,7 +309,7 @@ class SbrOsVecEnv(object):
             self._action.copy_(action.to(self.device, torch.float64).t())
         self._host_steps += 1
         return core.os_step(self.buf, self._action, self.params, self.sched, mode=self.mode, tol=self.tol,
-                            stream=stream, emit=self.emit)
+                            stream=stream, emit=self.emit, traj=self.traj)
 
     def step_k(self, actions_soa, rewards, stream=None):
         """K consecutive env.steps in ONE launch (sbr_os_step_k): actions_soa [K,2,N], rewards [K,N] (out, row k = the
@@ -285,7 +320,7 @@ class SbrOsVecEnv(object):
         self._host_steps += int(actions_soa.shape[0])
         self._lockstep = self._lockstep and not self.autoreset
         return core.os_step(self.buf, actions_soa, self.params, self.sched, mode=self.mode, tol=self.tol,
-                            stream=stream, emit=self.emit, rewards=rewards)
+                            stream=stream, emit=self.emit, rewards=rewards, traj=self.traj)
 
     def step_soa(self, action_soa, stream=None):
         """Zero-copy variant for device-side policies: action_soa is the kernel's own layout [2,N] (float64, CUDA,
@@ -295,7 +330,7 @@ class SbrOsVecEnv(object):
             raise ValueError("action_soa must be [2,N], got %s" % (tuple(action_soa.shape),))
         self._host_steps += 1
         return core.os_step(self.buf, action_soa, self.params, self.sched, mode=self.mode, tol=self.tol,
-                            stream=stream, emit=self.emit)
+                            stream=stream, emit=self.emit, traj=self.traj)
 
     def step(self, action):
         b = self.buf

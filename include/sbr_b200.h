@@ -245,6 +245,28 @@ int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action
                   uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
 
 /*
+ * Optional trajectory dump of the interval-per-step path = what SbrOS.trajectory() hands a plotting / analysis script
+ * (gym_SBR_oneshot.py:1275-1288: the module-level lists t_t, x_t, So_t, EC, reward_t, reward_EQI_t ...), sampled at
+ * the ENDS of the PID intervals (the reference also keeps the 8-9 interior output points of every interval).
+ * sbr_os_step_traj = sbr_os_step_k that also writes, for every interval it runs, the record
+ *   traj[k][SBR_TRAJ_ROWS][ld], k = number of that interval since the reset (from 0):
+ *   t, x[14], KLa, EC flow, the clipped DO / NO3 set-points in force, and -- in the record of a step's last interval --
+ *   the step's reward and the diagnostics the reference appends to reward_EQI_t / reward_OCI_t / reward_AE_t /
+ *   reward_EC_t: EQI/10, and the aeration / carbon cost terms normalised by their maxima and their sum
+ *   (module_reward_EQIOCI.py:60-112; NaN in other records).
+ * The terminal step appends two more records: the state after settle + draw and after the idle phase.
+ * traj_cap = number of records the buffer holds (470 covers an episode); later records are dropped.  Not meant for
+ * the timed path: 184 B per env and interval.
+ */
+enum { SBR_TRAJ_T = 0, SBR_TRAJ_X = 1, SBR_TRAJ_KLA = 15, SBR_TRAJ_EC = 16, SBR_TRAJ_U_DO = 17, SBR_TRAJ_U_EC = 18,
+       SBR_TRAJ_REWARD = 19, SBR_TRAJ_EQI = 20, SBR_TRAJ_OCI = 21, SBR_TRAJ_AE = 22, SBR_TRAJ_ECO = 23,
+       SBR_TRAJ_ROWS = 24 };
+int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
+                     const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                     uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
+                     double* traj, int traj_cap, void* stream);
+
+/*
  * SBR-v4 (SbrEnv4, gym_SBR_env4.py:71-1294): interval-per-step env whose FILL phase is stepped inside step() too,
  * with a 1-D action = change of the DO set-point.  NOTE: the reference's step() raises TypeError on numpy >= 1.18
  * (float `num` in np.linspace, :286,921,982,1207); parity is against the unmodified source run with numpy < 1.18

@@ -175,9 +175,9 @@ int twin_os_step(int64_t n, int64_t ld, double* st, const double* action, const 
         ctl.kla_last = ring.back(1);
         OsStepOut o;
         if (mode == SBR_MODE_RK4)
-            os_step_env<SBR_MODE_RK4>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o);
+            os_step_env<SBR_MODE_RK4>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o, OsTraj{nullptr, 0, 0});
         else
-            os_step_env<SBR_MODE_DP45>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o);
+            os_step_env<SBR_MODE_DP45>(x, ctl, ring, action[i], action[ld + i], *p, c, *s, t, dp, o, OsTraj{nullptr, 0, 0});
         os_emit_obs(ctl.t, x, o.first, od, oe, os);
         for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
         store_ctrl(st, ld, i, ctl, dp.h);

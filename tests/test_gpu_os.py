@@ -344,3 +344,52 @@ def test_optional_outputs_and_unaligned_buffers(built, cuda_device):
         core.os_step(view, wide_act[:, 1:1 + n], p, s, tol=tol)
     assert torch.equal(view.st[rows], full.st[rows]) and torch.equal(view.state, full.state)
     assert torch.equal(view.reward, full.reward)
+
+
+def test_trajectory_dump_matches_reference_trajectory(built, cuda_device):
+    """SbrOS.trajectory() (gym_SBR_oneshot.py:1275-1288): the kernel's optional per-interval record against the
+    unmodified reference's t_t / x_t / reward lists at the end of every env.step of a whole episode
+    (oracle/make_golden_traj.py), and the reference's 18-tuple order through the single-env wrapper."""
+    import os
+    from conftest import GOLDEN
+    from gym_sbr2_b200.envs.single import SbrOS
+    g = np.load(os.path.join(GOLDEN, "sbros_v1_traj_seed0_const.npz"))
+    env = SbrOS(device=cuda_device)
+    np.random.seed(0)
+    env.reset()
+    assert np.array_equal(env.influent_mixed[1:], g["influent"][1:])       # same numpy stream as the reference
+    done, steps = False, 0
+    while not done:
+        _, _, _, done, _ = env.step(g["action"])
+        steps += 1
+    assert steps == 463 == len(g["step_end_index"])
+    tr = env._vec.trajectory(0)
+    # 463 steps, three of them with two intervals, plus the post-draw and post-idle records, plus the post-fill state
+    assert len(tr["t"]) == 1 + 466 + 2 and len(tr["step_end"]) == 463
+    assert tr["t"][0] == g["t_fill_end"] and tr["t"][-1] == 0.5
+    ok, worst = parity.os_close(tr["x"][0] / parity.STATE_SCALE, g["x_fill_end"] / parity.STATE_SCALE)
+    assert ok, worst
+    ends = tr["step_end"].copy()
+    ends[-1] = len(tr["t"]) - 1                       # the reference's last step ends after settle + draw + idle
+    assert np.allclose(tr["t"][ends], g["t_step_end"], rtol=0, atol=1e-12)
+    ok, worst = parity.os_close(tr["x"][ends] / parity.STATE_SCALE, g["x_step_end"] / parity.STATE_SCALE)
+    assert ok, worst
+    for mine, ref in (("reward", "reward_t"), ("reward_EQI", "reward_EQI_t"), ("reward_OCI", "reward_OCI_t"),
+                      ("reward_AE", "reward_AE_t"), ("reward_EC", "reward_EC_t")):
+        assert np.allclose(tr[mine], g[ref], rtol=1e-5, atol=1e-9), mine
+    assert np.array_equal(tr["u_do"][tr["step_end"] - 1], g["u_do_step_end"])
+    assert np.array_equal(tr["u_ec"][tr["step_end"] - 1], g["u_ec_step_end"])
+    tup = env.trajectory()
+    assert len(tup) == 18 == len(g["tuple_names"]) and tup[9] is None and len(tup[12]) == 463
+    assert np.array_equal(np.asarray(tup[5]), tr["x"][:, 8]) and len(tup[4]) == 463
+    # the dump is off unless asked for, and it does not change the step
+    plain = SbrOsVecEnv(1, device=cuda_device, mode="dp45")
+    infl = torch.as_tensor(g["influent"])[:, None].to(cuda_device)
+    plain.reset(influent=infl)
+    assert plain.traj is None
+    a = torch.as_tensor(g["action"])[None, :].to(cuda_device)
+    for _ in range(463):
+        plain.step(a)
+    assert torch.equal(plain.buf.st[:14], env._vec.buf.st[:14])
+    with pytest.raises(RuntimeError):
+        plain.trajectory()
