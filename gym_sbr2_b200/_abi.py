@@ -56,7 +56,7 @@ class SbrOsSchedule(C.Structure):
 
 
 class SbrTol(C.Structure):
-    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("flags", C.c_int32)]
 
 
 class SbrLibraryError(RuntimeError):
@@ -83,6 +83,7 @@ _PROTOS = {
     "sbr_integrate_interval": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int,
                                          C.c_double, C.c_int, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_rhs": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int, _P, _P]),
+    "sbr_settle_draw": (C.c_int, [C.c_int64, C.c_int64, _P, C.c_double, C.POINTER(SbrParams), _P, _P, _P, _P]),
     "sbr_os_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                                _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_os_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
@@ -149,5 +150,8 @@ def default_params():
     return p
 
 
-def make_tol(rtol=1e-8, atol=1e-10, max_steps=200):
-    return SbrTol(float(rtol), float(atol), int(max_steps), 0)
+FLAG_RAW_KLA = 1
+
+
+def make_tol(rtol=1e-8, atol=1e-10, max_steps=200, flags=0):
+    return SbrTol(float(rtol), float(atol), int(max_steps), int(flags))

@@ -121,6 +121,25 @@ def rhs(x, kla, params, tail, ec=None, loading=None, stream=None):
     return dx
 
 
+def settle_draw(x, params, settle_time, stream=None):
+    """Settle + draw stage on x [14,n] IN PLACE (sub_phases_FB.py:716-915).  Returns (sX [10,n], out [9,n] = Xf, Qw,
+    EQI, eff[6], status [n])."""
+    lib = _abi.load()
+    n = x.shape[1]
+    f = dict(dtype=torch.float64, device=x.device)
+    sX, out = torch.empty((10, n), **f), torch.empty((9, n), **f)
+    status = torch.empty((n,), dtype=torch.int32, device=x.device)
+    px, l0 = _dev_ptr(x, _abi.NX, n, name="x")
+    ps, l1 = _dev_ptr(sX, 10, n, name="sX")
+    po, l2 = _dev_ptr(out, 9, n, name="out")
+    pst, _ = _dev_ptr(status, 1, n, dtype=torch.int32, name="status")
+    ld = _same_ld([l0, l1, l2], "settle_draw")
+    with torch.cuda.device(x.device):
+        rc = lib.sbr_settle_draw(n, ld, px, float(settle_time), C.byref(params), ps, po, pst, _stream_ptr(stream))
+    _abi.check(rc, "sbr_settle_draw")
+    return sX, out, status
+
+
 class OsBuffers(object):
     """Device buffers of the interval-per-step path: persistent state + per-step outputs (allocated once)."""
 

@@ -305,6 +305,9 @@ SBR_HD void rk4_step(double (&x)[SBR_NX], double t, double h, const Flow& f, con
 #ifndef SBR_DP_FIRST
 #define SBR_DP_FIRST 0.7
 #endif
+#ifndef SBR_DP_K7_IN_K1
+#define SBR_DP_K7_IN_K1 0
+#endif
 // Step-size factor safety * en^(-1/10): it only steers the controller, so the device uses the MUFU lg2/ex2 pair
 // (2 instructions) instead of the ~30-instruction software log2f.
 SBR_HD float pow_m01(float en) {
@@ -526,6 +529,7 @@ SBR_HD int integrate_interval(double (&x)[SBR_NX], double T, int n_sub, const Co
 // ---------------------------------------------------------------------------------------------------------
 struct PidA {
     double Kc, Kc_tauI, Kc_tauD, dt, inv_dt, lo, hi;
+    bool bypass;       // SBR_FLAG_RAW_KLA: the "set-point" IS the phase's KLa, no controller
 };
 
 // Clipping as the reference does it (np.clip / min(max(a, lo), hi) / if-elif chains): a NaN action is NOT
@@ -537,6 +541,7 @@ SBR_HD PidA make_pid_a(const SbrParams& p, const Coef& c) {
     PidA q;
     q.Kc = p.pid_Kc; q.Kc_tauI = c.pidA_KcI; q.Kc_tauD = c.pidA_KcD;
     q.dt = p.pid_dt; q.inv_dt = c.pidA_inv_dt; q.lo = p.kla_min; q.hi = p.kla_max;
+    q.bypass = false;
     return q;
 }
 
@@ -546,6 +551,7 @@ SBR_HD PidA make_pid_a(const SbrParams& p, const Coef& c) {
 // on the host (1/dt, at most 1 ulp from the reference's division), like the interval-per-step PIDs.
 SBR_HD double pid_a_update(const PidA& pid, double sp, double so_i, double so_prev, bool first, double& ie,
                            double& bias) {
+    if (pid.bypass) return sp;                   // raw-KLa action: constant over the phase
     const double e = sp - so_i;
     double dcv = 0.0;
     if (!first) {
@@ -716,7 +722,15 @@ SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, cons
                         sol[i] = fma(hs * tb.b6, k2[i], sol[i]);
                         err[i] = fma(tb.e6, k2[i], err[i]);
                     }
-                const double g7 = stage<TAIL>(sol, k2, t + hs, f, c, a);     // k7 = f(5th-order solution)
+#if SBR_DP_K7_IN_K1
+                // k1..k5 are dead (their shares of sol / err were taken above), so k7 = f(5th-order solution) lands in
+                // k1's registers: an accepted step then needs no k1 <- k7 copy (18 moves); a rejected one (2-3 % of the
+                // attempts) re-evaluates k1 = f(x) instead
+                double (&k7)[SBR_NX] = k1;
+#else
+                double (&k7)[SBR_NX] = k2;
+#endif
+                const double g7 = stage<TAIL>(sol, k7, t + hs, f, c, a);     // k7 = f(5th-order solution)
                 st.n_rhs += 6;
                 // error estimate, RMS norm over the active components (h is factored out of the 9 components; the
                 // per-component scale only steers the controller, so its reciprocal is the raw MUFU approximation).
@@ -726,7 +740,7 @@ SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, cons
 #pragma unroll
                 for (int i = 0; i < SBR_NX; ++i)
                     if (active(i)) {
-                        const double e_i = fma(tb.e7, k2[i], err[i]);
+                        const double e_i = fma(tb.e7, k7[i], err[i]);
                         const double sc = fma(tol.rtol, fabs(sol[i]), tol.atol * tol_scale(i));
                         const double q = e_i * rcp_rough(sc);
                         en3[aidx(i) % 3] = fma(q, q, en3[aidx(i) % 3]);
@@ -740,9 +754,15 @@ SBR_HD int dp45_segment(double (&x)[SBR_NX], const SbrSchedule& s, int ph0, cons
                     g1 = g7;
 #pragma unroll
                     for (int i = 0; i < SBR_NX; ++i)
-                        if (active(i)) { x[i] = sol[i]; k1[i] = k2[i]; }
+                        if (active(i)) { x[i] = sol[i]; if (!SBR_DP_K7_IN_K1) k1[i] = k2[i]; }
                 } else {
                     st.n_rej += 1;
+#if SBR_DP_K7_IN_K1
+#pragma unroll
+                    for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
+                    stage<TAIL>(y, k1, t, f, c, a);
+                    st.n_rhs += 1;
+#endif
                 }
                 // step-size controller: h *= clamp(safety * en^(-1/10), 0.2, max growth)  (en is the SQUARED norm).
                 // A rejected step costs the whole warp 6 RHS evaluations (the other 31 envs wait), so the constants
@@ -962,10 +982,14 @@ template <int MODE>
 SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading load, double q_fill,
                      const SbrParams& p, const Coef& c, const SbrSchedule& s, const SbrTol& tol,
                      Dp45State& st, CycleOut& o, const Park& park) {
-    const PidA pid = make_pid_a(p, c);
+    PidA pid = make_pid_a(p, c);
+    // SBR_FLAG_RAW_KLA (BASELINE configs[1] "random KLa actions"): the three actions are the KLa of phases 3, 5 and 8
+    // as fractions of kla_max, the other reacting phases run unaerated, and no DO controller is in the loop
+    pid.bypass = (tol.flags & SBR_FLAG_RAW_KLA) != 0;
     double sp3[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sp3[j] = clip_keep_nan(action[j], 0.0, 1.0) * p.action_scale;   // np.clip (:133)
+    for (int j = 0; j < 3; ++j)                                                                   // np.clip (:133)
+        sp3[j] = clip_keep_nan(action[j], 0.0, 1.0) * (pid.bypass ? p.kla_max : p.action_scale);
     TailArgs a;
     a.kla = 0.0; a.q = q_fill; a.ec_conc = 0.0; a.load = load;
     int status = 0;

@@ -76,9 +76,13 @@ struct CycleArgs {
 // the step loop) is 0.7 % faster at 2^20 envs but 19 % slower at 4096 envs (one warp per sub-partition: latency is what
 // counts) and differs from this build in the last bits, which would make results depend on the batch size
 // (profiles/r01f_ab_cycle_rk4_occupancy.log) -- not taken.
+#ifdef SBR_CYCLE_MAXNREG        // A/B builds: an explicit register cap instead of the resident-CTA hint
+#define SBR_CYCLE_BOUNDS __maxnreg__(SBR_CYCLE_MAXNREG)
+#else
+#define SBR_CYCLE_BOUNDS __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : 1)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, MODE == SBR_MODE_DP45 ? SBR_CYCLE_DP45_MINBLOCKS : 1) sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
-                                                              SbrTol tol) {
+__global__ void SBR_CYCLE_BOUNDS sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s, SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
     // adaptive mode: per-env scratch column for parked stage vectors and per-phase KLa sums (sbr::Park)
     __shared__ double s_park[(MODE == SBR_MODE_DP45 ? sbr::PARK_SLOTS : 1) * kBlock];
@@ -745,6 +749,27 @@ __global__ void __launch_bounds__(256) sbr_permute_rows_kernel(PermuteArgs g) {
         ((int32_t*)g.dst[b])[r * g.ld_dst[b] + id] = ((const int32_t*)g.src[b])[r * g.ld_src[b] + is];
 }
 
+// Stage-level seam of the settle + draw phases (unit tests): x in/out, sX [10][ld], out [9][ld] = Xf, Qw, EQI, eff[6].
+__global__ void __launch_bounds__(128) sbr_settle_draw_kernel(int64_t n, int64_t ld, double* x, double T, SbrParams p,
+                                                              double* sX_out, double* out, int32_t* status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xs[SBR_NX], sX[10], Xf;
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) xs[k] = x[k * ld + i];
+    sbr::settle_closed_form(xs, T, p.settler_area, p.settler_vmax, sX, Xf);
+    sbr::DrawOut d;
+    sbr::draw_and_waste(xs, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k * ld + i] = xs[k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sX_out[k * ld + i] = sX[k];
+    out[i] = Xf; out[ld + i] = d.Qw; out[2 * ld + i] = d.EQI;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) out[(3 + k) * ld + i] = d.eff[k];
+    if (status) status[i] = d.status;
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread, `iters` rounds of 8 DFMAs each.
 __global__ void sbr_fp64_probe_kernel(int iters, double* sink) {
     const double a = 1.0000001, b = 1e-9 * (double)(threadIdx.x + 1);
@@ -816,7 +841,7 @@ int check_common(int64_t n, int64_t ld, const SbrParams* p) {
 
 SbrTol tol_or_default(const SbrTol* tol) {
     SbrTol t;
-    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.reserved = 0;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
     if (tol) t = *tol;
     return t;
 }
@@ -1095,6 +1120,17 @@ int sbr_permute_rows(int64_t n, const int64_t* perm, int nbuf, const void* const
     const dim3 grid((unsigned)((n + 255) / 256), (unsigned)total);
     sbr_permute_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     return check_launch("sbr_permute_rows");
+}
+
+int sbr_settle_draw(int64_t n, int64_t ld, double* x, double settle_time, const SbrParams* p, double* sX, double* out,
+                    int32_t* status, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!x || !sX || !out) return fail(SBR_ERR_ARG, "sbr_settle_draw: NULL buffer%s");
+    if (!(settle_time > 0.0)) return fail(SBR_ERR_ARG, "sbr_settle_draw: settle_time must be positive%s");
+    sbr_settle_draw_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, ld, x, settle_time, *p, sX,
+                                                                                          out, status);
+    return check_launch("sbr_settle_draw");
 }
 
 int sbr_reward_stats_init(double* stats, void* stream) {

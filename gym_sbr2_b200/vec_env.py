@@ -99,7 +99,7 @@ class SbrV2VecEnv(object):
     scenario = 0                     # buffer_tank(0), gym_SBR_env2.py:104
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="rk4", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, rng="philox", substeps=None, order="auto", env_offset=0):
+                 params=None, rng="philox", substeps=None, order="auto", env_offset=0, action_kind="do_setpoint"):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -108,7 +108,12 @@ class SbrV2VecEnv(object):
         self.params = params if params is not None else _abi.default_params()
         self.sched = schedule.cycle_schedule(substeps=substeps)     # RK4 sub-steps per interval (None = reference grid)
         self.mode = {"rk4": _abi.MODE_RK4, "dp45": _abi.MODE_DP45}[mode] if isinstance(mode, str) else int(mode)
-        self.tol = _abi.make_tol(rtol, atol, max_steps)
+        # action_kind="kla": the three actions are the KLa of phases 3, 5, 8 as fractions of 240 1/d, the DO controller
+        # is bypassed (BASELINE configs[1] "random KLa actions"; no reference env takes a raw KLa -- see the header)
+        if action_kind not in ("do_setpoint", "kla"):
+            raise ValueError("action_kind must be 'do_setpoint' or 'kla'")
+        self.action_kind = action_kind
+        self.tol = _abi.make_tol(rtol, atol, max_steps, flags=_abi.FLAG_RAW_KLA if action_kind == "kla" else 0)
         # divergence-aware ordering: with adaptive steps, envs are handed to the kernel in the order of their first DO
         # set-point (the per-env step count is a function of it), physically reordered by one gather launch before
         # and one scatter launch after the cycle kernel so that its loads and stores stay unit-stride; results are

@@ -140,14 +140,19 @@ enum {
     SBR_V4_ROWS
 };
 
-/* Adaptive-step controls (SBR_MODE_DP45). */
+/* Adaptive-step controls (SBR_MODE_DP45) and per-launch option flags (both modes). */
+#define SBR_FLAG_RAW_KLA 1   /* sbr_cycle_v2: the actions are the KLa of phases 3, 5, 8 as fractions of kla_max (held
+                                constant over the phase; the other reacting phases are unaerated), the DO -> KLa PID is
+                                bypassed.  BASELINE configs[1] "random KLa actions".  No registered reference env takes a
+                                raw KLa (the open-loop sim_rxn of sub_phases_PID_off.py:178-225 is dead code that ends up
+                                at KLa = 0); the oracle is the same odeint-per-interval drive with the KLa held fixed. */
 typedef struct SbrTol {
     double rtol, atol;     /* mixed tolerance: err_i <= atol * scale_i + rtol * |x_i|          */
     int32_t max_steps;     /* accepted + rejected steps per 72-s PID interval (default 200; typical need: 1-5);
                               the one-shot fill and idle solves of the interval-per-step path get max_steps x
                               (their length / control interval).  Bounds the work of an env that has left the
                               physical regime: one stuck env stalls its whole warp                       */
-    int32_t reserved;
+    int32_t flags;         /* SBR_FLAG_* (0 = the reference's behaviour)                                   */
 } SbrTol;
 
 int sbr_abi_version(void);
@@ -190,6 +195,17 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
 int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, const double* ec,
                            const double* loading, const SbrParams* p, int tail, double T, int n_sub,
                            int mode, const SbrTol* tol, uint32_t* counters, void* stream);
+
+/*
+ * Stage-level entry of the settle + draw phases (unit tests): settling.sim_settling (sub_phases_FB.py:716-775; the
+ * reference's 10-layer odeint solve has constant settling velocity max(vmax, ...) and therefore a closed form) followed
+ * by drawing.sim_drawing + cal_eq (:780-915).
+ *   x [14][ld] in: state at the start of the settle phase; out: reactor state after decant and wasting
+ *   sX [10][ld] out: layer solids after settling; out [9][ld]: Xf, Qw, EQI, eff[6] = [Qeff, Ntot, COD, Snh, BOD5, Sno]
+ *   status [n] out (may be NULL): SBR_ST_WASTE / SBR_ST_LAYERS
+ */
+int sbr_settle_draw(int64_t n, int64_t ld, double* x, double settle_time, const SbrParams* p, double* sX, double* out,
+                    int32_t* status, void* stream);
 
 /* Kinetic right-hand side only: dx [14][ld] = f(x) -- replaces rxn.dxdt / filling.dxdt / reaction_dxdt
  * (sub_phases_FB.py:51-176, 278-404; gym_SBR_oneshot.py:1658-1787). */

@@ -20,6 +20,11 @@ def action_plan(kind, rng, n=600):
     if kind == "walk":                        # slowly varying set-points, as an RL policy would produce
         a = np.cumsum(0.15 * rng.randn(n, 2), axis=0) + [2.0, 6.0]
         return np.stack([np.clip(a[:, 0], 0.5, 7), np.clip(a[:, 1], 0, 14)], axis=1)
+    if kind == "aggr":                        # aggressive but physical: DO set-point slammed between the ends of its
+        do = np.where((np.arange(n) // 10) % 2 == 0, 7.5, 0.5)             # range every 10 steps, NO3 set-point
+        return np.stack([do, 9 + 6 * rng.rand(n)], axis=1)                 # high enough that little carbon is dosed
+    if kind == "aggr_random":                 # per-step random set-points over the upper NO3 range
+        return np.stack([8 * rng.rand(n), 8 + 7 * rng.rand(n)], axis=1)
     raise ValueError(kind)
 
 
@@ -53,9 +58,12 @@ def run_episode(seed, kind, tight=None):
     return out
 
 
-def make_os(out_dir, versions):
+def make_os(out_dir, versions, only=None):
     from make_golden import tight_odeint
-    episodes = [(0, "const"), (1, "const_hi"), (2, "walk"), (3, "clip"), (4, "random"), (5, "walk"), (6, "walk")]
+    episodes = [(0, "const"), (1, "const_hi"), (2, "walk"), (3, "clip"), (4, "random"), (5, "walk"), (6, "walk"),
+                (7, "aggr"), (8, "aggr_random")]
+    if only is not None:
+        episodes = [e for e in episodes if e in only]
     for seed, kind in episodes:
         try:
             ep = run_episode(seed, kind)
@@ -65,6 +73,8 @@ def make_os(out_dir, versions):
         print("os seed %d %-8s steps %d sumR %.9g finite %s" % (seed, kind, ep["n_steps"], ep["reward"].sum(),
                                                                bool(np.isfinite(ep["state"]).all())), flush=True)
         np.savez_compressed(os.path.join(out_dir, "sbros_v1_seed%d_%s.npz" % (seed, kind)), versions=versions, **ep)
+    if only is not None:
+        return
     with tight_odeint():
         ep = run_episode(0, "const")
     print("os tight seed 0 const sumR %.9g" % ep["reward"].sum(), flush=True)

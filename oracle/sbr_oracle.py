@@ -143,7 +143,7 @@ def cycle_schedule():
     return out
 
 
-def pid_phase(x, t_start, t_end, sp, kla_bias, rhs, rhs_args=(), pid=PID_A, ode_kw=None, tap=None):
+def pid_phase(x, t_start, t_end, sp, kla_bias, rhs, rhs_args=(), pid=PID_A, ode_kw=None, tap=None, raw_kla=False):
     """One PID-controlled phase: filling.sim_rxn / rxn.sim_rxn (sub_phases_FB.py:178-271, 406-500).
 
     Positional PID on So sampled at interval starts; the bias is the *clamped* output of interval 0
@@ -169,6 +169,10 @@ def pid_phase(x, t_start, t_end, sp, kla_bias, rhs, rhs_args=(), pid=PID_A, ode_
             dcv[i] = (So[i] - So[i - 1]) / dtc
             ie[i] = ie[i - 1] + e[i] * dtc
         Kla[i] = Kc * e[i] + Kc / tauI * ie[i] + Kc * tauD * dcv[i] + Kla[0]
+        if raw_kla:
+            # PID bypass (no reference env): `sp` IS the KLa, held over the phase -- the same odeint-per-interval
+            # drive as the open-loop sim_rxn of sub_phases_PID_off.py:178-225 with the KLa fixed
+            Kla[i] = sp
         if Kla[i] > pid['hi']:
             Kla[i] = pid['hi']
             ie[i] = ie[i] - e[i] * dtc
@@ -286,7 +290,7 @@ def fill_flow():
     return QIN / (T_CYCLE * T_RATIO[0])
 
 
-def cycle_v2(setpoints3, influent, x0=X0_INIT, kla0=0.0, ode_kw=None, tap=None):
+def cycle_v2(setpoints3, influent, x0=X0_INIT, kla0=0.0, ode_kw=None, tap=None, raw_kla=False):
     """One whole 12-h cycle = SBR_model_FB.run (SBR_model_FB.py:8-295) for the SBR-v2 env.
 
     setpoints3: DO set-points (g/m3) of phases 3, 5 and 8 (already scaled, i.e. 8*action).
@@ -303,15 +307,17 @@ def cycle_v2(setpoints3, influent, x0=X0_INIT, kla0=0.0, ode_kw=None, tap=None):
     for k in range(5):
         if k == 0:
             x, K = pid_phase(x, sched[k][0], sched[k][1], sp[k], kla, rhs_fill, (list(influent),),
-                             ode_kw=ode_kw, tap=taps[k])
+                             ode_kw=ode_kw, tap=taps[k], raw_kla=raw_kla)
         else:
-            x, K = pid_phase(x, sched[k][0], sched[k][1], sp[k], kla, rhs_react, ode_kw=ode_kw, tap=taps[k])
+            x, K = pid_phase(x, sched[k][0], sched[k][1], sp[k], kla, rhs_react, ode_kw=ode_kw, tap=taps[k],
+                             raw_kla=raw_kla)
         klas[k] = K
         kla = K[-1]
     x5 = x
     sX, Xf = settle(x5, sched[5][0], sched[5][1], ode_kw=ode_kw)
     x7, Qw, EQI, eff, status = draw(x5, sX, Xf)
-    x8, K8 = pid_phase(x7, sched[7][0], sched[7][1], sp[7], klas[4][-1], rhs_react, ode_kw=ode_kw, tap=taps[7])
+    x8, K8 = pid_phase(x7, sched[7][0], sched[7][1], sp[7], klas[4][-1], rhs_react, ode_kw=ode_kw, tap=taps[7],
+                       raw_kla=raw_kla)
     klas[7] = K8
     if tap is not None:
         tap.update(taps)
@@ -320,12 +326,14 @@ def cycle_v2(setpoints3, influent, x0=X0_INIT, kla0=0.0, ode_kw=None, tap=None):
                 n_intervals=[len(klas[k]) if k in klas else 0 for k in range(8)])
 
 
-def sbr_v2_step(action, influent_mixed, x0=X0_INIT, ode_kw=None, tap=None):
-    """SbrEnv2.step (gym_SBR_env2.py:131-171): returns dict(obs[3], reward, done, OCI, ...)."""
+def sbr_v2_step(action, influent_mixed, x0=X0_INIT, ode_kw=None, tap=None, raw_kla=False):
+    """SbrEnv2.step (gym_SBR_env2.py:131-171): returns dict(obs[3], reward, done, OCI, ...).
+    raw_kla=True: the actions are KLa values (fractions of 240 1/d) of phases 3, 5, 8, the PID is bypassed."""
     a = np.clip(np.asarray(action, dtype=float), 0.0, 1.0)
     infl = list(influent_mixed)
     infl[0] = fill_flow()
-    out = cycle_v2([a[0] * 8, a[1] * 8, a[2] * 8], infl, x0=x0, ode_kw=ode_kw, tap=tap)
+    scale = PID_A['hi'] if raw_kla else 8
+    out = cycle_v2([a[0] * scale, a[1] * scale, a[2] * scale], infl, x0=x0, ode_kw=ode_kw, tap=tap, raw_kla=raw_kla)
     Snh = out['eff'][3]
     reward, OCI = reward_v2(out['kla'][2], out['kla'][4], out['kla'][7], out['Qw'], QIN, QEFF, Snh)
     out.update(reward=reward, OCI=OCI, done=True,

@@ -21,7 +21,7 @@ int twin_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influen
                   double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol) {
     const Coef c = make_coef(*p);
     SbrTol t;
-    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.reserved = 0;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
     if (tol) t = *tol;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t i = 0; i < n; ++i) {
@@ -52,7 +52,7 @@ int twin_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla,
                             const SbrTol* tol, uint32_t* counters) {
     const Coef c = make_coef(*p);
     SbrTol t;
-    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.reserved = 0;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
     if (tol) t = *tol;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t i = 0; i < n; ++i) {
@@ -107,7 +107,7 @@ static const double kX0Init[SBR_NX] = {   // gym_SBR_oneshot.py:201-203
 
 static SbrTol tol_or_default(const SbrTol* tol) {
     SbrTol t;
-    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.reserved = 0;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
     if (tol) t = *tol;
     return t;
 }

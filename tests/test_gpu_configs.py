@@ -43,7 +43,10 @@ def test_config3_65536_envs_adaptive_steps_vs_oracle_and_rk4(built, cuda_device)
     infl = env.influent.cpu().numpy()
     act = action.cpu().numpy()
     x_np, r_np, o_np = x_dp.cpu().numpy(), r_dp.cpu().numpy(), obs.cpu().numpy()
-    for i in np.random.RandomState(1).choice(n, 12, replace=False):
+    # ... 32 random envs and the 32 slowest ones (largest RHS count: the envs the step controller worked hardest on)
+    subset = np.concatenate([np.random.RandomState(1).choice(n, 32, replace=False),
+                             torch.topk(rhs, 32).indices.cpu().numpy()])
+    for i in subset:
         ref = O.sbr_v2_step(act[i], infl[:, i])
         ok, worst = parity.state_close(x_np[:, i], ref["x_last"])
         assert ok, (i, worst)
@@ -82,14 +85,15 @@ def test_config4_stiff_stress_2p18_tight_tolerance_vs_tight_lsoda(built, cuda_de
     print("config4 RHS/env: mean %.0f max %.0f rejects/env %.1f" % (cnt[0].mean(), cnt[0].max(), cnt[1].mean()))
     kw = dict(rtol=1e-12, atol=1e-12, mxstep=50000)
     checked = 0
-    for i in rng.choice(base, 10, replace=False):
+    slowest = torch.topk(cnt[0][:base], 32).indices.cpu().numpy()           # the stiffest starts of the batch
+    for i in np.concatenate([rng.choice(base, 32, replace=False), slowest]):
         ref = O.sbr_v2_step(act[:, i], infl[:, i], x0=x0[:, i], ode_kw=kw)
         assert (st[i] != 0) == (ref["status"] != 0), i
         if st[i] == 0:
             ok, worst = parity.state_close(xl[:, i], ref["x_last"], rtol=1e-6, atol_frac=1e-10)
             assert ok, (i, worst)
             checked += 1
-    assert checked >= 6
+    assert checked >= 48, checked
 
 
 def test_interval_path_65536_envs_subset_vs_oracle(built, cuda_device):
@@ -130,3 +134,36 @@ def test_interval_path_65536_envs_subset_vs_oracle(built, cuda_device):
     assert float(info["episode_steps"].min()) == steps
     cnt = info["counters"].to(torch.float64)
     print("interval path RHS/env-step: mean %.1f max %.0f" % (cnt[0].mean(), cnt[0].max()))
+
+
+def test_wide_setpoints_step_limit_flags_are_the_unphysical_envs(built, cuda_device):
+    """bench.py's stress case (DO set-point U(1,7), NO3 set-point U(2,12) per step): heavy carbon dosing drives some envs
+    into negative ammonia, towards the pole of Snh / (Knh + Snh) -- the regime where the reference's own LSODA gives up
+    ("excess work").  There the adaptive stepper runs into max_steps inside one interval and says so: the flagged envs
+    carry SBR_ST_STEPLIMIT and nothing else, every one of them has left the physical regime (Snh < 0), and with a
+    larger step budget the same episode finishes without a flag."""
+    n = 16384
+    def run(max_steps):
+        env = SbrOsVecEnv(n, device=cuda_device, seed=77, mode="dp45", max_steps=max_steps)
+        env.reset()
+        gen = torch.Generator(device=cuda_device).manual_seed(5)
+        acts = [torch.stack([1 + 6 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=gen),
+                             2 + 10 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=gen)], dim=1)
+                for _ in range(8)]
+        flagged = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+        min_snh = torch.full((n,), 1e9, dtype=torch.float64, device=cuda_device)
+        for k in range(463):
+            env.step_async(acts[k % 8])
+            flagged |= env.buf.status
+            min_snh = torch.minimum(min_snh, env.buf.st[10])
+        return flagged, min_snh, env
+    flagged, min_snh, env = run(200)
+    bad = flagged != 0
+    print("stress: %d of %d envs flagged, bits %s, min Snh of flagged envs in [%.3f, %.3f], %d unflagged envs below 0"
+          % (int(bad.sum()), n, sorted(set(flagged[bad].cpu().tolist())), float(min_snh[bad].min()) if bool(bad.any()) else 0,
+             float(min_snh[bad].max()) if bool(bad.any()) else 0, int(((min_snh < 0) & ~bad).sum())))
+    assert bool(bad.any()) and bool((flagged[bad] == _abi.ST_STEPLIMIT).all())
+    assert bool((min_snh[bad] < 0).all())                                    # flagged => unphysical
+    assert bool(env.buf.done.all()) and bool(torch.isfinite(env.buf.st[:14]).all())
+    flagged2, _, _ = run(20000)
+    assert int((flagged2 & _abi.ST_STEPLIMIT).sum()) == 0

@@ -258,3 +258,59 @@ def test_fp64_probe_runs(built, cuda_device):
     sink, flops = core.fp64_probe(148 * 8, 256, 2000, cuda_device)
     torch.cuda.synchronize()
     assert flops == 2.0 * 8 * 2000 * 148 * 8 * 256 and bool(torch.isfinite(sink).all())
+
+
+def test_settle_and_draw_stage_matches_reference_samples(built, cuda_device, stage_samples):
+    """A7 / A8 (and B5) at stage level: the settler's closed form and the draw / waste / effluent-quality arithmetic
+    through sbr_settle_draw against samples recorded from the unmodified reference's sim_settling (two 10-layer odeint
+    solves) and sim_drawing + cal_eq (sub_phases_FB.py:716-915), tests/golden/stage_samples.npz."""
+    s = stage_samples
+    n = len(s["settle_x"])
+    x = core.soa1(torch.as_tensor(np.ascontiguousarray(s["settle_x"].T)).to(cuda_device))
+    sX, out, status = core.settle_draw(x, _abi.default_params(), schedule.cycle_schedule().settle_time)
+    assert int(status.abs().max()) == 0
+    sX, out, x7 = sX.cpu().numpy().T, out.cpu().numpy().T, x.cpu().numpy().T
+    # the layer solids come from the reference's LSODA solve (rtol 1.49e-8): the closed form is the exact solution
+    assert np.allclose(sX, s["settle_sX"], rtol=2e-7, atol=1e-6 * s["settle_Xf"][:, None])
+    assert np.array_equal(out[:, 0], s["settle_Xf"])
+    for i in range(n):
+        ok, worst = parity.state_close(x7[i], s["draw_x7"][i])
+        assert ok, (i, worst)
+    assert np.allclose(out[:, 1], s["draw_Qw"], rtol=1e-5) and np.allclose(out[:, 2], s["draw_EQI"], rtol=1e-5)
+    assert np.allclose(out[:, 3:], s["draw_eff"], rtol=1e-5, atol=1e-9)
+    with pytest.raises(_abi.SbrLibraryError):
+        core.settle_draw(x, _abi.default_params(), 0.0)
+
+
+@pytest.mark.parametrize("mode", ["rk4", "dp45"])
+def test_config1_4096_envs_random_kla_actions(built, cuda_device, mode):
+    """BASELINE configs[1] as written: 4096 vectorised envs, random KLa actions (PID bypassed, action_kind='kla'), one
+    cycle each: every env against the CPU twin, 64 of them (the largest KLa sums among them) against the scipy oracle
+    (LSODA at 1e-12: open loop, the default-tolerance LSODA is itself 1.5 tolerance units from its converged run)."""
+    TIGHT = dict(rtol=1e-12, atol=1e-12, mxstep=50000)
+    n = 4096
+    env = SbrV2VecEnv(n, device=cuda_device, seed=21, mode=mode, action_kind="kla")
+    env.reset()
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    action = torch.rand((n, 3), dtype=torch.float64, device=cuda_device, generator=g)
+    obs, reward, done, info = env.step(action)
+    assert int(info["status"].max()) == 0 and bool(done.all())
+    kla3 = info["kla3_mean"].cpu().numpy()
+    act = action.cpu().numpy()
+    assert np.allclose(kla3, 240 * act[:, 0], rtol=1e-12)                      # constant over phase 3: mean == value
+    x, r = info["x_last"].cpu().numpy(), reward.cpu().numpy()
+    ld = env._loading.cpu().numpy()
+    t = twin.cycle_v2(env.x0.cpu().numpy(), ld, act.T.copy(), twin.default_params(), env.sched,
+                      mode=env.mode, tol=env.tol)
+    bound = 1e-5 * np.abs(t["x_last"]) + 1e-9 * parity.STATE_SCALE[:, None]
+    assert (np.abs(x - t["x_last"]) <= bound * (0.05 if mode == "dp45" else 1e-4)).all()
+    infl = env.influent.cpu().numpy()
+    pick = np.concatenate([np.random.RandomState(0).choice(n, 48, replace=False), np.argsort(-act.sum(axis=1))[:16]])
+    for i in pick:
+        ref = O.sbr_v2_step(act[i], infl[:, i], raw_kla=True, ode_kw=TIGHT)
+        ok, worst = parity.state_close(x[:, i], ref["x_last"])
+        assert ok, (i, worst)
+        if abs(ref["eff"][3] - 4) > 1e-3:
+            assert abs(r[i] - ref["reward"]) <= 1e-5 * abs(ref["reward"]) + 1e-7, i
+    with pytest.raises(ValueError):
+        SbrV2VecEnv(8, device=cuda_device, action_kind="raw")

@@ -19,7 +19,12 @@ import pytest
 from oracle import sbr_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-EPISODES = ["seed0_const", "seed1_const_hi", "seed2_walk", "seed3_clip", "seed4_random", "seed5_walk", "seed6_walk"]
+EPISODES = ["seed0_const", "seed1_const_hi", "seed2_walk", "seed3_clip", "seed4_random", "seed5_walk", "seed6_walk",
+            "seed7_aggr", "seed8_aggr_random"]
+# aggressive set-point sequences under which the reference stays physical to the end (no LSODA warning, Snh > 0):
+# the DO set-point slammed between 0.5 and 7.5 every 10 steps / drawn per step from U(0, 8), NO3 set-points in the
+# upper range so that little carbon is dosed.  These are pinned over ALL 463 steps, terminal settle / draw / idle included.
+FULLY_PHYSICAL = ["seed7_aggr", "seed8_aggr_random"]
 X1_STATE = np.array([0.5, 1.32, 30, 30, 1500, 150, 3000, 2000, 600, 8, 20, 20, 10, 10, 10])
 
 
@@ -42,6 +47,14 @@ def physical_steps(g, well_conditioned=False):
     if well_conditioned:
         bad = bad | ((np.asarray(g["action"])[:n, 1] <= 0) & (np.abs(raw[:, 10]) < 1e-8))
     return int(np.argmax(bad)) if bad.any() else n
+
+
+def test_aggressive_episodes_stay_physical_to_the_end():
+    for name in FULLY_PHYSICAL:
+        g = load_episode(name)
+        assert physical_steps(g, well_conditioned=True) == int(g["n_steps"]) == 463, name
+        a = np.asarray(g["action"])
+        assert a[:, 0].max() > 7 and a[:, 0].min() < 1                       # the whole DO set-point range is visited
 
 
 def test_known_answers_seed0():

@@ -92,3 +92,32 @@ def test_rhs_matches_reference_samples(built, stage_samples):
         scale = np.abs(ref).max(axis=1, keepdims=True)
         assert np.abs(dx.T - ref).max() <= 1e-12 * scale.max()
         assert np.all(np.abs(dx.T - ref) <= 1e-12 * np.abs(ref) + 1e-13 * scale)
+
+
+@pytest.mark.parametrize("mode", [_abi.MODE_RK4, _abi.MODE_DP45])
+def test_raw_kla_actions_bypass_the_pid(built, golden_v2, mode):
+    """SBR_FLAG_RAW_KLA (BASELINE configs[1] "random KLa actions"): the actions are the KLa of phases 3, 5 and 8 as
+    fractions of 240 1/d, held over the phase, the other phases unaerated.  Oracle: the same odeint-per-interval drive
+    with the KLa fixed (no registered reference env takes a raw KLa), LSODA at 1e-12: without the PID's feedback
+    nothing damps LSODA's default-tolerance error (measured 1.5 tolerance units in Snh against its own converged run)."""
+    TIGHT = dict(rtol=1e-12, atol=1e-12, mxstep=50000)
+    g = golden_v2
+    rng = np.random.RandomState(5)
+    idx = rng.choice(len(g["seed"]), 6, replace=False)
+    x0, infl, _ = _inputs(g)
+    act = rng.rand(3, len(idx))
+    act[:, 0] = [0.0, 1.0, 0.5]                                     # the ends of the range in one case
+    tol = _abi.make_tol(1e-8, 1e-10, 200, flags=_abi.FLAG_RAW_KLA)
+    out = twin.cycle_v2(x0[:, idx], infl[:, idx], act, twin.default_params(), schedule.cycle_schedule(), mode=mode, tol=tol)
+    assert out["status"].max() == 0
+    for j, i in enumerate(idx):
+        ref = O.sbr_v2_step(act[:, j], g["influent"][i], raw_kla=True, ode_kw=TIGHT)
+        assert np.all(ref["kla"][2] == act[0, j] * 240) and np.all(ref["kla"][1] == 0)
+        ok, worst = parity.state_close(out["x_last"][:, j], ref["x_last"])
+        assert ok, (j, worst)
+        assert abs(out["reward"][j] - ref["reward"]) <= 1e-5 * abs(ref["reward"]) + 1e-7
+        for k, name in ((2, "kla3_mean"), (4, "kla5_mean"), (7, "kla8_mean")):
+            assert out["aux"][_abi.AUX_NAMES.index(name), j] == pytest.approx(ref["kla"][k].mean(), rel=1e-12, abs=1e-12)
+    # the flag changes the result (it is not silently ignored)
+    plain = twin.cycle_v2(x0[:, idx], infl[:, idx], act, twin.default_params(), schedule.cycle_schedule(), mode=mode)
+    assert not np.allclose(plain["x_last"], out["x_last"], rtol=1e-3)
