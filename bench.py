@@ -33,6 +33,9 @@ F_REACT, F_FILL = 66, 106
 OVH_REACT = 2 * (3 * 9 + 4 * 11)     # RK4 step: 3 stage-input + 4 accumulate FMAs over 9 / 11 active components
 OVH_FILL = 2 * (3 * 14 + 4 * 14)
 F_EPILOGUE = 400
+# Dormand-Prince step on the 9 active components: 15 stage-input FMAs + 5 solution FMAs + 6 error FMAs per component,
+# ~5 flops per component for the norm (SURVEY.md 8d counts these over all 14 components: 828 instead of 513)
+DP45_STEP_OVH = 2 * 9 * 15 + 2 * 9 * 5 + 2 * 9 * 6 + 5 * 9
 BYTES_PER_ENV = (14 + 14 + 3) * 8 + (14 + 3 + 1 + 12) * 8 + 4 + 8   # SoA reads + writes per env per cycle
 
 
@@ -286,7 +289,7 @@ def cycle_dp45_leg(torch, device, core, env, n):
             cnt = o.counters.to(torch.float64)
             rhs = float(cnt[0].mean())
             steps = (rhs - 6) / 6.0
-            flops = rhs * F_REACT + steps * (2 * 9 * 15 + 2 * 9 * 5 + 2 * 9 * 6 + 5 * 9) + F_EPILOGUE
+            flops = rhs * F_REACT + steps * DP45_STEP_OVH + F_EPILOGUE
             key = "rtol%g_%s" % (rtol, "ordered" if ordered else "env_order")
             res[key] = {
                 "rtol": rtol, "atol": atol, "ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3),
@@ -344,6 +347,12 @@ def v4_path_leg(torch, device, args):
             "ms_per_fill_step": fill[len(fill) // 2], "ms_per_react_step": react[len(react) // 2],
             "ms_terminal_step": per[492], "all_done": bool(env.buf.done.all()),
             "bad_status": int((env.buf.status != 0).sum()), "config": {"integrator": "dp45", "rtol": 1e-8, "atol": 1e-10},
+            "parity_note": "against the default-tolerance reference the So component is bounded at 4 tolerance units, not 1 "
+                           "(tests/test_twin_parity_v4.py V4_SO_SLACK): this env's PID has derivative action 300 x dSo per "
+                           "interval, which amplifies LSODA's own noise -- the default-tolerance reference is itself up "
+                           "to 1.9 units from LSODA at 1e-12 in So, this kernel < 0.05; against the 1e-12 oracle the plain "
+                           "tolerance is asserted.  The oracle is the unmodified source with numpy < 1.18 linspace "
+                           "semantics restored (oracle/make_golden_v4.py).",
             "gpu_launches": 494, "mean_episode_return": float(env.buf.st[_abi.V4_RETURN].mean())}
 
 
@@ -486,7 +495,7 @@ def headline_strong_leg(torch, tdist, device, rank, world, args, core, peak):
     else:
         cnt = o.counters.to(torch.float64)
         rhs = float(cnt[0].mean())
-        flops_env = rhs * F_REACT + (rhs - 6) / 6.0 * (2 * 9 * 15 + 2 * 11 * 5 + 2 * 11 * 6 + 5 * 11) + F_EPILOGUE
+        flops_env = rhs * F_REACT + (rhs - 6) / 6.0 * DP45_STEP_OVH + F_EPILOGUE
     tf = n * flops_env / (ms * 1e-3) / 1e12
     ctas = (n + 63) // 64
     return {"total_envs": total, "envs_per_gpu": n, "ms_per_cycle_step": ms, "cycle_steps_per_sec": total / (ms * 1e-3),
@@ -494,6 +503,44 @@ def headline_strong_leg(torch, tdist, device, rank, world, args, core, peak):
             "roofline": {"bound": "fp64", "achieved_per_gpu": tf, "peak": peak, "frac": tf / peak, "unit": "TFLOP/s"},
             "grid": "%d CTAs of 64 threads per GPU over 148 SMs" % ctas,
             "reward_sum_all_ranks": float(chk[0]), "bad_status": int(chk[1])}
+
+
+def cycle_rk4_leg(torch, device, core, env, n, peak):
+    """The headline batch through fixed-step RK4 on the reference's own output grid (9-10 sub-steps per PID interval:
+    deterministic work, the highest roofline fraction, 2.3x the right-hand-side evaluations of the adaptive mode)."""
+    from gym_sbr2_b200 import _abi, schedule
+    sched = schedule.cycle_schedule()
+    ms = []
+    for _ in range(4):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        o = core.cycle_v2(env.x0, env._loading, env._action, env.params, sched, out=env._out, mode=_abi.MODE_RK4)
+        eb.record()
+        torch.cuda.synchronize()
+        ms.append(ea.elapsed_time(eb))
+    ms = sum(ms[1:]) / 3
+    flops_env, steps_env = cycle_flops_rk4(sched)
+    tf = n * flops_env / (ms * 1e-3) / 1e12
+    return {"kernel_ms": ms, "cycle_steps_per_sec": n / (ms * 1e-3), "rhs_per_env": 4.0 * steps_env,
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": peak, "frac": tf / peak, "unit": "TFLOP/s",
+                         "flops_per_env": flops_env}, "bad_status": int((o.status != 0).sum())}
+
+
+def headline_accuracy_leg(torch, device, core, env, n):
+    """How far the adaptive headline setting is from a converged solution, over the whole batch: x_last against RK4
+    with 40 sub-steps per interval (4x finer than the reference grid), in units of the parity tolerance
+    (1e-5 relative + 1e-9 x_1_state)."""
+    from gym_sbr2_b200 import _abi, schedule
+    o = env.step_soa(env._action)
+    x_dp = o.x_last.clone()
+    fine = core.cycle_v2(env.x0, env._loading, env._action, env.params, schedule.cycle_schedule(substeps=40),
+                         mode=_abi.MODE_RK4)
+    scale = torch.tensor([1.32, 30, 30, 1500, 150, 3000, 2000, 600, 8, 20, 20, 10, 10, 10], dtype=torch.float64,
+                         device=device)[:, None]
+    w = ((x_dp - fine.x_last).abs() / (1e-5 * fine.x_last.abs() + 1e-9 * scale)).max(dim=0).values
+    return {"against": "RK4, 40 sub-steps per PID interval", "tolerance_units": {
+        "median": float(w.median()), "p999": float(torch.quantile(w[:1 << 18], 0.999)), "max": float(w.max()),
+        "frac_above_1": float((w > 1).double().mean())}}
 
 
 def cycle_substeps_leg(torch, device, core, env, n, substeps):
@@ -568,9 +615,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
-    ap.add_argument("--mode", default="rk4", choices=["rk4", "dp45"])
-    ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--atol", type=float, default=1e-10)
+    ap.add_argument("--mode", default="dp45", choices=["rk4", "dp45"],
+                    help="headline integrator: adaptive Dormand-Prince 5(4) (default) or RK4 on the reference's output grid")
+    ap.add_argument("--rtol", type=float, default=None, help="DP45 tolerance (default 1e-7)")
+    ap.add_argument("--atol", type=float, default=None, help="DP45 absolute tolerance per x_1_state unit (default 1e-9)")
     ap.add_argument("--ref-steps-per-proc", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
@@ -583,6 +631,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
+    args.rtol = 1e-7 if args.rtol is None else args.rtol
+    args.atol = 1e-9 if args.atol is None else args.atol
     if args.impl == "reference":
         return run_reference(args)
 
@@ -670,8 +720,7 @@ def main():
         rhs_mean, rej_mean = float(cnt[0].mean()), float(cnt[1].mean())
         n_phases = 6                                   # FSAL restarts once per phase, not per interval
         dp_steps = (rhs_mean - n_phases) / 6.0
-        ovh = 2 * 9 * (1 + 2 + 3 + 4 + 5) + 2 * 11 * 5 + 2 * 11 * 6 + 5 * 11
-        flops_env = rhs_mean * F_REACT + dp_steps * ovh + F_EPILOGUE      # fill RHS counted as react: conservative
+        flops_env = rhs_mean * F_REACT + dp_steps * DP45_STEP_OVH + F_EPILOGUE   # fill RHS counted as react: conservative
     achieved_tf = n * flops_env / (kern_avg * 1e-3) / 1e12
     peak_burst, peak_sustained = measure_fp64_peak(core, torch, device)
     peak = peak_sustained if kern_avg * K > 500 else peak_burst
@@ -687,7 +736,8 @@ def main():
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get("sbr_cycle_v2_bytes_per_env") * n
+            traffic = json.load(open(tj)).get("sbr_cycle_v2_dp45_bytes_per_env" if args.mode == "dp45" else
+                                              "sbr_cycle_v2_bytes_per_env") * n
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
@@ -804,9 +854,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_interval_path:
         paths["sbros_v1"] = leg(interval_path_leg, torch, device, args, peak_burst, peak_sustained)
         paths["sbros_v1"]["cpu_baseline"] = cpu_os
-        if args.mode == "rk4":
-            paths["sbr_v2_dp45"] = leg(cycle_dp45_leg, torch, device, core, env, n)
-            paths["sbr_v2_rk4_7substeps"] = leg(cycle_substeps_leg, torch, device, core, env, n, 7)
+        # the other integrator settings on the same batch: adaptive at two tolerances in env order and ordered, RK4 on the
+        # reference's own grid (round 1's headline) and with 7 sub-steps per interval
+        paths["sbr_v2_dp45"] = leg(cycle_dp45_leg, torch, device, core, env, n)
+        paths["sbr_v2_rk4_reference_grid"] = leg(cycle_rk4_leg, torch, device, core, env, n, peak_burst)
+        paths["sbr_v2_rk4_7substeps"] = leg(cycle_substeps_leg, torch, device, core, env, n, 7)
+        if args.mode == "dp45":
+            paths["headline_accuracy"] = leg(headline_accuracy_leg, torch, device, core, env, n)
         paths["sbr_v4"] = leg(v4_path_leg, torch, device, args)
         paths["config1_small_batch"] = leg(small_batch_leg, torch, device)
     if not args.no_rollout:
