@@ -93,9 +93,9 @@ _PROTOS = {
     "sbr_os_step_traj": (C.c_int, [C.c_int64, C.c_int64, C.c_int, _P, _P, C.POINTER(SbrParams),
                                    C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P,
                                    C.c_int, _P]),
-    "sbr_v4_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), _P, _P, _P, _P]),
+    "sbr_v4_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), _P, _P, _P, _P, _P]),
     "sbr_v4_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
-                              _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+                              _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_influent_mix": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sbr_influent_sample": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P,
                                       _P, _P, _P, _P]),

@@ -236,8 +236,9 @@ class V4Buffers(object):
         self.counters = torch.zeros((2, n), dtype=torch.int32, device=device)
 
 
-def v4_reset(buf, influent, params, x0=None, mask=None, stream=None):
-    """SbrEnv4.reset for a batch (gym_SBR_env4.py:94-198).  influent [14,n] (row 0 = fill flow)."""
+def v4_reset(buf, influent, params, x0=None, mask=None, stream=None, order=None):
+    """SbrEnv4.reset for a batch (gym_SBR_env4.py:94-198).  influent [14,n] (row 0 = fill flow).
+    order: optional int32 [n] -- slot j of buf.st holds env order[j] (see sbr_v4_step in the header)."""
     lib = _abi.load()
     n = buf.st.shape[1]
     pst, l0 = _dev_ptr(buf.st, _abi.V4_ROWS, n, name="st")
@@ -246,15 +247,17 @@ def v4_reset(buf, influent, params, x0=None, mask=None, stream=None):
     pmk, _ = _dev_ptr(mask, 1, n, dtype=torch.uint8, name="mask")
     pob, l3 = _dev_ptr(buf.obs, _abi.NX, n, name="obs")
     pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    por, _ = _dev_ptr(order, 1, n, dtype=torch.int32, name="order")
     ld = _same_ld([l0, l1, l2 if x0 is not None else None, l3], "v4_reset")
     with torch.cuda.device(buf.st.device):
-        rc = lib.sbr_v4_reset(n, ld, px0, pin, pmk, C.byref(params), pst, pob, pdn, _stream_ptr(stream))
+        rc = lib.sbr_v4_reset(n, ld, px0, pin, pmk, C.byref(params), pst, pob, pdn, por, _stream_ptr(stream))
     _abi.check(rc, "sbr_v4_reset")
     return buf
 
 
-def v4_step(buf, influent, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None):
-    """SbrEnv4.step for a batch (gym_SBR_env4.py:200-358).  action [n]: change of the DO set-point."""
+def v4_step(buf, influent, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None, order=None):
+    """SbrEnv4.step for a batch (gym_SBR_env4.py:200-358).  action [n]: change of the DO set-point.
+    order: optional int32 [n] -- slot j of buf.st holds env order[j]; all other buffers are indexed by env."""
     lib = _abi.load()
     n = buf.st.shape[1]
     pst, l0 = _dev_ptr(buf.st, _abi.V4_ROWS, n, name="st")
@@ -265,11 +268,12 @@ def v4_step(buf, influent, action, params, sched, mode=_abi.MODE_DP45, tol=None,
     pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
     pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
     pct, l3 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    por, _ = _dev_ptr(order, 1, n, dtype=torch.int32, name="order")
     ld = _same_ld([l0, l1, l2, l3], "v4_step")
     tol = tol or _abi.make_tol()
     with torch.cuda.device(buf.st.device):
         rc = lib.sbr_v4_step(n, ld, pst, pin, pac, C.byref(params), C.byref(sched), pob, prw, pdn, pss, pct,
-                             int(mode), C.byref(tol), _stream_ptr(stream))
+                             int(mode), C.byref(tol), por, _stream_ptr(stream))
     _abi.check(rc, "sbr_v4_step")
     return buf
 

@@ -513,20 +513,26 @@ struct V4Args {
     uint8_t* done;
     int32_t* status;
     uint32_t* counters;
+    const int32_t* order;     // may be NULL: slot j of st holds env order[j]; every other buffer is indexed by env
 };
 
+// `order` (divergence-aware placement): the persistent state st is kept in SLOT order -- slots sorted by how many
+// steps the env needed recently, so that the 32 envs of a warp finish together -- while everything the caller sees
+// (action, observation, reward, done, status, counters, influent, x0, mask) stays indexed by env.  j = thread's slot,
+// i = the env it works on.
 __global__ void __launch_bounds__(128) sbr_v4_reset_kernel(V4Args g, SbrParams p) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n) return;
+    const int64_t i = g.order ? (int64_t)g.order[j] : j;
     if (g.mask && g.mask[i] == 0) return;
     double x[SBR_NX];
 #pragma unroll
-    for (int k = 0; k < SBR_NX; ++k) { x[k] = g.x0 ? g.x0[k * g.ld + i] : c_x0_init[k]; g.st[k * g.ld + i] = x[k]; }
+    for (int k = 0; k < SBR_NX; ++k) { x[k] = g.x0 ? g.x0[k * g.ld + i] : c_x0_init[k]; g.st[k * g.ld + j] = x[k]; }
     const sbr::Loading load{g.influent + i, (int)g.ld};
     sbr::v4_reset_obs(x, load, p, sbr::Column{g.obs + i, g.ld});
 #pragma unroll
-    for (int r = SBR_V4_T; r < SBR_V4_ROWS; ++r) g.st[r * g.ld + i] = 0.0;
-    g.st[SBR_V4_QW * g.ld + i] = NAN;
+    for (int r = SBR_V4_T; r < SBR_V4_ROWS; ++r) g.st[r * g.ld + j] = 0.0;
+    g.st[SBR_V4_QW * g.ld + j] = NAN;
     g.done[i] = 0;
 }
 
@@ -534,24 +540,25 @@ template <int MODE>
 __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                                 SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= g.n) return;
+    const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;          // slot of the state
+    if (j >= g.n) return;
+    const int64_t i = g.order ? (int64_t)g.order[j] : j;                   // env (see sbr_v4_reset_kernel)
     // every load of the launch is issued before the first use (one DRAM round trip, as in sbr_os_step_kernel)
     double x[SBR_NX];
 #pragma unroll
-    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + j];
     const uint8_t was_done = g.done[i];
     sbr::V4Ctrl ctl;
-    ctl.t = g.st[SBR_V4_T * g.ld + i];
-    ctl.u = g.st[SBR_V4_U * g.ld + i];
-    ctl.so_prev = g.st[SBR_V4_SO_PREV * g.ld + i];
-    ctl.ie = g.st[SBR_V4_IE * g.ld + i];
-    ctl.kla_last = g.st[SBR_V4_KLA_LAST * g.ld + i];
-    ctl.kla_sum = g.st[SBR_V4_KLA_SUM * g.ld + i];
+    ctl.t = g.st[SBR_V4_T * g.ld + j];
+    ctl.u = g.st[SBR_V4_U * g.ld + j];
+    ctl.so_prev = g.st[SBR_V4_SO_PREV * g.ld + j];
+    ctl.ie = g.st[SBR_V4_IE * g.ld + j];
+    ctl.kla_last = g.st[SBR_V4_KLA_LAST * g.ld + j];
+    ctl.kla_sum = g.st[SBR_V4_KLA_SUM * g.ld + j];
     sbr::Dp45State dp;
-    dp.h = g.st[SBR_V4_H * g.ld + i];
+    dp.h = g.st[SBR_V4_H * g.ld + j];
     const double action = g.action[i];
-    const double ret0 = g.st[SBR_V4_RETURN * g.ld + i], steps0 = g.st[SBR_V4_STEPS * g.ld + i];
+    const double ret0 = g.st[SBR_V4_RETURN * g.ld + j], steps0 = g.st[SBR_V4_STEPS * g.ld + j];
     const sbr::Column ob{g.obs + i, g.ld};
     if (was_done) {
         // stepping a finished episode is a no-op: same observation, reward 0
@@ -572,17 +579,17 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_k
     sbr::V4Out o;
     sbr::v4_step_env<MODE>(x, ctl, action, load, p, c, s, tol, dp, ob, o);
 #pragma unroll
-    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
-    g.st[SBR_V4_T * g.ld + i] = ctl.t;
-    g.st[SBR_V4_U * g.ld + i] = ctl.u;
-    g.st[SBR_V4_SO_PREV * g.ld + i] = ctl.so_prev;
-    g.st[SBR_V4_IE * g.ld + i] = ctl.ie;
-    g.st[SBR_V4_KLA_LAST * g.ld + i] = ctl.kla_last;
-    g.st[SBR_V4_KLA_SUM * g.ld + i] = ctl.kla_sum;
-    g.st[SBR_V4_H * g.ld + i] = dp.h;
-    g.st[SBR_V4_RETURN * g.ld + i] = ret0 + o.reward;
-    g.st[SBR_V4_STEPS * g.ld + i] = steps0 + 1.0;
-    if (o.done) { g.st[SBR_V4_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
+    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + j] = x[k];
+    g.st[SBR_V4_T * g.ld + j] = ctl.t;
+    g.st[SBR_V4_U * g.ld + j] = ctl.u;
+    g.st[SBR_V4_SO_PREV * g.ld + j] = ctl.so_prev;
+    g.st[SBR_V4_IE * g.ld + j] = ctl.ie;
+    g.st[SBR_V4_KLA_LAST * g.ld + j] = ctl.kla_last;
+    g.st[SBR_V4_KLA_SUM * g.ld + j] = ctl.kla_sum;
+    g.st[SBR_V4_H * g.ld + j] = dp.h;
+    g.st[SBR_V4_RETURN * g.ld + j] = ret0 + o.reward;
+    g.st[SBR_V4_STEPS * g.ld + j] = steps0 + 1.0;
+    if (o.done) { g.st[SBR_V4_QW * g.ld + j] = o.Qw; g.done[i] = 1; }
     g.reward[i] = o.reward;
     if (g.status) g.status[i] = o.status;
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
@@ -1038,26 +1045,27 @@ int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const S
 }
 
 int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
-                 const SbrParams* p, double* st, double* obs, uint8_t* done, void* stream) {
+                 const SbrParams* p, double* st, double* obs, uint8_t* done, const int32_t* order, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if (!influent || !st || !obs || !done) return fail(SBR_ERR_ARG, "sbr_v4_reset: NULL buffer%s");
     if (ld > 2147483647LL) return fail(SBR_ERR_ARG, "sbr_v4_reset: ld too large%s");
-    V4Args g{n, ld, st, x0, influent, mask, nullptr, obs, nullptr, done, nullptr, nullptr};
+    V4Args g{n, ld, st, x0, influent, mask, nullptr, obs, nullptr, done, nullptr, nullptr, order};
     sbr_v4_reset_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, *p);
     return check_launch("sbr_v4_reset");
 }
 
 int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
                 const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
-                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, const int32_t* order, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
     if (!st || !influent || !action || !obs || !reward || !done)
         return fail(SBR_ERR_ARG, "sbr_v4_step: NULL buffer%s");
+    if (n > 2147483647LL) return fail(SBR_ERR_ARG, "sbr_v4_step: n too large%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_v4_step: bad mode%s");
-    V4Args g{n, ld, st, nullptr, influent, nullptr, action, obs, reward, done, status, counters};
+    V4Args g{n, ld, st, nullptr, influent, nullptr, action, obs, reward, done, status, counters, order};
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);

@@ -369,7 +369,7 @@ class SbrV4VecEnv(object):
     max_episode_steps = 493
 
     def __init__(self, num_envs, device="cuda", seed=None, mode="dp45", rtol=1e-8, atol=1e-10, max_steps=200,
-                 params=None, autoreset=False, rk4_sub_interval=0, env_offset=0):
+                 params=None, autoreset=False, rk4_sub_interval=0, env_offset=0, order="auto"):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -389,7 +389,63 @@ class SbrV4VecEnv(object):
         self._loading = torch.zeros((_abi.NX, n), **f)          # ... with row 0 = the fill flow
         self._action = torch.zeros((n,), **f)
         self.fill_flow = schedule.os_fill_flow(self.params.Qin)               # gym_SBR_env4.py:193
+        # divergence-aware placement (adaptive mode): the envs of this path need 1 to 25 integrator steps per interval,
+        # persistently per env (correlation 0.9 from one step to the next), and a warp pays for its slowest env.  The
+        # persistent state is therefore kept in SLOT order -- slots re-sorted by the previous step's RHS count every few
+        # steps (one argsort + one sbr_permute_rows of the state) -- while actions, observations, rewards ... stay
+        # indexed by env: the kernels take the slot -> env map (`order`).  Results are bit-identical either way.
+        if order not in ("auto", "steps", "none"):
+            raise ValueError("order must be 'auto', 'steps' or 'none'")
+        self.order = ("steps" if self.mode == _abi.MODE_DP45 and n > 64 else "none") if order == "auto" else order
+        self._slot_env = None                   # int32 [N] slot -> env, None = identity
+        self._st_alt = None                     # gather target of a re-sort (swapped with buf.st)
         self._init_lockstep()
+
+    def _resort_due(self):
+        k = self._host_steps
+        return self.order == "steps" and ((k < 64 and k % 8 == 7) or (k >= 64 and k % 32 == 31))
+
+    # envs are placed in groups of `place_group` consecutive envs (one 32-byte sector of every env-indexed row): a slot
+    # order that scatters single envs turns each of the kernel's env-indexed loads and stores into a partial-sector
+    # access (measured: 0.32 -> 0.64 ms per step), whole sectors cost what unit-stride rows cost
+    place_group = 4
+
+    def _resort(self):
+        """Re-sort the state slots, group-wise, by the RHS count of the step that just ran."""
+        b = self.buf
+        G, n = self.place_group, self.num_envs
+        ng = n // G
+        cnt = b.counters[0]
+        key = cnt if self._slot_env is None else cnt[self._slot_env.long()]
+        gkey = key[: ng * G].view(ng, G).max(dim=1).values
+        gperm = torch.argsort(gkey)
+        perm = (gperm[:, None] * G + torch.arange(G, device=self.device)[None, :]).reshape(-1)
+        if ng * G < n:
+            perm = torch.cat([perm, torch.arange(ng * G, n, device=self.device)])
+        if self._st_alt is None:
+            self._st_alt = torch.empty_like(b.st)
+        core.permute_rows(perm, [(b.st, self._st_alt)])
+        b.st, self._st_alt = self._st_alt, b.st
+        self._slot_env = perm.to(torch.int32) if self._slot_env is None else self._slot_env[perm]
+
+    def unsort(self):
+        """Put the state back into env order (checkpoints, direct access to buf.st)."""
+        if self._slot_env is not None:
+            b = self.buf
+            if self._st_alt is None:
+                self._st_alt = torch.empty_like(b.st)
+            core.permute_rows(self._slot_env.long(), [(b.st, self._st_alt)], scatter=True)
+            b.st, self._st_alt = self._st_alt, b.st
+            self._slot_env = None
+
+    def _st_row(self, row):
+        """Row `row` of the persistent state in env order."""
+        r = self.buf.st[row]
+        if self._slot_env is None:
+            return r
+        out = torch.empty_like(r)
+        out[self._slot_env.long()] = r
+        return out
 
     _scenario_arg = -1               # np.random.choice(8, 1) per reset, gym_SBR_env4.py:104: drawn by the sampler
     _init_rng, _draw_influent = _init_rng, _draw_influent
@@ -422,7 +478,9 @@ class SbrV4VecEnv(object):
         self._loading[0] = self.fill_flow
         if x0 is not None:
             x0 = x0.to(self.device, torch.float64).contiguous()
-        core.v4_reset(self.buf, self._loading, self.params, x0=x0, mask=mask)
+        if mask is None:
+            self._slot_env = None                # a full reset rewrites every slot: back to the identity placement
+        core.v4_reset(self.buf, self._loading, self.params, x0=x0, mask=mask, order=self._slot_env)
         return self.buf.obs.t()
 
     def step_async(self, action, stream=None):
@@ -431,9 +489,12 @@ class SbrV4VecEnv(object):
             raise ValueError("action must be [N] or [N,1], got %s" % (tuple(action.shape),))
         with _on(stream):
             self._action.copy_(action.to(self.device, torch.float64))
+            out = core.v4_step(self.buf, self._loading, self._action, self.params, self.sched, mode=self.mode,
+                               tol=self.tol, order=self._slot_env)
+            if self._resort_due():
+                self._resort()
         self._host_steps += 1
-        return core.v4_step(self.buf, self._loading, self._action, self.params, self.sched, mode=self.mode,
-                            tol=self.tol, stream=stream)
+        return out
 
     def step(self, action):
         b = self.buf
@@ -443,9 +504,9 @@ class SbrV4VecEnv(object):
             if restarted is not self._no_restart:
                 reset_obs = b.obs.t().clone()
         self.step_async(action)
-        info = dict(status=b.status, counters=b.counters, t=b.st[_abi.V4_T], u=b.st[_abi.V4_U], Qw=b.st[_abi.V4_QW],
-                    episode_return=b.st[_abi.V4_RETURN], episode_steps=b.st[_abi.V4_STEPS], restarted=restarted,
-                    reset_obs=reset_obs)
+        info = dict(status=b.status, counters=b.counters, t=self._st_row(_abi.V4_T), u=self._st_row(_abi.V4_U),
+                    Qw=self._st_row(_abi.V4_QW), episode_return=self._st_row(_abi.V4_RETURN),
+                    episode_steps=self._st_row(_abi.V4_STEPS), restarted=restarted, reset_obs=reset_obs)
         return b.obs.t(), b.reward, b.done.bool(), info
 
     def render(self, mode="human", close=False):
@@ -531,6 +592,8 @@ _BUF_FIELDS = ("st", "done", "obs_do", "obs_ec", "state", "obs", "reward", "stat
 
 def _state_dict_buf(kind):
     def state_dict(self):
+        if hasattr(self, "unsort"):
+            self.unsort()                        # checkpoints hold the state in env order
         b = self.buf
         sd = dict(kind=kind, num_envs=self.num_envs, influent=self.influent.clone(), loading=self._loading.clone(),
                   rng_state=_rng_state(self), lockstep=self._lockstep, host_steps=self._host_steps,
@@ -542,6 +605,8 @@ def _state_dict_buf(kind):
     def load_state_dict(self, sd):
         if sd["kind"] != kind or sd["num_envs"] != self.num_envs:
             raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
+        if hasattr(self, "unsort"):
+            self._slot_env = None
         for k, v in sd["buf"].items():
             getattr(self.buf, k).copy_(v)
         self._lockstep, self._host_steps = bool(sd["lockstep"]), int(sd["host_steps"])

@@ -297,12 +297,21 @@ int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* act
  *   module_reward_continuous.sbr_reward (module_reward_continuous.py:4-65); obs = x / x_1 (:236).
  *     action [n] in; influent [14][ld] in (read during the fill phase only); the schedule is the SbrOsSchedule of the
  *     SBROS-v1 path (same module_batch_time marks; t_fill doubles as t_memory1[-1])
+ * order [n] (int32, may be NULL = identity): divergence-aware placement of the persistent state.  Row r of st holds at
+ *   SLOT j the state of env order[j]; every other buffer (x0, influent, mask, action, obs, reward, done, status, counters)
+ *   stays indexed by env.  The envs of this path need very different numbers of integrator steps per interval (1 to
+ *   25), persistently so; a caller that re-sorts the slots by the previous steps' counters[0] every few steps (one
+ *   sbr_permute_rows of st) gets warps whose envs finish together.  Keep runs of 4 consecutive envs together (one
+ *   32-byte sector of every env-indexed row): scattering single envs makes every env-indexed access a partial sector
+ *   (measured on 2^20 envs: 0.32 ms per step unordered, 0.64 ms with single envs scattered, 0.29 ms with groups of 4;
+ *   0.17-0.18 ms is what the kernel takes when ALL its buffers are in sorted order, profiles/r02j_*).  Results do not
+ *   depend on the placement (bit-identical, tested).
  */
 int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent, const uint8_t* mask,
-                 const SbrParams* p, double* st, double* obs, uint8_t* done, void* stream);
+                 const SbrParams* p, double* st, double* obs, uint8_t* done, const int32_t* order, void* stream);
 int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
                 const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
-                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, const int32_t* order, void* stream);
 
 /*
  * Influent generator, the step before the path = buffer_tank3.influent.buffer_tank (buffer_tank3.py:18-108): per env

@@ -89,3 +89,35 @@ def test_vec_env_api_scenarios_autoreset(built, cuda_device):
     env.autoreset = True
     obs3, reward, done, info = env.step(a)
     assert not bool(done.any()) and float(info["episode_steps"].max()) == 1 and bool(info["restarted"].all())
+
+
+def test_state_placement_does_not_change_results(built, cuda_device):
+    """order='steps': the persistent state lives in slots re-sorted by the previous step's RHS count (first at step 8,
+    then every 8 / 32 steps), everything the caller sees stays indexed by env.  A whole episode with per-env scenarios
+    and random delta actions, a masked reset in the middle: observations, rewards, done flags, info and the final
+    state are bit-identical to the identity placement."""
+    n = 4096
+    a = SbrV4VecEnv(n, device=cuda_device, seed=11, order="steps")
+    b = SbrV4VecEnv(n, device=cuda_device, seed=11, order="none")
+    assert a.order == "steps" and SbrV4VecEnv(n, device=cuda_device).order == "steps" and b.order == "none"
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa, ob)
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    mask = (torch.arange(n, device=cuda_device) % 5 == 0)
+    for k in range(493):
+        act = 0.2 * torch.randn(n, dtype=torch.float64, device=cuda_device, generator=g) + 0.02
+        if k == 100:
+            a.reset(mask=mask); b.reset(mask=mask)
+            assert a._slot_env is not None                      # the masked reset ran with the placement in force
+        ra, rb = a.step(act), b.step(act)
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]), k
+        if k % 50 == 0 or k > 485:
+            for key in ("t", "u", "episode_return", "episode_steps", "counters", "status"):
+                assert torch.equal(ra[3][key], rb[3][key]), (k, key)
+    assert a._slot_env is not None and not torch.equal(a._slot_env.long(), torch.arange(n, device=cuda_device))
+    assert bool(ra[2][~mask].all()) and not bool(ra[2][mask].any())          # the restarted envs are 101 steps behind
+    qa = ra[3]["Qw"]
+    assert torch.equal(torch.nan_to_num(qa, nan=-1.0), torch.nan_to_num(rb[3]["Qw"], nan=-1.0))
+    a.unsort()
+    assert a._slot_env is None
+    assert torch.equal(a.buf.st.view(torch.int64), b.buf.st.view(torch.int64))
