@@ -367,11 +367,11 @@ def small_batch_leg(torch, device, n=4096):
     env.reset()
     b = env.buf
     for _ in range(5):
-        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+        env.step_soa(pol.act_into(b.obs_do, b.obs_ec, env._action))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(200):
-        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+        env.step_soa(pol.act_into(b.obs_do, b.obs_ec, env._action))
     torch.cuda.synchronize()
     t_eager = (time.perf_counter() - t0) / 200
     env.reset()

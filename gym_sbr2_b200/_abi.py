@@ -15,7 +15,7 @@ AUX_ROWS = 12
 PERMUTE_MAX = 8
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 5
+ABI_VERSION = 6
 # rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
 OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
@@ -59,6 +59,21 @@ class SbrTol(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("flags", C.c_int32)]
 
 
+class SbrCntConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32),
+                ("Kc_DO", C.c_double), ("tauI_DO", C.c_double), ("tauD_DO", C.c_double),
+                ("Kc_EC", C.c_double), ("tauI_EC", C.c_double), ("tauD_EC", C.c_double),
+                ("ec_conc", C.c_double), ("ec_fill_max", C.c_double), ("u_ec_init", C.c_double),
+                ("u_ec_max", C.c_double), ("tm2_0", C.c_double), ("tm2_1", C.c_double), ("tm4_0", C.c_double)]
+
+
+# kinds of the sbr_cnt_* entry points (enum SBR_CNT_* of include/sbr_b200.h) and their persistent-state rows
+CNT_V0, CNT_V1, CNT_V2, CNT_MA1, CNT_OS2 = range(5)
+(CNT_T, CNT_U_DO, CNT_U_EC, CNT_SO_PREV, CNT_CV_LAST, CNT_CV_PREV, CNT_IE_DO, CNT_IE_EC, CNT_KLA_LAST, CNT_EC_LAST,
+ CNT_H, CNT_RETURN, CNT_STEPS, CNT_QW, CNT_ROWS) = range(14, 29)
+CNT_NOBS_MAX = 33
+
+
 class SbrLibraryError(RuntimeError):
     pass
 
@@ -96,6 +111,11 @@ _PROTOS = {
     "sbr_v4_reset": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), _P, _P, _P, _P, _P]),
     "sbr_v4_step": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrOsSchedule),
                               _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P, _P]),
+    "sbr_cnt_obs_rows": (C.c_int, [C.c_int]),
+    "sbr_cnt_reset": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(SbrCntConfig), _P, _P, _P, C.POINTER(SbrParams),
+                                C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_cnt_step": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(SbrCntConfig), _P, _P, C.POINTER(SbrParams),
+                               C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_influent_mix": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "sbr_influent_sample": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int64, _P, C.c_int64, C.c_int, _P, _P,
                                       _P, _P, _P, _P]),
@@ -103,6 +123,7 @@ _PROTOS = {
     "sbr_permute_rows": (C.c_int, [C.c_int64, _P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), C.c_int, _P]),
+    "sbr_policy_mlp": (C.c_int, [C.c_int64, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),

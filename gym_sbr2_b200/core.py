@@ -385,6 +385,30 @@ def permute_rows(perm, pairs, scatter=False, stream=None):
     _abi.check(rc, "sbr_permute_rows")
 
 
+def policy_mlp(obs_a, obs_b, w1, w2, lo, span, action, stream=None):
+    """action[o] = lo[o] + span[o] * sigmoid(w2 @ tanh(w1 @ [obs_a; obs_b])) per env in one launch (sbr_policy_mlp).
+    obs_a [ra,n], obs_b [rb,n] (or None) float64 SoA; w1 [hidden, ra+rb], w2 [n_out, hidden], lo / span [n_out] float32;
+    action [n_out, n] float64 out."""
+    lib = _abi.load()
+    n = obs_a.shape[1]
+    ra, rb = obs_a.shape[0], (0 if obs_b is None else obs_b.shape[0])
+    hidden, n_out = w1.shape[0], w2.shape[0]
+    pa, l0 = _dev_ptr(obs_a, ra, n, name="obs_a")
+    pb, l1 = _dev_ptr(obs_b, rb, n, name="obs_b") if obs_b is not None else (None, None)
+    pact, l2 = _dev_ptr(action, n_out, n, name="action") if n_out > 1 else (_dev_ptr(action.reshape(-1), 1, n)[0], None)
+    ld = _same_ld([l0, l1, l2], "policy_mlp")
+    for t, shape, name in ((w1, (hidden, ra + rb), "w1"), (w2, (n_out, hidden), "w2"), (lo, (n_out,), "lo"),
+                           (span, (n_out,), "span")):
+        if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous CUDA float32 tensor of shape %s" % (name, shape))
+    with torch.cuda.device(obs_a.device):
+        rc = lib.sbr_policy_mlp(n, ld, pa, ra, pb, rb, C.c_void_p(w1.data_ptr()), C.c_void_p(w2.data_ptr()),
+                                C.c_void_p(lo.data_ptr()), C.c_void_p(span.data_ptr()), hidden, n_out, pact,
+                                _stream_ptr(stream))
+    _abi.check(rc, "sbr_policy_mlp")
+    return action
+
+
 def reward_stats(reward, status=None, out=None, stream=None):
     """[sum, sumsq, min, max, count] of the rewards of healthy envs, on the device (feeds the NCCL gather)."""
     lib = _abi.load()

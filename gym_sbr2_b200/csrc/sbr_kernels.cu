@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "sbr_core.cuh"
+#include "sbr_cnt.cuh"
 
 namespace {
 
@@ -595,6 +596,172 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_k
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// SBRCnt-v0/1/2, SBRCntMA-v1, SBROS-v2 (sbr_cnt.cuh): persistent per-env state st[SBR_CNT_ROWS][ld].  One env per
+// thread, every load issued before the first use; the kind is uniform over the launch.
+// ---------------------------------------------------------------------------------------------------------
+struct CntArgs {
+    int64_t n, ld;
+    double* st;
+    const double* x0;         // reset only (may be NULL)
+    const double* influent;   // reset only
+    const uint8_t* mask;      // reset only (may be NULL)
+    const double* action;     // step only: [2][ld]
+    double* obs;              // may be NULL in step
+    double* reward;           // step only
+    uint8_t* done;
+    int32_t* status;
+    uint32_t* counters;
+};
+
+__device__ __forceinline__ void cnt_load_ctrl(const CntArgs& g, int64_t i, sbr::CntCtrl& c, double& h) {
+    c.t = g.st[SBR_CNT_T * g.ld + i];
+    c.u_do = g.st[SBR_CNT_U_DO * g.ld + i];
+    c.u_ec = g.st[SBR_CNT_U_EC * g.ld + i];
+    c.so_prev = g.st[SBR_CNT_SO_PREV * g.ld + i];
+    c.cv_last = g.st[SBR_CNT_CV_LAST * g.ld + i];
+    c.cv_prev = g.st[SBR_CNT_CV_PREV * g.ld + i];
+    c.ie_do = g.st[SBR_CNT_IE_DO * g.ld + i];
+    c.ie_ec = g.st[SBR_CNT_IE_EC * g.ld + i];
+    c.kla_last = g.st[SBR_CNT_KLA_LAST * g.ld + i];
+    c.ec_last = g.st[SBR_CNT_EC_LAST * g.ld + i];
+    h = g.st[SBR_CNT_H * g.ld + i];
+}
+__device__ __forceinline__ void cnt_store_ctrl(const CntArgs& g, int64_t i, const sbr::CntCtrl& c, double h) {
+    g.st[SBR_CNT_T * g.ld + i] = c.t;
+    g.st[SBR_CNT_U_DO * g.ld + i] = c.u_do;
+    g.st[SBR_CNT_U_EC * g.ld + i] = c.u_ec;
+    g.st[SBR_CNT_SO_PREV * g.ld + i] = c.so_prev;
+    g.st[SBR_CNT_CV_LAST * g.ld + i] = c.cv_last;
+    g.st[SBR_CNT_CV_PREV * g.ld + i] = c.cv_prev;
+    g.st[SBR_CNT_IE_DO * g.ld + i] = c.ie_do;
+    g.st[SBR_CNT_IE_EC * g.ld + i] = c.ie_ec;
+    g.st[SBR_CNT_KLA_LAST * g.ld + i] = c.kla_last;
+    g.st[SBR_CNT_EC_LAST * g.ld + i] = c.ec_last;
+    g.st[SBR_CNT_H * g.ld + i] = h;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_cnt_reset_kernel(CntArgs g, sbr::CntCfg q, SbrParams p, sbr::Coef c,
+                                                               SbrOsSchedule s, SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    if (g.mask && g.mask[i] == 0) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0 ? g.x0[k * g.ld + i] : c_x0_init[k];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+    const sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    sbr::Dp45State dp;
+    dp.h = s.t_fill / (double)(s.fill_pts > 1 ? s.fill_pts - 1 : 1); dp.n_rhs = 0; dp.n_rej = 0;
+    sbr::CntCtrl ctl;
+    const int status = sbr::cnt_reset_env<MODE>(x, load, q, p, c, s, tol, dp, ctl, sbr::Column{g.obs + i, g.ld});
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
+    cnt_store_ctrl(g, i, ctl, s.t_delta / 9.0);
+    g.st[SBR_CNT_RETURN * g.ld + i] = 0.0;
+    g.st[SBR_CNT_STEPS * g.ld + i] = 0.0;
+    g.st[SBR_CNT_QW * g.ld + i] = NAN;
+    g.done[i] = 0;
+    if (g.status) g.status[i] = status;
+    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_cnt_step_kernel(CntArgs g, sbr::CntCfg q, SbrParams p,
+                                                                                     sbr::Coef c, SbrOsSchedule s, SbrTol tol) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.st[k * g.ld + i];
+    const uint8_t was_done = g.done[i];
+    sbr::CntCtrl ctl;
+    sbr::Dp45State dp;
+    cnt_load_ctrl(g, i, ctl, dp.h);
+    const double a0 = g.action[i];
+    const double a1 = q.kind == SBR_CNT_OS2 ? g.action[g.ld + i] : 0.0;
+    const double ret0 = g.st[SBR_CNT_RETURN * g.ld + i], steps0 = g.st[SBR_CNT_STEPS * g.ld + i];
+    if (was_done) {
+        // stepping a finished episode is a no-op: the observation buffer keeps the terminal observation, reward 0
+        g.reward[i] = 0.0;
+        if (g.status) g.status[i] = SBR_ST_DONE;
+        if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
+        return;
+    }
+    if (!(dp.h > 0.0)) dp.h = s.t_delta / 9.0;
+    dp.n_rhs = 0; dp.n_rej = 0;
+    sbr::CntOut o;
+    sbr::cnt_step_env<MODE>(x, ctl, a0, a1, q, p, c, s, tol, dp, sbr::Column{g.obs ? g.obs + i : nullptr, g.ld}, o);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
+    cnt_store_ctrl(g, i, ctl, dp.h);
+    g.st[SBR_CNT_RETURN * g.ld + i] = ret0 + o.reward;
+    g.st[SBR_CNT_STEPS * g.ld + i] = steps0 + 1.0;
+    if (o.done) { g.st[SBR_CNT_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
+    g.reward[i] = o.reward;
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Policy head of the rollout path (BASELINE configs[4]: observations -> policy -> actions, every step): a two-layer
+// perceptron per env, action = lo + span * sigmoid(W2 tanh(W1 obs)), in ONE launch on the kernels' own SoA layout.
+// The torch expression of the same policy is nine launches that move ~1.3 GB per step at 2^20 envs -- as much time as
+// the env.step it feeds; this reads the 144 B of observation and writes the 16 B of action per env.  FP32 arithmetic
+// (the policy's dtype), weights broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPolMaxIn = 40, kPolMaxHidden = 64, kPolMaxOut = 4;
+struct PolicyArgs {
+    int64_t n, ld;
+    const double* obs_a;
+    const double* obs_b;      // may be NULL
+    const float* w1;          // [hidden][rows_a + rows_b]
+    const float* w2;          // [n_out][hidden]
+    const float* lo;          // [n_out]
+    const float* span;        // [n_out]
+    double* action;           // [n_out][ld]
+    int rows_a, rows_b, hidden, n_out;
+};
+
+__global__ void __launch_bounds__(128) sbr_policy_mlp_kernel(PolicyArgs g) {
+    __shared__ float s_w1[kPolMaxHidden * kPolMaxIn];
+    __shared__ float s_w2[kPolMaxOut * kPolMaxHidden];
+    const int n_in = g.rows_a + g.rows_b;
+    for (int k = threadIdx.x; k < g.hidden * n_in; k += blockDim.x) s_w1[k] = g.w1[k];
+    for (int k = threadIdx.x; k < g.n_out * g.hidden; k += blockDim.x) s_w2[k] = g.w2[k];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    float x[kPolMaxIn];
+#pragma unroll
+    for (int r = 0; r < kPolMaxIn; ++r) {
+        if (r < g.rows_a) x[r] = (float)g.obs_a[(int64_t)r * g.ld + i];
+        else if (r < n_in) x[r] = (float)g.obs_b[(int64_t)(r - g.rows_a) * g.ld + i];
+        else x[r] = 0.0f;
+    }
+    float y[kPolMaxOut] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int h = 0; h < g.hidden; ++h) {
+        const float* w = &s_w1[h * n_in];
+        float acc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kPolMaxIn; ++r)
+            if (r < n_in) acc = fmaf(w[r], x[r], acc);
+        const float t = tanhf(acc);
+#pragma unroll
+        for (int o = 0; o < kPolMaxOut; ++o)
+            if (o < g.n_out) y[o] = fmaf(s_w2[o * g.hidden + h], t, y[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < kPolMaxOut; ++o)
+        if (o < g.n_out) {
+            const float sg = 1.0f / (1.0f + expf(-y[o]));
+            g.action[(int64_t)o * g.ld + i] = (double)fmaf(g.span[o], sg, g.lo[o]);
+        }
+}
+
 // Influent mixing (buffer_tank3.py:50-107): one env per thread, tables staged in shared memory, 13 running sums in
 // registers, rnd read coalesced ([48][N]).  No FMA contraction and sequential sums => bit-identical to numpy.
 __global__ void __launch_bounds__(128) sbr_influent_mix_kernel(int64_t n, int64_t ld, const double* __restrict__ rnd,
@@ -1073,6 +1240,75 @@ int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const
     if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     else sbr_v4_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
     return check_launch("sbr_v4_step");
+}
+
+int sbr_cnt_obs_rows(int kind) {
+    return (kind >= 0 && kind < SBR_CNT_KINDS) ? sbr::cnt_obs_rows(kind) : -1;
+}
+
+static int check_cnt_config(const SbrCntConfig* q) {
+    if (!q) return fail(SBR_ERR_ARG, "SbrCntConfig is NULL%s");
+    if (q->kind < 0 || q->kind >= SBR_CNT_KINDS) return fail(SBR_ERR_ARG, "SbrCntConfig: bad kind%s");
+    if (!(q->tauI_DO != 0.0)) return fail(SBR_ERR_ARG, "SbrCntConfig: tauI_DO must be non-zero%s");
+    if (sbr::cnt_has_ec(q->kind) && !(q->tauI_EC != 0.0)) return fail(SBR_ERR_ARG, "SbrCntConfig: tauI_EC must be non-zero%s");
+    if ((q->kind == SBR_CNT_V1 || q->kind == SBR_CNT_V2) && !(q->tm2_1 > q->tm2_0 && q->tm4_0 > q->tm2_1))
+        return fail(SBR_ERR_ARG, "SbrCntConfig: phase stamps tm2_0 < tm2_1 < tm4_0 required%s");
+    return SBR_OK;
+}
+
+int sbr_cnt_reset(int64_t n, int64_t ld, const SbrCntConfig* cfg, const double* x0, const double* influent,
+                  const uint8_t* mask, const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs,
+                  uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if ((rc = check_os_schedule(s))) return rc;
+    if ((rc = check_cnt_config(cfg))) return rc;
+    if (!influent || !st || !obs || !done) return fail(SBR_ERR_ARG, "sbr_cnt_reset: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cnt_reset: bad mode%s");
+    CntArgs g{n, ld, st, x0, influent, mask, nullptr, obs, nullptr, done, status, counters};
+    const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
+    const sbr::CntCfg q = sbr::make_cnt_cfg(*cfg);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4) sbr_cnt_reset_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    else sbr_cnt_reset_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    return check_launch("sbr_cnt_reset");
+}
+
+int sbr_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, const double* action, const SbrParams* p,
+                 const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done, int32_t* status,
+                 uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if ((rc = check_os_schedule(s))) return rc;
+    if ((rc = check_cnt_config(cfg))) return rc;
+    if (!st || !action || !reward || !done) return fail(SBR_ERR_ARG, "sbr_cnt_step: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cnt_step: bad mode%s");
+    CntArgs g{n, ld, st, nullptr, nullptr, nullptr, action, obs, reward, done, status, counters};
+    const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
+    const sbr::CntCfg q = sbr::make_cnt_cfg(*cfg);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4) sbr_cnt_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    else sbr_cnt_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    return check_launch("sbr_cnt_step");
+}
+
+int sbr_policy_mlp(int64_t n, int64_t ld, const double* obs_a, int rows_a, const double* obs_b, int rows_b,
+                   const float* w1, const float* w2, const float* lo, const float* span, int hidden, int n_out,
+                   double* action, void* stream) {
+    if (n <= 0) return fail(SBR_ERR_ARG, "n must be positive%s");
+    if (ld < n) return fail(SBR_ERR_ARG, "ld must be >= n%s");
+    if (!obs_a || !w1 || !w2 || !lo || !span || !action || (rows_b > 0 && !obs_b))
+        return fail(SBR_ERR_ARG, "sbr_policy_mlp: NULL buffer%s");
+    if (rows_a < 1 || rows_b < 0 || rows_a + rows_b > kPolMaxIn || hidden < 1 || hidden > kPolMaxHidden || n_out < 1 ||
+        n_out > kPolMaxOut)
+        return fail(SBR_ERR_ARG, "sbr_policy_mlp: sizes out of range (inputs <= 40, hidden <= 64, outputs <= 4)%s");
+    PolicyArgs g{n, ld, obs_a, obs_b, w1, w2, lo, span, action, rows_a, rows_b, hidden, n_out};
+    sbr_policy_mlp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g);
+    return check_launch("sbr_policy_mlp");
 }
 
 int sbr_influent_mix(int64_t n, int64_t ld, const double* rnd, const double* mean, const double* std,

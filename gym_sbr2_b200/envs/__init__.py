@@ -3,16 +3,13 @@
 `SbrEnv2`, `SbrOS` and `SbrEnv4` are thin wrappers over a batch of ONE env of the CUDA vector envs, returning numpy / Python
 values exactly shaped like the reference's; "identical seeds" means `np.random.seed(s)` before `reset()` as in the
 reference (global numpy RNG, buffer_tank3.py:68) -- the influent draw consumes the same random numbers.
-The classes whose reference `step()` cannot run raise UnsupportedEnvError on construction.
+`SbrCnt0`, `SbrCnt1`, `SbrCnt2`, `SbrCntMA1` and `SbrOS1` wrap the CUDA path of the five ids whose reference `step()` dies
+in its reward module (repaired reward, disclosed in oracle/make_golden_cnt.py).  `SbrEnv` / `SbrEnv1` (`SBR-v0/1`), whose
+reference `step()` cannot run at all, raise UnsupportedEnvError on construction.
 """
-from .single import SbrEnv2, SbrEnv4, SbrOS, unsupported_class
+from .single import SbrCnt0, SbrCnt1, SbrCnt2, SbrCntMA1, SbrEnv2, SbrEnv4, SbrOS, SbrOS1, unsupported_class
 
 SbrEnv = unsupported_class("SBR-v0")
 SbrEnv1 = unsupported_class("SBR-v1")
-SbrCnt0 = unsupported_class("SBRCnt-v0")
-SbrCnt1 = unsupported_class("SBRCnt-v1")
-SbrCnt2 = unsupported_class("SBRCnt-v2")
-SbrCntMA1 = unsupported_class("SBRCntMA-v1")
-SbrOS1 = unsupported_class("SBROS-v2")
 
 __all__ = ["SbrEnv", "SbrEnv1", "SbrEnv2", "SbrEnv4", "SbrCnt0", "SbrCnt1", "SbrCnt2", "SbrCntMA1", "SbrOS", "SbrOS1"]

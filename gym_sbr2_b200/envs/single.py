@@ -5,6 +5,7 @@ import torch
 from .. import influent as influent_mod
 from ..registration import ENV_TABLE, UnsupportedEnvError
 from ..spaces import Box, env_base
+from ..cnt import SbrCntVecEnv
 from ..vec_env import SbrOsVecEnv, SbrV2VecEnv, SbrV4VecEnv
 
 _Base = env_base()
@@ -151,3 +152,112 @@ class SbrEnv4(_Base):
 
     def render(self, mode="human", close=False):
         print("Reward for this step: {}".format(self.reward))
+
+
+class _CntEnv(_Base):
+    """Batch-of-one view of SbrCntVecEnv under the reference's class name.  The reference's step() of these ids
+    raises NameError inside module_reward_continuous1.sbr_reward; states / observations / done follow the unmodified
+    env modules, the reward is the repaired form disclosed in oracle/make_golden_cnt.py."""
+    metadata = {"render.modes": ["human"]}
+    kind = None
+
+    def __init__(self, device=None, mode="dp45", rtol=1e-8, atol=1e-10):
+        self._vec = SbrCntVecEnv(self.kind, 1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
+        self.influent_mixed = None
+        self.reward = 0
+
+    def _shape_obs(self, obs):
+        return obs[0].cpu().numpy()
+
+    def reset(self):
+        self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)         # buffer_tank(0) in all five files
+        obs = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
+        return self._shape_reset(obs)
+
+    def _shape_reset(self, obs):
+        return self._shape_obs(obs)
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1))
+        obs, reward, done, info = self._vec.step(a)
+        self.reward = float(reward[0])
+        return self._shape_obs(obs), self.reward, bool(done[0]), {}
+
+    def render(self, mode="human", close=False):
+        print("Reward for this step: {}".format(self.reward))
+
+
+class SbrCnt0(_CntEnv):
+    """`SBRCnt-v0` (gym_SBR_continuous0.py:85-1284): action = change of the DO set-point (declared [-0.05, 0.05]);
+    state = [t, Si, Xbh, Xba, So, Sno, Snh] / x_1, shape (1, 7) like the reference's x_2 / x_1; 466 steps per episode."""
+    kind = "cnt0"
+
+    def __init__(self, **kw):
+        self.action_space = Box(np.array([-0.05]), np.array([0.05]), dtype=np.float32)                     # :92
+        self.observation_space = Box(low=np.array([0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9]), high=np.ones([7]) * 1.3,
+                                     dtype=np.float32)                                                     # :96-98
+        super().__init__(**kw)
+
+    def _shape_obs(self, obs):
+        return obs.cpu().numpy()                                     # (1, 7)
+
+
+class SbrCnt1(_CntEnv):
+    """`SBRCnt-v1` (gym_SBR_continuous1.py:82-1399): the agent moves the DO set-point in the aerobic phases only (228
+    steps per episode; the anoxic phases are simulated whole inside a step); state = [t/0.5, So/8, Snh/30, dSo, dSnh]."""
+    kind = "cnt1"
+
+    def __init__(self, **kw):
+        self.action_space = Box(np.array([-1]), np.array([1]), dtype=np.float32)                           # :89
+        self.observation_space = Box(low=np.array([0, 0, 0, -1, -1]), high=np.ones([5]) * 1.0, dtype=np.float32)
+        super().__init__(**kw)
+
+
+class SbrCnt2(SbrCnt1):
+    """`SBRCnt-v2` (gym_SBR_continuous2.py:96-1560): SbrCnt1 plus a carbon controller on Ss whose set-point the first
+    action also moves."""
+    kind = "cnt2"
+
+
+class SbrCntMA1(SbrCnt1):
+    """`SBRCntMA-v1` (gym_SBR_continuous_MA1.py:96-1578): one 1-D action moves the carbon set-point (on Sno) in the
+    anoxic phases and the DO set-point in the aerobic ones; 463 steps per episode."""
+    kind = "ma1"
+
+
+class SbrOS1(_CntEnv):
+    """`SBROS-v2` (gym_SBR_oneshot1.py:98-2089): absolute [DO set-point, NO3 set-point] actions; returns the SBROS-v1
+    style 5-tuple (obs, state, reward, done, info) with obs = (obs_DO, obs_EC)."""
+    kind = "os2"
+
+    def __init__(self, **kw):
+        self.action_space = Box(np.array([-1]), np.array([1]), dtype=np.float32)                           # :105
+        self.observation_space = Box(low=np.array([0, 0, 0, -1, -1]), high=np.ones([5]) * 1.0, dtype=np.float32)
+        super().__init__(**kw)
+
+    def _shape_reset(self, obs):
+        return (obs[0][0].cpu().numpy().tolist(), obs[1][0].cpu().numpy().tolist())
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1, 2))
+        (obs_do, obs_ec), state, reward, done, info = self._vec.step(a)
+        self.reward = float(reward[0])
+        obs = (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
+        return obs, state[0].cpu().numpy(), self.reward, bool(done[0]), {}
+
+    def get_available_actions(self, pre_action, n_agents, n_action):
+        """Action masks of the discrete multi-agent wrapper (gym_SBR_oneshot1.py:434-454)."""
+        action_list = ([-1, -0.5, 0, 0.5, 1], [-1, -0.5, 0, 0.5, 1])
+        action_boundary = ([0, 8], [0, 15])
+        avail_us = []
+        for agent_i in range(0, n_agents):
+            avail_u = np.ones(n_action)
+            for i in range(0, n_action):
+                v = pre_action[agent_i] + action_list[agent_i][i]
+                avail_u[i] = 1 if action_boundary[agent_i][0] <= v <= action_boundary[agent_i][1] else 0
+            avail_us.append(avail_u)
+        return avail_us

@@ -5,8 +5,11 @@ and users call `gym.make(id)`.  The same ten ids are registered here, under the 
   * `SBR-v2` (`SbrEnv2`) and `SBROS-v1` (`SbrOS`) -- the two ids whose `step()` runs in the reference on a current
     toolchain -- and `SBR-v4` (`SbrEnv4`, whose reference `step()` only needs numpy < 1.18 `linspace`
     semantics restored, SURVEY.md 8f rank 1) are served by the CUDA path;
-  * the other seven raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
-    (they crash inside `step()` there), instead of pretending to work.
+  * `SBRCnt-v0/1/2`, `SBRCntMA-v1`, `SBROS-v2` -- whose reference `step()` raises NameError inside the reward module
+    they share (module_reward_continuous1.py:32,61) -- are served by the CUDA path with that reward repaired as
+    oracle/make_golden_cnt.py discloses (states, observations and `done` follow the unmodified env modules);
+  * `SBR-v0` and `SBR-v1` raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
+    (they crash inside `step()` there, in the physics call itself), instead of pretending to work.
 `gym` / `gymnasium` are optional: when one is importable the ids are registered with it as well (so `gym.make`
 works unchanged); otherwise `gym_sbr2_b200.make(id)` is the equivalent.
 """
@@ -24,17 +27,14 @@ ENV_TABLE = {
     # supported with a disclosure: the reference's step() raises TypeError on numpy >= 1.18 (float `num` in np.linspace,
     # gym_SBR_env4.py:286); parity is against the unmodified source under numpy < 1.18 linspace semantics
     "SBR-v4": ("SbrEnv4", "gym_SBR_env4.py", True, None),
-    "SBRCnt-v0": ("SbrCnt0", "gym_SBR_continuous0.py", False,
-                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
-    "SBRCnt-v1": ("SbrCnt1", "gym_SBR_continuous1.py", False,
-                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
-    "SBRCnt-v2": ("SbrCnt2", "gym_SBR_continuous2.py", False,
-                  "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
-    "SBRCntMA-v1": ("SbrCntMA1", "gym_SBR_continuous_MA1.py", False,
-                    "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    # supported with a disclosure: the reference's step() raises NameError inside module_reward_continuous1.sbr_reward
+    # (:32 `So`, :61 `r_snh`); the reward is the repaired form of oracle/make_golden_cnt.py, the rest is the reference's
+    "SBRCnt-v0": ("SbrCnt0", "gym_SBR_continuous0.py", True, None),
+    "SBRCnt-v1": ("SbrCnt1", "gym_SBR_continuous1.py", True, None),
+    "SBRCnt-v2": ("SbrCnt2", "gym_SBR_continuous2.py", True, None),
+    "SBRCntMA-v1": ("SbrCntMA1", "gym_SBR_continuous_MA1.py", True, None),
     "SBROS-v1": ("SbrOS", "gym_SBR_oneshot.py", True, None),
-    "SBROS-v2": ("SbrOS1", "gym_SBR_oneshot1.py", False,
-                 "reference step() raises NameError: So (module_reward_continuous1.py:32)"),
+    "SBROS-v2": ("SbrOS1", "gym_SBR_oneshot1.py", True, None),
 }
 
 registry = {}

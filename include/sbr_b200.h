@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 5
+#define SBR_ABI_VERSION 6
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -314,6 +314,74 @@ int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const
                 int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, const int32_t* order, void* stream);
 
 /*
+ * The other five interval-per-step ids of the reference, one entry-point pair for all of them:
+ *   SBR_CNT_V0  SBRCnt-v0   SbrCnt0   gym_SBR_continuous0.py:85-1284   1-D action = change of the DO set-point, every
+ *                                                                       reacting interval is a step, 7-value observation
+ *   SBR_CNT_V1  SBRCnt-v1   SbrCnt1   gym_SBR_continuous1.py:82-1399   the agent acts in the aerobic phases only: the two
+ *                                                                       anoxic phases are simulated whole inside a step
+ *   SBR_CNT_V2  SBRCnt-v2   SbrCnt2   gym_SBR_continuous2.py:96-1560   as V1 + a carbon controller on Ss
+ *   SBR_CNT_MA1 SBRCntMA-v1 SbrCntMA1 gym_SBR_continuous_MA1.py:96-1578  two agents sharing one 1-D action: carbon set-point
+ *                                                                       (on Sno) in the anoxic phases, DO set-point in the aerobic
+ *   SBR_CNT_OS2 SBROS-v2    SbrOS1    gym_SBR_oneshot1.py:98-2089      as MA1 with ABSOLUTE set-points [DO, NO3] and the
+ *                                                                       SBROS-v1 observation triple (obs_DO, obs_EC, state)
+ * Physics, steppers, settler and draw are those of sbr_os_step.  NOTE: in the reference every step() of these five ids
+ * raises NameError inside module_reward_continuous1.sbr_reward (:32, :61); parity is against the unmodified env modules
+ * run with that one function repaired as oracle/make_golden_cnt.py documents, and the reward here is that repaired form.
+ *
+ * SbrCntConfig: what differs between the five files as data.  gym_sbr2_b200.cnt.cnt_config(kind) fills it with the
+ * reference's constants; the three time stamps come from module_batch_time.batch_time like SbrOsSchedule's.
+ */
+enum { SBR_CNT_V0 = 0, SBR_CNT_V1, SBR_CNT_V2, SBR_CNT_MA1, SBR_CNT_OS2, SBR_CNT_KINDS };
+typedef struct SbrCntConfig {
+    int32_t kind;                        /* SBR_CNT_*                                                                */
+    int32_t reserved;
+    double Kc_DO, tauI_DO, tauD_DO;      /* DO -> KLa PID (gym_SBR_continuous0.py:80-82: 10, 0.5, 5e-5; the others 100, 20, 0) */
+    double Kc_EC, tauI_EC, tauD_EC;      /* carbon PID (V2 / OS2: 1, 20, 0; MA1: 10, 0.5, 0); unused by V0, V1          */
+    double ec_conc;                      /* gCOD/m3 of the dosed carbon (V2 / OS2: 400000/20648.38*1.32; MA1: 4000/...) */
+    double ec_fill_max;                  /* EC_control_par[5] = 5: upper clamp of the dosing flow, fill phase only     */
+    double u_ec_init, u_ec_max;          /* carbon set-point after reset (2) and its upper clip (V2: 5; MA1 / OS2: 15)  */
+    double tm2_0, tm2_1, tm4_0;          /* t_memory2[0], t_memory2[-1], t_memory4[0] (whole-phase solves of V1 / V2)   */
+} SbrCntConfig;
+
+/* Rows of the persistent per-env state st[r * ld + i] of these envs (module globals / growing lists in the reference). */
+enum {
+    SBR_CNT_X = 0,           /* rows 0..13: reactor state                                                      */
+    SBR_CNT_T = 14,          /* running time `t`                                                               */
+    SBR_CNT_U_DO,            /* DO set-point in force (`u` / `u_DO`)                                           */
+    SBR_CNT_U_EC,            /* carbon-controller set-point in force (`u_EC`)                                  */
+    SBR_CNT_SO_PREV,         /* So[-2]                                                                         */
+    SBR_CNT_CV_LAST,         /* [-1] of the carbon controller's measured-value list (Ss / Sno)                 */
+    SBR_CNT_CV_PREV,         /* [-2] of it                                                                     */
+    SBR_CNT_IE_DO, SBR_CNT_IE_EC,   /* PID integrals                                                           */
+    SBR_CNT_KLA_LAST,        /* Kla[-1]                                                                        */
+    SBR_CNT_EC_LAST,         /* EC[-1]                                                                         */
+    SBR_CNT_H,               /* DP45 step-size proposal carried across intervals                               */
+    SBR_CNT_RETURN, SBR_CNT_STEPS, SBR_CNT_QW,
+    SBR_CNT_ROWS
+};
+#define SBR_CNT_NOBS_MAX 33  /* observation rows: V0 7; V1, V2, MA1 5; OS2 9 + 9 + 15 (obs_DO, obs_EC, state)        */
+/* observation rows of a kind (7 / 5 / 33), or -1 */
+int sbr_cnt_obs_rows(int kind);
+/*
+ * sbr_cnt_reset = reset() (gym_SBR_continuous0.py:120-235 and the same function of the other four files): one fill
+ *   solve over [0, t_fill] with the controllers at set-point 0, history seeding, reset observation from the
+ *   flow-weighted mix of influent and reactor.
+ *     x0 [14][ld] (NULL = x0_init), influent [14][ld] (row 0 = fill flow), mask [n] (NULL = all)
+ *     st [SBR_CNT_ROWS][ld] out; obs [sbr_cnt_obs_rows(kind)][ld] out; done [n] out (cleared)
+ * sbr_cnt_step = step(action):
+ *     action [2][ld] in: row 0 = the 1-D action (V0..MA1) or the DO set-point (OS2); row 1 = the NO3 set-point (OS2 only)
+ *     obs out (may be NULL), reward [n] out, done [n] in/out, status / counters may be NULL
+ *   An env whose done flag is set is left untouched (reward 0, status SBR_ST_DONE).
+ * The schedule is the SbrOsSchedule of the SBROS-v1 path (same module_batch_time marks).
+ */
+int sbr_cnt_reset(int64_t n, int64_t ld, const SbrCntConfig* cfg, const double* x0, const double* influent,
+                  const uint8_t* mask, const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs,
+                  uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+int sbr_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, const double* action, const SbrParams* p,
+                 const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done, int32_t* status,
+                 uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+
+/*
  * Influent generator, the step before the path = buffer_tank3.influent.buffer_tank (buffer_tank3.py:18-108): per env
  * one shared rnd ~ N(0,1)^48 perturbs the 48-point mean profiles of the flow and the 13 concentrations
  * (profile = mean + std * rnd, std = 0.1 * mean for Ss, Xi, Xs, Xbh, Snh, Snd, Xnd and the flow, 0 otherwise, :50-66) and
@@ -364,6 +432,19 @@ int sbr_philox_normals(int64_t n, int64_t ld, uint64_t seed, int64_t env_offset,
 int sbr_permute_rows(int64_t n, const int64_t* perm, int nbuf, const void* const* src, void* const* dst,
                      const int64_t* ld_src, const int64_t* ld_dst, const int32_t* rows, const int32_t* elem_bytes,
                      int scatter, void* stream);
+
+/*
+ * Policy head of a rollout, fused into one launch on the SoA observation buffers (no reference counterpart: the
+ * reference steps one env under a Python agent; BASELINE configs[4] feeds the observations of 2^20 envs to a small
+ * policy every step):  action[o][i] = lo[o] + span[o] * sigmoid( sum_h w2[o][h] * tanh( sum_r w1[h][r] * obs[r][i] ) )
+ * with obs = the rows of obs_a followed by the rows of obs_b (obs_b may be NULL with rows_b = 0), FP32 arithmetic.
+ *   obs_a [rows_a][ld], obs_b [rows_b][ld] in (float64, e.g. obs_DO and obs_EC of sbr_os_step)
+ *   w1 [hidden][rows_a + rows_b], w2 [n_out][hidden], lo / span [n_out]: device float32
+ *   action [n_out][ld] out (float64, the layout sbr_os_step reads);  rows_a + rows_b <= 40, hidden <= 64, n_out <= 4
+ */
+int sbr_policy_mlp(int64_t n, int64_t ld, const double* obs_a, int rows_a, const double* obs_b, int rows_b,
+                   const float* w1, const float* w2, const float* lo, const float* span, int hidden, int n_out,
+                   double* action, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

@@ -15,10 +15,11 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(HERE, "sbr_twin.cpp")
-    core = os.path.join(os.path.dirname(os.path.dirname(HERE)), "gym_sbr2_b200", "csrc", "sbr_core.cuh")
+    csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "gym_sbr2_b200", "csrc")
+    deps = [src, os.path.join(csrc, "sbr_core.cuh"), os.path.join(csrc, "sbr_cnt.cuh"),
+            os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "sbr_b200.h")]
     os.makedirs(BUILD_DIR, exist_ok=True)
-    if (not force and os.path.exists(LIB)
-            and os.path.getmtime(LIB) >= max(os.path.getmtime(src), os.path.getmtime(core))):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.check_call(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", LIB, src])
     return LIB
@@ -178,5 +179,47 @@ class V4Batch(object):
                               C.byref(self.params), C.byref(self.sched), _ptr(self.obs), _ptr(self.reward),
                               _ptr(self.done), _ptr(self.status), _ptr(self.counters), C.c_int(self.mode),
                               C.byref(self.tol))
+        assert rc == 0
+        return self.obs.copy(), self.reward.copy(), self.done.copy()
+
+
+class CntBatch(object):
+    """Host-memory twin of the SBRCnt-v0/1/2, SBRCntMA-v1, SBROS-v2 path: same buffers and call sequence as
+    sbr_cnt_reset / sbr_cnt_step.  `cfg`: an _abi.SbrCntConfig (gym_sbr2_b200.cnt.cnt_config(kind))."""
+
+    def __init__(self, cfg, n, obs_rows, params=None, sched=None, mode=1, tol=None):
+        from gym_sbr2_b200 import schedule
+        self.cfg = cfg
+        self.n = n
+        self.params = params or default_params()
+        self.sched = sched or schedule.os_schedule()
+        self.mode = mode
+        self.tol = tol or _abi.make_tol()
+        self.st = np.zeros((_abi.CNT_ROWS, n))
+        self.obs = np.zeros((obs_rows, n)); self.reward = np.zeros(n); self.done = np.ones(n, dtype=np.uint8)
+        self.status = np.zeros(n, dtype=np.int32); self.counters = np.zeros((2, n), dtype=np.uint32)
+
+    def reset(self, influent, x0=None, mask=None):
+        lib = load()
+        influent = np.ascontiguousarray(influent, dtype=np.float64)
+        x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        n = self.n
+        rc = lib.twin_cnt_reset(C.c_int64(n), C.c_int64(n), C.byref(self.cfg), _ptr(x0), _ptr(influent), _ptr(mask),
+                                C.byref(self.params), C.byref(self.sched), _ptr(self.st), _ptr(self.obs),
+                                _ptr(self.done), _ptr(self.status), _ptr(self.counters), C.c_int(self.mode),
+                                C.byref(self.tol))
+        assert rc == 0
+        return self.obs.copy()
+
+    def step(self, action):
+        lib = load()
+        action = np.ascontiguousarray(action, dtype=np.float64)
+        n = self.n
+        assert action.shape == (2, n)
+        rc = lib.twin_cnt_step(C.c_int64(n), C.c_int64(n), C.byref(self.cfg), _ptr(self.st), _ptr(action),
+                               C.byref(self.params), C.byref(self.sched), _ptr(self.obs), _ptr(self.reward),
+                               _ptr(self.done), _ptr(self.status), _ptr(self.counters), C.c_int(self.mode),
+                               C.byref(self.tol))
         assert rc == 0
         return self.obs.copy(), self.reward.copy(), self.done.copy()

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "../../gym_sbr2_b200/csrc/sbr_core.cuh"
+#include "../../gym_sbr2_b200/csrc/sbr_cnt.cuh"
 
 using namespace sbr;
 
@@ -241,6 +242,83 @@ int twin_v4_step(int64_t n, int64_t ld, double* st, const double* influent, cons
         st[SBR_V4_KLA_SUM * ld + i] = ctl.kla_sum; st[SBR_V4_H * ld + i] = dp.h;
         st[SBR_V4_RETURN * ld + i] += o.reward; st[SBR_V4_STEPS * ld + i] += 1.0;
         if (o.done) { st[SBR_V4_QW * ld + i] = o.Qw; done[i] = 1; }
+        reward[i] = o.reward;
+        if (status) status[i] = o.status;
+        if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
+    }
+    return 0;
+}
+
+static void twin_cnt_load(const double* st, int64_t ld, int64_t i, CntCtrl& c, double& h) {
+    c.t = st[SBR_CNT_T * ld + i]; c.u_do = st[SBR_CNT_U_DO * ld + i]; c.u_ec = st[SBR_CNT_U_EC * ld + i];
+    c.so_prev = st[SBR_CNT_SO_PREV * ld + i]; c.cv_last = st[SBR_CNT_CV_LAST * ld + i];
+    c.cv_prev = st[SBR_CNT_CV_PREV * ld + i]; c.ie_do = st[SBR_CNT_IE_DO * ld + i]; c.ie_ec = st[SBR_CNT_IE_EC * ld + i];
+    c.kla_last = st[SBR_CNT_KLA_LAST * ld + i]; c.ec_last = st[SBR_CNT_EC_LAST * ld + i]; h = st[SBR_CNT_H * ld + i];
+}
+static void twin_cnt_store(double* st, int64_t ld, int64_t i, const CntCtrl& c, double h) {
+    st[SBR_CNT_T * ld + i] = c.t; st[SBR_CNT_U_DO * ld + i] = c.u_do; st[SBR_CNT_U_EC * ld + i] = c.u_ec;
+    st[SBR_CNT_SO_PREV * ld + i] = c.so_prev; st[SBR_CNT_CV_LAST * ld + i] = c.cv_last;
+    st[SBR_CNT_CV_PREV * ld + i] = c.cv_prev; st[SBR_CNT_IE_DO * ld + i] = c.ie_do; st[SBR_CNT_IE_EC * ld + i] = c.ie_ec;
+    st[SBR_CNT_KLA_LAST * ld + i] = c.kla_last; st[SBR_CNT_EC_LAST * ld + i] = c.ec_last; st[SBR_CNT_H * ld + i] = h;
+}
+
+int twin_cnt_reset(int64_t n, int64_t ld, const SbrCntConfig* cfg, const double* x0, const double* influent,
+                   const uint8_t* mask, const SbrParams* p, const SbrOsSchedule* s, double* st, double* obs,
+                   uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    const CntCfg q = make_cnt_cfg(*cfg);
+    const SbrTol t = tol_or_default(tol);
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && mask[i] == 0) continue;
+        double x[SBR_NX], load[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) { x[k] = x0 ? x0[k * ld + i] : kX0Init[k]; load[k] = influent[k * ld + i]; }
+        Dp45State dp;
+        dp.h = s->t_fill / (double)(s->fill_pts > 1 ? s->fill_pts - 1 : 1); dp.n_rhs = 0; dp.n_rej = 0;
+        CntCtrl ctl;
+        const Loading L{load, 1};
+        const int stt = mode == SBR_MODE_RK4
+            ? cnt_reset_env<SBR_MODE_RK4>(x, L, q, *p, c, *s, t, dp, ctl, Column{obs + i, ld})
+            : cnt_reset_env<SBR_MODE_DP45>(x, L, q, *p, c, *s, t, dp, ctl, Column{obs + i, ld});
+        for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
+        twin_cnt_store(st, ld, i, ctl, s->t_delta / 9.0);
+        st[SBR_CNT_RETURN * ld + i] = 0.0; st[SBR_CNT_STEPS * ld + i] = 0.0; st[SBR_CNT_QW * ld + i] = NAN;
+        done[i] = 0;
+        if (status) status[i] = stt;
+        if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
+    }
+    return 0;
+}
+
+int twin_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, const double* action, const SbrParams* p,
+                  const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done, int32_t* status,
+                  uint32_t* counters, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    const CntCfg q = make_cnt_cfg(*cfg);
+    const SbrTol t = tol_or_default(tol);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        if (done[i]) {
+            reward[i] = 0.0;
+            if (status) status[i] = SBR_ST_DONE;
+            if (counters) { counters[i] = 0; counters[ld + i] = 0; }
+            continue;
+        }
+        double x[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) x[k] = st[k * ld + i];
+        CntCtrl ctl;
+        Dp45State dp;
+        twin_cnt_load(st, ld, i, ctl, dp.h);
+        if (!(dp.h > 0.0)) dp.h = s->t_delta / 9.0;
+        dp.n_rhs = 0; dp.n_rej = 0;
+        const double a0 = action[i], a1 = q.kind == SBR_CNT_OS2 ? action[ld + i] : 0.0;
+        CntOut o;
+        const Column ob{obs ? obs + i : nullptr, ld};
+        if (mode == SBR_MODE_RK4) cnt_step_env<SBR_MODE_RK4>(x, ctl, a0, a1, q, *p, c, *s, t, dp, ob, o);
+        else cnt_step_env<SBR_MODE_DP45>(x, ctl, a0, a1, q, *p, c, *s, t, dp, ob, o);
+        for (int k = 0; k < SBR_NX; ++k) st[k * ld + i] = x[k];
+        twin_cnt_store(st, ld, i, ctl, dp.h);
+        st[SBR_CNT_RETURN * ld + i] += o.reward; st[SBR_CNT_STEPS * ld + i] += 1.0;
+        if (o.done) { st[SBR_CNT_QW * ld + i] = o.Qw; done[i] = 1; }
         reward[i] = o.reward;
         if (status) status[i] = o.status;
         if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }

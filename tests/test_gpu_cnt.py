@@ -1,0 +1,111 @@
+"""GPU parity tests of `SBRCnt-v0/1/2`, `SBRCntMA-v1`, `SBROS-v2` (sbr_cnt_reset / sbr_cnt_step through the C ABI):
+whole episodes of the unmodified reference env modules (reward repaired as oracle/make_golden_cnt.py discloses), every
+env of a 2048 batch against the g++ twin, and the vector-env API."""
+import numpy as np
+import pytest
+import torch
+
+from gym_sbr2_b200 import _abi, cnt, schedule
+from oracle.twin import binding as twin
+from test_twin_parity_cnt import CNT_EPISODES, run_cnt
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuCntBatch(object):
+    """numpy-in / numpy-out adapter over the CUDA entry points with the interface of oracle.twin.binding.CntBatch."""
+
+    def __init__(self, kind, n, device, mode=_abi.MODE_DP45):
+        self.n, self.device, self.mode = n, device, mode
+        self.cfg = cnt.cnt_config(kind)
+        self.params, self.sched, self.tol = _abi.default_params(), schedule.os_schedule(), _abi.make_tol()
+        self.buf = cnt.CntBuffers(n, device, cnt.OBS_ROWS[kind])
+
+    def _sync(self):
+        torch.cuda.synchronize()
+        b = self.buf
+        self.st, self.status = b.st.cpu().numpy(), b.status.cpu().numpy()
+        self.counters, self.done = b.counters.cpu().numpy().astype(np.uint32), b.done.cpu().numpy()
+
+    def reset(self, influent, x0=None, mask=None):
+        infl = torch.as_tensor(np.ascontiguousarray(influent)).to(self.device, torch.float64)
+        if self.n == 1:
+            infl = infl.reshape(14, 1).contiguous()
+        cnt.cnt_reset(self.cfg, self.buf, infl, self.params, self.sched, mode=self.mode, tol=self.tol)
+        self._sync()
+        return self.buf.obs.cpu().numpy()
+
+    def step(self, action):
+        a = torch.as_tensor(np.ascontiguousarray(action, dtype=np.float64)).to(self.device)
+        b = cnt.cnt_step(self.cfg, self.buf, a, self.params, self.sched, mode=self.mode, tol=self.tol)
+        self._sync()
+        return b.obs.cpu().numpy(), b.reward.cpu().numpy(), self.done.copy()
+
+
+@pytest.mark.parametrize("episode", CNT_EPISODES)
+def test_dp45_episodes_match_reference(built, cuda_device, episode):
+    run_cnt(lambda kind: GpuCntBatch(kind, 1, cuda_device), episode)
+
+
+@pytest.mark.parametrize("kind", sorted(cnt.KINDS))
+def test_2048_envs_every_env_against_cpu_twin(built, cuda_device, kind):
+    """2048 envs with per-env influent and random actions over the start of the episode (the whole-phase solve of
+    cnt1 / cnt2, the anoxic -> aerobic switch of ma1 / os2): every env against the g++ build of the same arithmetic."""
+    from gym_sbr2_b200 import influent
+    n = 2048
+    rng = np.random.RandomState(41)
+    infl = np.stack([influent.mix_numpy(0, rng.randn(48)) for _ in range(64)], axis=1)
+    infl = np.tile(infl, (1, n // 64)).copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    g = GpuCntBatch(kind, n, cuda_device)
+    c = twin.CntBatch(cnt.cnt_config(kind), n, cnt.OBS_ROWS[kind], mode=_abi.MODE_DP45)
+    og, oc = g.reset(infl), c.reset(infl)
+    assert np.allclose(og, oc, rtol=1e-9, atol=1e-12)
+    steps = 70 if kind in ("ma1", "os2", "cnt0") else 12
+    for k in range(steps):
+        act = np.zeros((2, n))
+        if kind == "os2":
+            act[0], act[1] = rng.uniform(0.5, 4.0, n), rng.uniform(0.0, 0.4, n)
+        else:
+            act[0] = rng.uniform(-1, 1, n) * (0.05 if kind == "cnt0" else 0.5)
+        (sg, rg, dg), (sc, rc, dc) = g.step(act), c.step(act)
+        assert np.array_equal(dg, dc) and np.array_equal(g.status, c.status), k
+        assert np.all(np.abs(g.st[:14] - c.st[:14]) <= 2e-6 * np.abs(c.st[:14]) + 2e-8), (k, np.abs(g.st[:14] - c.st[:14]).max())
+        assert np.all(np.abs(sg - sc) <= 2e-6 * np.abs(sc) + 2e-6), k
+        assert np.mean(rg == rc) > 0.999, k                     # a So within 1e-6 of a reward threshold may flip its bin
+
+
+@pytest.mark.parametrize("kind", sorted(cnt.KINDS))
+def test_vec_env_episode_api(built, cuda_device, kind):
+    n = 96
+    env = cnt.SbrCntVecEnv(kind, n, device=cuda_device, seed=5)
+    obs = env.reset()
+    if kind == "os2":
+        assert obs[0].shape == (n, 9) and obs[1].shape == (n, 9)
+    else:
+        assert obs.shape == (n, cnt.OBS_ROWS[kind]) and bool(torch.isfinite(obs).all())
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    for k in range(env.max_episode_steps):
+        if kind == "os2":
+            a = torch.stack([1.0 + 2.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g),
+                             torch.zeros(n, dtype=torch.float64, device=cuda_device)], dim=1)
+        else:
+            a = torch.full((n, 1), 0.05 if kind == "cnt0" else 0.25, dtype=torch.float64, device=cuda_device)
+            if k >= 8:
+                a.zero_()
+            if kind in ("ma1", "cnt2") and k < 2:
+                a.fill_(-2.0)                    # carbon set-point to 0 before the controller can run away
+        out = env.step(a)
+        done, info = out[-2], out[-1]
+        assert bool(done.all()) == (k == env.max_episode_steps - 1), k
+    assert int(info["status"].max()) == 0 and bool(torch.isfinite(info["Qw"]).all())
+    assert float(info["episode_steps"].min()) == env.max_episode_steps
+    assert float(env.buf.st[0].max()) < 1.4                    # the reactor stayed physical
+    before = env.buf.st.clone()
+    out = env.step(a)                                           # finished: no-op
+    assert torch.equal(torch.nan_to_num(env.buf.st), torch.nan_to_num(before)) and float(out[-3].abs().max()) == 0.0
+    sd = env.state_dict()
+    env2 = cnt.SbrCntVecEnv(kind, n, device=cuda_device, seed=5)
+    env2.load_state_dict(sd)
+    assert torch.equal(torch.nan_to_num(env2.buf.st), torch.nan_to_num(env.buf.st))
+    assert torch.equal(env2.buf.obs, env.buf.obs)

@@ -130,3 +130,23 @@ def test_checkpoint_resume_policy_driven(built, cuda_device, tmp_path, rng):
     assert torch.equal(a.influent, b.influent)
     assert torch.equal(out_a[2], out_b[2]) and torch.equal(out_a[0][0], out_b[0][0])
     assert float(out_a[4]["episode_steps"].max()) == 27
+
+
+def test_fused_policy_kernel_matches_torch_fp32_reference(built, cuda_device):
+    """sbr_policy_mlp (one launch on the SoA observation rows) against the plain torch fp32 expression of the same
+    two-layer perceptron: fp32 rounding apart (sum order, tanh / exp implementations), identical actions."""
+    n = 5000                                                     # ragged: not a multiple of the CTA size
+    policy = rollout.TinyPolicy(cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(9)
+    obs_do = torch.rand((9, n), dtype=torch.float64, device=cuda_device, generator=g) * 2 - 0.5
+    obs_ec = torch.rand((9, n), dtype=torch.float64, device=cuda_device, generator=g) * 2 - 0.5
+    ref = policy.forward_torch(obs_do, obs_ec)
+    out = torch.full((2, n), float("nan"), dtype=torch.float64, device=cuda_device)
+    got = policy.act_into(obs_do, obs_ec, out)
+    assert got.data_ptr() == out.data_ptr() and bool(torch.isfinite(out).all())
+    assert float((out - ref).abs().max()) <= 2e-5               # outputs span 6.5 / 13: ~1e-6 relative in fp32
+    assert float(out[0].min()) >= 0.5 and float(out[0].max()) <= 7.0 and float(out[1].max()) <= 14.0
+    assert torch.equal(policy.forward_soa(obs_do, obs_ec), out)
+    # argument errors surface as exceptions, not as a silent fallback
+    with pytest.raises(Exception):
+        core.policy_mlp(obs_do, obs_ec, policy.w1t.double(), policy.w2t, policy.lo_flat, policy.span_flat, out)

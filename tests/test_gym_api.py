@@ -22,9 +22,12 @@ def test_all_ten_reference_ids_registered_under_reference_class_names():
         assert hasattr(envs, cls)
 
 
+SERVED = ("SBR-v2", "SBROS-v1", "SBR-v4", "SBRCnt-v0", "SBRCnt-v1", "SBRCnt-v2", "SBRCntMA-v1", "SBROS-v2")
+
+
 def test_unsupported_ids_name_the_reference_failure():
     for env_id in REF_IDS:
-        if env_id in ("SBR-v2", "SBROS-v1", "SBR-v4"):
+        if env_id in SERVED:
             continue
         with pytest.raises(sbr.UnsupportedEnvError) as e:
             sbr.make(env_id)
@@ -35,7 +38,7 @@ def test_supported_ids_fail_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
-    for env_id in ("SBR-v2", "SBROS-v1", "SBR-v4"):
+    for env_id in SERVED:
         with pytest.raises(_abi.SbrLibraryError):
             sbr.make(env_id)
 
@@ -124,3 +127,45 @@ def test_sbr_v4_episode_through_make(built, cuda_device):
         if done:
             break
     assert k == 493
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,kind,name", [("SBRCnt-v0", "cnt0", "seed1_up"), ("SBRCnt-v1", "cnt1", "seed1_up"),
+                                             ("SBRCnt-v2", "cnt2", "seed1_up"), ("SBRCntMA-v1", "ma1", "seed0_up"),
+                                             ("SBROS-v2", "os2", "seed1_walk")])
+def test_cnt_family_episode_through_make(built, cuda_device, env_id, kind, name):
+    """The five ids whose reference step() dies in its reward module: tuple shapes of the reference, the same RNG
+    consumption (np.random.seed before reset), observations against the reference run with the repaired reward."""
+    from test_twin_parity_cnt import load_cnt, obs_close
+    g = load_cnt(kind, name)
+    env = sbr.make(env_id)
+    np.random.seed(int(g["seed"]))
+    obs0 = env.reset()
+    assert np.array_equal(env.influent_mixed[1:], g["influent"][1:])
+    if kind == "os2":
+        assert isinstance(obs0, tuple) and len(obs0[0]) == 9 and len(obs0[1]) == 9
+        flat0 = np.concatenate(obs0)
+    else:
+        assert obs0.shape == ((1, 7) if kind == "cnt0" else (5,))
+        flat0 = obs0.reshape(-1)
+    assert obs_close(flat0, g["reset_obs"], kind)[0]
+    k = 0
+    while True:
+        out = env.step(g["action"][k] if kind == "os2" else g["action"][k][:1])
+        if kind == "os2":
+            assert len(out) == 5
+            obs, state, reward, done, info = out
+            assert state.shape == (15,)
+            flat = np.concatenate(obs)
+        else:
+            assert len(out) == 4
+            obs, reward, done, info = out
+            flat = obs.reshape(-1)
+        assert isinstance(done, bool) and done == bool(g["done"][k]) and info == {}
+        ok, worst = obs_close(flat, g["obs"][k], kind)
+        assert ok, (k, worst)
+        assert reward == g["reward"][k], k
+        k += 1
+        if done:
+            break
+    assert k == int(g["n_steps"])

@@ -22,10 +22,10 @@ for n in (4096, 65536):
     env.reset()
     b = env.buf
     for _ in range(5):
-        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+        env.step_soa(pol.act_into(b.obs_do, b.obs_ec, env._action))
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(200):
-        env.step_soa(pol.forward_soa(b.obs_do, b.obs_ec).contiguous())
+        env.step_soa(pol.act_into(b.obs_do, b.obs_ec, env._action))
     torch.cuda.synchronize(); t_pol = (time.perf_counter() - t0) / 200
     # CUDA graph: policy + step, 8 steps per replay
     env.reset()
@@ -34,12 +34,12 @@ for n in (4096, 65536):
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         for _ in range(3):
-            act.copy_(pol.forward_soa(b.obs_do, b.obs_ec)); env.step_soa(act)
+            pol.act_into(b.obs_do, b.obs_ec, act); env.step_soa(act)
     torch.cuda.current_stream().wait_stream(s)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(8):
-            act.copy_(pol.forward_soa(b.obs_do, b.obs_ec)); env.step_soa(act)
+            pol.act_into(b.obs_do, b.obs_ec, act); env.step_soa(act)
     env.reset()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(25):
