@@ -447,13 +447,23 @@ def rollout_leg(torch, tdist, device, rank, world, args):
         return ep, allr, float(t[0]), float(t[1]), float(t[2])
 
     ep_e, _, ms_eager, _, _ = timed_episode(lambda: rollout.collect_episode(env, policy))
-    ep, allr, ms_total, ms_gather, ms_local = timed_episode(lambda: rollout.collect_episode_graphed(env, big, small))
+    ep_g, _, ms_graph, _, _ = timed_episode(lambda: rollout.collect_episode_graphed(env, big, small))
+    # the fused rollout: 8 env.steps per launch with the policy head evaluated in-kernel between them (sbr_os_rollout_k);
+    # same arithmetic as the step-by-step loops above, bit for bit (tested), so the returns below are theirs too
+    rollout.collect_episode_fused(env, policy, K=8)              # warm-up
+    ep, allr, ms_total, ms_gather, ms_local = timed_episode(lambda: rollout.collect_episode_fused(env, policy, K=8))
     _, stats = rollout.gather_episode_returns(ep["returns"], total) if world == 1 else (None, rollout.return_stats(allr))
+    same = bool(torch.equal(ep["returns"], ep_g["returns"]))
     return {"total_envs": total, "envs_per_rank": hi - lo, "episode_steps": ep["steps"], "ms_episode": ms_total,
             "interval_steps_per_sec": total * ep["steps"] / (ms_total * 1e-3), "ms_reward_gather": ms_gather,
             "ms_episode_slowest_rank_before_gather": ms_local, "ms_episode_eager_loop": ms_eager,
-            "stepper": "CUDA graphs (8 and 1 [policy, env.step] iterations per replay)",
-            "gathered_returns": int(allr.numel()), "all_done": bool(ep["all_done"]) and bool(ep_e["all_done"]),
+            "ms_episode_cuda_graphs": ms_graph,
+            "stepper": "fused rollout kernel sbr_os_rollout_k (8 env.steps per launch, policy head in-kernel); "
+                       "ms_episode_cuda_graphs: [sbr_policy_mlp, sbr_os_step] per step captured in CUDA graphs; "
+                       "ms_episode_eager_loop: the same two launches per step from Python",
+            "fused_equals_stepwise_bitwise": same,
+            "gathered_returns": int(allr.numel()),
+            "all_done": bool(ep["all_done"]) and bool(ep_e["all_done"]) and bool(ep_g["all_done"]),
             "return_stats": stats,
             "scaling": "strong", "collective": "all_gather of per-env returns (%d B per rank)" % ((hi - lo) * 8)}
 

@@ -67,6 +67,11 @@ class SbrCntConfig(C.Structure):
                 ("u_ec_max", C.c_double), ("tm2_0", C.c_double), ("tm2_1", C.c_double), ("tm4_0", C.c_double)]
 
 
+class SbrPolicyMlp(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("w2", C.c_void_p), ("lo", C.c_void_p), ("span", C.c_void_p),
+                ("n_in", C.c_int32), ("hidden", C.c_int32), ("n_out", C.c_int32), ("reserved", C.c_int32)]
+
+
 # kinds of the sbr_cnt_* entry points (enum SBR_CNT_* of include/sbr_b200.h) and their persistent-state rows
 CNT_V0, CNT_V1, CNT_V2, CNT_MA1, CNT_OS2 = range(5)
 (CNT_T, CNT_U_DO, CNT_U_EC, CNT_SO_PREV, CNT_CV_LAST, CNT_CV_PREV, CNT_IE_DO, CNT_IE_EC, CNT_KLA_LAST, CNT_EC_LAST,
@@ -123,6 +128,9 @@ _PROTOS = {
     "sbr_permute_rows": (C.c_int, [C.c_int64, _P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), C.c_int, _P]),
+    "sbr_os_rollout_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int, _P, _P, C.POINTER(SbrPolicyMlp), C.POINTER(SbrParams),
+                                   C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int,
+                                   C.POINTER(SbrTol), _P]),
     "sbr_policy_mlp": (C.c_int, [C.c_int64, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),

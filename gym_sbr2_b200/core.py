@@ -223,6 +223,45 @@ def os_step(buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, stream=No
     return buf
 
 
+def os_rollout_k(buf, action, policy, rewards, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None,
+                 emit=("obs_do", "obs_ec"), act_log=None, obs_log=None):
+    """K = rewards.shape[0] consecutive env.steps in ONE launch with the policy head evaluated in-kernel between them
+    (sbr_os_rollout_k).  action [2,n] in/out: the set-points of the first step in, those of the step after the last one
+    out.  policy: an _abi.SbrPolicyMlp (18 -> hidden -> 2).  rewards [K,n] out.  act_log [K,2,n] / obs_log [K,18,n]:
+    optional per-step records for the learner."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    K = rewards.shape[0]
+    if rewards.shape != (K, n) or not rewards.is_contiguous():
+        raise ValueError("rewards must be contiguous [K, n]")
+    pst, l0 = _dev_ptr(buf.st, _abi.OS_ROWS, n, name="st")
+    pac, l1 = _dev_ptr(action, 2, n, name="action")
+    prw, l2 = _dev_ptr(rewards, K, n, name="rewards") if K > 1 else (C.c_void_p(rewards.data_ptr()), None)
+    pod, l3 = _dev_ptr(buf.obs_do if "obs_do" in emit else None, _abi.OS_NOBS, n, name="obs_do")
+    poe, l4 = _dev_ptr(buf.obs_ec if "obs_ec" in emit else None, _abi.OS_NOBS, n, name="obs_ec")
+    pse, l5 = _dev_ptr(buf.state if "state" in emit else None, _abi.OS_NSTATE, n, name="state")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l6 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    pal = pol = None
+    l7 = l8 = None
+    if act_log is not None:
+        if act_log.shape != (K, 2, n) or not act_log.is_contiguous():
+            raise ValueError("act_log must be contiguous [K, 2, n]")
+        pal, l7 = _dev_ptr(act_log.view(2 * K, n), 2 * K, n, name="act_log")
+    if obs_log is not None:
+        if obs_log.shape != (K, 2 * _abi.OS_NOBS, n) or not obs_log.is_contiguous():
+            raise ValueError("obs_log must be contiguous [K, 18, n]")
+        pol, l8 = _dev_ptr(obs_log.view(2 * _abi.OS_NOBS * K, n), 2 * _abi.OS_NOBS * K, n, name="obs_log")
+    ld = _same_ld([l0, l1, l2, l3 if pod else None, l4 if poe else None, l5 if pse else None, l6, l7, l8], "os_rollout_k")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_os_rollout_k(n, ld, K, pst, pac, C.byref(policy), C.byref(params), C.byref(sched), pod, poe, pse,
+                                  prw, pdn, pss, pct, pal, pol, int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_os_rollout_k")
+    return buf
+
+
 class V4Buffers(object):
     """Device buffers of the SBR-v4 path: persistent state + per-step outputs (allocated once)."""
 

@@ -294,6 +294,76 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const CUtensorMap* tm,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Policy head of the rollout path (BASELINE configs[4]: observations -> policy -> actions, every step): a two-layer
+// perceptron per env, action = lo + span * sigmoid(W2 tanh(W1 obs)), in ONE launch on the kernels' own SoA layout.
+// The torch expression of the same policy is nine launches that move ~1.3 GB per step at 2^20 envs -- as much time as
+// the env.step it feeds; this reads the 144 B of observation and writes the 16 B of action per env.  FP32 arithmetic
+// (the policy's dtype), weights broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPolMaxIn = 40, kPolMaxHidden = 64, kPolMaxOut = 4;
+struct PolicyArgs {
+    int64_t n, ld;
+    const double* obs_a;
+    const double* obs_b;      // may be NULL
+    const float* w1;          // [hidden][rows_a + rows_b]
+    const float* w2;          // [n_out][hidden]
+    const float* lo;          // [n_out]
+    const float* span;        // [n_out]
+    double* action;           // [n_out][ld]
+    int rows_a, rows_b, hidden, n_out;
+};
+
+// The perceptron itself, shared by the stand-alone kernel and the fused rollout (sbr_os_rollout_k) so that both produce
+// the same bits: explicit fmaf chains in input order, tanhf, 1 / (1 + expf(-y)).
+__device__ __forceinline__ void policy_eval(const float* s_w1, const float* s_w2, const float* lo, const float* span,
+                                            int n_in, int hidden, int n_out, const float (&x)[kPolMaxIn],
+                                            float (&out)[kPolMaxOut]) {
+    float y[kPolMaxOut] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int h = 0; h < hidden; ++h) {
+        const float* w = &s_w1[h * n_in];
+        float acc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kPolMaxIn; ++r)
+            if (r < n_in) acc = fmaf(w[r], x[r], acc);
+        const float t = tanhf(acc);
+#pragma unroll
+        for (int o = 0; o < kPolMaxOut; ++o)
+            if (o < n_out) y[o] = fmaf(s_w2[o * hidden + h], t, y[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < kPolMaxOut; ++o) {
+        out[o] = 0.0f;
+        if (o < n_out) {
+            const float sg = 1.0f / (1.0f + expf(-y[o]));
+            out[o] = fmaf(span[o], sg, lo[o]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) sbr_policy_mlp_kernel(PolicyArgs g) {
+    __shared__ float s_w1[kPolMaxHidden * kPolMaxIn];
+    __shared__ float s_w2[kPolMaxOut * kPolMaxHidden];
+    const int n_in = g.rows_a + g.rows_b;
+    for (int k = threadIdx.x; k < g.hidden * n_in; k += blockDim.x) s_w1[k] = g.w1[k];
+    for (int k = threadIdx.x; k < g.n_out * g.hidden; k += blockDim.x) s_w2[k] = g.w2[k];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    float x[kPolMaxIn];
+#pragma unroll
+    for (int r = 0; r < kPolMaxIn; ++r) {
+        if (r < g.rows_a) x[r] = (float)g.obs_a[(int64_t)r * g.ld + i];
+        else if (r < n_in) x[r] = (float)g.obs_b[(int64_t)(r - g.rows_a) * g.ld + i];
+        else x[r] = 0.0f;
+    }
+    float out[kPolMaxOut];
+    policy_eval(s_w1, s_w2, g.lo, g.span, n_in, g.hidden, g.n_out, x, out);
+#pragma unroll
+    for (int o = 0; o < kPolMaxOut; ++o)
+        if (o < g.n_out) g.action[(int64_t)o * g.ld + i] = (double)out[o];
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // sbr_os_step / sbr_os_step_k: persistent warps, one tile of 32 consecutive envs at a time.
 //
 // One env.step is ~1.5 k FP64 instructions on ~0.65 kB of state: arithmetic intensity sits at the ridge, and with
@@ -310,7 +380,7 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const CUtensorMap* tm,
 struct OsStepArgs {
     int64_t n, ld, num_tiles;
     double* st;
-    const double* action;     // [K][2][ld]
+    double* action;           // [K][2][ld] in; fused rollout: [2][ld] in/out
     double* obs_do;           // may be NULL
     double* obs_ec;           // may be NULL
     double* state;            // may be NULL
@@ -320,6 +390,14 @@ struct OsStepArgs {
     uint32_t* counters;       // may be NULL
     double* traj;             // may be NULL: [traj_cap][SBR_TRAJ_ROWS][ld]
     int K, tma, traj_cap;
+    // fused rollout (sbr_os_rollout_k): the policy head evaluated in-kernel between the K steps (NULL = off)
+    const float* pol_w1;      // [hidden][18]
+    const float* pol_w2;      // [2][hidden]
+    const float* pol_lo;      // [2]
+    const float* pol_span;    // [2]
+    int pol_hidden;
+    double* act_log;          // may be NULL: [K][2][ld] the set-points each step ran with
+    double* obs_log;          // may be NULL: [K][18][ld] the observation after each step
 };
 
 constexpr int kOsTile = 32;                        // envs per tile = one warp
@@ -335,7 +413,14 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
     __shared__ __align__(128) double s_stage[kOsWarps][2][kOsStageRows * kOsTile];
     __shared__ __align__(128) uint8_t s_done[kOsWarps][2][128];
     __shared__ __align__(8) uint64_t s_bar[kOsWarps][2];
+    __shared__ float s_pw1[kPolMaxHidden * 2 * SBR_OS_NOBS];
+    __shared__ float s_pw2[2 * kPolMaxHidden];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (g.pol_w1) {
+        for (int k = threadIdx.x; k < g.pol_hidden * 2 * SBR_OS_NOBS; k += kOsBlock) s_pw1[k] = g.pol_w1[k];
+        for (int k = threadIdx.x; k < 2 * g.pol_hidden; k += kOsBlock) s_pw2[k] = g.pol_w2[k];
+        __syncthreads();
+    }
     if (lane == 0) {
         mbar_init(&s_bar[warp][0], 1);
         mbar_init(&s_bar[warp][1], 1);
@@ -404,7 +489,8 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
             double qw = NAN;
             const sbr::Column od{g.obs_do ? g.obs_do + i : nullptr, g.ld}, oe{g.obs_ec ? g.obs_ec + i : nullptr, g.ld},
                 os{g.state ? g.state + i : nullptr, g.ld};
-            if (g.K > 1) {
+            double a_do = 0.0, a_ec = 0.0;
+            if (g.K > 1 && !g.pol_w1) {
                 for (int k = 1; k < g.K; ++k) {
                     prefetch_l2(g.action + (int64_t)(2 * k) * g.ld + i);
                     prefetch_l2(g.action + (int64_t)(2 * k + 1) * g.ld + i);
@@ -417,8 +503,9 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
                     g.reward[(int64_t)k * g.ld + i] = 0.0;
                     continue;
                 }
-                const double a_do = k == 0 ? sg[kOsRowAct * kOsTile] : g.action[(int64_t)(2 * k) * g.ld + i];
-                const double a_ec = k == 0 ? sg[(kOsRowAct + 1) * kOsTile] : g.action[(int64_t)(2 * k + 1) * g.ld + i];
+                if (k == 0) { a_do = sg[kOsRowAct * kOsTile]; a_ec = sg[(kOsRowAct + 1) * kOsTile]; }
+                else if (!g.pol_w1) { a_do = g.action[(int64_t)(2 * k) * g.ld + i]; a_ec = g.action[(int64_t)(2 * k + 1) * g.ld + i]; }
+                if (g.act_log) { g.act_log[(int64_t)(2 * k) * g.ld + i] = a_do; g.act_log[(int64_t)(2 * k + 1) * g.ld + i] = a_ec; }
                 sbr::OsStepOut o;
                 sbr::os_step_env<MODE>(x, ctl, ring, a_do, a_ec, p, c, s, tol, dp, o,
                                        sbr::OsTraj{g.traj ? g.traj + i : nullptr, g.ld, g.traj_cap});
@@ -431,7 +518,26 @@ __global__ void __launch_bounds__(kOsBlock, os_step_minblocks(MODE)) sbr_os_step
                 if (o.done) { is_done = true; qw = o.Qw; }
                 // the observation of the last step that ran (the terminal one if the episode ends inside the launch)
                 if (k == g.K - 1 || o.done) sbr::os_emit_obs(ctl.t, x, o.first, od, oe, os);
+                if (g.pol_w1) {
+                    // fused rollout: the set-points of the NEXT step from this step's observation, evaluated on the
+                    // registers that hold the state (same arithmetic as os_emit_obs -> sbr_policy_mlp, hence same bits)
+                    double ob[2 * SBR_OS_NOBS];
+                    sbr::os_emit_obs(ctl.t, x, o.first, sbr::Column{ob, 1}, sbr::Column{ob + SBR_OS_NOBS, 1},
+                                     sbr::Column{nullptr, 1});
+                    if (g.obs_log) {
+#pragma unroll
+                        for (int r = 0; r < 2 * SBR_OS_NOBS; ++r)
+                            g.obs_log[((int64_t)k * 2 * SBR_OS_NOBS + r) * g.ld + i] = ob[r];
+                    }
+                    float xin[kPolMaxIn], act[kPolMaxOut];
+#pragma unroll
+                    for (int r = 0; r < kPolMaxIn; ++r) xin[r] = r < 2 * SBR_OS_NOBS ? (float)ob[r] : 0.0f;
+                    policy_eval(s_pw1, s_pw2, g.pol_lo, g.pol_span, 2 * SBR_OS_NOBS, g.pol_hidden, 2, xin, act);
+                    a_do = (double)act[0]; a_ec = (double)act[1];
+                }
             }
+            // fused rollout: the first step of the next launch finds its set-points where this launch found its own
+            if (g.pol_w1 && !was_done) { g.action[i] = a_do; g.action[g.ld + i] = a_ec; }
             if (was_done) {
                 sbr::os_emit_obs(ctl.t, x, sbr::obs_ref(x), od, oe, os);
             } else {
@@ -704,62 +810,6 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_cnt_step_
     g.reward[i] = o.reward;
     if (g.status) g.status[i] = o.status;
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Policy head of the rollout path (BASELINE configs[4]: observations -> policy -> actions, every step): a two-layer
-// perceptron per env, action = lo + span * sigmoid(W2 tanh(W1 obs)), in ONE launch on the kernels' own SoA layout.
-// The torch expression of the same policy is nine launches that move ~1.3 GB per step at 2^20 envs -- as much time as
-// the env.step it feeds; this reads the 144 B of observation and writes the 16 B of action per env.  FP32 arithmetic
-// (the policy's dtype), weights broadcast from shared memory.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kPolMaxIn = 40, kPolMaxHidden = 64, kPolMaxOut = 4;
-struct PolicyArgs {
-    int64_t n, ld;
-    const double* obs_a;
-    const double* obs_b;      // may be NULL
-    const float* w1;          // [hidden][rows_a + rows_b]
-    const float* w2;          // [n_out][hidden]
-    const float* lo;          // [n_out]
-    const float* span;        // [n_out]
-    double* action;           // [n_out][ld]
-    int rows_a, rows_b, hidden, n_out;
-};
-
-__global__ void __launch_bounds__(128) sbr_policy_mlp_kernel(PolicyArgs g) {
-    __shared__ float s_w1[kPolMaxHidden * kPolMaxIn];
-    __shared__ float s_w2[kPolMaxOut * kPolMaxHidden];
-    const int n_in = g.rows_a + g.rows_b;
-    for (int k = threadIdx.x; k < g.hidden * n_in; k += blockDim.x) s_w1[k] = g.w1[k];
-    for (int k = threadIdx.x; k < g.n_out * g.hidden; k += blockDim.x) s_w2[k] = g.w2[k];
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n) return;
-    float x[kPolMaxIn];
-#pragma unroll
-    for (int r = 0; r < kPolMaxIn; ++r) {
-        if (r < g.rows_a) x[r] = (float)g.obs_a[(int64_t)r * g.ld + i];
-        else if (r < n_in) x[r] = (float)g.obs_b[(int64_t)(r - g.rows_a) * g.ld + i];
-        else x[r] = 0.0f;
-    }
-    float y[kPolMaxOut] = {0.0f, 0.0f, 0.0f, 0.0f};
-    for (int h = 0; h < g.hidden; ++h) {
-        const float* w = &s_w1[h * n_in];
-        float acc = 0.0f;
-#pragma unroll
-        for (int r = 0; r < kPolMaxIn; ++r)
-            if (r < n_in) acc = fmaf(w[r], x[r], acc);
-        const float t = tanhf(acc);
-#pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o)
-            if (o < g.n_out) y[o] = fmaf(s_w2[o * g.hidden + h], t, y[o]);
-    }
-#pragma unroll
-    for (int o = 0; o < kPolMaxOut; ++o)
-        if (o < g.n_out) {
-            const float sg = 1.0f / (1.0f + expf(-y[o]));
-            g.action[(int64_t)o * g.ld + i] = (double)fmaf(g.span[o], sg, g.lo[o]);
-        }
 }
 
 // Influent mixing (buffer_tank3.py:50-107): one env per thread, tables staged in shared memory, 13 running sums in
@@ -1167,22 +1217,34 @@ int sbr_os_step_k(int64_t n, int64_t ld, int K, double* st, const double* action
                             nullptr, 0, stream);
 }
 
-int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
-                     const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
-                     uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
-                     double* traj, int traj_cap, void* stream) {
+namespace {
+struct OsPolicy {
+    const float* w1; const float* w2; const float* lo; const float* span; int hidden;
+    double* act_log; double* obs_log;
+};
+
+int os_step_launch(const char* what, int64_t n, int64_t ld, int K, double* st, double* action, const SbrParams* p,
+                   const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                   uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
+                   double* traj, int traj_cap, const OsPolicy* pol, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
-    if (K < 1 || K > 4096) return fail(SBR_ERR_ARG, "sbr_os_step_k: K must be in 1..4096%s");
-    if (!st || !action || !reward || !done) return fail(SBR_ERR_ARG, "sbr_os_step: NULL buffer%s");
-    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_os_step: bad mode%s");
+    if (K < 1 || K > 4096) return fail(SBR_ERR_ARG, "%s: K must be in 1..4096", what);
+    if (!st || !action || !reward || !done) return fail(SBR_ERR_ARG, "%s: NULL buffer", what);
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "%s: bad mode", what);
     OsStepArgs g;
     g.n = n; g.ld = ld; g.num_tiles = (n + kOsTile - 1) / kOsTile;
     g.st = st; g.action = action; g.obs_do = obs_do; g.obs_ec = obs_ec; g.state = state; g.reward = reward;
     g.done = done; g.status = status; g.counters = counters; g.K = K;
-    if (traj && traj_cap < 1) return fail(SBR_ERR_ARG, "sbr_os_step_traj: traj_cap must be positive%s");
+    if (traj && traj_cap < 1) return fail(SBR_ERR_ARG, "%s: traj_cap must be positive", what);
     g.traj = traj; g.traj_cap = traj ? traj_cap : 0;
+    g.pol_w1 = nullptr; g.pol_w2 = nullptr; g.pol_lo = nullptr; g.pol_span = nullptr; g.pol_hidden = 0;
+    g.act_log = nullptr; g.obs_log = nullptr;
+    if (pol) {
+        g.pol_w1 = pol->w1; g.pol_w2 = pol->w2; g.pol_lo = pol->lo; g.pol_span = pol->span; g.pol_hidden = pol->hidden;
+        g.act_log = pol->act_log; g.obs_log = pol->obs_log;
+    }
     // TMA needs 16-byte aligned bases and row pitches (and 32-bit coordinates); anything else takes the plain-load fill
     CUtensorMap tm_st, tm_act, tm_done;
     memset(&tm_st, 0, sizeof(tm_st)); memset(&tm_act, 0, sizeof(tm_act)); memset(&tm_done, 0, sizeof(tm_done));
@@ -1201,7 +1263,29 @@ int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* act
     else
         sbr_os_step_kernel<SBR_MODE_DP45><<<os_step_grid<SBR_MODE_DP45>(g.num_tiles), kOsBlock, 0, cs>>>(
             g, *p, c, *s, t, tm_st, tm_act, tm_done);
-    return check_launch("sbr_os_step");
+    return check_launch(what);
+}
+}  // namespace
+
+int sbr_os_step_traj(int64_t n, int64_t ld, int K, double* st, const double* action, const SbrParams* p,
+                     const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state, double* reward,
+                     uint8_t* done, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
+                     double* traj, int traj_cap, void* stream) {
+    return os_step_launch("sbr_os_step", n, ld, K, st, const_cast<double*>(action), p, s, obs_do, obs_ec, state, reward,
+                          done, status, counters, mode, tol, traj, traj_cap, nullptr, stream);
+}
+
+int sbr_os_rollout_k(int64_t n, int64_t ld, int K, double* st, double* action, const SbrPolicyMlp* policy,
+                     const SbrParams* p, const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state,
+                     double* reward, uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log,
+                     int mode, const SbrTol* tol, void* stream) {
+    if (!policy || !policy->w1 || !policy->w2 || !policy->lo || !policy->span)
+        return fail(SBR_ERR_ARG, "sbr_os_rollout_k: NULL policy%s");
+    if (policy->n_in != 2 * SBR_OS_NOBS || policy->n_out != 2 || policy->hidden < 1 || policy->hidden > kPolMaxHidden)
+        return fail(SBR_ERR_ARG, "sbr_os_rollout_k: the policy must map 18 observations to 2 set-points (hidden <= 64)%s");
+    const OsPolicy pol{policy->w1, policy->w2, policy->lo, policy->span, policy->hidden, act_log, obs_log};
+    return os_step_launch("sbr_os_rollout_k", n, ld, K, st, action, p, s, obs_do, obs_ec, state, reward, done, status,
+                          counters, mode, tol, nullptr, 0, &pol, stream);
 }
 
 int sbr_os_step(int64_t n, int64_t ld, double* st, const double* action, const SbrParams* p,

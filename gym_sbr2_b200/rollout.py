@@ -36,6 +36,12 @@ class TinyPolicy(torch.nn.Module):
         """obs_do, obs_ec: [9, N] float64 -> action [2, N] float64, ONE launch (sbr_policy_mlp)."""
         return core.policy_mlp(obs_do, obs_ec, self.w1t, self.w2t, self.lo_flat, self.span_flat, action)
 
+    def as_struct(self):
+        """The weights as the C ABI's SbrPolicyMlp (for the fused rollout, sbr_os_rollout_k)."""
+        from . import _abi
+        return _abi.SbrPolicyMlp(self.w1t.data_ptr(), self.w2t.data_ptr(), self.lo_flat.data_ptr(),
+                                 self.span_flat.data_ptr(), 18, self.w1t.shape[0], 2, 0)
+
     def forward_soa(self, obs_do, obs_ec):
         """obs_do, obs_ec: [9, N] float64 -> action [2, N] float64 (a fresh tensor)."""
         out = torch.empty((2, obs_do.shape[1]), dtype=torch.float64, device=obs_do.device)
@@ -118,6 +124,38 @@ def collect_episode_graphed(env, big, small):
     from . import _abi
     b = env.buf
     return dict(returns=b.st[_abi.OS_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status)
+
+
+@torch.no_grad()
+def collect_episode_fused(env, policy, K=8, store=False):
+    """One whole SBROS-v1 episode through the FUSED rollout kernel (sbr_os_rollout_k): K env.steps per launch with the
+    policy evaluated in-kernel between them -- observations stay on the SM, one launch moves the state once per K steps.
+    Bit-identical to collect_episode (same step and policy arithmetic).  store=True also returns the [T,N] rewards and
+    the per-step set-points / observations a PPO update consumes (written as streams by the kernel)."""
+    from . import _abi
+    env.reset()
+    b = env.buf
+    n = env.num_envs
+    steps = env.max_episode_steps
+    pol = policy.as_struct()
+    action = env._action
+    policy.act_into(b.obs_do, b.obs_ec, action)                       # the first step's set-points, from the reset observation
+    nl = (steps + K - 1) // K
+    rewards = torch.zeros((nl * K, n), dtype=torch.float64, device=env.device)
+    acts = torch.empty((nl * K, 2, n), dtype=torch.float64, device=env.device) if store else None
+    obs = torch.empty((nl * K, 18, n), dtype=torch.float64, device=env.device) if store else None
+    env._lockstep = False
+    done_steps = 0
+    for j in range(nl):
+        k = min(K, steps - done_steps)
+        sl = slice(j * K, j * K + k)
+        core.os_rollout_k(b, action, pol, rewards[sl], env.params, env.sched, mode=env.mode, tol=env.tol,
+                          emit=env.emit, act_log=None if acts is None else acts[sl],
+                          obs_log=None if obs is None else obs[sl])
+        done_steps += k
+    return dict(returns=b.st[_abi.OS_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status,
+                rewards=rewards[:steps] if store else None, actions=None if acts is None else acts[:steps],
+                observations=None if obs is None else obs[:steps])
 
 
 def return_stats(allr):

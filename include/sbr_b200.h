@@ -446,6 +446,30 @@ int sbr_policy_mlp(int64_t n, int64_t ld, const double* obs_a, int rows_a, const
                    const float* w1, const float* w2, const float* lo, const float* span, int hidden, int n_out,
                    double* action, void* stream);
 
+/*
+ * Fused rollout of the interval-per-step path: K consecutive env.steps in ONE launch with the policy head evaluated
+ * in-kernel between them, on the registers that hold the state -- the observation never leaves the SM.  No reference
+ * counterpart (the reference steps one env under a Python agent); it is sbr_os_step_k + sbr_policy_mlp called K times,
+ * bit for bit, at the memory traffic of one step per K.
+ *   action [2][ld] IN/OUT: in = the set-points of the launch's first step (after a reset: sbr_policy_mlp on the reset
+ *          observation); out = the set-points of the step after the launch's last one, so consecutive launches chain
+ *   policy: the two-layer perceptron of sbr_policy_mlp on obs = [obs_DO (9), obs_EC (9)] -> [DO set-point, NO3 set-point]
+ *   reward [K][ld] out; obs_do / obs_ec / state: observation after the last step that ran (each may be NULL)
+ *   act_log [K][2][ld] (may be NULL): the set-points step k ran with; obs_log [K][18][ld] (may be NULL): the
+ *          observation after step k -- what a PPO update consumes.  Both are write-only streams.
+ */
+typedef struct SbrPolicyMlp {
+    const float* w1;          /* device [hidden][n_in]  */
+    const float* w2;          /* device [n_out][hidden] */
+    const float* lo;          /* device [n_out]         */
+    const float* span;        /* device [n_out]         */
+    int32_t n_in, hidden, n_out, reserved;
+} SbrPolicyMlp;
+int sbr_os_rollout_k(int64_t n, int64_t ld, int K, double* st, double* action, const SbrPolicyMlp* policy,
+                     const SbrParams* p, const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state,
+                     double* reward, uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log,
+                     int mode, const SbrTol* tol, void* stream);
+
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the
  * envs whose status is 0 (all envs if status == NULL).  stats must be zero-initialised by the caller with

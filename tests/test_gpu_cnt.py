@@ -90,10 +90,11 @@ def test_vec_env_episode_api(built, cuda_device, kind):
             a = torch.stack([1.0 + 2.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g),
                              torch.zeros(n, dtype=torch.float64, device=cuda_device)], dim=1)
         else:
-            a = torch.full((n, 1), 0.05 if kind == "cnt0" else 0.25, dtype=torch.float64, device=cuda_device)
-            if k >= 8:
-                a.zero_()
-            if kind in ("ma1", "cnt2") and k < 2:
+            # raise the DO set-point to 2 g/m3 over the first 8 aerobic steps, hold it otherwise
+            up = range(60, 68) if kind == "ma1" else range(1, 9)
+            a = torch.full((n, 1), (0.05 if kind == "cnt0" else 0.25) if k in up else 0.0, dtype=torch.float64,
+                           device=cuda_device)
+            if kind in ("ma1", "cnt2") and k == 0:
                 a.fill_(-2.0)                    # carbon set-point to 0 before the controller can run away
         out = env.step(a)
         done, info = out[-2], out[-1]

@@ -150,3 +150,28 @@ def test_fused_policy_kernel_matches_torch_fp32_reference(built, cuda_device):
     # argument errors surface as exceptions, not as a silent fallback
     with pytest.raises(Exception):
         core.policy_mlp(obs_do, obs_ec, policy.w1t.double(), policy.w2t, policy.lo_flat, policy.span_flat, out)
+
+
+@pytest.mark.parametrize("K", [8, 5])
+def test_fused_rollout_matches_stepwise_rollout(built, cuda_device, K):
+    """sbr_os_rollout_k (K steps per launch, policy evaluated in-kernel on the registers that hold the state) against
+    the step-by-step rollout [sbr_policy_mlp, sbr_os_step]: returns, final state, per-step rewards, set-points and
+    observations are bit-identical."""
+    n = 300                                                      # ragged tiles, odd number of launches for K = 5
+    policy = rollout.TinyPolicy(cuda_device)
+    env_e = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45")
+    eager = rollout.collect_episode(env_e, policy, store=True)
+    env_f = SbrOsVecEnv(n, device=cuda_device, seed=5, mode="dp45")
+    fused = rollout.collect_episode_fused(env_f, policy, K=K, store=True)
+    assert bool(fused["all_done"]) and fused["steps"] == 463
+    assert torch.equal(fused["returns"], eager["returns"])
+    assert torch.equal(fused["rewards"], eager["rewards"])
+    assert torch.equal(torch.nan_to_num(env_f.buf.st), torch.nan_to_num(env_e.buf.st))
+    assert torch.equal(env_f.buf.obs_do, env_e.buf.obs_do) and torch.equal(env_f.buf.obs_ec, env_e.buf.obs_ec)
+    # the logged set-points are what the stand-alone policy kernel computes from the logged observations
+    acts, obs = fused["actions"], fused["observations"]
+    chk = torch.empty((2, n), dtype=torch.float64, device=cuda_device)
+    for k in (0, 17, 200, 461):
+        policy.act_into(obs[k, :9].contiguous(), obs[k, 9:].contiguous(), chk)
+        assert torch.equal(chk, acts[k + 1]), k
+    assert int(fused["status"].max()) == 0
