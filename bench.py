@@ -329,8 +329,8 @@ def v4_path_leg(torch, device, args):
     gen = torch.Generator(device=device).manual_seed(6)
     acts = [0.2 * torch.randn(n, dtype=torch.float64, device=device, generator=gen) + 0.02 for _ in range(8)]
     env.reset()
-    for k in range(3):
-        env.step_async(acts[k])
+    for k in range(10):                      # through the first re-sort of the state slots (step 8): its one-time
+        env.step_async(acts[k % 8])          # set-up (argsort workspace, the second state buffer) is not episode time
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(495)]
     ev[0].record()
@@ -431,6 +431,7 @@ def rollout_leg(torch, tdist, device, rank, world, args):
         if world > 1:
             tdist.barrier()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        env.epoch.zero_()                                        # every timed episode replays the SAME influent draws
         e0.record()
         ep = collect()
         e1.record()

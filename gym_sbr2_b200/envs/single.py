@@ -165,6 +165,26 @@ class _CntEnv(_Base):
         self._vec = SbrCntVecEnv(self.kind, 1, device=_device(device), mode=mode, rtol=rtol, atol=atol)
         self.influent_mixed = None
         self.reward = 0
+        self._log = dict(t=[], x=[], u_do=[], u_ec=[], state=[], ec=[])
+
+    def _record(self, state=None):
+        st = self._vec.buf.st[:, 0].cpu().numpy()
+        L = self._log
+        L["t"].append(float(st[14])); L["x"].append(st[:14].copy()); L["u_do"].append(float(st[15]))
+        L["u_ec"].append(float(st[16])); L["ec"].append(float(st[23]))
+        if state is not None:
+            L["state"].append(np.asarray(state, dtype=np.float64).reshape(-1))
+
+    def trajectory(self):
+        """What the reference's trajectory() hands a plotting script (gym_SBR_continuous1.py:423-436: t_t, x_t, u_t,
+        state_t, So_t; the carbon-controller envs add u_EC_t, Ss_t, (Sno_t,) EC: gym_SBR_continuous2.py:483-496,
+        gym_SBR_continuous_MA1.py:506-519), sampled at the END of every step() (the reference also lists the 8-9
+        interior output points of every control interval), starting with the state after the fill phase.  Returns a dict
+        with the reference's names: t_t, x_t [T,14], u_DO_t (`u_t` of SbrCnt1), u_EC_t, state_t, So_t, Ss_t, Sno_t, EC."""
+        L = self._log
+        x = np.array(L["x"]) if L["x"] else np.zeros((0, 14))
+        return dict(t_t=list(L["t"]), x_t=x, u_DO_t=list(L["u_do"]), u_EC_t=list(L["u_ec"]), state_t=list(L["state"]),
+                    So_t=x[:, 8].tolist(), Ss_t=x[:, 2].tolist(), Sno_t=x[:, 9].tolist(), EC=list(L["ec"]))
 
     def _shape_obs(self, obs):
         return obs[0].cpu().numpy()
@@ -172,7 +192,10 @@ class _CntEnv(_Base):
     def reset(self):
         self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)         # buffer_tank(0) in all five files
         obs = self._vec.reset(influent=torch.as_tensor(self.influent_mixed, dtype=torch.float64)[:, None])
-        return self._shape_reset(obs)
+        self._log = dict(t=[], x=[], u_do=[], u_ec=[], state=[], ec=[])
+        out = self._shape_reset(obs)
+        self._record(None if self.kind == "os2" else out)
+        return out
 
     def _shape_reset(self, obs):
         return self._shape_obs(obs)
@@ -183,7 +206,9 @@ class _CntEnv(_Base):
         a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1))
         obs, reward, done, info = self._vec.step(a)
         self.reward = float(reward[0])
-        return self._shape_obs(obs), self.reward, bool(done[0]), {}
+        out = self._shape_obs(obs)
+        self._record(out)
+        return out, self.reward, bool(done[0]), {}
 
     def render(self, mode="human", close=False):
         print("Reward for this step: {}".format(self.reward))
@@ -247,7 +272,9 @@ class SbrOS1(_CntEnv):
         (obs_do, obs_ec), state, reward, done, info = self._vec.step(a)
         self.reward = float(reward[0])
         obs = (obs_do[0].cpu().numpy().tolist(), obs_ec[0].cpu().numpy().tolist())
-        return obs, state[0].cpu().numpy(), self.reward, bool(done[0]), {}
+        state = state[0].cpu().numpy()
+        self._record(state)
+        return obs, state, self.reward, bool(done[0]), {}
 
     def get_available_actions(self, pre_action, n_agents, n_action):
         """Action masks of the discrete multi-agent wrapper (gym_SBR_oneshot1.py:434-454)."""

@@ -169,3 +169,10 @@ def test_cnt_family_episode_through_make(built, cuda_device, env_id, kind, name)
         if done:
             break
     assert k == int(g["n_steps"])
+    # trajectory(): one record after the fill phase and one per step(), at the states the next step continues from
+    tr = env.trajectory()
+    assert len(tr["t_t"]) == k + 1 and tr["x_t"].shape == (k + 1, 14) and len(tr["state_t"]) >= k
+    from gym_sbr2_b200 import parity
+    assert parity.state_close(tr["x_t"][0], g["x_fill"], atol_frac=1e-7)[0]
+    assert parity.state_close(tr["x_t"][k // 2], g["x_cont"][k // 2 - 1], atol_frac=1e-7)[0]
+    assert abs(tr["u_DO_t"][k // 2] - g["u_do"][k // 2 - 1]) < 1e-12
