@@ -356,6 +356,55 @@ def v4_path_leg(torch, device, args):
             "gpu_launches": 494, "mean_episode_return": float(env.buf.st[_abi.V4_RETURN].mean())}
 
 
+def cnt_family_leg(torch, device, args):
+    """SBRCnt-v0/1/2, SBRCntMA-v1, SBROS-v2: one whole episode of each at --interval-envs envs (reset + every env.step),
+    per-env DO set-points ramped to U(1, 3) g/m3 in the first aerobic steps, carbon set-point held at 0."""
+    from gym_sbr2_b200 import _abi
+    from gym_sbr2_b200.cnt import SbrCntVecEnv
+    n = args.interval_envs
+    out = {}
+    for kind in ("cnt0", "cnt1", "cnt2", "ma1", "os2"):
+        env = SbrCntVecEnv(kind, n, device=device, seed=77)
+        gen = torch.Generator(device=device).manual_seed(8)
+        target = 1.0 + 2.0 * torch.rand(n, dtype=torch.float64, device=device, generator=gen)
+        zero = torch.zeros(n, dtype=torch.float64, device=device)
+        steps = env.max_episode_steps
+        up = range(60, 64) if kind == "ma1" else range(1, 5)
+
+        def action(k):
+            if kind == "os2":
+                return torch.stack([target, zero], dim=1)
+            if k == 0 and kind in ("cnt2", "ma1"):
+                return zero - 2.0                       # carbon set-point 2 -> 0 before its controller can run away
+            return target / 4 if k in up else zero
+
+        acts = [action(k) for k in range(min(steps, 70))]
+        env.reset()
+        for k in range(3):
+            env.step_async(acts[k])
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
+        ev[0].record()
+        env.reset()
+        for k in range(steps):
+            ev[k + 1].record()
+            env.step_async(acts[k] if k < len(acts) else acts[-1])
+        ev[steps + 1].record()
+        torch.cuda.synchronize()
+        per = sorted(ev[k + 1].elapsed_time(ev[k + 2]) for k in range(steps // 2, steps - 1))
+        ms = ev[0].elapsed_time(ev[steps + 1])
+        b = env.buf
+        out[kind] = {"id": {"cnt0": "SBRCnt-v0", "cnt1": "SBRCnt-v1", "cnt2": "SBRCnt-v2", "ma1": "SBRCntMA-v1",
+                            "os2": "SBROS-v2"}[kind], "envs": n, "episode_steps": steps, "ms_per_episode": ms,
+                     "env_steps_per_sec": n * steps / (ms * 1e-3), "ms_per_step_median_second_half": per[len(per) // 2],
+                     "all_done": bool(b.done.all()), "bad_status": int((b.status != 0).sum()),
+                     "max_volume_m3": float(b.st[0].max()), "gpu_launches": steps + 1}
+    out["note"] = ("cnt1 / cnt2 episodes are 228 env.steps because two steps each simulate a whole anoxic phase (46 / 171 "
+                   "control intervals in one solve); reward = the reference's threshold table with its unbound names bound "
+                   "as oracle/make_golden_cnt.py documents")
+    return out
+
+
 def small_batch_leg(torch, device, n=4096):
     """BASELINE config[1] size (4096 envs): one env.step is ~10 us of GPU work, so the Python loop and launches
     dominate; reports the per-step WALL time of policy + step eagerly and through a CUDA graph (8 steps per replay),
@@ -873,6 +922,7 @@ def main():
         if args.mode == "dp45":
             paths["headline_accuracy"] = leg(headline_accuracy_leg, torch, device, core, env, n)
         paths["sbr_v4"] = leg(v4_path_leg, torch, device, args)
+        paths["sbr_cnt_family"] = leg(cnt_family_leg, torch, device, args)
         paths["config1_small_batch"] = leg(small_batch_leg, torch, device)
     if not args.no_rollout:
         paths["headline_strong_scaling"] = (leg(headline_strong_leg, torch, tdist, device, rank, world, args, core, peak)
