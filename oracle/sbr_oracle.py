@@ -692,3 +692,235 @@ class SbrEnv4Oracle(object):
         reward = reward_v4(self.Kla, bt, QIN, self.Qw, self.eff)
         done = (bt == 2) and (self.t >= T_CYCLE)
         return self.x / X1_V4, reward, done
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SBRCnt-v0/1/2, SBRCntMA-v1, SBROS-v2: gym_SBR_continuous0/1/2.py, gym_SBR_continuous_MA1.py,
+# gym_SBR_oneshot1.py.  Pinned by tests/test_oracle_golden_cnt.py to episodes of the unmodified env modules run with the
+# repaired reward (oracle/make_golden_cnt.py holds the disclosure).
+# ----------------------------------------------------------------------------------------------------------
+def batch_time_stamps(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=OS_T_DELTA):
+    """module_batch_time.batch_time (module_batch_time.py:3-116): the full stamp list t_memoryK of each phase."""
+    out = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + t_delta
+        t_end = t_start + t_cycle * t_ratio[k]
+        t_save = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+        mem = [t_save[0]]
+        for i in range(len(t_save) - 1):
+            t_range = np.linspace(t_save[i], t_save[i + 1], int((t_save[i + 1] - t_save[i]) / t_delta))
+            mem.extend(t_range[1:])
+        out.append([float(v) for v in mem])
+    return out
+
+
+CNT_KIND = {
+    # DO PID (Kc, tauI, tauD); carbon PID (Kc, tauI, tauD); EC_conc; carbon set-point clip; controlled variable index
+    "cnt0": dict(do=(10, 0.5, 0.00005), ec=None),                                           # gym_SBR_continuous0.py:80-82
+    "cnt1": dict(do=(100, 20, 0), ec=None),                                                 # gym_SBR_continuous1.py:77-79
+    "cnt2": dict(do=(100, 20, 0), ec=(1, 20, 0), conc=400000 / 20648.38 * 1.32, u_ec_max=5, cv=2),   # ..2.py:81-94
+    "ma1": dict(do=(100, 20, 0), ec=(10, 0.5, 0), conc=4000 / 20648.38 * 1.32, u_ec_max=15, cv=9),   # .._MA1.py:80-93
+    "os2": dict(do=(100, 20, 0), ec=(1, 20, 0), conc=400000 / 20648.38 * 1.32, u_ec_max=15, cv=9),   # gym_SBR_oneshot1.py:82-95
+}
+
+
+def reward_cnt(x_out, done, eff):
+    """module_reward_continuous1.sbr_reward (module_reward_continuous1.py:5-65) with its three unbound names bound as
+    oracle/make_golden_cnt.py documents."""
+    so = x_out[8]
+    if done:
+        return 0 if np.isscalar(eff) else (0 if eff[3] < 4 else -246)
+    if so < 1.5:
+        return -100
+    if 2.5 < so < 3.5:
+        return 0
+    if 3.5 <= so < 5:
+        return -10
+    if 5 <= so:
+        return -50
+    return 10
+
+
+class SbrCntOracle(object):
+    """Restatement of SbrCnt0 / SbrCnt1 / SbrCnt2 / SbrCntMA1 / SbrOS1 with explicit per-env state instead of module
+    globals.  reset(influent_mixed) -> obs; step(action) -> (obs, reward, done), for "os2" ((obs_DO, obs_EC), state,
+    reward, done)."""
+
+    def __init__(self, kind, ode_kw=None):
+        self.kind, self.K = kind, CNT_KIND[kind]
+        self.ode_kw = ode_kw or {}
+        self.tm = batch_time_stamps()
+
+    # -- controllers (Sim_rxn of every file; e.g. gym_SBR_continuous2.py:900-965) ------------------------------------
+    def _pid_do(self, sp, t_start, Kla):
+        Kc, tauI, tauD = self.K["do"]
+        self.e_DO.append(sp - self.So[-1])
+        if t_start > 0:
+            self.dcv_DO.append((self.So[-1] - self.So[-2]) / OS_DT)
+            self.ie_DO.append(self.ie_DO[-1] + self.e_DO[-1] * OS_DT)
+        else:
+            self.dcv_DO.append(0)
+            self.ie_DO.append(0)
+        Kla.append(Kc * self.e_DO[-1] + Kc / tauI * self.ie_DO[-1] + Kc * tauD * self.dcv_DO[-1] + Kla[-1])
+        if Kla[-1] > 240:
+            Kla[-1] = 240
+            self.ie_DO[-1] = self.ie_DO[-1] - self.e_DO[-1] * OS_DT
+        if Kla[-1] < 0:
+            Kla[-1] = 0
+            self.ie_DO[-1] = self.ie_DO[-1] - self.e_DO[-1] * OS_DT
+        return Kla[-1]
+
+    def _pid_ec(self, sp, t_start, fill):
+        Kc, tauI, tauD = self.K["ec"]
+        self.e_EC.append(sp - self.CV[-1])
+        if t_start > 0:
+            self.dcv_EC.append((self.CV[-1] - self.CV[-2]) / OS_DT)
+            self.ie_EC.append(self.ie_EC[-1] + self.e_EC[-1] * OS_DT)
+        else:
+            self.dcv_EC.append(0)
+            self.ie_EC.append(0)
+        ec = Kc * self.e_EC[-1] + Kc / tauI * self.ie_EC[-1] + Kc * tauD * self.dcv_EC[-1] + self.EC[-1]
+        if fill:                                   # Sim_filling clamps to EC_control_par[4..5] = [0, 5] (:750-760)
+            if ec > 5:
+                ec = 5
+                self.ie_EC[-1] = self.ie_EC[-1] - self.e_EC[-1] * OS_DT
+            if ec < 0:
+                ec = 0
+                self.ie_EC[-1] = self.ie_EC[-1] - self.e_EC[-1] * OS_DT
+            self.EC.append(ec)
+        else:                                      # Sim_rxn: lower clamp only, ten copies appended (:958-965)
+            if ec < 0:
+                ec = 0
+                self.ie_EC[-1] = self.ie_EC[-1] - self.e_EC[-1] * OS_DT
+            self.EC.extend([ec] * 10)
+        return ec
+
+    def _sim_rxn(self, x, t_range, u_do, Kla, u_ec):
+        kla = self._pid_do(u_do, t_range[0], Kla)
+        if self.K["ec"] is None:
+            x_out = odeint(rhs_react, x, t_range, args=(kla,), **self.ode_kw)
+        else:
+            ec = self._pid_ec(u_ec, t_range[0], False)
+            x_out = odeint(rhs_react_ec, x, t_range, args=(kla, ec, self.K["conc"]), **self.ode_kw)
+            self.CV.append(x_out[-1][self.K["cv"]])
+        self.So.append(x_out[-1][8])
+        return x_out
+
+    # -- reset (gym_SBR_continuous0.py:120-235 and the same function of the other four files) -----------------------
+    def reset(self, influent_mixed, x0=X0_INIT):
+        k = self.kind
+        self.infl = list(influent_mixed)
+        x0 = np.array(x0, dtype=float)
+        self.t, self.u_do, self.u_ec = 0, 0, (2 if self.K["ec"] is not None else 0)
+        self.dcv_DO, self.ie_DO, self.e_DO, self.dcv_EC, self.ie_EC, self.e_EC = [], [], [], [], [], []
+        self.So, self.Kla, self.EC = [x0[8]], [0], [0]
+        self.CV = [x0[self.K["cv"]]] if self.K["ec"] is not None else []
+        self.infl[0] = QIN / self.tm[0][-1]
+        t_range = np.linspace(0, 0 + T_RATIO[0] * 0.5, int((0 + T_RATIO[0] * 0.5 - 0) / OS_DT))
+        kla = self._pid_do(0, 0, self.Kla)
+        if self.K["ec"] is not None:
+            self._pid_ec(0, 0, True)               # EC = 0: the fill RHS's in-place dilution is then a no-op
+        x_out = odeint(rhs_fill, x0, t_range, args=(kla, self.infl), **self.ode_kw)
+        self.So.append(x_out[-1][8])
+        if self.K["ec"] is not None:
+            self.CV.append(x_out[-1][2])           # Ss list; SbrCntMA1 / SbrOS1 store Ss in their Sno list too (:788)
+        self.t = float(t_range[-1])
+        self.x = x_out[-1]
+        self.x_out = x_out
+        mix = lambda i: (QIN * self.infl[i] + self.x[i] * IV) / (QIN + IV)
+        if k == "cnt0":
+            return np.array([[self.t] + [mix(i) for i in (1, 5, 6, 8, 9, 10)]]) / np.array([0.5, 30, 2599., 168., 2., 13., 0.005])
+        if k == "os2":
+            o_do, o_ec, _ = _obs_os(self.t, np.array([0.0] + [mix(i) for i in range(1, 14)]), x_out[0], x_out[-1])
+            return o_do, o_ec
+        return self._obs5(np.array([0.0] + [mix(i) for i in range(1, 14)]), x_out)
+
+    def _obs5(self, x, x_out):
+        d_so, d_snh = (x_out[-1][8] - x_out[0][8]) / 8, (x_out[-1][10] - x_out[0][10]) / 20
+        return np.array([self.t / 0.5, x[8] / 8., x[10] / 30, _clip1(d_so), _clip1(d_snh)])
+
+    def _run_step(self, u_do, u_ec):
+        """run_step (gym_SBR_continuous0.py:326-358): one control interval from the running time."""
+        t_range = np.linspace(self.t, self.t + OS_T_DELTA, int(((self.t + OS_T_DELTA) - self.t) / OS_DT))
+        self.x_out = self._sim_rxn(self.x, t_range, u_do, self.Kla, u_ec)
+        self.x = self.x_out[-1]
+        self.t = float(t_range[-1])
+
+    def _whole_phase(self, stamps, u_ec):
+        """SbrCnt1 / SbrCnt2: a whole anoxic phase in one Sim_rxn call at DO set-point 0 with a fresh `[0]` KLa list
+        (gym_SBR_continuous1.py:281-295, 331-344); SbrCnt2's tuple unpacking rebinds the global Kla to that list (:351)."""
+        Kla = [0]
+        x_out1 = self._sim_rxn(self.x, stamps, 0, Kla, u_ec)
+        if self.kind == "cnt2":
+            self.Kla = Kla
+        self.x = x_out1[-1]
+        self.t = float(stamps[-1])
+
+    def _terminal(self):
+        """Sim_Settling_Drawing + Sim_idle (gym_SBR_continuous0.py:913-1236)."""
+        t, x_in = self.t, self.x
+        t_set = np.linspace(t, t + T_RATIO[5] * T_CYCLE, int((T_RATIO[5] * T_CYCLE) / OS_T_DELTA))
+        Xf = 0.75 * (x_in[3] + x_in[4] + x_in[5] + x_in[6] + x_in[7])
+        z = x_in[0] / ((1.25 / 2) ** 2)
+        sX = odeint(settler_rhs, [Xf] * 10, t_set, args=(z, Xf), **self.ode_kw)[-1]
+        x_n, self.Qw, _, eff, self.draw_status = draw(x_in, sX, Xf)
+        t_draw = np.linspace(t_set[-1], t_set[-1] + T_RATIO[6] * T_CYCLE, int((T_RATIO[6] * T_CYCLE) / OS_T_DELTA))
+        self.So += [x_in[8]] * len(t_set) + [x_n[8]] * (len(t_draw) - 1)
+        t_idle = np.linspace(t_draw[-1], T_CYCLE, int((T_CYCLE - t_draw[-1]) / OS_DT))
+        kla = self._pid_do(self.u_do, t_draw[-1], self.Kla)
+        x_idle = odeint(rhs_react, x_n, t_idle, args=(kla,), **self.ode_kw)
+        self.So.append(x_idle[-1][8])
+        self.t = float(t_idle[-1])
+        self.x = x_idle[-1]
+        return x_in, x_n, x_idle[-1], eff
+
+    def step(self, action):
+        k, tm = self.kind, self.tm
+        a = np.asarray(action, dtype=float).reshape(-1)
+        clip = lambda v, hi: 0 if v < 0 else (hi if v > hi else v)
+        if k in ("cnt0", "cnt1", "cnt2"):
+            if k == "cnt1" and self.t < tm[1][0]:
+                self._whole_phase(tm[1], 0)
+            self.u_do = clip(self.u_do + a[0], 8)
+            if k == "cnt2":
+                self.u_ec = clip(self.u_ec, 5)
+                if self.t < tm[1][0]:
+                    self.u_ec = clip(self.u_ec + a[0], 5)
+                    self._whole_phase(tm[1], self.u_ec)
+            self._run_step(self.u_do, self.u_ec)
+            x_obs, x_out = self.x, self.x_out
+            if k != "cnt0" and tm[2][-1] <= self.t < tm[3][-1]:
+                self._whole_phase(tm[3], self.u_ec)
+        else:
+            for p_ in range(4):
+                t = self.t
+                cond = (t < tm[2][0], tm[2][0] <= t <= tm[2][-1], tm[2][-1] < t <= tm[3][-1], t > tm[3][-1])[p_]
+                if not cond:
+                    continue
+                if p_ % 2 == 0:
+                    self.u_ec = clip(self.u_ec + a[0] if k == "ma1" else a[1], 15)
+                    self.u_do = 0
+                else:
+                    self.u_do = clip(self.u_do + a[0] if k == "ma1" else a[0], 8)
+                    self.u_ec = 0
+                self._run_step(self.u_do, self.u_ec)
+            x_obs, x_out = self.x, self.x_out
+        reward = reward_cnt(x_out[-1], False, 0)
+        if k == "cnt0":
+            obs = np.array([[self.t] + [x_obs[i] for i in (1, 5, 6, 8, 9, 10)]]) / np.array([0.5, 30, 2599., 168., 2., 13., 0.005])
+        elif k == "os2":
+            obs = _obs_os(self.t, x_obs, x_out[0], x_out[-1])
+        else:
+            obs = self._obs5(x_obs, x_out)
+        done = self.t >= tm[4][-1]
+        if done:
+            x_pre, x_draw, x_idle, eff = self._terminal()
+            if k == "cnt0":
+                reward = reward_cnt(x_idle, True, eff)
+                obs = np.array([[self.t] + [x_idle[i] for i in (1, 5, 6, 8, 9, 10)]]) / np.array([0.5, 30, 2599., 168., 2., 13., 0.005])
+            elif k == "os2":
+                obs = _obs_os(self.t, x_draw, x_pre, x_idle)
+        if k == "os2":
+            return (obs[0], obs[1]), obs[2], reward, done
+        return obs, reward, done

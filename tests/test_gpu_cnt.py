@@ -110,3 +110,39 @@ def test_vec_env_episode_api(built, cuda_device, kind):
     env2.load_state_dict(sd)
     assert torch.equal(torch.nan_to_num(env2.buf.st), torch.nan_to_num(env.buf.st))
     assert torch.equal(env2.buf.obs, env.buf.obs)
+
+
+@pytest.mark.parametrize("kind", sorted(cnt.KINDS))
+def test_random_actions_against_scipy_oracle(built, cuda_device, kind):
+    """A batch of 6 envs with fresh influent draws and random per-env action sequences (not the fixtures) on the GPU
+    against the scipy restatement of the reference env (oracle.SbrCntOracle, pinned to the reference's own episodes by
+    tests/test_oracle_golden_cnt.py), every env replayed on the CPU."""
+    import warnings
+    from gym_sbr2_b200 import influent, parity
+    from oracle import sbr_oracle as O
+    from test_twin_parity_cnt import STATE_ATOL, obs_close, random_plan
+    n = 6
+    rng = np.random.RandomState(123)
+    steps = 130 if kind in ("cnt0", "ma1", "os2") else 50
+    infl = np.stack([influent.mix_numpy(0, rng.randn(48)) for _ in range(n)], axis=1)
+    plans = [random_plan(kind, rng, steps) for _ in range(n)]
+    load = infl.copy()
+    load[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    g = GpuCntBatch(kind, n, cuda_device)
+    g.reset(load)
+    oracles = [O.SbrCntOracle(kind) for _ in range(n)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for j, o in enumerate(oracles):
+            o.reset(np.concatenate([[0.66], infl[1:, j]]))
+        for k in range(steps):
+            act = np.stack([p[k] for p in plans], axis=1)
+            ob, r, d = g.step(act)
+            for j, o in enumerate(oracles):
+                out = o.step(plans[j][k] if kind == "os2" else plans[j][k][:1])
+                ok, w = parity.state_close(g.st[:14, j], o.x, atol_frac=STATE_ATOL)
+                assert ok, (kind, j, k, w)
+                ref_obs = np.concatenate(out[0]) if kind == "os2" else np.asarray(out[0]).reshape(-1)
+                assert obs_close(ob[:, j], ref_obs, kind)[0], (kind, j, k)
+                assert bool(d[j]) == bool(out[-1])
+    assert int(g.status.max()) == 0

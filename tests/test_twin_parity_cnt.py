@@ -116,3 +116,50 @@ def test_rk4_fine_grid_agrees_with_dp45(built):
         act = np.array([[g["action"][k][0]], [0.0]])
         a.step(act); b.step(act)
         assert parity.state_close(a.st[:14, 0], b.st[:14, 0], atol_frac=STATE_ATOL)[0], k
+
+
+def random_plan(kind, rng, n):
+    """Action sequences that keep the reference physical: DO set-points moving around 1-3 g/m3, carbon set-point at 0."""
+    a = np.zeros((n, 2))
+    if kind == "os2":
+        a[:, 0] = np.clip(2.0 + np.cumsum(0.1 * rng.randn(n)), 0.3, 5.0)
+        return a
+    a[:, 0] = 0.03 * rng.randn(n) * (0.1 if kind == "cnt0" else 1.0)
+    up = range(60, 64) if kind == "ma1" else range(1, 5)
+    for k in up:
+        a[k, 0] += rng.uniform(0.25, 0.75) * (0.06 if kind == "cnt0" else 1.0)
+    if kind in ("cnt2", "ma1"):
+        a[0, 0] = -2.0
+    if kind == "ma1":
+        a[1:60, 0] = 0.0
+    return a
+
+
+@pytest.mark.parametrize("kind", sorted(cnt.KINDS))
+def test_random_actions_against_oracle(built, kind):
+    """Fresh influent draws and random action sequences (not the fixtures): the g++ build of the stepper against the scipy
+    restatement of the reference env (oracle.SbrCntOracle, itself pinned to the reference by test_oracle_golden_cnt)."""
+    import warnings
+    from gym_sbr2_b200 import influent, schedule
+    from oracle import sbr_oracle as O
+    rng = np.random.RandomState(77)
+    steps = 140 if kind in ("cnt0", "ma1", "os2") else 60
+    for trial in range(2):
+        infl = influent.mix_numpy(0, rng.randn(48))
+        plan = random_plan(kind, rng, steps)
+        o = O.SbrCntOracle(kind)
+        b = twin.CntBatch(cnt.cnt_config(kind), 1, cnt.OBS_ROWS[kind], mode=_abi.MODE_DP45)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o.reset(np.concatenate([[0.66], infl[1:]]))
+            load = infl.copy()
+            load[0] = schedule.os_fill_flow(b.params.Qin)          # influent_mixed[0] := Qin / t_memory1[-1]
+            b.reset(load[:, None])
+            for k in range(steps):
+                out = o.step(plan[k] if kind == "os2" else plan[k][:1])
+                ob, r, d = b.step(plan[k][:, None])
+                ok, w = parity.state_close(b.st[:14, 0], o.x, atol_frac=STATE_ATOL)
+                assert ok, (kind, trial, k, w)
+                ref_obs = np.concatenate(out[0]) if kind == "os2" else np.asarray(out[0]).reshape(-1)
+                assert obs_close(ob[:, 0], ref_obs, kind)[0], (kind, trial, k)
+                assert float(np.max(o.x[0])) < 1.4
