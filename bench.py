@@ -343,7 +343,32 @@ def v4_path_leg(torch, device, args):
     per = [ev[k + 1].elapsed_time(ev[k + 2]) for k in range(493)]
     ms_episode = ev[0].elapsed_time(ev[494])
     fill, react = sorted(per[3:26]), sorted(per[40:490])
+    # the fused rollout: 8 steps per launch behind a 14 -> 32 -> 1 policy head evaluated in-kernel, every buffer in slot
+    # order, slots fully re-sorted by RHS count every second launch (sbr_v4_rollout_k); the step-by-step loop with the same
+    # policy [sbr_policy_mlp, sbr_v4_step] beside it
+    from gym_sbr2_b200 import rollout
+    policy = rollout.TinyPolicy(device, n_in=14, lo=(-0.1,), span=(0.4,), seed=3)
+    fused = {}
+    try:
+        rollout.collect_episode_v4_fused(env, policy, K=8)                       # warm-up
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        env.epoch.zero_()
+        e0.record()
+        ep_f = rollout.collect_episode_v4_fused(env, policy, K=8)
+        e1.record()
+        env.epoch.zero_()
+        ep_s = rollout.collect_episode_v4(env, policy)
+        e2.record()
+        torch.cuda.synchronize()
+        dev_ret = float((ep_f["returns"] - ep_s["returns"]).abs().max() / ep_s["returns"].abs().max())
+        fused = {"ms_episode_fused_k8": e0.elapsed_time(e1), "ms_episode_stepwise_same_policy": e1.elapsed_time(e2),
+                 "interval_steps_per_sec_fused": n * 493 / (e0.elapsed_time(e1) * 1e-3),
+                 "fused_vs_stepwise_max_rel_dev_of_returns": dev_ret, "all_done": bool(ep_f["all_done"]),
+                 "mean_episode_return": float(ep_f["returns"].mean())}
+    except Exception as exc:                                     # noqa: BLE001
+        fused = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     return {"envs": n, "ms_per_episode": ms_episode, "interval_steps_per_sec": n * 493 / (ms_episode * 1e-3),
+            "fused_rollout": fused,
             "ms_per_fill_step": fill[len(fill) // 2], "ms_per_react_step": react[len(react) // 2],
             "ms_terminal_step": per[492], "all_done": bool(env.buf.done.all()),
             "bad_status": int((env.buf.status != 0).sum()), "config": {"integrator": "dp45", "rtol": 1e-8, "atol": 1e-10},

@@ -317,6 +317,42 @@ def v4_step(buf, influent, action, params, sched, mode=_abi.MODE_DP45, tol=None,
     return buf
 
 
+def v4_rollout_k(buf, influent, action, policy, rewards, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None,
+                 emit_obs=True, act_log=None, obs_log=None):
+    """K = rewards.shape[0] consecutive SbrEnv4.step calls in ONE launch with the policy head (14 -> hidden -> 1) evaluated
+    in-kernel between them (sbr_v4_rollout_k).  Every buffer is indexed like buf.st (no slot map).  action [n] in/out."""
+    lib = _abi.load()
+    n = buf.st.shape[1]
+    K = rewards.shape[0]
+    if rewards.shape != (K, n) or not rewards.is_contiguous():
+        raise ValueError("rewards must be contiguous [K, n]")
+    pst, l0 = _dev_ptr(buf.st, _abi.V4_ROWS, n, name="st")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    pac, _ = _dev_ptr(action, 1, n, name="action")
+    prw, l2 = _dev_ptr(rewards, K, n, name="rewards") if K > 1 else (C.c_void_p(rewards.data_ptr()), None)
+    pob, l3 = _dev_ptr(buf.obs if emit_obs else None, _abi.NX, n, name="obs")
+    pdn, _ = _dev_ptr(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = _dev_ptr(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l4 = _dev_ptr(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    pal = pol = None
+    l5 = l6 = None
+    if act_log is not None:
+        if act_log.shape != (K, n) or not act_log.is_contiguous():
+            raise ValueError("act_log must be contiguous [K, n]")
+        pal, l5 = _dev_ptr(act_log, K, n, name="act_log") if K > 1 else (C.c_void_p(act_log.data_ptr()), None)
+    if obs_log is not None:
+        if obs_log.shape != (K, _abi.NX, n) or not obs_log.is_contiguous():
+            raise ValueError("obs_log must be contiguous [K, 14, n]")
+        pol, l6 = _dev_ptr(obs_log.view(_abi.NX * K, n), _abi.NX * K, n, name="obs_log")
+    ld = _same_ld([l0, l1, l2, l3 if emit_obs else None, l4, l5, l6], "v4_rollout_k")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_v4_rollout_k(n, ld, K, pst, pin, pac, C.byref(policy), C.byref(params), C.byref(sched), pob, prw, pdn,
+                                  pss, pct, pal, pol, int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_v4_rollout_k")
+    return buf
+
+
 _INFLUENT_TABLES = {}
 
 

@@ -58,6 +58,11 @@ __host__ __device__ constexpr int os_step_minblocks(int mode) {
 __host__ __device__ constexpr int cnt_step_minblocks(int mode) {
     return mode == SBR_MODE_DP45 ? SBR_CNT_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
 }
+// the fused rollout runs on fully sorted slots (little divergence left): spill-free code beats the third warp, as in
+// sbr_os_step
+#ifndef SBR_V4_FUSED_MINBLOCKS_DP45
+#define SBR_V4_FUSED_MINBLOCKS_DP45 4
+#endif
 __host__ __device__ constexpr int v4_step_minblocks(int mode) {
     return mode == SBR_MODE_DP45 ? SBR_V4_STEP_MINBLOCKS_DP45 : SBR_OS_STEP_MINBLOCKS_RK4;
 }
@@ -629,6 +634,16 @@ struct V4Args {
     int32_t* status;
     uint32_t* counters;
     const int32_t* order;     // may be NULL: slot j of st holds env order[j]; every other buffer is indexed by env
+    // fused rollout (sbr_v4_rollout_k): K steps per launch, the policy head evaluated in-kernel between them (NULL = off)
+    int K;
+    const float* pol_w1;      // [hidden][14]
+    const float* pol_w2;      // [1][hidden]
+    const float* pol_lo;      // [1]
+    const float* pol_span;    // [1]
+    int pol_hidden;
+    double* action_io;        // fused rollout: [n] in/out
+    double* act_log;          // may be NULL: [K][ld]
+    double* obs_log;          // may be NULL: [K][14][ld]
 };
 
 // `order` (divergence-aware placement): the persistent state st is kept in SLOT order -- slots sorted by how many
@@ -651,10 +666,19 @@ __global__ void __launch_bounds__(128) sbr_v4_reset_kernel(V4Args g, SbrParams p
     g.done[i] = 0;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
+// FUSED = false: sbr_v4_step (K = 1, no policy code in the kernel); FUSED = true: sbr_v4_rollout_k.
+template <int MODE, bool FUSED>
+__global__ void __launch_bounds__(kBlock, (FUSED && MODE == SBR_MODE_DP45) ? SBR_V4_FUSED_MINBLOCKS_DP45 : v4_step_minblocks(MODE))
+sbr_v4_step_kernel(V4Args g, SbrParams p, sbr::Coef c, SbrOsSchedule s,
                                                                 SbrTol tol) {
     __shared__ double s_load[SBR_NX * kBlock];
+    __shared__ float s_pw1[FUSED ? kPolMaxHidden * SBR_NX : 1];
+    __shared__ float s_pw2[FUSED ? kPolMaxHidden : 1];
+    if (FUSED) {
+        for (int k = threadIdx.x; k < g.pol_hidden * SBR_NX; k += kBlock) s_pw1[k] = g.pol_w1[k];
+        for (int k = threadIdx.x; k < g.pol_hidden; k += kBlock) s_pw2[k] = g.pol_w2[k];
+        __syncthreads();
+    }
     const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;          // slot of the state
     if (j >= g.n) return;
     const int64_t i = g.order ? (int64_t)g.order[j] : j;                   // env (see sbr_v4_reset_kernel)
@@ -672,14 +696,14 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_k
     ctl.kla_sum = g.st[SBR_V4_KLA_SUM * g.ld + j];
     sbr::Dp45State dp;
     dp.h = g.st[SBR_V4_H * g.ld + j];
-    const double action = g.action[i];
-    const double ret0 = g.st[SBR_V4_RETURN * g.ld + j], steps0 = g.st[SBR_V4_STEPS * g.ld + j];
-    const sbr::Column ob{g.obs + i, g.ld};
+    double action = FUSED ? g.action_io[i] : g.action[i];
+    double ret = g.st[SBR_V4_RETURN * g.ld + j], steps = g.st[SBR_V4_STEPS * g.ld + j];
+    const sbr::Column ob{g.obs ? g.obs + i : nullptr, g.ld};
     if (was_done) {
         // stepping a finished episode is a no-op: same observation, reward 0
 #pragma unroll
         for (int k = 0; k < SBR_NX; ++k) ob.set(k, x[k] * sbr::inv_x1_v4(k));
-        g.reward[i] = 0.0;
+        for (int k = 0; k < (FUSED ? g.K : 1); ++k) g.reward[(int64_t)k * g.ld + i] = 0.0;
         if (g.status) g.status[i] = SBR_ST_DONE;
         if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
         return;
@@ -691,8 +715,45 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_k
         for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
     }
     const sbr::Loading load{&s_load[threadIdx.x], kBlock};
-    sbr::V4Out o;
-    sbr::v4_step_env<MODE>(x, ctl, action, load, p, c, s, tol, dp, ob, o);
+    int status = 0;
+    bool is_done = false;
+    double qw = NAN;
+    for (int k = 0; k < (FUSED ? g.K : 1); ++k) {
+        if (is_done) { g.reward[(int64_t)k * g.ld + i] = 0.0; continue; }
+        if (FUSED && g.act_log) g.act_log[(int64_t)k * g.ld + i] = action;
+        sbr::V4Out o;
+        // the observation of the last step that ran goes to `obs`; the steps before it only feed the policy head
+        double obl[FUSED ? SBR_NX : 1];
+        const bool last = !FUSED || k == g.K - 1;
+        const sbr::Column oc = (FUSED && !last) ? sbr::Column{obl, 1} : ob;
+        sbr::v4_step_env<MODE>(x, ctl, action, load, p, c, s, tol, dp, oc, o);
+        g.reward[(int64_t)k * g.ld + i] = o.reward;
+        ret += o.reward;
+        steps += 1.0;
+        status |= o.status;
+        if (o.done) {
+            is_done = true; qw = o.Qw;
+            if (FUSED && !last) {
+#pragma unroll
+                for (int r = 0; r < SBR_NX; ++r) ob.set(r, obl[FUSED ? r : 0]);
+            }
+        }
+        if (FUSED) {
+            // fused rollout: the set-point change of the NEXT step from this step's observation x / x_1 (same arithmetic
+            // as v4_step_env -> sbr_policy_mlp, hence the same bits)
+            float xin[kPolMaxIn], act[kPolMaxOut];
+#pragma unroll
+            for (int r = 0; r < kPolMaxIn; ++r) xin[r] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < SBR_NX; ++r) xin[r] = (float)(x[r] * sbr::inv_x1_v4(r));
+            if (g.obs_log) {
+#pragma unroll
+                for (int r = 0; r < SBR_NX; ++r) g.obs_log[((int64_t)k * SBR_NX + r) * g.ld + i] = x[r] * sbr::inv_x1_v4(r);
+            }
+            policy_eval(s_pw1, s_pw2, g.pol_lo, g.pol_span, SBR_NX, g.pol_hidden, 1, xin, act);
+            action = (double)act[0];
+        }
+    }
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + j] = x[k];
     g.st[SBR_V4_T * g.ld + j] = ctl.t;
@@ -702,11 +763,11 @@ __global__ void __launch_bounds__(kBlock, v4_step_minblocks(MODE)) sbr_v4_step_k
     g.st[SBR_V4_KLA_LAST * g.ld + j] = ctl.kla_last;
     g.st[SBR_V4_KLA_SUM * g.ld + j] = ctl.kla_sum;
     g.st[SBR_V4_H * g.ld + j] = dp.h;
-    g.st[SBR_V4_RETURN * g.ld + j] = ret0 + o.reward;
-    g.st[SBR_V4_STEPS * g.ld + j] = steps0 + 1.0;
-    if (o.done) { g.st[SBR_V4_QW * g.ld + j] = o.Qw; g.done[i] = 1; }
-    g.reward[i] = o.reward;
-    if (g.status) g.status[i] = o.status;
+    g.st[SBR_V4_RETURN * g.ld + j] = ret;
+    g.st[SBR_V4_STEPS * g.ld + j] = steps;
+    if (is_done) { g.st[SBR_V4_QW * g.ld + j] = qw; g.done[i] = 1; }
+    if (FUSED) g.action_io[i] = action;             // the first step of the next launch finds its action here
+    if (g.status) g.status[i] = status;
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
@@ -1314,24 +1375,59 @@ int sbr_v4_reset(int64_t n, int64_t ld, const double* x0, const double* influent
     return check_launch("sbr_v4_reset");
 }
 
-int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
-                const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
-                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, const int32_t* order, void* stream) {
+namespace {
+int v4_step_launch(const char* what, int64_t n, int64_t ld, int K, double* st, const double* influent, const double* action,
+                   double* action_io, const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs,
+                   double* reward, uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log,
+                   int mode, const SbrTol* tol, const int32_t* order, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
-    if (!st || !influent || !action || !obs || !reward || !done)
-        return fail(SBR_ERR_ARG, "sbr_v4_step: NULL buffer%s");
-    if (n > 2147483647LL) return fail(SBR_ERR_ARG, "sbr_v4_step: n too large%s");
-    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_v4_step: bad mode%s");
+    if (!st || !influent || !(action || action_io) || !reward || !done) return fail(SBR_ERR_ARG, "%s: NULL buffer", what);
+    if (n > 2147483647LL) return fail(SBR_ERR_ARG, "%s: n too large", what);
+    if (K < 1 || K > 4096) return fail(SBR_ERR_ARG, "%s: K must be in 1..4096", what);
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "%s: bad mode", what);
     V4Args g{n, ld, st, nullptr, influent, nullptr, action, obs, reward, done, status, counters, order};
+    g.K = K;
+    g.pol_w1 = nullptr; g.pol_w2 = nullptr; g.pol_lo = nullptr; g.pol_span = nullptr; g.pol_hidden = 0;
+    g.action_io = action_io; g.act_log = act_log; g.obs_log = obs_log;
+    if (policy) {
+        g.pol_w1 = policy->w1; g.pol_w2 = policy->w2; g.pol_lo = policy->lo; g.pol_span = policy->span;
+        g.pol_hidden = policy->hidden;
+    }
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t cs = (cudaStream_t)stream;
-    if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
-    else sbr_v4_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
-    return check_launch("sbr_v4_step");
+    if (policy) {
+        if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4, true><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+        else sbr_v4_step_kernel<SBR_MODE_DP45, true><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    } else {
+        if (mode == SBR_MODE_RK4) sbr_v4_step_kernel<SBR_MODE_RK4, false><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+        else sbr_v4_step_kernel<SBR_MODE_DP45, false><<<grid, kBlock, 0, cs>>>(g, *p, c, *s, t);
+    }
+    return check_launch(what);
+}
+}  // namespace
+
+int sbr_v4_step(int64_t n, int64_t ld, double* st, const double* influent, const double* action,
+                const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done,
+                int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, const int32_t* order, void* stream) {
+    if (!obs) return fail(SBR_ERR_ARG, "sbr_v4_step: NULL buffer%s");
+    return v4_step_launch("sbr_v4_step", n, ld, 1, st, influent, action, nullptr, nullptr, p, s, obs, reward, done, status,
+                          counters, nullptr, nullptr, mode, tol, order, stream);
+}
+
+int sbr_v4_rollout_k(int64_t n, int64_t ld, int K, double* st, const double* influent, double* action,
+                     const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
+                     uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
+                     const SbrTol* tol, void* stream) {
+    if (!policy || !policy->w1 || !policy->w2 || !policy->lo || !policy->span)
+        return fail(SBR_ERR_ARG, "sbr_v4_rollout_k: NULL policy%s");
+    if (policy->n_in != SBR_NX || policy->n_out != 1 || policy->hidden < 1 || policy->hidden > kPolMaxHidden)
+        return fail(SBR_ERR_ARG, "sbr_v4_rollout_k: the policy must map 14 observations to 1 action (hidden <= 64)%s");
+    return v4_step_launch("sbr_v4_rollout_k", n, ld, K, st, influent, nullptr, action, policy, p, s, obs, reward, done, status,
+                          counters, act_log, obs_log, mode, tol, nullptr, stream);
 }
 
 int sbr_cnt_obs_rows(int kind) {

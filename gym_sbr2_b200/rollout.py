@@ -11,15 +11,19 @@ from . import core, dist
 
 class TinyPolicy(torch.nn.Module):
     """obs_DO (9) ++ obs_EC (9) -> [DO set-point in (0.5, 7), NO3 set-point in (1, 14)] (float32 MLP, fixed seed).
-    Works directly on the kernels' struct-of-arrays layout: input [18, N], output [2, N] -- no transposes."""
+    Works directly on the kernels' struct-of-arrays layout: input [18, N], output [2, N] -- no transposes.
+    n_in / lo / span change the shape: TinyPolicy(device, n_in=14, lo=[-0.2], span=[0.4]) is the SBR-v4 stand-in
+    (14 observations -> one change of the DO set-point)."""
 
-    def __init__(self, device, seed=0, hidden=32):
+    def __init__(self, device, seed=0, hidden=32, n_in=18, lo=(0.5, 1.0), span=(6.5, 13.0)):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
-        self.w1t = (torch.randn(hidden, 18, generator=g) * 0.3).to(device)
-        self.w2t = (torch.randn(2, hidden, generator=g) * 0.3).to(device)
-        self.lo = torch.tensor([[0.5], [1.0]], device=device)
-        self.span = torch.tensor([[6.5], [13.0]], device=device)
+        n_out = len(lo)
+        self.n_in, self.n_out = int(n_in), n_out
+        self.w1t = (torch.randn(hidden, n_in, generator=g) * 0.3).to(device)
+        self.w2t = (torch.randn(n_out, hidden, generator=g) * 0.3).to(device)
+        self.lo = torch.tensor([[v] for v in lo], dtype=torch.float32, device=device)
+        self.span = torch.tensor([[v] for v in span], dtype=torch.float32, device=device)
         self.w1t, self.w2t = self.w1t.contiguous(), self.w2t.contiguous()
         self.lo_flat, self.span_flat = self.lo.reshape(-1).contiguous(), self.span.reshape(-1).contiguous()
 
@@ -27,7 +31,7 @@ class TinyPolicy(torch.nn.Module):
     def forward_torch(self, obs_do, obs_ec):
         """The policy as a plain torch expression (nine launches, ~1.3 GB of traffic per step at 2^20 envs): the
         fp32 reference the fused kernel is tested against."""
-        x = torch.cat([obs_do, obs_ec], dim=0).to(torch.float32)
+        x = (obs_do if obs_ec is None else torch.cat([obs_do, obs_ec], dim=0)).to(torch.float32)
         y = torch.sigmoid(self.w2t @ torch.tanh(self.w1t @ x))
         return (self.lo + self.span * y).to(torch.float64)
 
@@ -40,7 +44,7 @@ class TinyPolicy(torch.nn.Module):
         """The weights as the C ABI's SbrPolicyMlp (for the fused rollout, sbr_os_rollout_k)."""
         from . import _abi
         return _abi.SbrPolicyMlp(self.w1t.data_ptr(), self.w2t.data_ptr(), self.lo_flat.data_ptr(),
-                                 self.span_flat.data_ptr(), 18, self.w1t.shape[0], 2, 0)
+                                 self.span_flat.data_ptr(), self.n_in, self.w1t.shape[0], self.n_out, 0)
 
     def forward_soa(self, obs_do, obs_ec):
         """obs_do, obs_ec: [9, N] float64 -> action [2, N] float64 (a fresh tensor)."""
@@ -156,6 +160,69 @@ def collect_episode_fused(env, policy, K=8, store=False):
     return dict(returns=b.st[_abi.OS_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status,
                 rewards=rewards[:steps] if store else None, actions=None if acts is None else acts[:steps],
                 observations=None if obs is None else obs[:steps])
+
+
+@torch.no_grad()
+def collect_episode_v4(env, policy, max_steps=None):
+    """One SBR-v4 episode step by step: [sbr_policy_mlp on obs = x / x_1 -> change of the DO set-point, sbr_v4_step]."""
+    from . import _abi
+    env.reset()
+    b = env.buf
+    steps = max_steps or env.max_episode_steps
+    act = torch.empty((1, env.num_envs), dtype=torch.float64, device=env.device)
+    for _ in range(steps):
+        policy.act_into(b.obs, None, act)
+        env.step_async(act[0])
+    return dict(returns=env._st_row(_abi.V4_RETURN).clone(), steps=steps, all_done=b.done.bool().all(), status=b.status)
+
+
+@torch.no_grad()
+def collect_episode_v4_fused(env, policy, K=8, resort_every=2):
+    """One whole SBR-v4 episode through the fused rollout kernel (sbr_v4_rollout_k): K steps per launch with the policy head
+    evaluated in-kernel.  Every device buffer of the rollout lives in SLOT order -- slots fully re-sorted (single envs) by
+    the last launch's RHS count every `resort_every` launches with one sbr_permute_rows -- so the kernel has no
+    env-indexed access at all; the slot -> env map is only applied to what leaves the rollout (the episode returns).
+    Bit-identical to collect_episode_v4 (results do not depend on the placement)."""
+    from . import _abi
+    env.unsort()                                      # the collector manages the placement itself
+    env.reset()
+    b = env.buf
+    n, dev = env.num_envs, env.device
+    steps = env.max_episode_steps
+    pol = policy.as_struct()
+    action = torch.empty((1, n), dtype=torch.float64, device=dev)
+    policy.act_into(b.obs, None, action)              # the first step's action, from the reset observation
+    action = action[0].contiguous()
+    load = env._loading
+    nl = (steps + K - 1) // K
+    rewards = torch.zeros((K, n), dtype=torch.float64, device=dev)
+    slot_env = None                                   # int64 [n]: slot j holds env slot_env[j]
+    alt = dict(st=torch.empty_like(b.st), load=torch.empty_like(load), action=torch.empty_like(action),
+               done=torch.empty((n,), dtype=torch.int32, device=dev))
+    done_steps = 0
+    for j in range(nl):
+        k = min(K, steps - done_steps)
+        core.v4_rollout_k(b, load, action, pol, rewards[:k], env.params, env.sched, mode=env.mode, tol=env.tol,
+                          emit_obs=False)
+        done_steps += k
+        if resort_every and (j + 1) % resort_every == 0 and j + 1 < nl:
+            perm = torch.argsort(b.counters[0])
+            done32 = b.done.to(torch.int32)
+            core.permute_rows(perm, [(b.st, alt["st"]), (load, alt["load"]), (action, alt["action"]), (done32, alt["done"])])
+            b.st, alt["st"] = alt["st"], b.st
+            load, alt["load"] = alt["load"], load
+            action, alt["action"] = alt["action"], action
+            b.done.copy_(alt["done"].to(torch.uint8))
+            slot_env = perm if slot_env is None else slot_env[perm]
+    ret, all_done, status = b.st[_abi.V4_RETURN].clone(), b.done.bool().all(), b.status
+    if slot_env is not None:                           # back to env order: state, returns
+        out = torch.empty_like(ret)
+        out[slot_env] = ret
+        ret = out
+        core.permute_rows(slot_env, [(b.st, alt["st"])], scatter=True)
+        b.st, alt["st"] = alt["st"], b.st
+    env._lockstep = False
+    return dict(returns=ret, steps=steps, all_done=all_done, status=status)
 
 
 def return_stats(allr):

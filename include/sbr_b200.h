@@ -469,6 +469,20 @@ int sbr_os_rollout_k(int64_t n, int64_t ld, int K, double* st, double* action, c
                      const SbrParams* p, const SbrOsSchedule* s, double* obs_do, double* obs_ec, double* state,
                      double* reward, uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log,
                      int mode, const SbrTol* tol, void* stream);
+/*
+ * The same for SBR-v4: K consecutive SbrEnv4.step calls in one launch with a 14 -> hidden -> 1 policy head evaluated
+ * in-kernel on obs = x / x_1.  Every per-env buffer is indexed like st (no `order` map): a caller that wants
+ * divergence-aware placement permutes ALL of them between launches (sbr_permute_rows), which is what makes this path
+ * fast -- no env-indexed access is left in the kernel (the slot placement of sbr_v4_step pays for its scattered
+ * observation / action rows: 0.29 ms per step against 0.17-0.18 ms with everything sorted).
+ *   action [n] IN/OUT (change of the DO set-point; chained like sbr_os_rollout_k's), reward [K][ld] out,
+ *   obs [14][ld] out (may be NULL): observation after the last step that ran;
+ *   act_log [K][ld], obs_log [K][14][ld] (may be NULL): per-step records for the learner.
+ */
+int sbr_v4_rollout_k(int64_t n, int64_t ld, int K, double* st, const double* influent, double* action,
+                     const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
+                     uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
+                     const SbrTol* tol, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

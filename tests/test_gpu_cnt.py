@@ -146,3 +146,34 @@ def test_random_actions_against_scipy_oracle(built, cuda_device, kind):
                 assert obs_close(ob[:, j], ref_obs, kind)[0], (kind, j, k)
                 assert bool(d[j]) == bool(out[-1])
     assert int(g.status.max()) == 0
+
+
+@pytest.mark.parametrize("kind", ["cnt1", "os2"])
+def test_rk4_mode_against_cpu_twin(built, cuda_device, kind):
+    """Fixed-step mode (the reference's output grid as RK4 sub-steps; a whole-phase solve = 9 sub-steps per control interval
+    it spans): GPU and g++ builds of the same arithmetic agree to rounding, RHS counters exactly."""
+    from gym_sbr2_b200 import influent
+    n = 512
+    rng = np.random.RandomState(9)
+    infl = np.stack([influent.mix_numpy(0, rng.randn(48)) for _ in range(32)], axis=1)
+    infl = np.tile(infl, (1, n // 32)).copy()
+    infl[0] = schedule.os_fill_flow(_abi.default_params().Qin)
+    g = GpuCntBatch(kind, n, cuda_device, mode=_abi.MODE_RK4)
+    c = twin.CntBatch(cnt.cnt_config(kind), n, cnt.OBS_ROWS[kind], mode=_abi.MODE_RK4)
+    g.reset(infl); c.reset(infl)
+    assert np.array_equal(g.counters, c.counters)
+    for k in range(6):
+        act = np.zeros((2, n))
+        act[0] = rng.uniform(0.5, 3.0, n) if kind == "os2" else rng.uniform(0.0, 0.5, n)
+        g.step(act); c.step(act)
+        assert np.array_equal(g.counters, c.counters), k
+        assert np.all(np.abs(g.st[:14] - c.st[:14]) <= 1e-9 * np.abs(c.st[:14]) + 1e-11), k
+    # cnt1's first step runs the whole anoxic phase 2 (0.0415 d = 49.8 control intervals -> 50 x 9 sub-steps) plus one
+    # control interval of 9 sub-steps
+    if kind == "cnt1":
+        g2 = GpuCntBatch(kind, 1, cuda_device, mode=_abi.MODE_RK4)
+        g2.reset(infl[:, :1].copy())
+        g2.step(np.zeros((2, 1)))
+        q = cnt.cnt_config(kind)
+        n_iv = int(np.ceil((q.tm2_1 - q.tm2_0) / schedule.os_schedule().t_delta))
+        assert n_iv == 50 and int(g2.counters[0, 0]) == 4 * (n_iv * 9 + 9)

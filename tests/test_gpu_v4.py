@@ -121,3 +121,28 @@ def test_state_placement_does_not_change_results(built, cuda_device):
     a.unsort()
     assert a._slot_env is None
     assert torch.equal(a.buf.st.view(torch.int64), b.buf.st.view(torch.int64))
+
+
+@pytest.mark.parametrize("K,resort", [(8, 2), (5, 1), (8, 0)])
+def test_fused_rollout_matches_stepwise_rollout(built, cuda_device, K, resort):
+    """sbr_v4_rollout_k (K steps per launch, 14 -> 32 -> 1 policy head in-kernel, every buffer in slot order and fully
+    re-sorted by RHS count between launches) against the step-by-step rollout [sbr_policy_mlp, sbr_v4_step]: per-env
+    episode returns and final states agree to rounding (two instantiations of the same arithmetic), done everywhere."""
+    from gym_sbr2_b200 import rollout
+    n = 1000
+    policy = rollout.TinyPolicy(cuda_device, n_in=14, lo=(-0.1,), span=(0.4,), seed=3)
+    env_s = SbrV4VecEnv(n, device=cuda_device, seed=21)
+    step = rollout.collect_episode_v4(env_s, policy)
+    env_f = SbrV4VecEnv(n, device=cuda_device, seed=21)
+    fused = rollout.collect_episode_v4_fused(env_f, policy, K=K, resort_every=resort)
+    assert bool(step["all_done"]) and bool(fused["all_done"]) and fused["steps"] == 493
+    assert int(fused["status"].max()) == 0
+    env_s.unsort()
+    rs, rf = step["returns"], fused["returns"]
+    assert float((rs - rf).abs().max()) <= 1e-9 * float(rs.abs().max())
+    assert torch.allclose(env_f.buf.st[:14], env_s.buf.st[:14], rtol=1e-9, atol=1e-12)
+    assert torch.equal(env_f.buf.st[_abi.V4_STEPS], env_s.buf.st[_abi.V4_STEPS])
+    # the policy moves the set-point (state feedback through 14 observations) and it stays inside [0, 8]
+    u = env_f.buf.st[_abi.V4_U]
+    assert float(u.min()) >= 0.0 and float(u.max()) <= 8.0 and float(u.max()) > 0.5
+    assert torch.equal(env_f.buf.st[_abi.V4_U], env_s.buf.st[_abi.V4_U])
