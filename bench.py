@@ -419,7 +419,26 @@ def cnt_family_leg(torch, device, args):
         per = sorted(ev[k + 1].elapsed_time(ev[k + 2]) for k in range(steps // 2, steps - 1))
         ms = ev[0].elapsed_time(ev[steps + 1])
         b = env.buf
-        out[kind] = {"id": {"cnt0": "SBRCnt-v0", "cnt1": "SBRCnt-v1", "cnt2": "SBRCnt-v2", "ma1": "SBRCntMA-v1",
+        fused_ms = None
+        try:                                    # the same episode behind a stand-in policy head, fused (8 steps per launch)
+            from gym_sbr2_b200 import rollout
+            from gym_sbr2_b200.cnt import POLICY_INPUTS
+            if kind == "os2":
+                pol = rollout.TinyPolicy(device, n_in=18, lo=(0.5, 0.0), span=(3.0, 0.0), seed=4)
+            else:
+                sp = 0.004 if kind == "cnt0" else 0.06
+                pol = rollout.TinyPolicy(device, n_in=POLICY_INPUTS[kind], lo=(-sp / 4,), span=(sp,), seed=4)
+            rollout.collect_episode_cnt_fused(env, pol, K=8)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            epf = rollout.collect_episode_cnt_fused(env, pol, K=8)
+            f1.record()
+            torch.cuda.synchronize()
+            fused_ms = f0.elapsed_time(f1) if bool(epf["all_done"]) else None
+        except Exception:                                        # noqa: BLE001
+            fused_ms = None
+        out[kind] = {"ms_per_episode_fused_k8_behind_policy": fused_ms,
+                     "id": {"cnt0": "SBRCnt-v0", "cnt1": "SBRCnt-v1", "cnt2": "SBRCnt-v2", "ma1": "SBRCntMA-v1",
                             "os2": "SBROS-v2"}[kind], "envs": n, "episode_steps": steps, "ms_per_episode": ms,
                      "env_steps_per_sec": n * steps / (ms * 1e-3), "ms_per_step_median_second_half": per[len(per) // 2],
                      "all_done": bool(b.done.all()), "bad_status": int((b.status != 0).sum()),

@@ -133,6 +133,9 @@ _PROTOS = {
                                    C.POINTER(SbrTol), _P]),
     "sbr_v4_rollout_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int, _P, _P, _P, C.POINTER(SbrPolicyMlp), C.POINTER(SbrParams),
                                    C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
+    "sbr_cnt_rollout_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.POINTER(SbrCntConfig), _P, _P, C.POINTER(SbrPolicyMlp),
+                                    C.POINTER(SbrParams), C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, C.c_int,
+                                    C.POINTER(SbrTol), _P]),
     "sbr_policy_mlp": (C.c_int, [C.c_int64, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),

@@ -104,6 +104,47 @@ def cnt_step(cfg, buf, action, params, sched, mode=_abi.MODE_DP45, tol=None, str
     return buf
 
 
+def cnt_rollout_k(cfg, buf, action, policy, rewards, params, sched, mode=_abi.MODE_DP45, tol=None, stream=None,
+                  emit_obs=True, act_log=None, obs_log=None):
+    """K = rewards.shape[0] consecutive step() calls in ONE launch with the policy head evaluated in-kernel between them
+    (sbr_cnt_rollout_k).  action [2,n] in/out (row 1: kind os2 only); policy: an _abi.SbrPolicyMlp mapping the kind's
+    observation rows (7 / 5 / 18) to 1 (os2: 2) actions."""
+    lib = _abi.load()
+    n = buf.n
+    K = rewards.shape[0]
+    if rewards.shape != (K, n) or not rewards.is_contiguous():
+        raise ValueError("rewards must be contiguous [K, n]")
+    d = core._dev_ptr
+    pst, l0 = d(buf.st, _abi.CNT_ROWS, n, name="st")
+    pac, l1 = d(action, 2, n, name="action")
+    prw, l2 = d(rewards, K, n, name="rewards") if K > 1 else (C.c_void_p(rewards.data_ptr()), None)
+    pob, l3 = d(buf.obs if emit_obs else None, buf.obs.shape[0], n, name="obs")
+    pdn, _ = d(buf.done, 1, n, dtype=torch.uint8, name="done")
+    pss, _ = d(buf.status, 1, n, dtype=torch.int32, name="status")
+    pct, l4 = d(buf.counters, 2, n, dtype=torch.int32, name="counters")
+    pal = pol = None
+    l5 = l6 = None
+    if act_log is not None:
+        if act_log.shape != (K, 2, n) or not act_log.is_contiguous():
+            raise ValueError("act_log must be contiguous [K, 2, n]")
+        pal, l5 = d(act_log.view(2 * K, n), 2 * K, n, name="act_log")
+    if obs_log is not None:
+        rows = obs_log.shape[1]
+        if obs_log.dim() != 3 or obs_log.shape[0] != K or obs_log.shape[2] != n or not obs_log.is_contiguous():
+            raise ValueError("obs_log must be contiguous [K, n_in, n]")
+        pol, l6 = d(obs_log.view(rows * K, n), rows * K, n, name="obs_log")
+    ld = core._same_ld([l0, l1, l2, l3 if emit_obs else None, l4, l5, l6], "cnt_rollout_k")
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(buf.st.device):
+        rc = lib.sbr_cnt_rollout_k(n, ld, K, C.byref(cfg), pst, pac, C.byref(policy), C.byref(params), C.byref(sched), pob,
+                                   prw, pdn, pss, pct, pal, pol, int(mode), C.byref(tol), core._stream_ptr(stream))
+    _abi.check(rc, "sbr_cnt_rollout_k")
+    return buf
+
+
+POLICY_INPUTS = {"cnt0": 7, "cnt1": 5, "cnt2": 5, "ma1": 5, "os2": 18}
+
+
 class SbrCntVecEnv(object):
     """N x one of `SBRCnt-v0/1/2`, `SBRCntMA-v1`, `SBROS-v2` (kind = "cnt0" | "cnt1" | "cnt2" | "ma1" | "os2").
 

@@ -783,10 +783,20 @@ struct CntArgs {
     const uint8_t* mask;      // reset only (may be NULL)
     const double* action;     // step only: [2][ld]
     double* obs;              // may be NULL in step
-    double* reward;           // step only
+    double* reward;           // step only ([K][ld] in the fused rollout)
     uint8_t* done;
     int32_t* status;
     uint32_t* counters;
+    // fused rollout (sbr_cnt_rollout_k): K steps per launch, the policy head evaluated in-kernel between them
+    int K;
+    const float* pol_w1;      // [hidden][n_in]
+    const float* pol_w2;      // [n_out][hidden]
+    const float* pol_lo;      // [n_out]
+    const float* pol_span;    // [n_out]
+    int pol_hidden;
+    double* action_io;        // fused rollout: [2][ld] in/out
+    double* act_log;          // may be NULL: [K][2][ld]
+    double* obs_log;          // may be NULL: [K][n_in][ld]
 };
 
 __device__ __forceinline__ void cnt_load_ctrl(const CntArgs& g, int64_t i, sbr::CntCtrl& c, double& h) {
@@ -844,9 +854,24 @@ __global__ void __launch_bounds__(kBlock) sbr_cnt_reset_kernel(CntArgs g, sbr::C
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kBlock, cnt_step_minblocks(MODE)) sbr_cnt_step_kernel(CntArgs g, sbr::CntCfg q, SbrParams p,
+// observation rows the policy head of the fused rollout reads: all of them, for SBROS-v2 obs_DO and obs_EC (not `state`)
+__host__ __device__ constexpr int cnt_policy_inputs(int kind) {
+    return kind == SBR_CNT_OS2 ? 2 * SBR_OS_NOBS : sbr::cnt_obs_rows(kind);
+}
+
+// FUSED = false: sbr_cnt_step (one step, no policy code in the kernel); FUSED = true: sbr_cnt_rollout_k.
+template <int MODE, bool FUSED>
+__global__ void __launch_bounds__(kBlock, (FUSED && MODE == SBR_MODE_DP45) ? SBR_V4_FUSED_MINBLOCKS_DP45 : cnt_step_minblocks(MODE))
+sbr_cnt_step_kernel(CntArgs g, sbr::CntCfg q, SbrParams p,
                                                                                      sbr::Coef c, SbrOsSchedule s, SbrTol tol) {
+    __shared__ float s_pw1[FUSED ? kPolMaxHidden * 2 * SBR_OS_NOBS : 1];
+    __shared__ float s_pw2[FUSED ? 2 * kPolMaxHidden : 1];
+    const int n_in = cnt_policy_inputs(q.kind), n_out = q.kind == SBR_CNT_OS2 ? 2 : 1;
+    if (FUSED) {
+        for (int k = threadIdx.x; k < g.pol_hidden * n_in; k += kBlock) s_pw1[k] = g.pol_w1[k];
+        for (int k = threadIdx.x; k < n_out * g.pol_hidden; k += kBlock) s_pw2[k] = g.pol_w2[k];
+        __syncthreads();
+    }
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= g.n) return;
     double x[SBR_NX];
@@ -856,28 +881,67 @@ __global__ void __launch_bounds__(kBlock, cnt_step_minblocks(MODE)) sbr_cnt_step
     sbr::CntCtrl ctl;
     sbr::Dp45State dp;
     cnt_load_ctrl(g, i, ctl, dp.h);
-    const double a0 = g.action[i];
-    const double a1 = q.kind == SBR_CNT_OS2 ? g.action[g.ld + i] : 0.0;
-    const double ret0 = g.st[SBR_CNT_RETURN * g.ld + i], steps0 = g.st[SBR_CNT_STEPS * g.ld + i];
+    const double* act_in = FUSED ? g.action_io : g.action;
+    double a0 = act_in[i];
+    double a1 = q.kind == SBR_CNT_OS2 ? act_in[g.ld + i] : 0.0;
+    double ret = g.st[SBR_CNT_RETURN * g.ld + i], steps = g.st[SBR_CNT_STEPS * g.ld + i];
+    const int K = FUSED ? g.K : 1;
     if (was_done) {
         // stepping a finished episode is a no-op: the observation buffer keeps the terminal observation, reward 0
-        g.reward[i] = 0.0;
+        for (int k = 0; k < K; ++k) g.reward[(int64_t)k * g.ld + i] = 0.0;
         if (g.status) g.status[i] = SBR_ST_DONE;
         if (g.counters) { g.counters[i] = 0; g.counters[g.ld + i] = 0; }
         return;
     }
     if (!(dp.h > 0.0)) dp.h = s.t_delta / 9.0;
     dp.n_rhs = 0; dp.n_rej = 0;
-    sbr::CntOut o;
-    sbr::cnt_step_env<MODE>(x, ctl, a0, a1, q, p, c, s, tol, dp, sbr::Column{g.obs ? g.obs + i : nullptr, g.ld}, o);
+    const sbr::Column ob{g.obs ? g.obs + i : nullptr, g.ld};
+    int status = 0;
+    bool is_done = false;
+    double qw = NAN;
+    for (int k = 0; k < K; ++k) {
+        if (is_done) { g.reward[(int64_t)k * g.ld + i] = 0.0; continue; }
+        if (FUSED && g.act_log) { g.act_log[(int64_t)(2 * k) * g.ld + i] = a0; g.act_log[(int64_t)(2 * k + 1) * g.ld + i] = a1; }
+        sbr::CntOut o;
+        double obl[FUSED ? SBR_CNT_NOBS_MAX : 1];
+        sbr::cnt_step_env<MODE>(x, ctl, a0, a1, q, p, c, s, tol, dp, FUSED ? sbr::Column{obl, 1} : ob, o);
+        g.reward[(int64_t)k * g.ld + i] = o.reward;
+        ret += o.reward;
+        steps += 1.0;
+        status |= o.status;
+        if (o.done) { is_done = true; qw = o.Qw; }
+        if (FUSED) {
+            const int rows = sbr::cnt_obs_rows(q.kind);
+            // the observation of the last step that ran goes to `obs`; every step's feeds the policy head
+            if (k == K - 1 || o.done) {
+#pragma unroll
+                for (int r = 0; r < SBR_CNT_NOBS_MAX; ++r)
+                    if (r < rows) ob.set(r, obl[FUSED ? r : 0]);
+            }
+            if (g.obs_log) {
+#pragma unroll
+                for (int r = 0; r < 2 * SBR_OS_NOBS; ++r)
+                    if (r < n_in) g.obs_log[((int64_t)k * n_in + r) * g.ld + i] = obl[FUSED ? r : 0];
+            }
+            float xin[kPolMaxIn], act[kPolMaxOut];
+#pragma unroll
+            for (int r = 0; r < kPolMaxIn; ++r) xin[r] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 2 * SBR_OS_NOBS; ++r)
+                if (r < n_in) xin[r] = (float)obl[FUSED ? r : 0];
+            policy_eval(s_pw1, s_pw2, g.pol_lo, g.pol_span, n_in, g.pol_hidden, n_out, xin, act);
+            a0 = (double)act[0];
+            if (q.kind == SBR_CNT_OS2) a1 = (double)act[1];
+        }
+    }
 #pragma unroll
     for (int k = 0; k < SBR_NX; ++k) g.st[k * g.ld + i] = x[k];
     cnt_store_ctrl(g, i, ctl, dp.h);
-    g.st[SBR_CNT_RETURN * g.ld + i] = ret0 + o.reward;
-    g.st[SBR_CNT_STEPS * g.ld + i] = steps0 + 1.0;
-    if (o.done) { g.st[SBR_CNT_QW * g.ld + i] = o.Qw; g.done[i] = 1; }
-    g.reward[i] = o.reward;
-    if (g.status) g.status[i] = o.status;
+    g.st[SBR_CNT_RETURN * g.ld + i] = ret;
+    g.st[SBR_CNT_STEPS * g.ld + i] = steps;
+    if (is_done) { g.st[SBR_CNT_QW * g.ld + i] = qw; g.done[i] = 1; }
+    if (FUSED) { g.action_io[i] = a0; if (q.kind == SBR_CNT_OS2) g.action_io[g.ld + i] = a1; }
+    if (g.status) g.status[i] = status;
     if (g.counters) { g.counters[i] = dp.n_rhs; g.counters[g.ld + i] = dp.n_rej; }
 }
 
@@ -1454,6 +1518,7 @@ int sbr_cnt_reset(int64_t n, int64_t ld, const SbrCntConfig* cfg, const double* 
     if (!influent || !st || !obs || !done) return fail(SBR_ERR_ARG, "sbr_cnt_reset: NULL buffer%s");
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cnt_reset: bad mode%s");
     CntArgs g{n, ld, st, x0, influent, mask, nullptr, obs, nullptr, done, status, counters};
+    g.K = 1;
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
     const sbr::CntCfg q = sbr::make_cnt_cfg(*cfg);
@@ -1464,24 +1529,61 @@ int sbr_cnt_reset(int64_t n, int64_t ld, const SbrCntConfig* cfg, const double* 
     return check_launch("sbr_cnt_reset");
 }
 
-int sbr_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, const double* action, const SbrParams* p,
-                 const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done, int32_t* status,
-                 uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+namespace {
+int cnt_step_launch(const char* what, int64_t n, int64_t ld, int K, const SbrCntConfig* cfg, double* st, const double* action,
+                    double* action_io, const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs,
+                    double* reward, uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log,
+                    int mode, const SbrTol* tol, void* stream) {
     int rc = check_common(n, ld, p);
     if (rc) return rc;
     if ((rc = check_os_schedule(s))) return rc;
     if ((rc = check_cnt_config(cfg))) return rc;
-    if (!st || !action || !reward || !done) return fail(SBR_ERR_ARG, "sbr_cnt_step: NULL buffer%s");
-    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cnt_step: bad mode%s");
+    if (!st || !(action || action_io) || !reward || !done) return fail(SBR_ERR_ARG, "%s: NULL buffer", what);
+    if (K < 1 || K > 4096) return fail(SBR_ERR_ARG, "%s: K must be in 1..4096", what);
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "%s: bad mode", what);
     CntArgs g{n, ld, st, nullptr, nullptr, nullptr, action, obs, reward, done, status, counters};
+    g.K = K;
+    g.pol_w1 = nullptr; g.pol_w2 = nullptr; g.pol_lo = nullptr; g.pol_span = nullptr; g.pol_hidden = 0;
+    g.action_io = action_io; g.act_log = act_log; g.obs_log = obs_log;
+    if (policy) {
+        if (!policy->w1 || !policy->w2 || !policy->lo || !policy->span) return fail(SBR_ERR_ARG, "%s: NULL policy", what);
+        if (policy->n_in != cnt_policy_inputs(cfg->kind) || policy->n_out != (cfg->kind == SBR_CNT_OS2 ? 2 : 1) ||
+            policy->hidden < 1 || policy->hidden > kPolMaxHidden)
+            return fail(SBR_ERR_ARG, "%s: the policy must map the kind's observation rows (7 / 5 / 18) to 1 (SBROS-v2: 2) "
+                                     "actions, hidden <= 64", what);
+        g.pol_w1 = policy->w1; g.pol_w2 = policy->w2; g.pol_lo = policy->lo; g.pol_span = policy->span;
+        g.pol_hidden = policy->hidden;
+    }
     const SbrTol t = tol_or_default(tol);
     const sbr::Coef c = sbr::make_coef(*p);
     const sbr::CntCfg q = sbr::make_cnt_cfg(*cfg);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     cudaStream_t cs = (cudaStream_t)stream;
-    if (mode == SBR_MODE_RK4) sbr_cnt_step_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
-    else sbr_cnt_step_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
-    return check_launch("sbr_cnt_step");
+    if (policy) {
+        if (mode == SBR_MODE_RK4) sbr_cnt_step_kernel<SBR_MODE_RK4, true><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+        else sbr_cnt_step_kernel<SBR_MODE_DP45, true><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    } else {
+        if (mode == SBR_MODE_RK4) sbr_cnt_step_kernel<SBR_MODE_RK4, false><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+        else sbr_cnt_step_kernel<SBR_MODE_DP45, false><<<grid, kBlock, 0, cs>>>(g, q, *p, c, *s, t);
+    }
+    return check_launch(what);
+}
+}  // namespace
+
+int sbr_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, const double* action, const SbrParams* p,
+                 const SbrOsSchedule* s, double* obs, double* reward, uint8_t* done, int32_t* status,
+                 uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    return cnt_step_launch("sbr_cnt_step", n, ld, 1, cfg, st, action, nullptr, nullptr, p, s, obs, reward, done, status,
+                           counters, nullptr, nullptr, mode, tol, stream);
+}
+
+int sbr_cnt_rollout_k(int64_t n, int64_t ld, int K, const SbrCntConfig* cfg, double* st, double* action,
+                      const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
+                      uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
+                      const SbrTol* tol, void* stream) {
+    if (!policy) return fail(SBR_ERR_ARG, "sbr_cnt_rollout_k: NULL policy%s");
+    return cnt_step_launch("sbr_cnt_rollout_k", n, ld, K, cfg, st, nullptr, action, policy, p, s, obs, reward, done, status,
+                           counters, act_log, obs_log, mode, tol, stream);
 }
 
 int sbr_policy_mlp(int64_t n, int64_t ld, const double* obs_a, int rows_a, const double* obs_b, int rows_b,

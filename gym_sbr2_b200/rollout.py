@@ -225,6 +225,46 @@ def collect_episode_v4_fused(env, policy, K=8, resort_every=2):
     return dict(returns=ret, steps=steps, all_done=all_done, status=status)
 
 
+def _cnt_policy_obs(env):
+    """The observation rows the policy head of a SBRCnt / SBROS-v2 env reads (all of them; os2: obs_DO ++ obs_EC)."""
+    o = env.buf.obs
+    return o[:18] if env.kind == "os2" else o
+
+
+@torch.no_grad()
+def collect_episode_cnt(env, policy, max_steps=None):
+    """One episode of a SbrCntVecEnv step by step: [sbr_policy_mlp on the env's observation rows, sbr_cnt_step]."""
+    from . import _abi, cnt
+    env.reset()
+    b = env.buf
+    steps = max_steps or env.max_episode_steps
+    for _ in range(steps):
+        a = env._action if env.kind == "os2" else env._action[:1]
+        policy.act_into(_cnt_policy_obs(env), None, a)
+        cnt.cnt_step(env.cfg, b, env._action, env.params, env.sched, mode=env.mode, tol=env.tol)
+    return dict(returns=b.st[_abi.CNT_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status)
+
+
+@torch.no_grad()
+def collect_episode_cnt_fused(env, policy, K=8):
+    """The same episode through the fused rollout kernel (sbr_cnt_rollout_k): K steps per launch, policy head in-kernel."""
+    from . import _abi, cnt
+    env.reset()
+    b = env.buf
+    n = env.num_envs
+    steps = env.max_episode_steps
+    pol = policy.as_struct()
+    a = env._action if env.kind == "os2" else env._action[:1]
+    policy.act_into(_cnt_policy_obs(env), None, a)
+    rewards = torch.zeros((K, n), dtype=torch.float64, device=env.device)
+    done_steps = 0
+    while done_steps < steps:
+        k = min(K, steps - done_steps)
+        cnt.cnt_rollout_k(env.cfg, b, env._action, pol, rewards[:k], env.params, env.sched, mode=env.mode, tol=env.tol)
+        done_steps += k
+    return dict(returns=b.st[_abi.CNT_RETURN].clone(), steps=steps, all_done=b.done.bool().all(), status=b.status)
+
+
 def return_stats(allr):
     ok = torch.isfinite(allr)
     r = allr[ok]

@@ -483,6 +483,17 @@ int sbr_v4_rollout_k(int64_t n, int64_t ld, int K, double* st, const double* inf
                      const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
                      uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
                      const SbrTol* tol, void* stream);
+/*
+ * ... and for the five ids of sbr_cnt_step: K consecutive step() calls in one launch with the policy head evaluated
+ * in-kernel on the kind's observation (7 values for SBRCnt-v0, 5 for SBRCnt-v1/2 and SBRCntMA-v1, obs_DO ++ obs_EC = 18 for
+ * SBROS-v2) -> 1 action (SBROS-v2: 2).
+ *   action [2][ld] IN/OUT (row 1: SBROS-v2 only), reward [K][ld] out, obs out (may be NULL): observation after the last
+ *   step that ran; act_log [K][2][ld], obs_log [K][n_in][ld] (may be NULL).
+ */
+int sbr_cnt_rollout_k(int64_t n, int64_t ld, int K, const SbrCntConfig* cfg, double* st, double* action,
+                      const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
+                      uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
+                      const SbrTol* tol, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

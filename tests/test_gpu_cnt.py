@@ -177,3 +177,68 @@ def test_rk4_mode_against_cpu_twin(built, cuda_device, kind):
         q = cnt.cnt_config(kind)
         n_iv = int(np.ceil((q.tm2_1 - q.tm2_0) / schedule.os_schedule().t_delta))
         assert n_iv == 50 and int(g2.counters[0, 0]) == 4 * (n_iv * 9 + 9)
+
+
+def test_poisoned_actions_are_flagged_and_masked_reset_restarts_only_the_chosen_envs(built, cuda_device):
+    """NaN / huge actions do not crash a launch: the env is flagged (SBR_ST_NONFINITE) or clipped like the reference's
+    if / elif chain clips the accumulated set-point; reset(mask) restarts the marked envs and leaves the others alone."""
+    n = 64
+    env = cnt.SbrCntVecEnv("cnt1", n, device=cuda_device, seed=2)
+    env.reset()
+    a = torch.zeros((n, 1), dtype=torch.float64, device=cuda_device)
+    a[3] = float("nan")
+    a[5] = 1e9                                   # clipped to the set-point's upper bound 8
+    a[7] = -1e9                                  # ... and to 0
+    out = env.step(a)
+    info = out[-1]
+    assert int(info["status"][3]) & _abi.ST_NONFINITE
+    assert float(info["u_do"][5]) == 8.0 and float(info["u_do"][7]) == 0.0
+    ok = torch.ones(n, dtype=torch.bool, device=cuda_device)
+    ok[3] = False
+    assert int(info["status"][ok].max()) == 0
+    for _ in range(5):
+        env.step(torch.zeros_like(a))
+    before = env.buf.st.clone()
+    mask = torch.zeros(n, dtype=torch.bool, device=cuda_device)
+    mask[3] = mask[10] = True
+    env.reset(mask=mask)
+    after = env.buf.st
+    assert torch.equal(torch.nan_to_num(after[:, ~mask]), torch.nan_to_num(before[:, ~mask]))
+    assert float(after[_abi.CNT_STEPS, 3]) == 0.0 and float(after[_abi.CNT_STEPS, 10]) == 0.0
+    assert float(after[_abi.CNT_STEPS, 0]) == 6.0 and bool(torch.isfinite(after[:14, 3]).all())
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((n, 3), dtype=torch.float64, device=cuda_device))
+    with pytest.raises(ValueError):
+        cnt.SbrCntVecEnv("nope", 4, device=cuda_device)
+
+
+def cnt_policy(kind, device):
+    """Stand-in policy heads on the kind's observation rows: small set-point moves (absolute set-points for os2)."""
+    from gym_sbr2_b200 import rollout
+    if kind == "os2":
+        return rollout.TinyPolicy(device, n_in=18, lo=(0.5, 0.0), span=(3.0, 0.0), seed=4)      # NO3 set-point held at 0
+    span = 0.004 if kind == "cnt0" else 0.06
+    return rollout.TinyPolicy(device, n_in=cnt.POLICY_INPUTS[kind], lo=(-span / 4,), span=(span,), seed=4)
+
+
+@pytest.mark.parametrize("kind", sorted(cnt.KINDS))
+def test_fused_rollout_matches_stepwise_rollout(built, cuda_device, kind):
+    """sbr_cnt_rollout_k (K steps per launch, policy head in-kernel) against [sbr_policy_mlp, sbr_cnt_step] step by step:
+    same episode, per-env returns and final state to rounding (two instantiations of one arithmetic)."""
+    from gym_sbr2_b200 import rollout
+    n = 500
+    policy = cnt_policy(kind, cuda_device)
+    env_s = cnt.SbrCntVecEnv(kind, n, device=cuda_device, seed=31)
+    step = rollout.collect_episode_cnt(env_s, policy)
+    env_f = cnt.SbrCntVecEnv(kind, n, device=cuda_device, seed=31)
+    fused = rollout.collect_episode_cnt_fused(env_f, policy, K=7)
+    assert bool(step["all_done"]) and bool(fused["all_done"])
+    assert torch.equal(env_f.buf.st[_abi.CNT_STEPS], env_s.buf.st[_abi.CNT_STEPS])
+    assert float(env_f.buf.st[_abi.CNT_STEPS].min()) == env_f.max_episode_steps
+    rs, rf = step["returns"], fused["returns"]
+    assert float((rs - rf).abs().max()) <= 1e-9 * max(1.0, float(rs.abs().max()))
+    assert torch.allclose(env_f.buf.st[:14], env_s.buf.st[:14], rtol=1e-9, atol=1e-12)
+    assert torch.allclose(env_f.buf.obs, env_s.buf.obs, rtol=1e-9, atol=1e-12)
+    assert torch.allclose(env_f.buf.st[_abi.CNT_U_DO], env_s.buf.st[_abi.CNT_U_DO], rtol=1e-9, atol=1e-12)
+    # (the carbon controllers of cnt2 / ma1 run away under a random policy, as in the reference: no physicality claim here)
+    assert torch.equal(step["status"], fused["status"])
