@@ -486,9 +486,29 @@ def small_batch_leg(torch, device, n=4096):
         v2.step(a3)
     torch.cuda.synchronize()
     t_cycle = (time.perf_counter() - t0) / 5
+    # the same 4096 cycles in the adaptive mode, and the fused SBROS-v1 rollout (8 steps per launch) at this size
+    v2d = SbrV2VecEnv(n, device=device, seed=1, mode="dp45", rtol=1e-7, atol=1e-9)
+    v2d.reset()
+    v2d.step(a3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        v2d.step(a3)
+    torch.cuda.synchronize()
+    t_cycle_dp = (time.perf_counter() - t0) / 5
+    env.reset()
+    rollout.collect_episode_fused(env, pol, K=8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rollout.collect_episode_fused(env, pol, K=8)
+    torch.cuda.synchronize()
+    t_fused = (time.perf_counter() - t0) / env.max_episode_steps
     return {"envs": n, "sbros_v1_us_per_step_eager": t_eager * 1e6, "sbros_v1_us_per_step_cuda_graph": t_graph * 1e6,
+            "sbros_v1_us_per_step_fused_rollout_k8": t_fused * 1e6,
             "sbros_v1_interval_steps_per_sec_cuda_graph": n / t_graph,
-            "sbr_v2_ms_per_cycle_launch": t_cycle * 1e3, "sbr_v2_cycle_steps_per_sec": n / t_cycle}
+            "sbros_v1_interval_steps_per_sec_fused_rollout_k8": n / t_fused,
+            "sbr_v2_ms_per_cycle_launch": t_cycle * 1e3, "sbr_v2_cycle_steps_per_sec": n / t_cycle,
+            "sbr_v2_dp45_ms_per_cycle_launch": t_cycle_dp * 1e3, "sbr_v2_dp45_cycle_steps_per_sec": n / t_cycle_dp}
 
 
 def rollout_leg(torch, tdist, device, rank, world, args):
