@@ -419,8 +419,10 @@ def cnt_family_leg(torch, device, args):
         per = sorted(ev[k + 1].elapsed_time(ev[k + 2]) for k in range(steps // 2, steps - 1))
         ms = ev[0].elapsed_time(ev[steps + 1])
         b = env.buf
-        fused_ms = None
-        try:                                    # the same episode behind a stand-in policy head, fused (8 steps per launch)
+        stats = {"all_done": bool(b.done.all()), "bad_status": int((b.status != 0).sum()),
+                 "max_volume_m3": float(b.st[0].max())}
+        fused = {}
+        try:        # the same env behind a stand-in policy head: step by step [sbr_policy_mlp, sbr_cnt_step] and fused (K = 8)
             from gym_sbr2_b200 import rollout
             from gym_sbr2_b200.cnt import POLICY_INPUTS
             if kind == "os2":
@@ -429,20 +431,27 @@ def cnt_family_leg(torch, device, args):
                 sp = 0.004 if kind == "cnt0" else 0.06
                 pol = rollout.TinyPolicy(device, n_in=POLICY_INPUTS[kind], lo=(-sp / 4,), span=(sp,), seed=4)
             rollout.collect_episode_cnt_fused(env, pol, K=8)
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            env.epoch.zero_()
             f0.record()
             epf = rollout.collect_episode_cnt_fused(env, pol, K=8)
             f1.record()
+            env.epoch.zero_()
+            eps = rollout.collect_episode_cnt(env, pol)
+            f2.record()
             torch.cuda.synchronize()
-            fused_ms = f0.elapsed_time(f1) if bool(epf["all_done"]) else None
-        except Exception:                                        # noqa: BLE001
-            fused_ms = None
-        out[kind] = {"ms_per_episode_fused_k8_behind_policy": fused_ms,
+            fused = {"ms_per_episode_fused_k8": f0.elapsed_time(f1), "ms_per_episode_stepwise_same_policy": f1.elapsed_time(f2),
+                     "all_done": bool(epf["all_done"]) and bool(eps["all_done"]),
+                     "max_rel_dev_of_returns": float((epf["returns"] - eps["returns"]).abs().max()
+                                                     / eps["returns"].abs().max().clamp_min(1.0))}
+        except Exception as exc:                                 # noqa: BLE001
+            fused = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        out[kind] = {"behind_a_policy": fused,
                      "id": {"cnt0": "SBRCnt-v0", "cnt1": "SBRCnt-v1", "cnt2": "SBRCnt-v2", "ma1": "SBRCntMA-v1",
                             "os2": "SBROS-v2"}[kind], "envs": n, "episode_steps": steps, "ms_per_episode": ms,
                      "env_steps_per_sec": n * steps / (ms * 1e-3), "ms_per_step_median_second_half": per[len(per) // 2],
-                     "all_done": bool(b.done.all()), "bad_status": int((b.status != 0).sum()),
-                     "max_volume_m3": float(b.st[0].max()), "gpu_launches": steps + 1}
+                     "all_done": stats["all_done"], "bad_status": stats["bad_status"],
+                     "max_volume_m3": stats["max_volume_m3"], "gpu_launches": steps + 1}
     out["note"] = ("cnt1 / cnt2 episodes are 228 env.steps because two steps each simulate a whole anoxic phase (46 / 171 "
                    "control intervals in one solve); reward = the reference's threshold table with its unbound names bound "
                    "as oracle/make_golden_cnt.py documents")
