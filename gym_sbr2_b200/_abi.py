@@ -15,7 +15,7 @@ AUX_ROWS = 12
 PERMUTE_MAX = 8
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 6
+ABI_VERSION = 7
 # rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
 OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
@@ -79,6 +79,14 @@ CNT_V0, CNT_V1, CNT_V2, CNT_MA1, CNT_OS2 = range(5)
 CNT_NOBS_MAX = 33
 
 
+class SbrIlcLayout(C.Structure):
+    _fields_ = [("off", C.c_int32 * 6), ("n_samples", C.c_int32), ("tp", C.c_int32 * 6)]
+
+
+# rows of sbr_cycle_ilc's `out` (enum SBR_ILC_*)
+ILC_QEFF, ILC_QW, ILC_REWARD, ILC_OCI, ILC_KLA3_MEAN, ILC_KLA5_MEAN, ILC_KLA8_MEAN, ILC_OUT_ROWS = range(8)
+
+
 class SbrLibraryError(RuntimeError):
     pass
 
@@ -137,6 +145,11 @@ _PROTOS = {
                                     C.POINTER(SbrParams), C.POINTER(SbrOsSchedule), _P, _P, _P, _P, _P, _P, _P, C.c_int,
                                     C.POINTER(SbrTol), _P]),
     "sbr_policy_mlp": (C.c_int, [C.c_int64, C.c_int64, _P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "sbr_cycle_ilc": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrSchedule),
+                                C.POINTER(SbrIlcLayout), C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int,
+                                C.POINTER(SbrTol), _P]),
+    "sbr_ilc_update": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(SbrIlcLayout), _P, _P, _P, _P, _P, _P, _P, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, _P]),
     "sbr_reward_stats_init": (C.c_int, [_P, _P]),
     "sbr_reward_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "sbr_fp64_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_double), _P]),

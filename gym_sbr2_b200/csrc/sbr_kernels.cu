@@ -12,6 +12,7 @@
 
 #include "sbr_core.cuh"
 #include "sbr_cnt.cuh"
+#include "sbr_ilc.cuh"
 
 namespace {
 
@@ -129,6 +130,91 @@ __global__ void SBR_CYCLE_BOUNDS sbr_cycle_v2_kernel(CycleArgs g, SbrParams p, s
         g.counters[i] = st.n_rhs;
         g.counters[g.ld + i] = st.n_rej;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch-to-batch (ILC) feed-forward path of SBR-v0 (sbr_ilc.cuh).  Sample memories are [S][ld]: sample j of env i
+// at base[j * ld + i], so that the per-sample stores of a warp are one 256-byte line.
+// ---------------------------------------------------------------------------------------------------------
+struct IlcCycleArgs {
+    int64_t n, ld;
+    const double* x0;
+    const double* influent;
+    const double* sp;
+    const double* kla_base;
+    const double* u;
+    double* so_mem;
+    double* kla_mem;
+    double* x_last;
+    double* out;
+    int32_t* status;
+    uint32_t* counters;
+    double t_fill;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_cycle_ilc_kernel(IlcCycleArgs g, SbrParams p, sbr::Coef c, SbrSchedule s,
+                                                              SbrIlcLayout lay, SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0[k * g.ld + i];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+    const double sp8[8] = {0.0, 0.0, g.sp[i], 0.0, g.sp[g.ld + i], 0.0, 0.0, g.sp[2 * g.ld + i]};
+    sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    const bool ff = g.kla_base != nullptr;
+    sbr::IlcIo io;
+    io.so = sbr::Column{g.so_mem + i, g.ld};
+    io.kla_mem = sbr::Column{g.kla_mem ? g.kla_mem + i : nullptr, g.ld};
+    io.kla_base = sbr::Column{ff ? const_cast<double*>(g.kla_base) + i : nullptr, g.ld};
+    io.u = sbr::Column{ff ? const_cast<double*>(g.u) + i : nullptr, g.ld};
+    const int off[6] = {lay.off[0], lay.off[1], lay.off[2], lay.off[3], lay.off[4], lay.off[5]};
+    sbr::IlcOut o;
+    sbr::Dp45State st;
+    st.h = s.interval[0] / (double)s.n_sub[0];
+    st.n_rhs = 0;
+    st.n_rej = 0;
+    sbr::cycle_ilc<MODE>(x, sp8, load, load(0), g.t_fill, ff, p, c, s, tol, st, io, off, o);
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.x_last[k * g.ld + i] = x[k];
+    if (g.out) {
+        g.out[SBR_ILC_QEFF * g.ld + i] = o.Qeff; g.out[SBR_ILC_QW * g.ld + i] = o.Qw;
+        g.out[SBR_ILC_REWARD * g.ld + i] = o.reward; g.out[SBR_ILC_OCI * g.ld + i] = o.OCI;
+        g.out[SBR_ILC_KLA3_MEAN * g.ld + i] = o.kla_mean[0]; g.out[SBR_ILC_KLA5_MEAN * g.ld + i] = o.kla_mean[1];
+        g.out[SBR_ILC_KLA8_MEAN * g.ld + i] = o.kla_mean[2];
+    }
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) {
+        g.counters[i] = st.n_rhs;
+        g.counters[g.ld + i] = st.n_rej;
+    }
+}
+
+struct IlcUpdateArgs {
+    int64_t n, ld;
+    const double* w;
+    const double* D;
+    const double* sp6;
+    const double* so_mem;
+    double* e_sum;
+    double* e_last;
+    double* u;
+    double dt, Kc, KcI, KcD;
+};
+
+// one thread per (env, phase): blockIdx.y = phase
+__global__ void __launch_bounds__(128) sbr_ilc_update_kernel(IlcUpdateArgs g, SbrIlcLayout lay) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= g.n) return;
+    const int j = blockIdx.y;
+    const int off = lay.off[j], n = (j < 5 ? lay.off[j + 1] : lay.n_samples) - off;
+    const int64_t base = (int64_t)off * g.ld + i;
+    sbr::ilc_update_phase(n, lay.tp[j], g.sp6[j * g.ld + i], g.dt, g.w + off, g.D + off,
+                          sbr::Column{const_cast<double*>(g.so_mem) + base, g.ld}, sbr::Column{g.e_sum + base, g.ld},
+                          sbr::Column{g.e_last + base, g.ld}, sbr::Column{g.u + base, g.ld}, g.Kc, g.KcI, g.KcD);
 }
 
 struct IntervalArgs {
@@ -1273,6 +1359,65 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
     else
         sbr_cycle_v2_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, st>>>(g, *p, c, *s, t);
     return check_launch("sbr_cycle_v2");
+}
+
+static int check_ilc_layout(const SbrIlcLayout* lay, const SbrSchedule* s, const char* who) {
+    if (!lay || lay->n_samples < 1) return fail(SBR_ERR_ARG, "%s: NULL or empty layout", who);
+    for (int j = 0; j < 6; ++j) {
+        const int hi = j < 5 ? lay->off[j + 1] : lay->n_samples;
+        if (lay->off[j] < 0 || hi <= lay->off[j]) return fail(SBR_ERR_ARG, "%s: layout offsets must increase", who);
+        if (s) {
+            const int ph = j < 5 ? j : 7;
+            // the indices 9 i + ii + 1 the reference reads (sub_phases_batchPID_fbPID.py:185,230) must stay inside the phase
+            const int need = s->n_int[ph] * s->n_sub[ph] + 1, last = 9 * (s->n_int[ph] - 1) + s->n_sub[ph];
+            if (hi - lay->off[j] < need || last >= hi - lay->off[j])
+                return fail(SBR_ERR_ARG, "%s: layout holds fewer samples than the schedule writes", who);
+        }
+    }
+    return SBR_OK;
+}
+
+int sbr_cycle_ilc(int64_t n, int64_t ld, const double* x0, const double* influent, const double* sp,
+                  const SbrParams* p, const SbrSchedule* s, const SbrIlcLayout* lay, double t_fill,
+                  const double* kla_base, const double* u, double* so_mem, double* kla_mem, double* x_last,
+                  double* out, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: bad mode%s");
+    if (rc) return rc;
+    if (!x0 || !influent || !sp || !s || !so_mem || !x_last) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: NULL buffer%s");
+    if ((kla_base == nullptr) != (u == nullptr))
+        return fail(SBR_ERR_ARG, "sbr_cycle_ilc: kla_base and u go together (both NULL = cycle 0)%s");
+    if (!(t_fill > 0.0)) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: t_fill must be positive%s");
+    for (int k = 0; k < SBR_NPHASE; ++k) {
+        if (k == 5 || k == 6) continue;
+        if (s->n_int[k] < 1 || s->n_sub[k] < 1 || !(s->interval[k] > 0))
+            return fail(SBR_ERR_ARG, "sbr_cycle_ilc: schedule needs n_int, n_sub >= 1 and interval > 0%s");
+    }
+    rc = check_ilc_layout(lay, s, "sbr_cycle_ilc");
+    if (rc) return rc;
+    IlcCycleArgs g{n, ld, x0, influent, sp, kla_base, u, so_mem, kla_mem, x_last, out, status, counters, t_fill};
+    const sbr::Coef c = sbr::make_coef(*p);
+    const SbrTol t = tol_or_default(tol);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    if (mode == SBR_MODE_RK4)
+        sbr_cycle_ilc_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(g, *p, c, *s, *lay, t);
+    else
+        sbr_cycle_ilc_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, (cudaStream_t)stream>>>(g, *p, c, *s, *lay, t);
+    return check_launch("sbr_cycle_ilc");
+}
+
+int sbr_ilc_update(int64_t n, int64_t ld, const SbrIlcLayout* lay, const double* w, const double* D, const double* sp6,
+                   const double* so_mem, double* e_sum, double* e_last, double* u, double dt, double Kc, double tauI,
+                   double tauD, void* stream) {
+    if (n <= 0 || ld < n) return fail(SBR_ERR_ARG, "sbr_ilc_update: need 0 < n <= ld%s");
+    if (!w || !D || !sp6 || !so_mem || !e_sum || !e_last || !u) return fail(SBR_ERR_ARG, "sbr_ilc_update: NULL buffer%s");
+    if (!(tauI != 0.0)) return fail(SBR_ERR_ARG, "sbr_ilc_update: tauI must be non-zero%s");
+    int rc = check_ilc_layout(lay, nullptr, "sbr_ilc_update");
+    if (rc) return rc;
+    IlcUpdateArgs g{n, ld, w, D, sp6, so_mem, e_sum, e_last, u, dt, Kc, Kc / tauI, Kc * tauD};
+    const dim3 grid((unsigned)((n + 127) / 128), 6);
+    sbr_ilc_update_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, *lay);
+    return check_launch("sbr_ilc_update");
 }
 
 int sbr_integrate_interval(int64_t n, int64_t ld, double* x, const double* kla, const double* ec,

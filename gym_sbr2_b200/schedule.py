@@ -92,6 +92,24 @@ def batch_time_marks(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA * 10):
     return marks
 
 
+def phase_stamps(t_cycle=T_CYCLE, t_ratio=T_RATIO, t_delta=T_DELTA):
+    """The full output-stamp list t_memoryK of each phase, K = 1..8 (module_batch_time.py:3-116): the phase start, then the
+    int(gap / t_delta) - 1 later points of every PID interval.  These are the sample times of the batch-to-batch
+    controller's memories (gym_SBR_env0.py:48, module_batch_PID.py:32-35)."""
+    out = []
+    t_end = 0
+    for k in range(8):
+        t_start = t_end if k == 0 else t_end + t_delta
+        t_end = t_start + t_cycle * t_ratio[k]
+        t_save = np.linspace(t_start, t_end, int((t_end - t_start) / (t_delta * 10)))
+        mem = [float(t_save[0])]
+        for i in range(len(t_save) - 1):
+            t_range = np.linspace(t_save[i], t_save[i + 1], int((t_save[i + 1] - t_save[i]) / t_delta))
+            mem.extend(float(v) for v in t_range[1:])
+        out.append(mem)
+    return out
+
+
 def os_schedule(t_cycle=T_CYCLE, t_ratio=T_RATIO, dt=T_DELTA, rk4_sub_interval=0, rk4_sub_fill=0, rk4_sub_idle=0):
     """SbrOsSchedule: the time constants SbrOS.step / reset key on (gym_SBR_oneshot.py:28-36, 292, 860-963, 1122,
     2264-2420, 2554-2597)."""

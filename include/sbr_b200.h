@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 6
+#define SBR_ABI_VERSION 7
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -494,6 +494,60 @@ int sbr_cnt_rollout_k(int64_t n, int64_t ld, int K, const SbrCntConfig* cfg, dou
                       const SbrPolicyMlp* policy, const SbrParams* p, const SbrOsSchedule* s, double* obs, double* reward,
                       uint8_t* done, int32_t* status, uint32_t* counters, double* act_log, double* obs_log, int mode,
                       const SbrTol* tol, void* stream);
+
+/*
+ * Batch-to-batch (iterative-learning) feed-forward KLa of `SBR-v0` -- SURVEY.md 8(f) rank 4.  Two entry points replace
+ * what SbrEnv.step does before its (unrunnable) reward call (gym_SBR_env0.py:184-203):
+ *   sbr_ilc_update  = SbrEnv._take_action      -> module_batch_PID.batch_PID (module_batch_PID.py:7-275)
+ *   sbr_cycle_ilc   = SbrEnv._next_observation -> SBR_model_batchPID_fbPID.run (SBR_model_batchPID_fbPID.py:8-345;
+ *                     sim_rxn sub_phases_batchPID_fbPID.py:139-253, 388-500), and with kla_base == u == NULL the cycle 0
+ *                     the module runs at import, SBR_model_PID_on.run (gym_SBR_env0.py:105-106; sub_phases_PID_on.py:178-271)
+ * Per-env sample memories are [S][ld] (sample j of env i at base[j * ld + i]); S = layout.n_samples = the six
+ * PID-controlled phases (1, 2, 3, 4, 5, 8) concatenated, one sample per output point of the reference's odeint grid
+ * (phase start + n_sub per PID interval: 217 + 433 + 2008 + 1675 + 111 + 325 = 4769 with the default schedule).
+ * The stepper stops at every output point (the schedule's n_sub must be the reference grid, schedule.cycle_schedule()):
+ * mode SBR_MODE_RK4 = one RK4 step per point, SBR_MODE_DP45 = one adaptive Dormand-Prince solve per point (tol).
+ */
+typedef struct SbrIlcLayout {
+    int32_t off[6];        /* sample offset of phases 1, 2, 3, 4, 5, 8 */
+    int32_t n_samples;     /* S */
+    int32_t tp[6];         /* window length of the batch-to-batch error, int(3 tau_w / t_delta) (module_batch_PID.py:29) */
+} SbrIlcLayout;
+enum {
+    SBR_ILC_QEFF = 0, SBR_ILC_QW, SBR_ILC_REWARD, SBR_ILC_OCI, SBR_ILC_KLA3_MEAN, SBR_ILC_KLA5_MEAN, SBR_ILC_KLA8_MEAN,
+    SBR_ILC_OUT_ROWS
+};
+/*
+ *   x0 [14][ld], influent [14][ld] (row 0 = fill flow), sp [3][ld]: DO set-points of phases 3, 5, 8 (the others are 0;
+ *     the env clips the action to [0, 5], gym_SBR_env0.py:187)
+ *   p: SbrParams with THIS path's constants (pid_Kc 0.5/1.18, pid_tauI 0.0015, pid_tauD 0.005, pid_dt 0.05, kla_max 240 =
+ *     the KLa cycle 0 starts from, biomass_setpoint 5400, WV 1.32, IV 0.66; gym_SBR_env0.py:40-41,89)
+ *   t_fill: length of the fill phase in days (Qin = q_in t_fill)
+ *   kla_base, u [S][ld] in: KLa memory of cycle 0 and u_batch; both NULL = cycle 0
+ *   so_mem [S][ld] out; kla_mem [S][ld] out (may be NULL): cycle 0: feedback KLa per sample (the later kla_base),
+ *     feed-forward cycles: the clamped feed-forward profile the reference returns as Kla_memory
+ *   x_last [14][ld] out; out [SBR_ILC_OUT_ROWS][ld] (may be NULL): Qeff, Qw, reward, OCI, mean applied KLa of phases
+ *     3 / 5 / 8.  reward / OCI = module_reward.sbr_reward's formula on this cycle's applied KLa -- NOT pinned to the
+ *     reference, whose call site raises TypeError (gym_SBR_env0.py:203)
+ *   status [n] out (may be NULL): SBR_ST_NONFINITE / SBR_ST_STEPLIMIT; counters [2][ld] out (may be NULL): RHS
+ *     evaluations, rejected steps
+ */
+int sbr_cycle_ilc(int64_t n, int64_t ld, const double* x0, const double* influent, const double* sp,
+                  const SbrParams* p, const SbrSchedule* s, const SbrIlcLayout* lay, double t_fill,
+                  const double* kla_base, const double* u, double* so_mem, double* kla_mem, double* x_last,
+                  double* out, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol, void* stream);
+/*
+ *   w, D [S] in (device, shared by all envs): window weights and their window sums, computed on the host with the
+ *     reference's own expressions (gym_sbr2_b200/ilc.py)
+ *   sp6 [6][ld] in: set-point memory value of the six phases (gym_SBR_env0.py:251-253)
+ *   so_mem [S][ld] in: So memory the controller learns from
+ *   e_sum, e_last [S][ld] in/out: sum over all cycles and last row of memory_e_batch (start at 0)
+ *   u [S][ld] out: u_batch = Kc E + (Kc / tauI) e_sum + Kc tauD (E - previous E)   (module_batch_PID.py:214-262)
+ *   dt = t_delta (0.002 / 24)
+ */
+int sbr_ilc_update(int64_t n, int64_t ld, const SbrIlcLayout* lay, const double* w, const double* D, const double* sp6,
+                   const double* so_mem, double* e_sum, double* e_last, double* u, double dt, double Kc, double tauI,
+                   double tauD, void* stream);
 
 /* Per-GPU reduction of episode rewards (no reference counterpart; feeds the only collective of the design, an
  * NCCL all_gather of these 5 numbers per rank): stats[0..4] = sum, sum of squares, min, max, count over the

@@ -16,7 +16,7 @@ _lib = None
 def build(force=False):
     src = os.path.join(HERE, "sbr_twin.cpp")
     csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "gym_sbr2_b200", "csrc")
-    deps = [src, os.path.join(csrc, "sbr_core.cuh"), os.path.join(csrc, "sbr_cnt.cuh"),
+    deps = [src, os.path.join(csrc, "sbr_core.cuh"), os.path.join(csrc, "sbr_cnt.cuh"), os.path.join(csrc, "sbr_ilc.cuh"),
             os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "sbr_b200.h")]
     os.makedirs(BUILD_DIR, exist_ok=True)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
@@ -223,3 +223,41 @@ class CntBatch(object):
                                C.byref(self.tol))
         assert rc == 0
         return self.obs.copy(), self.reward.copy(), self.done.copy()
+
+
+def cycle_ilc(x0, influent, sp, params, sched, layout, t_fill, kla_base=None, u=None, want_kla_mem=True, mode=1,
+              tol=None):
+    """x0, influent [14, n]; sp [3, n]; kla_base, u [S, n] or None (cycle 0).  Returns dict of numpy arrays."""
+    lib = load()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    influent = np.ascontiguousarray(influent, dtype=np.float64)
+    sp = np.ascontiguousarray(sp, dtype=np.float64)
+    n, S = x0.shape[1], int(layout.n_samples)
+    kla_base = None if kla_base is None else np.ascontiguousarray(kla_base, dtype=np.float64)
+    u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+    so_mem = np.zeros((S, n)); kla_mem = np.zeros((S, n)) if want_kla_mem else None
+    x_last = np.empty((14, n)); out = np.empty((_abi.ILC_OUT_ROWS, n)); status = np.zeros(n, dtype=np.int32)
+    counters = np.zeros((2, n), dtype=np.uint32)
+    tol = tol or _abi.make_tol()
+    lib.twin_cycle_ilc.restype = C.c_int
+    rc = lib.twin_cycle_ilc(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(influent), _ptr(sp), C.byref(params),
+                            C.byref(sched), C.byref(layout), C.c_double(t_fill), _ptr(kla_base), _ptr(u), _ptr(so_mem),
+                            _ptr(kla_mem), _ptr(x_last), _ptr(out), _ptr(status), _ptr(counters), C.c_int(mode),
+                            C.byref(tol))
+    assert rc == 0
+    return dict(x_last=x_last, so_mem=so_mem, kla_mem=kla_mem, out=out, status=status, counters=counters)
+
+
+def ilc_update(layout, w, D, sp6, so_mem, e_sum, e_last, dt, Kc, tauI, tauD):
+    """e_sum, e_last [S, n] are updated in place; returns u [S, n]."""
+    lib = load()
+    n = so_mem.shape[1]
+    w = np.ascontiguousarray(w, dtype=np.float64); D = np.ascontiguousarray(D, dtype=np.float64)
+    sp6 = np.ascontiguousarray(sp6, dtype=np.float64); so_mem = np.ascontiguousarray(so_mem, dtype=np.float64)
+    assert e_sum.flags.c_contiguous and e_last.flags.c_contiguous
+    u = np.zeros_like(so_mem)
+    rc = lib.twin_ilc_update(C.c_int64(n), C.c_int64(n), C.byref(layout), _ptr(w), _ptr(D), _ptr(sp6), _ptr(so_mem),
+                             _ptr(e_sum), _ptr(e_last), _ptr(u), C.c_double(dt), C.c_double(Kc), C.c_double(tauI),
+                             C.c_double(tauD))
+    assert rc == 0
+    return u

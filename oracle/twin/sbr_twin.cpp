@@ -12,6 +12,7 @@
 
 #include "../../gym_sbr2_b200/csrc/sbr_core.cuh"
 #include "../../gym_sbr2_b200/csrc/sbr_cnt.cuh"
+#include "../../gym_sbr2_b200/csrc/sbr_ilc.cuh"
 
 using namespace sbr;
 
@@ -323,6 +324,58 @@ int twin_cnt_step(int64_t n, int64_t ld, const SbrCntConfig* cfg, double* st, co
         if (status) status[i] = o.status;
         if (counters) { counters[i] = dp.n_rhs; counters[ld + i] = dp.n_rej; }
     }
+    return 0;
+}
+
+int twin_cycle_ilc(int64_t n, int64_t ld, const double* x0, const double* influent, const double* sp, const SbrParams* p,
+                   const SbrSchedule* s, const SbrIlcLayout* lay, double t_fill, const double* kla_base, const double* u,
+                   double* so_mem, double* kla_mem, double* x_last, double* out, int32_t* status, uint32_t* counters,
+                   int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    SbrTol t;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
+    if (tol) t = *tol;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+        double x[SBR_NX], load[SBR_NX];
+        for (int k = 0; k < SBR_NX; ++k) { x[k] = x0[k * ld + i]; load[k] = influent[k * ld + i]; }
+        const double sp8[8] = {0.0, 0.0, sp[i], 0.0, sp[ld + i], 0.0, 0.0, sp[2 * ld + i]};
+        const bool ff = kla_base != nullptr;
+        IlcIo io;
+        io.so = Column{so_mem + i, ld};
+        io.kla_mem = Column{kla_mem ? kla_mem + i : nullptr, ld};
+        io.kla_base = Column{ff ? const_cast<double*>(kla_base) + i : nullptr, ld};
+        io.u = Column{ff ? const_cast<double*>(u) + i : nullptr, ld};
+        const int off[6] = {lay->off[0], lay->off[1], lay->off[2], lay->off[3], lay->off[4], lay->off[5]};
+        IlcOut o;
+        Dp45State st;
+        st.h = s->interval[0] / (double)s->n_sub[0]; st.n_rhs = 0; st.n_rej = 0;
+        if (mode == SBR_MODE_RK4) cycle_ilc<SBR_MODE_RK4>(x, sp8, Loading{load, 1}, load[0], t_fill, ff, *p, c, *s, t, st, io, off, o);
+        else cycle_ilc<SBR_MODE_DP45>(x, sp8, Loading{load, 1}, load[0], t_fill, ff, *p, c, *s, t, st, io, off, o);
+        for (int k = 0; k < SBR_NX; ++k) x_last[k * ld + i] = x[k];
+        if (out) {
+            out[SBR_ILC_QEFF * ld + i] = o.Qeff; out[SBR_ILC_QW * ld + i] = o.Qw;
+            out[SBR_ILC_REWARD * ld + i] = o.reward; out[SBR_ILC_OCI * ld + i] = o.OCI;
+            out[SBR_ILC_KLA3_MEAN * ld + i] = o.kla_mean[0]; out[SBR_ILC_KLA5_MEAN * ld + i] = o.kla_mean[1];
+            out[SBR_ILC_KLA8_MEAN * ld + i] = o.kla_mean[2];
+        }
+        if (status) status[i] = o.status;
+        if (counters) { counters[i] = st.n_rhs; counters[ld + i] = st.n_rej; }
+    }
+    return 0;
+}
+
+int twin_ilc_update(int64_t n, int64_t ld, const SbrIlcLayout* lay, const double* w, const double* D, const double* sp6,
+                    const double* so_mem, double* e_sum, double* e_last, double* u, double dt, double Kc, double tauI,
+                    double tauD) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < 6; ++j) {
+            const int off = lay->off[j], m = (j < 5 ? lay->off[j + 1] : lay->n_samples) - off;
+            const int64_t base = (int64_t)off * ld + i;
+            ilc_update_phase(m, lay->tp[j], sp6[j * ld + i], dt, w + off, D + off,
+                             Column{const_cast<double*>(so_mem) + base, ld}, Column{e_sum + base, ld},
+                             Column{e_last + base, ld}, Column{u + base, ld}, Kc, Kc / tauI, Kc * tauD);
+        }
     return 0;
 }
 
