@@ -4,12 +4,13 @@
 values exactly shaped like the reference's; "identical seeds" means `np.random.seed(s)` before `reset()` as in the
 reference (global numpy RNG, buffer_tank3.py:68) -- the influent draw consumes the same random numbers.
 `SbrCnt0`, `SbrCnt1`, `SbrCnt2`, `SbrCntMA1` and `SbrOS1` wrap the CUDA path of the five ids whose reference `step()` dies
-in its reward module (repaired reward, disclosed in oracle/make_golden_cnt.py).  `SbrEnv` / `SbrEnv1` (`SBR-v0/1`), whose
-reference `step()` cannot run at all, raise UnsupportedEnvError on construction.
+in its reward module (repaired reward, disclosed in oracle/make_golden_cnt.py).  `SbrEnv` (`SBR-v0`) serves the batch-to-batch feed-forward
+KLa path: everything its reference `step()` does before the reward call that cannot run (disclosed in
+oracle/make_golden_ilc.py).  `SbrEnv1` (`SBR-v1`), whose reference `step()` dies on the same call and has nothing of its
+own beyond it, raises UnsupportedEnvError on construction.
 """
-from .single import SbrCnt0, SbrCnt1, SbrCnt2, SbrCntMA1, SbrEnv2, SbrEnv4, SbrOS, SbrOS1, unsupported_class
+from .single import SbrCnt0, SbrCnt1, SbrCnt2, SbrCntMA1, SbrEnv, SbrEnv2, SbrEnv4, SbrOS, SbrOS1, unsupported_class
 
-SbrEnv = unsupported_class("SBR-v0")
 SbrEnv1 = unsupported_class("SBR-v1")
 
 __all__ = ["SbrEnv", "SbrEnv1", "SbrEnv2", "SbrEnv4", "SbrCnt0", "SbrCnt1", "SbrCnt2", "SbrCntMA1", "SbrOS", "SbrOS1"]

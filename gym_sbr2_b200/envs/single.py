@@ -6,6 +6,7 @@ from .. import influent as influent_mod
 from ..registration import ENV_TABLE, UnsupportedEnvError
 from ..spaces import Box, env_base
 from ..cnt import SbrCntVecEnv
+from ..ilc import ACTION_HIGH, ACTION_LOW, SbrIlcVecEnv
 from ..vec_env import SbrOsVecEnv, SbrV2VecEnv, SbrV4VecEnv
 
 _Base = env_base()
@@ -55,6 +56,51 @@ class SbrEnv2(_Base):
         obs, reward, done, info = self._vec.step(torch.as_tensor(action, dtype=torch.float64)[None, :])
         self.reward = float(reward[0])
         self.info = {k: v[..., 0].cpu().numpy() for k, v in info.items()}
+        return obs[0].cpu().numpy(), self.reward, True, {}
+
+    def render(self, mode="human", close=False):
+        print("Reward for this episode: {}".format(self.reward))
+
+
+class SbrEnv(_Base):
+    """`SBR-v0` (gym_SBR_env0.py:139-262): one step = one whole 12-h cycle under the batch-to-batch (iterative-learning)
+    feed-forward KLa plus the feedback DO-PID; action = DO set-points of phases 3, 5, 8 in [0, 5]; obs = the 14
+    normalised sums x_last + influent (first entry 1); done = True after every step, the plant state carries over.
+
+    The reference module runs cycle 0 at import and `reset()` only re-reads its globals (:150-176): here the first
+    `reset()` runs cycle 0, later calls return the current observation without touching the plant.  Deviations, all
+    forced by the reference (see gym_sbr2_b200/ilc.py): `step()` there raises before it returns (float linspace counts,
+    seven-argument reward call), so the reward is module_reward.sbr_reward's formula on this cycle's applied KLa -- by
+    construction, not pinned; the influent is the package's buffer_tank3 scenario-0 draw on the global numpy RNG, not
+    `buffer_tank2`.  learn="frozen" reproduces the module's behaviour (the controller keeps learning from cycle 0's
+    memories, :200), learn="feedback" feeds the last cycle's memories back."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device=None, learn="frozen"):
+        self.action_space = Box(np.array([0.0, 0.0, 0.0]), np.array([5.0, 5.0, 5.0]), dtype=np.float32)        # :145
+        self.observation_space = Box(low=np.zeros(14), high=np.full(14, 2.0), dtype=np.float32)                # :147
+        self.reward = 0
+        self._vec = SbrIlcVecEnv(1, device=_device(device), learn=learn)
+        self.influent_mixed = None
+        self.info = {}
+
+    def _draw(self):
+        self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)
+        return torch.as_tensor(self.influent_mixed, dtype=torch.float64)[None, :]
+
+    def reset(self):
+        if self.influent_mixed is None:
+            return self._vec.reset(influent=self._draw())[0].cpu().numpy()
+        return self._vec._obs()[0].cpu().numpy()
+
+    def step(self, action):
+        if self.influent_mixed is None:
+            raise RuntimeError("step() before reset()")
+        action = np.clip(np.asarray(action, dtype=np.float64), ACTION_LOW, ACTION_HIGH)
+        obs, reward, done, info = self._vec.step(torch.as_tensor(action, dtype=torch.float64)[None, :],
+                                                 influent=self._draw())
+        self.reward = float(reward[0])
+        self.info = {k: (v[..., 0].cpu().numpy() if torch.is_tensor(v) else v) for k, v in info.items()}
         return obs[0].cpu().numpy(), self.reward, True, {}
 
     def render(self, mode="human", close=False):

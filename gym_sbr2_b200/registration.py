@@ -8,8 +8,12 @@ and users call `gym.make(id)`.  The same ten ids are registered here, under the 
   * `SBRCnt-v0/1/2`, `SBRCntMA-v1`, `SBROS-v2` -- whose reference `step()` raises NameError inside the reward module
     they share (module_reward_continuous1.py:32,61) -- are served by the CUDA path with that reward repaired as
     oracle/make_golden_cnt.py discloses (states, observations and `done` follow the unmodified env modules);
-  * `SBR-v0` and `SBR-v1` raise `UnsupportedEnvError` from the constructor, naming the reference's own failure
-    (they crash inside `step()` there, in the physics call itself), instead of pretending to work.
+  * `SBR-v0` -- whose reference `step()` raises twice over (float `num` in np.linspace, then a seven-argument call of the
+    ten-parameter module_reward.sbr_reward) -- is served for what it computes before that call: the batch-to-batch
+    (iterative-learning) feed-forward KLa and the cycle under it, pinned against the reference's own functions
+    (oracle/make_golden_ilc.py); its reward is by construction;
+  * `SBR-v1` raises `UnsupportedEnvError` from the constructor, naming the reference's own failure, instead of
+    pretending to work.
 `gym` / `gymnasium` are optional: when one is importable the ids are registered with it as well (so `gym.make`
 works unchanged); otherwise `gym_sbr2_b200.make(id)` is the equivalent.
 """
@@ -19,8 +23,10 @@ ENTRY_PACKAGE = "gym_sbr2_b200.envs"
 
 # id -> (class name, reference module, supported?, reference failure mode when not)
 ENV_TABLE = {
-    "SBR-v0": ("SbrEnv", "gym_SBR_env0.py", False,
-               "reference step() raises TypeError: float `num` in np.linspace (sub_phases_batchPID_fbPID.py:144)"),
+    # supported with a disclosure: the reference's step() raises TypeError (float `num` in np.linspace,
+    # sub_phases_batchPID_fbPID.py:144; then sbr_reward() arity, gym_SBR_env0.py:203); parity is function by function
+    # against batch_PID / SBR_model_PID_on.run / SBR_model_batchPID_fbPID.run, the reward is by construction
+    "SBR-v0": ("SbrEnv", "gym_SBR_env0.py", True, None),
     "SBR-v1": ("SbrEnv1", "gym_SBR_env1.py", False,
                "reference step() raises TypeError: sbr_reward() arity mismatch (gym_SBR_env1.py:151 vs module_reward.py:4)"),
     "SBR-v2": ("SbrEnv2", "gym_SBR_env2.py", True, None),

@@ -22,7 +22,7 @@ def test_all_ten_reference_ids_registered_under_reference_class_names():
         assert hasattr(envs, cls)
 
 
-SERVED = ("SBR-v2", "SBROS-v1", "SBR-v4", "SBRCnt-v0", "SBRCnt-v1", "SBRCnt-v2", "SBRCntMA-v1", "SBROS-v2")
+SERVED = ("SBR-v0", "SBR-v2", "SBROS-v1", "SBR-v4", "SBRCnt-v0", "SBRCnt-v1", "SBRCnt-v2", "SBRCntMA-v1", "SBROS-v2")
 
 
 def test_unsupported_ids_name_the_reference_failure():
@@ -176,3 +176,21 @@ def test_cnt_family_episode_through_make(built, cuda_device, env_id, kind, name)
     assert parity.state_close(tr["x_t"][0], g["x_fill"], atol_frac=1e-7)[0]
     assert parity.state_close(tr["x_t"][k // 2], g["x_cont"][k // 2 - 1], atol_frac=1e-7)[0]
     assert abs(tr["u_DO_t"][k // 2] - g["u_do"][k // 2 - 1]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_sbr_v0_batch_to_batch_env_through_make(built, cuda_device):
+    """`SBR-v0`: reset() runs cycle 0 once, step() = batch-to-batch update + one feed-forward cycle; the reference's tuple
+    shapes (gym_SBR_env0.py:150-236).  Numbers are pinned in tests/test_gpu_ilc.py."""
+    env = sbr.make("SBR-v0")
+    assert env.action_space.shape == (3,) and env.observation_space.shape == (14,)
+    np.random.seed(0)
+    obs0 = env.reset()
+    assert isinstance(obs0, np.ndarray) and obs0.shape == (14,) and obs0[0] == 1.0
+    assert np.array_equal(env.reset(), obs0)                  # the reference's reset() does not touch the plant
+    obs, reward, done, info = env.step([2.0, 2.5, 1.5])
+    assert obs.shape == (14,) and done is True and info == {} and np.isfinite(reward)
+    u1 = env.info["u_batch"].copy()
+    assert np.abs(u1).max() > 0 and int(env.info["status"]) == 0
+    obs2, reward2, _, _ = env.step([7.0, -1.0, 1.5])          # clipped to [0, 5]
+    assert np.isfinite(obs2).all() and not np.array_equal(env.info["u_batch"], u1)
