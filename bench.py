@@ -520,6 +520,48 @@ def small_batch_leg(torch, device, n=4096):
             "sbr_v2_dp45_ms_per_cycle_launch": t_cycle_dp * 1e3, "sbr_v2_dp45_cycle_steps_per_sec": n / t_cycle_dp}
 
 
+def ilc_leg(torch, device, n=1 << 16):
+    """The batch-to-batch (ILC) feed-forward KLa path of `SBR-v0`: SbrIlcVecEnv.step = sbr_ilc_update (HBM-bound: seven
+    [4769][N] sample rows moved per update) + sbr_cycle_ilc (FP64-bound cycle that stops at every output point of the
+    reference's grid and stores So there).  CUDA events around each launch, three steps averaged."""
+    from gym_sbr2_b200 import _abi, ilc
+    env = ilc.SbrIlcVecEnv(n, device=device, seed=1, learn="feedback")
+    env.reset()
+    a = torch.rand((n, 3), dtype=torch.float64, device=device, generator=torch.Generator(device=device).manual_seed(5)) * 4 + 0.5
+    env.step(a)
+    torch.cuda.synchronize()
+    S = int(env.layout.n_samples)
+    t_up = t_cy = t_step = 0.0
+    reps = 3
+    for _ in range(reps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        env._sp.copy_(a.t())
+        env._sp6.zero_()
+        env._sp6[2], env._sp6[4], env._sp6[5] = a.t()[0], a.t()[1], a.t()[2]
+        e[0].record()
+        ilc.ilc_update(env.layout, env._w, env._D, env._sp6, env.so_learn, env.e_sum, env.e_last, env.u)
+        e[1].record()
+        ilc.cycle_ilc(env.x, env.influent, env._sp, env.params, env.sched, env.layout, kla_base=env.kla_base, u=env.u,
+                      out=env._cyc)
+        e[2].record()
+        torch.cuda.synchronize()
+        t_up += e[0].elapsed_time(e[1]) / reps
+        t_cy += e[1].elapsed_time(e[2]) / reps
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        env.step(a)
+        s1.record()
+        torch.cuda.synchronize()
+        t_step += s0.elapsed_time(s1) / reps
+    rhs = float(env._cyc.counters[0].double().mean())
+    bad = int((env._cyc.status != 0).sum())
+    return {"envs": n, "samples_per_env": S, "ms_per_step": t_step, "cycle_steps_per_sec": n / t_step * 1e3,
+            "update_kernel_ms": t_up, "update_kernel_gbs": 7 * S * n * 8 / t_up / 1e6, "hbm_peak_gbs": _hbm_peak(),
+            "cycle_kernel_ms": t_cy, "cycle_rhs_per_env": rhs, "bad_status": bad,
+            "memory_gb": 7 * S * n * 8 / 1e9,
+            "note": "integrator: one Dormand-Prince solve per output point (rtol 1e-8); reward by construction, not pinned"}
+
+
 def rollout_leg(torch, tdist, device, rank, world, args):
     """BASELINE config 5: --rollout-envs SBROS-v1 envs in total, sharded over the ranks by contiguous index blocks,
     one full episode (reset + 463 env.steps) driven by a small torch policy on the observation tensors, then an
@@ -997,6 +1039,7 @@ def main():
         paths["sbr_v4"] = leg(v4_path_leg, torch, device, args)
         paths["sbr_cnt_family"] = leg(cnt_family_leg, torch, device, args)
         paths["config1_small_batch"] = leg(small_batch_leg, torch, device)
+        paths["sbr_v0_ilc"] = leg(ilc_leg, torch, device)
     if not args.no_rollout:
         paths["headline_strong_scaling"] = (leg(headline_strong_leg, torch, tdist, device, rank, world, args, core, peak)
                                             if world == 1 else
