@@ -559,7 +559,7 @@ def ilc_leg(torch, device, n=1 << 16):
             "update_kernel_ms": t_up, "update_kernel_gbs": 7 * S * n * 8 / t_up / 1e6, "hbm_peak_gbs": _hbm_peak(),
             "cycle_kernel_ms": t_cy, "cycle_rhs_per_env": rhs, "bad_status": bad,
             "memory_gb": 7 * S * n * 8 / 1e9,
-            "note": "integrator: one Dormand-Prince solve per output point (rtol 1e-8); reward by construction, not pinned"}
+            "note": "integrator: Dormand-Prince per PID interval (rtol 1e-9), So memory from its continuous extension; reward by construction, not pinned"}
 
 
 def rollout_leg(torch, tdist, device, rank, world, args):

@@ -5,10 +5,11 @@
 //   batch-to-batch controller      module_batch_PID.batch_PID     (module_batch_PID.py:7-275)
 // Same kinetics, tails, RK4 stepper and settler as the cycle-per-step path (sbr_core.cuh).  What differs:
 //   * the DO controller samples So at EVERY output point of the reference's odeint grid (9, phase 5: 10 per PID
-//     interval) into a per-env memory -- the batch-to-batch controller works on those -- so the stepper stops at every
-//     output point: one RK4 step per point (MODE RK4) or one adaptive Dormand-Prince solve per point (MODE DP45, the
-//     default: cycle 0 starts aerated at KLa 240 and So then collapses from 7 to 0.004 g/m3 within a few points of the
-//     fill phase, where RK4 on the grid is 2e-5 g/m3 off in the memory although the end state agrees);
+//     interval) into a per-env memory -- the batch-to-batch controller works on those.  MODE DP45 (default): adaptive
+//     Dormand-Prince over the PID interval, the memory filled from the method's continuous extension
+//     (dp45_interval_dense); MODE RK4: one RK4 step per output point -- cycle 0 starts aerated at KLa 240 and So then
+//     collapses from 7 to 0.004 g/m3 within a few points of the fill phase, where RK4 on the grid is 2e-5 g/m3 off in
+//     the memory although the end state agrees;
 //   * KLa of an interval = feedback PID + clamp(u_batch + KLa memory of cycle 0) read at list position 9 i + 1 (:230);
 //   * the feedback bias starts from 0 (feed-forward cycles, :173-232: Kla[0] is never seeded) or from the incoming KLa
 //     (cycle 0, sub_phases_PID_on.py:218);
@@ -37,6 +38,127 @@ struct IlcOut {
     int status;
 };
 
+// Dormand-Prince 5(4) over ONE PID interval [0, T] with the So memory filled from the method's own continuous extension
+// (Hairer, Norsett & Wanner II.6, the 4th-order interpolant of dopri5: local error O(h^5) like the step itself, measured
+// against LSODA at 1e-12 in tests/test_twin_parity_ilc.py): output point p = 0 .. m-1 at time (p + 1) T / m lands in
+// so[j0 + p].  Same controller and constants as dp45_interval (sbr_core.cuh), whose stage vectors are all alive at the
+// accept -- this copy adds the six-term sum of the So component and the Horner evaluation per output point, so that the
+// stepper no longer stops at every point (7.3 right-hand sides per point, first-same-as-last lost each time).
+struct DpDense {
+    double d1, d3, d4, d5, d6, d7;
+};
+#define SBR_DP_DENSE                                                                                              \
+    {-12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,                 \
+     701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0}
+
+template <int TAIL>
+SBR_HD int dp45_interval_dense(double (&x)[SBR_NX], double T, int m, const Flow& f, const Coef& c, const TailArgs& a,
+                               const SbrTol& tol, Dp45State& st, double& xpq, const Column& so, int j0) {
+#ifdef __CUDA_ARCH__
+    const DpTab& tb = kDpTab;
+#else
+    const DpTab tb = SBR_DP_TABLEAU;
+#endif
+    const DpDense dd = SBR_DP_DENSE;
+    double k1[SBR_NX], k2[SBR_NX], k3[SBR_NX], k4[SBR_NX], k5[SBR_NX], k6[SBR_NX], y[SBR_NX];
+    double t = 0.0;
+    double h = st.h * SBR_DP_FIRST;
+    int status = 0, steps = 0, p = 0;
+    const double h_out = T / (double)m;
+#pragma unroll
+    for (int i = 0; i < SBR_NX; ++i) y[i] = x[i];
+    double g1 = stage<TAIL>(y, k1, 0.0, f, c, a);
+    st.n_rhs += 1;
+    while (t < T) {
+        if (steps >= tol.max_steps) { status = SBR_ST_STEPLIMIT; break; }
+        ++steps;
+        const double rem = T - t;
+        const float n_f = ceilf((float)rem * frcp_fast((float)h) * SBR_DP_NGUARD);
+        const bool last = !(n_f > 1.0f);
+        const double hs = last ? rem : rem * (double)frcp_fast(n_f);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i)) y[i] = fma(hs * tb.a21, k1[i], x[i]);
+        stage<TAIL>(y, k2, fma(tb.c2, hs, t), f, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i)) y[i] = fma(hs * tb.a32, k2[i], fma(hs * tb.a31, k1[i], x[i]));
+        const double g3 = stage<TAIL>(y, k3, fma(tb.c3, hs, t), f, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i)) y[i] = fma(hs * tb.a43, k3[i], fma(hs * tb.a42, k2[i], fma(hs * tb.a41, k1[i], x[i])));
+        const double g4 = stage<TAIL>(y, k4, fma(tb.c4, hs, t), f, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i))
+                y[i] = fma(hs * tb.a54, k4[i], fma(hs * tb.a53, k3[i], fma(hs * tb.a52, k2[i], fma(hs * tb.a51, k1[i], x[i]))));
+        const double g5 = stage<TAIL>(y, k5, fma(tb.c5, hs, t), f, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i))
+                y[i] = fma(hs * tb.a65, k5[i], fma(hs * tb.a64, k4[i], fma(hs * tb.a63, k3[i],
+                       fma(hs * tb.a62, k2[i], fma(hs * tb.a61, k1[i], x[i])))));
+        const double g6 = stage<TAIL>(y, k6, t + hs, f, c, a);
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i))
+                y[i] = fma(hs * tb.b6, k6[i], fma(hs * tb.b5, k5[i], fma(hs * tb.b4, k4[i],
+                       fma(hs * tb.b3, k3[i], fma(hs * tb.b1, k1[i], x[i])))));
+        const double g7 = stage<TAIL>(y, k2, t + hs, f, c, a);      // k7 = f(5th-order solution) lands in k2
+        st.n_rhs += 6;
+        double en3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < SBR_NX; ++i)
+            if (active(i)) {
+                const double err = fma(tb.e7, k2[i], fma(tb.e6, k6[i], fma(tb.e5, k5[i], fma(tb.e4, k4[i],
+                                   fma(tb.e3, k3[i], tb.e1 * k1[i])))));
+                const double sc = fma(tol.rtol, fabs(y[i]), tol.atol * tol_scale(i));
+                const double q = err * rcp_rough(sc);
+                en3[aidx(i) % 3] = fma(q, q, en3[aidx(i) % 3]);
+            }
+        const double en = ((en3[0] + en3[1]) + en3[2]) * (hs * hs * (1.0 / 9));
+        const bool finite = en < 1e300;
+        if (en <= 1.0 || !finite) {
+            const double t_new = (last || !finite) ? T : t + hs;
+            // continuous extension of the So component over [t, t + hs]
+            const double r2 = y[iSo] - x[iSo];
+            const double r3 = fma(hs, k1[iSo], -r2);
+            const double r4 = r2 - hs * k2[iSo] - r3;
+            const double r5 = hs * fma(dd.d7, k2[iSo], fma(dd.d6, k6[iSo], fma(dd.d5, k5[iSo], fma(dd.d4, k4[iSo],
+                              fma(dd.d3, k3[iSo], dd.d1 * k1[iSo])))));
+            const double inv_hs = 1.0 / hs;
+            while (p < m) {
+                const double tp = (double)(p + 1) * h_out;
+                if (p + 1 < m ? tp > t_new : t_new < T) break;        // the interval's last point goes with its last step
+                const double th = p + 1 < m ? (tp - t) * inv_hs : 1.0;
+                const double th1 = 1.0 - th;
+                so.set(j0 + p, fma(th, fma(th1, fma(th, fma(th1, r5, r4), r3), r2), x[iSo]));
+                ++p;
+            }
+            t = t_new;
+            xpq = fma(hs, fma(tb.b6, g6, fma(tb.b5, g5, fma(tb.b4, g4, fma(tb.b3, g3, tb.b1 * g1)))), xpq);
+            g1 = g7;
+#pragma unroll
+            for (int i = 0; i < SBR_NX; ++i)
+                if (active(i)) { x[i] = y[i]; k1[i] = k2[i]; }
+        } else {
+            st.n_rej += 1;
+        }
+        float fac = SBR_DP_MAXGROW;
+        if (en > 1e-20) {
+            fac = SBR_DP_SAFETY * pow_m01((float)en);
+            fac = fminf(SBR_DP_MAXGROW, fmaxf(0.2f, fac));
+        }
+        if (en > 1.0) fac = fminf(fac, 1.0f);
+        if (!(last && en <= 1.0)) h = hs * (double)fac;
+        else h = fmax(h, hs * (double)fac);
+    }
+    // an interval given up at the step limit still fills its memory (with the last state): the caller flags the env
+    while (p < m) { so.set(j0 + p, x[iSo]); ++p; }
+    st.h = h;
+    return status;
+}
+
 // One PID-controlled phase on the reference's output grid.  ff: feed-forward cycle (else cycle 0).  kla_carry: in = KLa the
 // phase starts from (cycle 0 only), out = the phase's last feedback KLa.  off = sample offset of the phase in the memories.
 template <int TAIL, int MODE>
@@ -64,19 +186,20 @@ SBR_HD int ilc_phase(double (&x)[SBR_NX], int n_int, int m, double T, double sp,
         const Flow f{x[iV], TAIL == TAIL_REACT ? 0.0 : a.q};
         const double snh0 = x[iSnh], sno0 = x[iSno];
         double xpq = 0.0;
-        for (int s = 0; s < m; ++s) {
-            if (MODE == SBR_MODE_RK4) {
+        if (MODE == SBR_MODE_RK4) {
+            for (int s = 0; s < m; ++s) {
                 rk4_step<TAIL>(x, (double)s * h, h, f, c, a, xpq);
                 st.n_rhs += 4;
-            } else {
-                const Flow fs{f.V((double)s * h), f.q};      // stage times of the solve count from this output point
-                status |= dp45_interval<TAIL>(x, h, fs, c, a, tol, st, xpq);
+                io.so.set(off + 1 + i * m + s, x[iSo]);
             }
-            const int j = off + 1 + i * m + s;
-            io.so.set(j, x[iSo]);
-            if (io.kla_mem.p) {
+        } else {
+            status |= dp45_interval_dense<TAIL>(x, T, m, f, c, a, tol, st, xpq, io.so, off + 1 + i * m);
+        }
+        if (io.kla_mem.p) {
+            for (int s = 0; s < m; ++s) {
                 const int v = off + 9 * i + s + 1;
-                io.kla_mem.set(j, ff ? clip_keep_nan(io.u.get(v) + io.kla_base.get(v), pid.lo, pid.hi) : kla_fb);
+                io.kla_mem.set(off + 1 + i * m + s,
+                               ff ? clip_keep_nan(io.u.get(v) + io.kla_base.get(v), pid.lo, pid.hi) : kla_fb);
             }
         }
         // passive components of the interval (closed forms, see sbr_core.cuh `active`)

@@ -33,6 +33,10 @@ CYCLE0_SETPOINTS = (2.0, 2.0, 2.0)                    # gym_SBR_env0.py:98: DO_s
 ACTION_LOW, ACTION_HIGH = 0.0, 5.0                    # gym_SBR_env0.py:145
 OBS_SCALE = [1.0, 60, 31, 1974, 107, 2237, 195, 988, 2, 4, 14, 3, 5, 12]   # gym_SBR_env0.py:159-172 (state[0] := 1)
 PHASES = (0, 1, 2, 3, 4, 7)                           # schedule index of the six PID-controlled phases
+# Default tolerance of the adaptive cycle: the So memory comes from the stepper's 4th-order continuous extension, whose
+# error is ~10x the step's.  Measured on cycle 0 against LSODA at 1e-12 (tests/test_twin_parity_ilc.py): rtol 1e-8 ->
+# 1.4e-7 g/m3 with 8.6 k right-hand sides, 1e-9 -> 1.0e-8 g/m3 with 11.2 k; the reference's own memory is 6.3e-7 off.
+ILC_RTOL, ILC_ATOL = 1e-9, 1e-11
 
 
 def apply_constants(p):
@@ -117,7 +121,7 @@ def cycle_ilc(x0, influent, sp, params, sched, lay, kla_base=None, u=None, out=N
     pout, l8 = core._dev_ptr(out.out, _abi.ILC_OUT_ROWS, n, name="out")
     pst, _ = core._dev_ptr(out.status, 1, n, dtype=torch.int32, name="status")
     pct, l9 = core._dev_ptr(out.counters, 2, n, dtype=torch.int32, name="counters")
-    tol = tol or _abi.make_tol()
+    tol = tol or _abi.make_tol(ILC_RTOL, ILC_ATOL)
     lds = [l0, l1, l2, l5, l7, l8, l9] + ([l3, l4] if kla_base is not None else []) + ([l6] if out.kla_mem is not None else [])
     ld = core._same_ld(lds, "cycle_ilc")
     t_fill = schedule.T_CYCLE * schedule.T_RATIO[0] if t_fill is None else float(t_fill)

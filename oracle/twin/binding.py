@@ -238,7 +238,7 @@ def cycle_ilc(x0, influent, sp, params, sched, layout, t_fill, kla_base=None, u=
     so_mem = np.zeros((S, n)); kla_mem = np.zeros((S, n)) if want_kla_mem else None
     x_last = np.empty((14, n)); out = np.empty((_abi.ILC_OUT_ROWS, n)); status = np.zeros(n, dtype=np.int32)
     counters = np.zeros((2, n), dtype=np.uint32)
-    tol = tol or _abi.make_tol()
+    tol = tol or _abi.make_tol(1e-9, 1e-11)         # gym_sbr2_b200.ilc.ILC_RTOL / ILC_ATOL
     lib.twin_cycle_ilc.restype = C.c_int
     rc = lib.twin_cycle_ilc(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(influent), _ptr(sp), C.byref(params),
                             C.byref(sched), C.byref(layout), C.c_double(t_fill), _ptr(kla_base), _ptr(u), _ptr(so_mem),

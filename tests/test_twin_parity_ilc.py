@@ -15,9 +15,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilc
 NAMES = ("1", "2", "3", "4", "5", "8")
 T_FILL = schedule.T_CYCLE * schedule.T_RATIO[0]
 # So sits at 1e-6..1e-3 g/m3 in the unaerated phases.  Measured against LSODA at rtol = atol = 1e-12 on cycle 0, the
-# reference's own default-tolerance So memory is up to 6.3e-7 g/m3 (20 % of the value) off, this code 5e-10: the absolute
+# reference's own default-tolerance So memory is up to 6.3e-7 g/m3 (20 % of the value) off, this code 1e-8: the absolute
 # floor below is the reference's distance to its converged solution, and test_so_memory_closer_to_converged... holds
-# the product to 1e-8.
+# the product to 2e-8.
 SO_RTOL, SO_ATOL = 1e-5, 1e-6
 KLA_ATOL = 2e-4            # KLa = Kc e + (Kc/tauI) ie + ...: the feedback KLa inherits So's noise through Kc/tauI = 283
 
@@ -126,7 +126,7 @@ def test_so_memory_closer_to_converged_solution_than_the_reference(g, setup):
     r = twin.cycle_ilc(g["x0"][:, None], g["influent"][:, None], np.array([[2.0], [2.0], [2.0]]), p, sched, lay, T_FILL)
     mine = np.abs(r["so_mem"][:, 0] - so_t).max()
     ref = np.abs(cat(g, "So0_") - so_t).max()
-    assert mine < 1e-8 and mine < 0.05 * ref, (mine, ref)
+    assert mine < 2e-8 and mine < 0.05 * ref, (mine, ref)
     ok, worst = parity.state_close(r["x_last"][:, 0], tight["x_last"], rtol=1e-7)
     assert ok, worst
     # RK4 with one step per output point keeps the end state but not the memory during the So collapse of the fill phase
@@ -134,4 +134,6 @@ def test_so_memory_closer_to_converged_solution_than_the_reference(g, setup):
                         mode=0)
     assert parity.state_close(r4["x_last"][:, 0], tight["x_last"])[0]
     assert np.abs(r4["so_mem"][:, 0] - so_t).max() > 1e-5
-    assert int(r["counters"][0, 0]) > 4 * (lay.n_samples - 6) and int(r4["counters"][0, 0]) == 4 * (lay.n_samples - 6)
+    # the continuous extension fills the memory from ~2-3 steps per PID interval: fewer right-hand sides than one RK4
+    # step per output point
+    assert 8000 < int(r["counters"][0, 0]) < 14000 and int(r4["counters"][0, 0]) == 4 * (lay.n_samples - 6)
