@@ -259,3 +259,22 @@ class SbrIlcVecEnv(object):
                     reward_pinned=False)
         self._next_influent(influent)                            # buffer_tank(0, 12) for the next cycle (:208)
         return self._obs(), o[_abi.ILC_REWARD].clone(), self._done, info
+
+    # -- checkpoint / resume (the reference keeps all of this in module globals and has no resume path) --
+    _CKPT = ("x", "influent", "kla_base", "so_learn", "e_sum", "e_last", "u", "_prev_sp")
+
+    def state_dict(self):
+        from . import vec_env
+        sd = dict(kind="SBR-v0", num_envs=self.num_envs, learn=self.learn, ready=self._ready,
+                  rng_state=vec_env._rng_state(self))
+        sd.update({k: getattr(self, k).clone() for k in self._CKPT})
+        return sd
+
+    def load_state_dict(self, sd):
+        from . import vec_env
+        if sd["kind"] != "SBR-v0" or sd["num_envs"] != self.num_envs:
+            raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
+        for k in self._CKPT:
+            getattr(self, k).copy_(sd[k])
+        self.learn, self._ready = sd["learn"], bool(sd["ready"])
+        vec_env._load_rng_state(self, sd["rng_state"])

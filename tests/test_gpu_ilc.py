@@ -147,3 +147,24 @@ def test_argument_errors(built, cuda_device):
     short = schedule.cycle_schedule(substeps=12)    # more samples than the layout holds
     with pytest.raises(_abi.SbrLibraryError):
         ilc.cycle_ilc(x, infl, sp, p, short, lay)
+
+
+def test_checkpoint_resume_is_bitwise(built, cuda_device):
+    """state_dict() after two steps, two more steps; a fresh env loaded from the checkpoint repeats them bit for bit
+    (controller memories, plant state and the influent stream are all part of the checkpoint)."""
+    n = 64
+    g = torch.Generator(device="cpu").manual_seed(2)
+    acts = [(torch.rand((n, 3), generator=g, dtype=torch.float64) * 4 + 0.5).to(cuda_device) for _ in range(4)]
+    env = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=5, learn="feedback")
+    env.reset()
+    for a in acts[:2]:
+        env.step(a)
+    sd = env.state_dict()
+    ref = [env.step(a) for a in acts[2:]]
+    ref = [(o.clone(), r.clone(), i["x_last"].clone(), i["u_batch"].clone()) for o, r, d, i in ref][-1]
+    env2 = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=99, learn="frozen")
+    env2.load_state_dict(sd)
+    for a in acts[2:]:
+        o, r, d, i = env2.step(a)
+    assert torch.equal(o, ref[0]) and torch.equal(r, ref[1]) and torch.equal(i["x_last"], ref[2])
+    assert torch.equal(i["u_batch"], ref[3])
