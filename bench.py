@@ -522,7 +522,7 @@ def small_batch_leg(torch, device, n=4096):
 
 def ilc_leg(torch, device, n=1 << 16):
     """The batch-to-batch (ILC) feed-forward KLa path of `SBR-v0`: SbrIlcVecEnv.step = sbr_ilc_update (HBM-bound: seven
-    [4769][N] sample rows moved per update) + sbr_cycle_ilc (FP64-bound cycle that stops at every output point of the
+    [4769][N] sample-row moves per update) + sbr_cycle_ilc (FP64-bound cycle that stops at every output point of the
     reference's grid and stores So there).  CUDA events around each launch, three steps averaged."""
     from gym_sbr2_b200 import _abi, ilc
     env = ilc.SbrIlcVecEnv(n, device=device, seed=1, learn="feedback")
@@ -558,7 +558,7 @@ def ilc_leg(torch, device, n=1 << 16):
     return {"envs": n, "samples_per_env": S, "ms_per_step": t_step, "cycle_steps_per_sec": n / t_step * 1e3,
             "update_kernel_ms": t_up, "update_kernel_gbs": 7 * S * n * 8 / t_up / 1e6, "hbm_peak_gbs": _hbm_peak(),
             "cycle_kernel_ms": t_cy, "cycle_rhs_per_env": rhs, "bad_status": bad,
-            "memory_gb": 7 * S * n * 8 / 1e9,
+            "memory_gb": 6 * S * n * 8 / 1e9,
             "note": "integrator: Dormand-Prince per PID interval (rtol 1e-9), So memory from its continuous extension; reward by construction, not pinned"}
 
 

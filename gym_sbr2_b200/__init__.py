@@ -4,7 +4,7 @@
     env = sbr.make("SBR-v2")                    # per-instance Gym env (batch of one on cuda:0)
     vec = sbr.SbrV2VecEnv(1 << 20, "cuda:0")    # the vectorised drop-in: torch CUDA tensors in and out
     (likewise SbrOsVecEnv, SbrV4VecEnv, SbrCntVecEnv(kind, n) for SBROS-v1, SBR-v4, SBRCnt-v0/1/2 / SBRCntMA-v1 / SBROS-v2,
-     SbrIlcVecEnv for the batch-to-batch feed-forward KLa path of SBR-v0)
+     SbrIlcVecEnv for the batch-to-batch feed-forward KLa path of SBR-v0, SbrV1VecEnv for SBR-v1)
 
 Importing the package registers the reference's ten env ids (with gym / gymnasium too when installed).
 """
@@ -21,7 +21,7 @@ def __getattr__(name):
     if name == "SbrCntVecEnv":
         from . import cnt
         return cnt.SbrCntVecEnv
-    if name == "SbrIlcVecEnv":
+    if name in ("SbrIlcVecEnv", "SbrV1VecEnv"):
         from . import ilc
-        return ilc.SbrIlcVecEnv
+        return getattr(ilc, name)
     raise AttributeError(name)

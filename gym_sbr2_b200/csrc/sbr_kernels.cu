@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kBlock) sbr_cycle_ilc_kernel(IlcCycleArgs g, S
     sbr::Loading load{&s_load[threadIdx.x], kBlock};
     const bool ff = g.kla_base != nullptr;
     sbr::IlcIo io;
-    io.so = sbr::Column{g.so_mem + i, g.ld};
+    io.so = sbr::Column{g.so_mem ? g.so_mem + i : nullptr, g.ld};
     io.kla_mem = sbr::Column{g.kla_mem ? g.kla_mem + i : nullptr, g.ld};
     io.kla_base = sbr::Column{ff ? const_cast<double*>(g.kla_base) + i : nullptr, g.ld};
     io.u = sbr::Column{ff ? const_cast<double*>(g.u) + i : nullptr, g.ld};
@@ -1384,7 +1384,7 @@ int sbr_cycle_ilc(int64_t n, int64_t ld, const double* x0, const double* influen
     int rc = check_common(n, ld, p);
     if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: bad mode%s");
     if (rc) return rc;
-    if (!x0 || !influent || !sp || !s || !so_mem || !x_last) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: NULL buffer%s");
+    if (!x0 || !influent || !sp || !s || !x_last) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: NULL buffer%s");
     if ((kla_base == nullptr) != (u == nullptr))
         return fail(SBR_ERR_ARG, "sbr_cycle_ilc: kla_base and u go together (both NULL = cycle 0)%s");
     if (!(t_fill > 0.0)) return fail(SBR_ERR_ARG, "sbr_cycle_ilc: t_fill must be positive%s");

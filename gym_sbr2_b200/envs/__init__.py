@@ -6,11 +6,9 @@ reference (global numpy RNG, buffer_tank3.py:68) -- the influent draw consumes t
 `SbrCnt0`, `SbrCnt1`, `SbrCnt2`, `SbrCntMA1` and `SbrOS1` wrap the CUDA path of the five ids whose reference `step()` dies
 in its reward module (repaired reward, disclosed in oracle/make_golden_cnt.py).  `SbrEnv` (`SBR-v0`) serves the batch-to-batch feed-forward
 KLa path: everything its reference `step()` does before the reward call that cannot run (disclosed in
-oracle/make_golden_ilc.py).  `SbrEnv1` (`SBR-v1`), whose reference `step()` dies on the same call and has nothing of its
-own beyond it, raises UnsupportedEnvError on construction.
+oracle/make_golden_ilc.py).  `SbrEnv1` (`SBR-v1`) is the same plant under the feedback PID alone: its cycle
+(SBR_model_FBc_implemented.run) is served and pinned, its reward call dies in the reference like `SBR-v0`'s.
 """
-from .single import SbrCnt0, SbrCnt1, SbrCnt2, SbrCntMA1, SbrEnv, SbrEnv2, SbrEnv4, SbrOS, SbrOS1, unsupported_class
-
-SbrEnv1 = unsupported_class("SBR-v1")
+from .single import SbrCnt0, SbrCnt1, SbrCnt2, SbrCntMA1, SbrEnv, SbrEnv1, SbrEnv2, SbrEnv4, SbrOS, SbrOS1
 
 __all__ = ["SbrEnv", "SbrEnv1", "SbrEnv2", "SbrEnv4", "SbrCnt0", "SbrCnt1", "SbrCnt2", "SbrCntMA1", "SbrOS", "SbrOS1"]

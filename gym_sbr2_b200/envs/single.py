@@ -3,25 +3,12 @@ import numpy as np
 import torch
 
 from .. import influent as influent_mod
-from ..registration import ENV_TABLE, UnsupportedEnvError
 from ..spaces import Box, env_base
 from ..cnt import SbrCntVecEnv
-from ..ilc import ACTION_HIGH, ACTION_LOW, SbrIlcVecEnv
+from ..ilc import ACTION_HIGH, ACTION_LOW, SbrIlcVecEnv, SbrV1VecEnv
 from ..vec_env import SbrOsVecEnv, SbrV2VecEnv, SbrV4VecEnv
 
 _Base = env_base()
-
-
-def unsupported_class(env_id):
-    cls_name, ref_module, _, why = ENV_TABLE[env_id]
-
-    def __init__(self, *a, **k):
-        raise UnsupportedEnvError(
-            "%s (%s, reference %s) is registered for API compatibility only: %s. It has no working oracle; the "
-            "ids that step in the reference are SBR-v2 and SBROS-v1." % (env_id, cls_name, ref_module, why))
-
-    return type(cls_name, (_Base,), {"__init__": __init__, "metadata": {"render.modes": ["human"]},
-                                     "__doc__": "Unsupported: %s" % why})
 
 
 def _device(device):
@@ -105,6 +92,34 @@ class SbrEnv(_Base):
 
     def render(self, mode="human", close=False):
         print("Reward for this episode: {}".format(self.reward))
+
+
+class SbrEnv1(_Base):
+    """`SBR-v1` (gym_SBR_env1.py:103-203): `SBR-v0`'s plant under its feedback DO-PID alone; one step = one whole cycle
+    (SBR_model_FBc_implemented.run) from the state the previous step ended in; action = DO set-points of phases 3, 5, 8
+    in [0, 5]; obs = the 14 normalised sums x + influent (first entry 1); done = True after every step.
+    As in the reference, `reset()` never moves the plant: the first call returns the observation of the module's initial
+    state, later calls that of the current one.  The reference's `step()` raises on a seven-argument call of the
+    ten-parameter reward (:151); the reward here is that function's formula on the cycle's applied KLa (by construction)."""
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device=None):
+        self.action_space = Box(np.array([0.0, 0.0, 0.0]), np.array([5.0, 5.0, 5.0]), dtype=np.float32)        # :109
+        self.observation_space = Box(low=np.zeros(14), high=np.full(14, 2.0), dtype=np.float32)                # :111
+        self.reward = 0
+        self._vec = SbrV1VecEnv(1, device=_device(device))
+        self.influent_mixed = None
+        self.info = {}
+
+    _draw = SbrEnv._draw
+
+    def reset(self):
+        if self.influent_mixed is None:
+            return self._vec.reset(influent=self._draw())[0].cpu().numpy()
+        return self._vec._obs()[0].cpu().numpy()
+
+    step = SbrEnv.step
+    render = SbrEnv.render
 
 
 class SbrOS(_Base):

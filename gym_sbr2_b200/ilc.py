@@ -93,10 +93,13 @@ def weights(sched, par=PAR_BATCH_PID, t_delta=schedule.T_DELTA):
 
 
 class IlcCycleOut(object):
-    def __init__(self, n, n_samples, device, want_kla_mem=True):
+    """Output buffers of sbr_cycle_ilc.  so_mem / kla_mem may be handed in (the env points them at its own memories so that
+    nothing is copied between the launches); kla_mem=False: the [S][n] KLa profile is not written at all."""
+
+    def __init__(self, n, n_samples, device, so_mem=None, kla_mem=None):
         f = dict(dtype=torch.float64, device=device)
-        self.so_mem = torch.zeros((n_samples, n), **f)
-        self.kla_mem = torch.zeros((n_samples, n), **f) if want_kla_mem else None
+        self.so_mem = None if so_mem is False else (torch.zeros((n_samples, n), **f) if so_mem is None else so_mem)
+        self.kla_mem = None if kla_mem is False else (torch.zeros((n_samples, n), **f) if kla_mem is None else kla_mem)
         self.x_last = torch.empty((_abi.NX, n), **f)
         self.out = torch.empty((_abi.ILC_OUT_ROWS, n), **f)
         self.status = torch.empty((n,), dtype=torch.int32, device=device)
@@ -122,7 +125,8 @@ def cycle_ilc(x0, influent, sp, params, sched, lay, kla_base=None, u=None, out=N
     pst, _ = core._dev_ptr(out.status, 1, n, dtype=torch.int32, name="status")
     pct, l9 = core._dev_ptr(out.counters, 2, n, dtype=torch.int32, name="counters")
     tol = tol or _abi.make_tol(ILC_RTOL, ILC_ATOL)
-    lds = [l0, l1, l2, l5, l7, l8, l9] + ([l3, l4] if kla_base is not None else []) + ([l6] if out.kla_mem is not None else [])
+    lds = [l0, l1, l2, l7, l8, l9] + ([l3, l4] if kla_base is not None else []) + ([l5] if out.so_mem is not None else []) \
+        + ([l6] if out.kla_mem is not None else [])
     ld = core._same_ld(lds, "cycle_ilc")
     t_fill = schedule.T_CYCLE * schedule.T_RATIO[0] if t_fill is None else float(t_fill)
     with torch.cuda.device(x0.device):
@@ -171,7 +175,8 @@ class SbrIlcVecEnv(object):
     num_obs = 14
     scenario = 0
 
-    def __init__(self, num_envs, device="cuda", seed=None, learn="frozen", params=None, rng="philox", env_offset=0):
+    def __init__(self, num_envs, device="cuda", seed=None, learn="frozen", params=None, rng="philox", env_offset=0,
+                 record_feed_forward=False):
         from . import vec_env
         if learn not in ("frozen", "feedback"):
             raise ValueError("learn must be 'frozen' or 'feedback'")
@@ -193,9 +198,15 @@ class SbrIlcVecEnv(object):
         self._sp = torch.zeros((3, n), **f)
         self._sp6 = torch.zeros((6, n), **f)
         self._prev_sp = torch.zeros((3, n), **f)
-        self._cyc = IlcCycleOut(n, S, self.device)
+        # sample memories [S][N] (38 kB per env each).  The cycle kernel writes its So memory into `_so_next` while the
+        # update kernel reads `so_learn`; learn="feedback" swaps the two after every cycle, so nothing is ever copied.
+        # The clamped feed-forward profile the reference returns as Kla_memory (and never reads) is only written on request:
+        # forming it costs two more reads and one more write of a sample row per cycle.
         self.kla_base = torch.zeros((S, n), **f)
         self.so_learn = torch.zeros((S, n), **f)               # the So memory the controller reads
+        self._so_next = torch.zeros((S, n), **f)
+        self.kla_ff = torch.zeros((S, n), **f) if record_feed_forward else None
+        self._cyc = IlcCycleOut(n, S, self.device, so_mem=self._so_next, kla_mem=False)
         self.e_sum = torch.zeros((S, n), **f)
         self.e_last = torch.zeros((S, n), **f)
         self.u = torch.zeros((S, n), **f)
@@ -224,9 +235,10 @@ class SbrIlcVecEnv(object):
         self.x.copy_(torch.tensor(X0_ILC, dtype=torch.float64, device=self.device)[:, None].expand(-1, n))
         for k in range(3):
             self._sp[k] = CYCLE0_SETPOINTS[k]
+        # cycle 0 writes straight into the feed-forward base and the controller's So memory
+        self._cyc.so_mem, self._cyc.kla_mem = self.so_learn, self.kla_base
         cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, out=self._cyc)
-        self.kla_base.copy_(self._cyc.kla_mem)
-        self.so_learn.copy_(self._cyc.so_mem)
+        self._cyc.so_mem, self._cyc.kla_mem = self._so_next, self.kla_ff
         self._prev_sp.copy_(self._sp)
         self.e_sum.zero_(); self.e_last.zero_(); self.u.zero_()
         self.x.copy_(self._cyc.x_last)
@@ -246,17 +258,19 @@ class SbrIlcVecEnv(object):
         scaled = self._prev_sp / self._prev_sp * self._sp
         self._sp6[2], self._sp6[4], self._sp6[5] = scaled[0], scaled[1], scaled[2]
         ilc_update(self.layout, self._w, self._D, self._sp6, self.so_learn, self.e_sum, self.e_last, self.u)
+        self._cyc.so_mem, self._cyc.kla_mem = self._so_next, self.kla_ff
         cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, kla_base=self.kla_base, u=self.u,
                   out=self._cyc)
+        so_written = self._so_next
         if self.learn == "feedback":
-            self.so_learn.copy_(self._cyc.so_mem)
+            self.so_learn, self._so_next = self._so_next, self.so_learn
             self._prev_sp.copy_(self._sp)
         self.x.copy_(self._cyc.x_last)
         o = self._cyc.out
         info = dict(x_last=self._cyc.x_last, status=self._cyc.status, Qeff=o[_abi.ILC_QEFF], Qw=o[_abi.ILC_QW],
                     OCI=o[_abi.ILC_OCI], kla3_mean=o[_abi.ILC_KLA3_MEAN], kla5_mean=o[_abi.ILC_KLA5_MEAN],
-                    kla8_mean=o[_abi.ILC_KLA8_MEAN], so_mem=self._cyc.so_mem, kla_ff=self._cyc.kla_mem, u_batch=self.u,
-                    reward_pinned=False)
+                    kla8_mean=o[_abi.ILC_KLA8_MEAN], so_mem=so_written, kla_ff=self.kla_ff, u_batch=self.u,
+                    counters=self._cyc.counters, reward_pinned=False)
         self._next_influent(influent)                            # buffer_tank(0, 12) for the next cycle (:208)
         return self._obs(), o[_abi.ILC_REWARD].clone(), self._done, info
 
@@ -277,4 +291,80 @@ class SbrIlcVecEnv(object):
         for k in self._CKPT:
             getattr(self, k).copy_(sd[k])
         self.learn, self._ready = sd["learn"], bool(sd["ready"])
+        vec_env._load_rng_state(self, sd["rng_state"])
+
+
+class SbrV1VecEnv(object):
+    """N x `SBR-v1` (gym_SBR_env1.py:103-203): the plant of `SBR-v0` under its feedback DO-PID alone -- every step is one
+    `SBR_model_FBc_implemented.run` (= SBR_model_PID_on.run: each cycle starts from KLa 240, each phase from the previous
+    phase's last KLa), from the state the previous step ended in.
+
+    reset(influent=None) -> obs [N,14] of the module's initial state (no cycle is run, :105-126);
+    step(action [N,3]) -> (obs, reward, done, info): action = DO set-points of phases 3, 5, 8 clipped to [0, 5] (:131).
+    The reference's step() raises on the same seven-argument reward call as `SBR-v0` (:151): the reward here is
+    module_reward.sbr_reward's formula on the cycle's applied KLa, by construction; the cycle is pinned against
+    SBR_model_FBc_implemented.run (tests/golden/ilc_seed0.npz, `v1_*`).  Influent as for SbrIlcVecEnv."""
+
+    num_actions = 3
+    num_obs = 14
+    scenario = 0
+
+    def __init__(self, num_envs, device="cuda", seed=None, params=None, rng="philox", env_offset=0):
+        from . import vec_env
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _abi.SbrLibraryError("SbrV1VecEnv needs a CUDA device: there is no CPU fallback")
+        self.lib = _abi.load()
+        self.params = apply_constants(params if params is not None else _abi.default_params())
+        self.sched = schedule.cycle_schedule()
+        self.layout = layout(self.sched)
+        vec_env._init_rng(self, seed, rng, env_offset)
+        n = self.num_envs
+        f = dict(dtype=torch.float64, device=self.device)
+        self.x = torch.tensor(X0_ILC, **f)[:, None].repeat(1, n).contiguous()
+        self.influent = torch.zeros((_abi.NX, n), **f)
+        self._sp = torch.zeros((3, n), **f)
+        self._cyc = IlcCycleOut(n, int(self.layout.n_samples), self.device, so_mem=False, kla_mem=False)
+        self._obs_scale = torch.tensor(OBS_SCALE, **f)[:, None]
+        self._done = torch.ones((n,), dtype=torch.bool, device=self.device)
+        self._ready = False
+
+    _next_influent = SbrIlcVecEnv._next_influent
+    _obs = SbrIlcVecEnv._obs
+
+    def reset(self, influent=None):
+        self._next_influent(influent)
+        self.influent[0] = FILL_FLOW
+        self.x.copy_(torch.tensor(X0_ILC, dtype=torch.float64, device=self.device)[:, None].expand(-1, self.num_envs))
+        self._ready = True
+        return self._obs()
+
+    def step(self, action, influent=None):
+        if not self._ready:
+            raise RuntimeError("call reset() first")
+        a = torch.as_tensor(action, dtype=torch.float64, device=self.device).reshape(self.num_envs, 3)
+        a = torch.where(a < ACTION_LOW, torch.full_like(a, ACTION_LOW), torch.where(a > ACTION_HIGH, torch.full_like(a, ACTION_HIGH), a))
+        self._sp.copy_(a.t())
+        self.influent[0] = FILL_FLOW
+        cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, out=self._cyc)
+        self.x.copy_(self._cyc.x_last)
+        o = self._cyc.out
+        info = dict(x_last=self._cyc.x_last, status=self._cyc.status, Qeff=o[_abi.ILC_QEFF], Qw=o[_abi.ILC_QW],
+                    OCI=o[_abi.ILC_OCI], kla3_mean=o[_abi.ILC_KLA3_MEAN], kla5_mean=o[_abi.ILC_KLA5_MEAN],
+                    kla8_mean=o[_abi.ILC_KLA8_MEAN], counters=self._cyc.counters, reward_pinned=False)
+        self._next_influent(influent)
+        return self._obs(), o[_abi.ILC_REWARD].clone(), self._done, info
+
+    def state_dict(self):
+        from . import vec_env
+        return dict(kind="SBR-v1", num_envs=self.num_envs, ready=self._ready, x=self.x.clone(),
+                    influent=self.influent.clone(), rng_state=vec_env._rng_state(self))
+
+    def load_state_dict(self, sd):
+        from . import vec_env
+        if sd["kind"] != "SBR-v1" or sd["num_envs"] != self.num_envs:
+            raise ValueError("checkpoint is for %s with %d envs" % (sd["kind"], sd["num_envs"]))
+        self.x.copy_(sd["x"]); self.influent.copy_(sd["influent"])
+        self._ready = bool(sd["ready"])
         vec_env._load_rng_state(self, sd["rng_state"])

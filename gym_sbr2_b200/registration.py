@@ -12,8 +12,8 @@ and users call `gym.make(id)`.  The same ten ids are registered here, under the 
     ten-parameter module_reward.sbr_reward) -- is served for what it computes before that call: the batch-to-batch
     (iterative-learning) feed-forward KLa and the cycle under it, pinned against the reference's own functions
     (oracle/make_golden_ilc.py); its reward is by construction;
-  * `SBR-v1` raises `UnsupportedEnvError` from the constructor, naming the reference's own failure, instead of
-    pretending to work.
+  * `SBR-v1` -- the same plant under the feedback PID alone, whose reference `step()` dies on the same reward call -- is
+    served likewise: its cycle (SBR_model_FBc_implemented.run, unmodified) is pinned, its reward is by construction.
 `gym` / `gymnasium` are optional: when one is importable the ids are registered with it as well (so `gym.make`
 works unchanged); otherwise `gym_sbr2_b200.make(id)` is the equivalent.
 """
@@ -27,8 +27,9 @@ ENV_TABLE = {
     # sub_phases_batchPID_fbPID.py:144; then sbr_reward() arity, gym_SBR_env0.py:203); parity is function by function
     # against batch_PID / SBR_model_PID_on.run / SBR_model_batchPID_fbPID.run, the reward is by construction
     "SBR-v0": ("SbrEnv", "gym_SBR_env0.py", True, None),
-    "SBR-v1": ("SbrEnv1", "gym_SBR_env1.py", False,
-               "reference step() raises TypeError: sbr_reward() arity mismatch (gym_SBR_env1.py:151 vs module_reward.py:4)"),
+    # supported with a disclosure: the reference's step() raises TypeError (sbr_reward() arity, gym_SBR_env1.py:151 vs
+    # module_reward.py:4); the cycle is pinned against SBR_model_FBc_implemented.run, the reward is by construction
+    "SBR-v1": ("SbrEnv1", "gym_SBR_env1.py", True, None),
     "SBR-v2": ("SbrEnv2", "gym_SBR_env2.py", True, None),
     # supported with a disclosure: the reference's step() raises TypeError on numpy >= 1.18 (float `num` in np.linspace,
     # gym_SBR_env4.py:286); parity is against the unmodified source under numpy < 1.18 linspace semantics

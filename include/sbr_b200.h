@@ -524,7 +524,7 @@ enum {
  *     the KLa cycle 0 starts from, biomass_setpoint 5400, WV 1.32, IV 0.66; gym_SBR_env0.py:40-41,89)
  *   t_fill: length of the fill phase in days (Qin = q_in t_fill)
  *   kla_base, u [S][ld] in: KLa memory of cycle 0 and u_batch; both NULL = cycle 0
- *   so_mem [S][ld] out; kla_mem [S][ld] out (may be NULL): cycle 0: feedback KLa per sample (the later kla_base),
+ *   so_mem [S][ld] out (may be NULL: `SBR-v1`, which keeps no memories); kla_mem [S][ld] out (may be NULL): cycle 0: feedback KLa per sample (the later kla_base),
  *     feed-forward cycles: the clamped feed-forward profile the reference returns as Kla_memory
  *   x_last [14][ld] out; out [SBR_ILC_OUT_ROWS][ld] (may be NULL): Qeff, Qw, reward, OCI, mean applied KLa of phases
  *     3 / 5 / 8.  reward / OCI = module_reward.sbr_reward's formula on this cycle's applied KLa -- NOT pinned to the

@@ -118,6 +118,26 @@ def main(out_dir):
         g["env_c%d_Qeff_Qw" % c] = np.array([r[27], r[28]], dtype=float)
         print("env cycle %d: x_last[8..10] %s Qw %.6g max|u3| %.4g" % (c, np.array(r[2])[8:11], r[28],
                                                                      np.abs(u_now[2][-1]).max()), flush=True)
+    # ---- `SBR-v1` (gym_SBR_env1.py): the same plant without the batch-to-batch controller.  Its step() dies on the same
+    # seven-argument reward call (:151); before it, _take_action writes the set-points and _next_observation runs
+    # SBR_model_FBc_implemented.run (= SBR_model_PID_on.run) from the carried-over state.  Unmodified, no shim needed. ----
+    import gym_SBR.envs.gym_SBR_env1 as m1
+    env1 = m1.SbrEnv1()
+    with ref_shim.quiet():
+        g["v1_reset_obs"] = np.array(env1.reset(), dtype=float)
+    g["v1_influent"] = np.array(m1.influent_mixed, dtype=float)
+    x1 = list(m1.x)
+    for c, a in enumerate(actions):
+        a = np.clip(a, env1.action_space.low, env1.action_space.high)
+        m1.influent_mixed[0] = 31.4285
+        with ref_shim.quiet():
+            env1._take_action(a)
+            r = env1._next_observation(m1.WV, m1.IV, m1.t_ratio, m1.influent_mixed, m1.DO_control_par, x1, m1.DO_setpoints)
+        x1 = r[2]                                        # `x = x_last` (gym_SBR_env1.py:158)
+        g["v1_c%d_x_last" % c] = np.array(r[2], dtype=float)
+        g["v1_c%d_Qeff_Qw" % c] = np.array([r[27], r[28]], dtype=float)
+        g["v1_c%d_kla3" % c] = np.array(r[29], dtype=float)
+        print("v1 cycle %d: x_last[8..10] %s Qw %.6g" % (c, np.array(r[2])[8:11], r[28]), flush=True)
     np.savez_compressed(os.path.join(out_dir, "ilc_seed0.npz"), **g)
     print("lengths", [len(t) for t in t_mem])
 

@@ -226,7 +226,7 @@ class CntBatch(object):
 
 
 def cycle_ilc(x0, influent, sp, params, sched, layout, t_fill, kla_base=None, u=None, want_kla_mem=True, mode=1,
-              tol=None):
+              tol=None, want_so_mem=True):
     """x0, influent [14, n]; sp [3, n]; kla_base, u [S, n] or None (cycle 0).  Returns dict of numpy arrays."""
     lib = load()
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -235,7 +235,7 @@ def cycle_ilc(x0, influent, sp, params, sched, layout, t_fill, kla_base=None, u=
     n, S = x0.shape[1], int(layout.n_samples)
     kla_base = None if kla_base is None else np.ascontiguousarray(kla_base, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
-    so_mem = np.zeros((S, n)); kla_mem = np.zeros((S, n)) if want_kla_mem else None
+    so_mem = np.zeros((S, n)) if want_so_mem else None; kla_mem = np.zeros((S, n)) if want_kla_mem else None
     x_last = np.empty((14, n)); out = np.empty((_abi.ILC_OUT_ROWS, n)); status = np.zeros(n, dtype=np.int32)
     counters = np.zeros((2, n), dtype=np.uint32)
     tol = tol or _abi.make_tol(1e-9, 1e-11)         # gym_sbr2_b200.ilc.ILC_RTOL / ILC_ATOL

@@ -342,7 +342,7 @@ int twin_cycle_ilc(int64_t n, int64_t ld, const double* x0, const double* influe
         const double sp8[8] = {0.0, 0.0, sp[i], 0.0, sp[ld + i], 0.0, 0.0, sp[2 * ld + i]};
         const bool ff = kla_base != nullptr;
         IlcIo io;
-        io.so = Column{so_mem + i, ld};
+        io.so = Column{so_mem ? so_mem + i : nullptr, ld};
         io.kla_mem = Column{kla_mem ? kla_mem + i : nullptr, ld};
         io.kla_base = Column{ff ? const_cast<double*>(kla_base) + i : nullptr, ld};
         io.u = Column{ff ? const_cast<double*>(u) + i : nullptr, ld};

@@ -84,7 +84,7 @@ def test_vec_env_closed_loop_matches_the_reference_chain(built, cuda_device, g, 
     the reference's env chain (memories frozen at cycle 0) and of the learning chain."""
     chain = "env" if learn == "frozen" else "learn"
     n = 4
-    env = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=0, learn=learn)
+    env = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=0, learn=learn, record_feed_forward=True)
     infl = np.tile(g["influent"][None, :], (n, 1))
     obs = env.reset(influent=infl)
     # reset observation (gym_SBR_env0.py:150-176): (x_last + influent) / scale, first entry 1
@@ -96,6 +96,8 @@ def test_vec_env_closed_loop_matches_the_reference_chain(built, cuda_device, g, 
         assert ok, (c, worst)
         assert np.allclose(info["u_batch"].cpu().numpy()[:, 0], cat(g, "%s_c%d_u" % (chain, c)), rtol=1e-4, atol=2e-4), c
         assert np.allclose([float(info["Qeff"][0]), float(info["Qw"][0])], g["%s_c%d_Qeff_Qw" % (chain, c)], rtol=1e-5)
+        if chain == "learn":       # the clamped feed-forward profile, written on request only
+            assert np.allclose(info["kla_ff"].cpu().numpy()[:, 2], cat(g, "learn_c%d_Kla" % c), rtol=1e-4, atol=2e-4)
         assert bool(done.all()) and bool(torch.isfinite(reward).all()) and info["reward_pinned"] is False
         assert obs.shape == (n, 14) and float(obs[0, 0]) == 1.0
         assert int(info["status"].abs().sum()) == 0
@@ -168,3 +170,20 @@ def test_checkpoint_resume_is_bitwise(built, cuda_device):
         o, r, d, i = env2.step(a)
     assert torch.equal(o, ref[0]) and torch.equal(r, ref[1]) and torch.equal(i["x_last"], ref[2])
     assert torch.equal(i["u_batch"], ref[3])
+
+
+def test_sbr_v1_vec_env_matches_the_reference_chain(built, cuda_device, g):
+    """SbrV1VecEnv: reset observation of the module's initial state, then three chained feedback-PID cycles
+    (SBR_model_FBc_implemented.run through gym_SBR_env1's own methods) with the module's influent held."""
+    n = 3
+    env = ilc.SbrV1VecEnv(n, device=cuda_device, seed=0)
+    infl = np.tile(g["v1_influent"][None, :], (n, 1))
+    obs = env.reset(influent=infl)
+    assert np.allclose(obs.cpu().numpy()[1], g["v1_reset_obs"], rtol=1e-12)
+    for c, a in enumerate(g["actions"]):
+        obs, reward, done, info = env.step(np.tile(a[None, :], (n, 1)), influent=infl)
+        ok, worst = parity.state_close(info["x_last"].cpu().numpy()[:, 2], g["v1_c%d_x_last" % c], rtol=2e-5)
+        assert ok, (c, worst)
+        assert np.allclose([float(info["Qeff"][0]), float(info["Qw"][0])], g["v1_c%d_Qeff_Qw" % c], rtol=1e-5)
+        assert abs(float(info["kla3_mean"][1]) - g["v1_c%d_kla3" % c][1:].mean()) < 1e-3
+        assert bool(done.all()) and int(info["status"].abs().sum()) == 0 and bool(torch.isfinite(reward).all())

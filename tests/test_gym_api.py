@@ -22,16 +22,15 @@ def test_all_ten_reference_ids_registered_under_reference_class_names():
         assert hasattr(envs, cls)
 
 
-SERVED = ("SBR-v0", "SBR-v2", "SBROS-v1", "SBR-v4", "SBRCnt-v0", "SBRCnt-v1", "SBRCnt-v2", "SBRCntMA-v1", "SBROS-v2")
+SERVED = tuple(REF_IDS)
 
 
-def test_unsupported_ids_name_the_reference_failure():
-    for env_id in REF_IDS:
-        if env_id in SERVED:
-            continue
-        with pytest.raises(sbr.UnsupportedEnvError) as e:
-            sbr.make(env_id)
-        assert "reference step() raises" in str(e.value)
+def test_every_reference_id_is_served_and_disclosures_are_recorded():
+    """All ten ids construct a CUDA-backed env; the table keeps, per id, whether the reference's own step() can run."""
+    assert all(row[2] for row in sbr.ENV_TABLE.values())
+    src = open(os.path.join(os.path.dirname(sbr.__file__), "registration.py")).read()
+    for env_id in ("SBR-v0", "SBR-v1", "SBR-v4", "SBRCnt-v0"):
+        assert re.search(r"supported with a disclosure[^\n]*\n(?:\s*#[^\n]*\n)*\s*\"%s\"" % re.escape(env_id), src), env_id
 
 
 def test_supported_ids_fail_loudly_without_cuda():
@@ -194,3 +193,20 @@ def test_sbr_v0_batch_to_batch_env_through_make(built, cuda_device):
     assert np.abs(u1).max() > 0 and int(env.info["status"]) == 0
     obs2, reward2, _, _ = env.step([7.0, -1.0, 1.5])          # clipped to [0, 5]
     assert np.isfinite(obs2).all() and not np.array_equal(env.info["u_batch"], u1)
+
+
+@pytest.mark.gpu
+def test_sbr_v1_env_through_make(built, cuda_device):
+    """`SBR-v1`: reset() returns the observation of the module's initial state and never moves the plant; step() = one
+    feedback-PID cycle from the carried-over state (gym_SBR_env1.py:105-175).  Numbers are pinned in tests/test_gpu_ilc.py."""
+    env = sbr.make("SBR-v1")
+    assert env.action_space.shape == (3,) and env.observation_space.shape == (14,)
+    np.random.seed(0)
+    obs0 = env.reset()
+    assert obs0.shape == (14,) and obs0[0] == 1.0
+    obs, reward, done, info = env.step([2.0, 2.0, 2.0])
+    assert obs.shape == (14,) and done is True and info == {} and np.isfinite(reward)
+    x1 = env.info["x_last"].copy()
+    assert np.array_equal(env.reset(), obs)                   # reset() does not touch the plant
+    env.step([2.0, 2.0, 2.0])
+    assert not np.array_equal(env.info["x_last"], x1) and int(env.info["status"]) == 0

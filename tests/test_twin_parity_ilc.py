@@ -137,3 +137,23 @@ def test_so_memory_closer_to_converged_solution_than_the_reference(g, setup):
     # the continuous extension fills the memory from ~2-3 steps per PID interval: fewer right-hand sides than one RK4
     # step per output point
     assert 8000 < int(r["counters"][0, 0]) < 14000 and int(r4["counters"][0, 0]) == 4 * (lay.n_samples - 6)
+
+
+def test_sbr_v1_chain_matches_reference(g, setup):
+    """`SBR-v1`: three chained feedback-PID cycles (SBR_model_FBc_implemented.run through the env's own methods) from the
+    module's x0 with the module's influent; no memories are kept (so_mem NULL)."""
+    p, sched, w, D, lay = setup
+    x = g["x0"][:, None]
+    infl = g["v1_influent"].copy()
+    infl[0] = ilc.FILL_FLOW
+    for c, a in enumerate(g["actions"]):
+        r = twin.cycle_ilc(x, infl[:, None], a[:, None], p, sched, lay, T_FILL, want_so_mem=False, want_kla_mem=False)
+        ok, worst = parity.state_close(r["x_last"][:, 0], g["v1_c%d_x_last" % c], rtol=2e-5)
+        assert ok, (c, worst)
+        assert np.allclose(r["out"][:2, 0], g["v1_c%d_Qeff_Qw" % c], rtol=1e-6, atol=1e-9)
+        # mean applied KLa of phase 3 against the reference's per-sample memory (one entry per output point after the first)
+        assert abs(r["out"][4, 0] - g["v1_c%d_kla3" % c][1:].mean()) < 1e-3
+        x = r["x_last"]
+    obs = (g["x0"] + g["v1_influent"]) / np.array(ilc.OBS_SCALE)
+    obs[0] = 1.0
+    assert np.allclose(obs, g["v1_reset_obs"], rtol=1e-12)

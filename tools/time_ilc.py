@@ -27,7 +27,7 @@ for n in (4096, 1 << 15, 1 << 17):
         t_rk4 = e0.elapsed_time(e1)
     S = int(env.layout.n_samples)
     rhs = float(env._cyc.counters[0].double().mean())
-    print("n=%7d  S=%d  update %.3f ms (%.0f GB/s over 7 sample rows)  cycle dp45 %.2f ms (%.3g cycle-steps/s)  cycle rk4-grid %.2f ms  memory %.2f GB"
-          % (n, S, t_up, 7 * S * n * 8 / t_up / 1e6, t_cy, n / t_cy * 1e3, t_rk4, 7 * S * n * 8 / 1e9), flush=True)
+    print("n=%7d  S=%d  update %.3f ms (%.0f GB/s over 7 sample-row moves)  cycle dp45 %.2f ms (%.3g cycle-steps/s)  cycle rk4-grid %.2f ms  memory %.2f GB"
+          % (n, S, t_up, 7 * S * n * 8 / t_up / 1e6, t_cy, n / t_cy * 1e3, t_rk4, 6 * S * n * 8 / 1e9), flush=True)
     del env
     torch.cuda.empty_cache()
