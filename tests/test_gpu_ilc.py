@@ -187,3 +187,24 @@ def test_sbr_v1_vec_env_matches_the_reference_chain(built, cuda_device, g):
         assert np.allclose([float(info["Qeff"][0]), float(info["Qw"][0])], g["v1_c%d_Qeff_Qw" % c], rtol=1e-5)
         assert abs(float(info["kla3_mean"][1]) - g["v1_c%d_kla3" % c][1:].mean()) < 1e-3
         assert bool(done.all()) and int(info["status"].abs().sum()) == 0 and bool(torch.isfinite(reward).all())
+
+
+def test_shards_reproduce_the_single_batch_run_bit_for_bit(built, cuda_device):
+    """the path shards by env index with no collective; per-env influent draws are keyed by the GLOBAL env
+    index, so two shards (env_offset) give exactly what one batch gives, through reset + two steps with drawn influent."""
+    n, cut = 192, 80
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    acts = [(torch.rand((n, 3), generator=gen, dtype=torch.float64) * 4 + 0.5).to(cuda_device) for _ in range(2)]
+    full = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=21, learn="feedback")
+    parts = [ilc.SbrIlcVecEnv(cut, device=cuda_device, seed=21, learn="feedback", env_offset=0),
+             ilc.SbrIlcVecEnv(n - cut, device=cuda_device, seed=21, learn="feedback", env_offset=cut)]
+    o_full = full.reset()
+    o_parts = torch.cat([parts[0].reset(), parts[1].reset()], dim=0)
+    assert torch.equal(o_full, o_parts)
+    for a in acts:
+        of, rf, _, inf_f = full.step(a)
+        res = [parts[0].step(a[:cut]), parts[1].step(a[cut:])]
+        assert torch.equal(of, torch.cat([r[0] for r in res], dim=0))
+        assert torch.equal(rf, torch.cat([r[1] for r in res], dim=0))
+        assert torch.equal(inf_f["u_batch"], torch.cat([r[3]["u_batch"] for r in res], dim=1))
+        assert torch.equal(inf_f["x_last"], torch.cat([r[3]["x_last"] for r in res], dim=1))
