@@ -384,25 +384,36 @@ def influent_mix(switch, rnd, out=None, stream=None):
 _ALL_TABLES = {}
 
 
-def _all_tables(device):
-    """Device copies of all 8 scenario tables: mean, std [8,14,48]."""
+def _all_tables(device, table_set="buffer_tank3"):
+    """Device copies of all 8 scenario tables: mean, std [8,14,48].  table_set="buffer_tank2": the one live branch of
+    buffer_tank2 (`SBR-v0/1`) in slot 0 -- same mean + std * rnd form, so the same sampler kernel serves it."""
     from . import influent as influent_mod
-    key = torch.device(device)
+    key = (torch.device(device), table_set)
     if key not in _ALL_TABLES:
-        t = influent_mod.tables()
-        mean = torch.as_tensor(t["mean"], dtype=torch.float64).contiguous()
-        std = torch.as_tensor(t["std_frac"][:, :, None] * t["mean"], dtype=torch.float64).contiguous()
-        _ALL_TABLES[key] = (mean.to(key), std.to(key))
+        if table_set == "buffer_tank2":
+            m2, s2 = influent_mod.tables_bt2()
+            mean = torch.zeros((8, _abi.NX, influent_mod.N_POINTS), dtype=torch.float64)
+            std = torch.zeros_like(mean)
+            mean[0], std[0] = torch.as_tensor(m2), torch.as_tensor(s2)
+        elif table_set == "buffer_tank3":
+            t = influent_mod.tables()
+            mean = torch.as_tensor(t["mean"], dtype=torch.float64).contiguous()
+            std = torch.as_tensor(t["std_frac"][:, :, None] * t["mean"], dtype=torch.float64).contiguous()
+        else:
+            raise ValueError("unknown influent table set %r" % (table_set,))
+        _ALL_TABLES[key] = (mean.to(key[0]), std.to(key[0]))
     return _ALL_TABLES[key]
 
 
 def influent_sample(n, device, seed, env_offset=0, scenario=0, epoch=None, epoch0=0, mask=None, out=None,
-                    scenario_out=None, stream=None):
+                    scenario_out=None, stream=None, table_set="buffer_tank3"):
     """N independent buffer_tank(scenario) calls (buffer_tank3.py:18-108) with counter-based randomness: the draws
     of env i depend only on (seed, env_offset + i, its episode number) -- see sbr_influent_sample in the header.
     scenario: 0..7 or -1 (drawn per env, SbrEnv4.reset); epoch: optional int64 [n], incremented for drawing envs."""
     lib = _abi.load()
-    mean, std = _all_tables(device)
+    mean, std = _all_tables(device, table_set)
+    if table_set == "buffer_tank2" and int(scenario) != 0:
+        raise ValueError("buffer_tank2 has one live scenario (slot 0)")
     if out is None:
         out = torch.zeros((_abi.NX, n), dtype=torch.float64, device=device)
     po, ld = _dev_ptr(out, _abi.NX, n, name="influent")

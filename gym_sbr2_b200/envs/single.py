@@ -58,8 +58,8 @@ class SbrEnv(_Base):
     `reset()` runs cycle 0, later calls return the current observation without touching the plant.  Deviations, all
     forced by the reference (see gym_sbr2_b200/ilc.py): `step()` there raises before it returns (float linspace counts,
     seven-argument reward call), so the reward is module_reward.sbr_reward's formula on this cycle's applied KLa -- by
-    construction, not pinned; the influent is the package's buffer_tank3 scenario-0 draw on the global numpy RNG, not
-    `buffer_tank2`.  learn="frozen" reproduces the module's behaviour (the controller keeps learning from cycle 0's
+    construction, not pinned.  The influent is buffer_tank2.influent.buffer_tank(0, 12) on the global numpy RNG, bit-exact
+    with the reference for the same np.random.seed (gym_SBR_env0.py:74,208).  learn="frozen" reproduces the module's behaviour (the controller keeps learning from cycle 0's
     memories, :200), learn="feedback" feeds the last cycle's memories back."""
     metadata = {"render.modes": ["human"]}
 
@@ -72,7 +72,7 @@ class SbrEnv(_Base):
         self.info = {}
 
     def _draw(self):
-        self.influent_mixed = influent_mod.sample_numpy(self._vec.scenario)
+        self.influent_mixed = influent_mod.sample_numpy_bt2()
         return torch.as_tensor(self.influent_mixed, dtype=torch.float64)[None, :]
 
     def reset(self):

@@ -6,6 +6,8 @@ sub_phases_PID_on.py (cycle 0), SBR_model_batchPID_fbPID.py / sub_phases_batchPI
 module_reward.sbr_reward, gym_SBR_env0.py:203), so what is reproduced -- and pinned by tests against the reference's own
 functions -- is everything `step()` does before that call: `_take_action` (batch_PID) and `_next_observation` (the cycle).
 The reward returned here is module_reward.sbr_reward's formula on this cycle's applied KLa: by construction, not pinned.
+The influent source of these two envs, buffer_tank2.influent.buffer_tank(0, 12), is gym_sbr2_b200/influent.py's
+`mix_numpy_bt2` (bit-exact) and, on the device, the counter-based sampler with the buffer_tank2 tables.
 
 Host side of the path: the constant tables of the batch-to-batch controller (window weights and their sums, computed
 with the reference's own expressions, mix-ups included), the sample layout, the torch-facing wrappers of the two C
@@ -167,13 +169,15 @@ class SbrIlcVecEnv(object):
     learn: "frozen" (default) = what SbrEnv.step does: its new memories land in local names (:200), so the controller
         learns from cycle 0's So memory for ever; "feedback" = the So / set-point memories of the last cycle are fed back
         (batch-to-batch learning as the module is evidently meant to work; pinned against the same two reference functions).
-    influent: [N,14] tensor (row 0 is overwritten with the fill flow 31.4285, :193) or None = per-env draws of the
-        package's buffer_tank3 scenario-0 generator; the reference's `buffer_tank2` tables are not reproduced.
+    influent: [N,14] tensor (row 0 is overwritten with the fill flow 31.4285, :193) or None = per-env draws of
+        buffer_tank2.influent.buffer_tank(0, 12) (gym_SBR_env0.py:74,208) from the counter-based device sampler (its mixing
+        arithmetic is bit-identical to the reference's for the same normals; rng must be "philox").
     """
 
     num_actions = 3
     num_obs = 14
     scenario = 0
+    influent_tables = "buffer_tank2"
 
     def __init__(self, num_envs, device="cuda", seed=None, learn="frozen", params=None, rng="philox", env_offset=0,
                  record_feed_forward=False):
@@ -191,6 +195,8 @@ class SbrIlcVecEnv(object):
         w, D, self.layout = weights(self.sched)
         f = dict(dtype=torch.float64, device=self.device)
         self._w, self._D = torch.as_tensor(w, **f), torch.as_tensor(D, **f)
+        if rng != "philox":
+            raise ValueError("SbrIlcVecEnv draws its influent from the counter-based sampler only (rng='philox')")
         vec_env._init_rng(self, seed, rng, env_offset)
         n, S = self.num_envs, int(self.layout.n_samples)
         self.x = torch.tensor(X0_ILC, **f)[:, None].repeat(1, n).contiguous()
@@ -308,6 +314,7 @@ class SbrV1VecEnv(object):
     num_actions = 3
     num_obs = 14
     scenario = 0
+    influent_tables = "buffer_tank2"
 
     def __init__(self, num_envs, device="cuda", seed=None, params=None, rng="philox", env_offset=0):
         from . import vec_env
@@ -319,6 +326,8 @@ class SbrV1VecEnv(object):
         self.params = apply_constants(params if params is not None else _abi.default_params())
         self.sched = schedule.cycle_schedule()
         self.layout = layout(self.sched)
+        if rng != "philox":
+            raise ValueError("SbrV1VecEnv draws its influent from the counter-based sampler only (rng='philox')")
         vec_env._init_rng(self, seed, rng, env_offset)
         n = self.num_envs
         f = dict(dtype=torch.float64, device=self.device)

@@ -6,7 +6,8 @@ rnd ~ N(0,1)^48 (std = 0.1*mean for Ss, Xi, Xs, Xbh, Snh, Snd, Xnd and q, 0 for 
 and returns the flow-weighted mean concentrations, `influent_mixed = [0.66, sum(c*q)/sum(q) ...]`
 (buffer_tank3.py:87-107).  Scenario 0 consumes one randn(48) from the RNG, scenarios 1..7 consume two and use
 the second (buffer_tank3.py:206,224).  The mean profiles are data, extracted from the reference by
-oracle/extract_influent_tables.py into data/influent_tables.npz.
+oracle/extract_influent_tables.py into data/influent_tables.npz.  `SBR-v0` / `SBR-v1` draw from buffer_tank2 instead
+(96-point profiles with explicit standard deviations; see `mix_numpy_bt2` below).
 
 `mix_numpy` is bit-exact with the reference (sequential sums, same operation order) and serves the single-env
 Gym wrappers, where "identical seeds" means np.random.seed(s) before reset().  `mix_torch` is the batched
@@ -67,6 +68,47 @@ def sample_numpy_random_scenario(rng=None):
     rng = np.random if rng is None else rng
     switch = int(rng.choice(8, 1)[0])
     return switch, sample_numpy(switch, rng)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# buffer_tank2.influent.buffer_tank(0, 12) -- the influent of `SBR-v0` / `SBR-v1` (gym_SBR_env0.py:74,208).  Its `switch`
+# is drawn and then forced to 1 (buffer_tank2.py:16-18); that branch perturbs 96-point profiles with their own
+# standard-deviation profiles and ONE shared rnd ~ N(0,1)^96 -- the flow with the OPPOSITE sign, q = q_m + q_s (-rnd)
+# (:246-261) -- and returns the flow-weighted means over the first 48 points (hours 0..12 of 24, :264-303).
+# ---------------------------------------------------------------------------------------------------------
+BT2_POINTS = 96
+
+
+def tables_bt2():
+    """(mean [14,48], std [14,48]) of the points buffer_tank2 uses, row 0 = flow with the sign of its perturbation folded
+    into std (so that every row is mean + std * rnd, the form sbr_influent_mix / sbr_influent_sample evaluate)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "influent_tables.npz")
+    z = np.load(path)
+    mean, std = z["bt2_mean"][:, :N_POINTS].copy(), z["bt2_std"][:, :N_POINTS].copy()
+    std[0] = -std[0]
+    return mean, std
+
+
+def mix_numpy_bt2(rnd):
+    """influent_mixed (14-vector, [0] = 0.66) from one rnd[96] (only its first 48 entries matter); bit-exact with the
+    reference (sequential sums, same operation order)."""
+    mean, std = tables_bt2()
+    rnd = np.asarray(rnd, dtype=np.float64)[:N_POINTS]
+    q = mean[0] + (-std[0]) * (-rnd)                # q_m + q_s * (-rnd), buffer_tank2.py:261
+    qsum = np.cumsum(q)[-1]
+    out = np.empty(14)
+    out[0] = 0.66
+    for j in range(1, 14):
+        out[j] = np.cumsum((mean[j] + std[j] * rnd) * q)[-1] / qsum
+    return out
+
+
+def sample_numpy_bt2(rng=None):
+    """One buffer_tank2 call: consumes np.random.choice(2, 1) and randn(96) from `rng` (default: the global numpy RNG, as
+    the reference does) and returns influent_mixed."""
+    rng = np.random if rng is None else rng
+    rng.choice(2, 1)
+    return mix_numpy_bt2(rng.randn(BT2_POINTS))
 
 
 def mix_torch(switch, rnd):

@@ -59,7 +59,8 @@ def _draw_influent(self, mask=None, out=None):
     if self.rng == "philox":
         return core.influent_sample(n, self.device, self.seed, env_offset=self.env_offset, scenario=scn,
                                     epoch=self.epoch, mask=mask, out=out,
-                                    scenario_out=getattr(self, "_scenario_i32", None))
+                                    scenario_out=getattr(self, "_scenario_i32", None),
+                                    table_set=getattr(self, "influent_tables", "buffer_tank3"))
     if scn < 0:
         raise ValueError("per-env scenario draws need rng='philox'")
     if self.rng == "numpy":

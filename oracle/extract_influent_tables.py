@@ -5,6 +5,9 @@ The reference stores eight scenarios (switch 0..7) as literal 48-point mean prof
 flow, a std of 0.1*mean for Ss, Xi, Xs, Xbh, Snh, Snd, Xnd and q (0 for the rest), and draws
 np.random.randn(48) once (switch 0) or twice (switch 1..7, first draw discarded).  Only the numbers are taken
 (parsed from the AST, nothing is executed); the generator itself is re-implemented in gym_sbr2_b200/influent.py.
+
+Also extracted: the one live branch of buffer_tank2.py (`SBR-v0` / `SBR-v1`; `switch` is forced to 1, :18): 96-point
+mean AND standard-deviation profiles per component and for the flow (keys bt2_mean, bt2_std [14, 96]).
 """
 import ast
 import os
@@ -42,6 +45,23 @@ def branch_tables(body):
     return means, stds, draws
 
 
+def buffer_tank2_tables():
+    ref2 = os.path.join(os.path.dirname(REF), "buffer_tank2.py")
+    tree = ast.parse(open(ref2).read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "buffer_tank"][0]
+    node = [n for n in fn.body if isinstance(n, ast.If)][0]
+    assert ast.unparse(node.test) == "switch == 0" and not isinstance(node.orelse[0], ast.If)
+    arr = {}
+    for n in node.orelse:                                  # the `else` branch = switch 1
+        if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Name) and isinstance(n.value, ast.Call) \
+                and getattr(n.value.func, "attr", "") == "array":
+            arr[n.targets[0].id] = np.array(ast.literal_eval(n.value.args[0]), dtype=float)
+    mean = np.stack([arr[name + "_m"] for name in ORDER])
+    std = np.stack([arr[name + "_s"] for name in ORDER])
+    assert mean.shape == (14, 96) and std.shape == (14, 96)
+    return mean, std
+
+
 def main():
     tree = ast.parse(open(REF).read())
     fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "buffer_tank"][0]
@@ -66,7 +86,8 @@ def main():
             frac[k, j] = s[name]
         draws[k] = d
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    np.savez(OUT, mean=mean, std_frac=frac, draws=draws, order=np.array(ORDER))
+    bt2_mean, bt2_std = buffer_tank2_tables()
+    np.savez(OUT, mean=mean, std_frac=frac, draws=draws, order=np.array(ORDER), bt2_mean=bt2_mean, bt2_std=bt2_std)
     print("wrote", OUT, "draws", draws.tolist(), "std fractions", frac[0].tolist())
 
 

@@ -138,6 +138,11 @@ def main(out_dir):
         g["v1_c%d_Qeff_Qw" % c] = np.array([r[27], r[28]], dtype=float)
         g["v1_c%d_kla3" % c] = np.array(r[29], dtype=float)
         print("v1 cycle %d: x_last[8..10] %s Qw %.6g" % (c, np.array(r[2])[8:11], r[28]), flush=True)
+    # ---- the influent source of both envs: three consecutive buffer_tank2.influent.buffer_tank(0, 12) calls on a seeded
+    # global numpy RNG (unmodified) ----
+    from gym_SBR.envs import buffer_tank2
+    np.random.seed(123)
+    g["bt2_seed123_draws"] = np.array([buffer_tank2.influent.buffer_tank(0, 12)[1] for _ in range(3)], dtype=float)
     np.savez_compressed(os.path.join(out_dir, "ilc_seed0.npz"), **g)
     print("lengths", [len(t) for t in t_mem])
 

@@ -208,3 +208,22 @@ def test_shards_reproduce_the_single_batch_run_bit_for_bit(built, cuda_device):
         assert torch.equal(rf, torch.cat([r[1] for r in res], dim=0))
         assert torch.equal(inf_f["u_batch"], torch.cat([r[3]["u_batch"] for r in res], dim=1))
         assert torch.equal(inf_f["x_last"], torch.cat([r[3]["x_last"] for r in res], dim=1))
+
+
+def test_device_sampler_serves_buffer_tank2_bit_for_bit(built, cuda_device):
+    """The counter-based sampler with the buffer_tank2 tables (the influent of SbrIlcVecEnv / SbrV1VecEnv) equals the
+    reference's arithmetic (influent.mix_numpy_bt2, pinned bit-exactly to buffer_tank2 in the CPU suite) on its own normals."""
+    from gym_sbr2_b200 import core, influent
+    n, seed, off = 300, 17, 1000
+    z = core.philox_normals(n, cuda_device, seed, env_offset=off, epoch0=2).cpu().numpy()          # [48, n]
+    got = core.influent_sample(n, cuda_device, seed, env_offset=off, scenario=0, epoch0=2,
+                               table_set="buffer_tank2").cpu().numpy()
+    for i in range(0, n, 37):
+        ref = influent.mix_numpy_bt2(np.concatenate([z[:, i], np.zeros(48)]))
+        assert np.array_equal(got[:, i], ref), i
+    env = ilc.SbrIlcVecEnv(8, device=cuda_device, seed=seed, env_offset=off)
+    env.reset()
+    first = core.influent_sample(8, cuda_device, seed, env_offset=off, scenario=0, epoch0=0, table_set="buffer_tank2")
+    assert torch.equal(env.influent[1:], first[1:]) and float(env.influent[0, 0]) == ilc.FILL_FLOW
+    with pytest.raises(ValueError):
+        core.influent_sample(8, cuda_device, seed, scenario=3, table_set="buffer_tank2")

@@ -157,3 +157,14 @@ def test_sbr_v1_chain_matches_reference(g, setup):
     obs = (g["x0"] + g["v1_influent"]) / np.array(ilc.OBS_SCALE)
     obs[0] = 1.0
     assert np.allclose(obs, g["v1_reset_obs"], rtol=1e-12)
+
+
+def test_buffer_tank2_generator_bit_exact_with_reference(g):
+    """The influent source of `SBR-v0/1`: buffer_tank2.influent.buffer_tank(0, 12) on a seeded global numpy RNG -- same RNG
+    consumption (choice(2, 1), randn(96)), same sums, bit for bit (three consecutive calls)."""
+    from gym_sbr2_b200 import influent
+    np.random.seed(123)
+    mine = np.array([influent.sample_numpy_bt2() for _ in range(3)])
+    assert np.array_equal(mine, g["bt2_seed123_draws"])
+    mean, std = influent.tables_bt2()
+    assert mean.shape == (14, 48) and (std[0] < 0).all() and (std[1] == 0).all()       # flow perturbed with the opposite sign
