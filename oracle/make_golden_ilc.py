@@ -36,9 +36,19 @@ def load_env0(seed):
     return m
 
 
-def main(out_dir):
+# per fixture: the seed of the module-level influent draw and the three actions of the two chains.  Fixture 1 touches the
+# edges of the action box [0, 5]; a zero set-point is only given to the env chain: in the learning chain it makes the NEXT
+# set-point memory 0 / 0 = NaN (gym_SBR_env0.py:251-253) -- covered by a product-side test, not by a reference run
+FIXTURES = {
+    0: (np.array([[2.0, 2.5, 1.5], [1.0, 3.0, 2.0], [3.5, 0.5, 4.0]]), None),
+    1: (np.array([[0.0, 5.0, 0.3], [4.8, 0.05, 5.0], [0.6, 2.2, 0.0]]),
+        np.array([[0.05, 5.0, 0.3], [4.8, 0.05, 5.0], [0.6, 2.2, 0.05]])),
+}
+
+
+def main(out_dir, seed=0):
     import scipy
-    m = load_env0(0)
+    m = load_env0(seed)
     from gym_SBR.envs.module_batch_PID import batch_PID
     from gym_SBR.envs import SBR_model_batchPID_fbPID as SBR
     g = dict(versions=np.array([np.__version__, scipy.__version__, sys.version.split()[0]]))
@@ -56,8 +66,9 @@ def main(out_dir):
         g["So0_" + n] = np.array(s, dtype=float)
         g["sp0_" + n] = np.array(p, dtype=float)
         g["kla0_" + n] = np.array(k, dtype=float)
-    actions = np.array([[2.0, 2.5, 1.5], [1.0, 3.0, 2.0], [3.5, 0.5, 4.0]])
-    g["actions"] = actions
+    actions, actions_learn = FIXTURES[seed]
+    actions_learn = actions if actions_learn is None else actions_learn
+    g["actions"], g["actions_learn"] = actions, actions_learn
 
     def run_cycle(x_last, sp_set, u_rows):
         with ref_shim.quiet():
@@ -70,7 +81,7 @@ def main(out_dir):
     u_rows = [np.zeros((1, len(t))) for t in t_mem]
     so_prev, sp_prev = [np.array(s, dtype=float) for s in so0], [np.array(p, dtype=float) for p in sp0]
     x_last = list(m.x_last)
-    for c, a in enumerate(actions):
+    for c, a in enumerate(actions_learn):
         sp_in = list(sp_prev)
         sp_in[2] = sp_prev[2] / sp_prev[2][0] * a[0]
         sp_in[4] = sp_prev[4] / sp_prev[4][0] * a[1]
@@ -143,9 +154,10 @@ def main(out_dir):
     from gym_SBR.envs import buffer_tank2
     np.random.seed(123)
     g["bt2_seed123_draws"] = np.array([buffer_tank2.influent.buffer_tank(0, 12)[1] for _ in range(3)], dtype=float)
-    np.savez_compressed(os.path.join(out_dir, "ilc_seed0.npz"), **g)
+    np.savez_compressed(os.path.join(out_dir, "ilc_seed%d.npz" % seed), **g)
     print("lengths", [len(t) for t in t_mem])
 
 
 if __name__ == "__main__":
-    main(os.path.join(os.path.dirname(HERE), "tests", "golden"))
+    # one fixture per process: the reference runs its cycle 0 at import
+    main(os.path.join(os.path.dirname(HERE), "tests", "golden"), int(sys.argv[1]) if len(sys.argv) > 1 else 0)

@@ -12,14 +12,15 @@ from oracle.twin import binding as twin
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilc_seed0.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilc_seed%d.npz")
 NAMES = ("1", "2", "3", "4", "5", "8")
 SO_RTOL, SO_ATOL, KLA_ATOL = 1e-5, 1e-6, 2e-4          # see tests/test_twin_parity_ilc.py
 
 
-@pytest.fixture(scope="module")
-def g():
-    return np.load(GOLDEN, allow_pickle=True)
+@pytest.fixture(scope="module", params=[0, 1], ids=["seed0", "seed1_box_edges"])
+def g(request):
+    """Fixture 0: mid-range set-points; fixture 1: another influent draw and set-points at the edges of the action box."""
+    return np.load(GOLDEN % request.param, allow_pickle=True)
 
 
 def cat(g, prefix):
@@ -49,7 +50,7 @@ def test_cycle0_and_feed_forward_cycles_match_reference(built, cuda_device, g):
     assert np.allclose(r0.kla_mem.cpu().numpy()[:, 0], cat(g, "kla0_"), rtol=1e-5, atol=KLA_ATOL)
     assert int(r0.status.abs().sum()) == 0
     for c in range(3):
-        a = g["actions"][c]
+        a = g["actions_learn"][c]
         x_in = g["x_last0"] if c == 0 else g["learn_c%d_x_last" % (c - 1)]
         r = ilc.cycle_ilc(col(x_in, n, cuda_device), col(g["influent"], n, cuda_device), col(a, n, cuda_device), p, sched, lay,
                           kla_base=col(cat(g, "kla0_"), n, cuda_device), u=col(cat(g, "learn_c%d_u" % c), n, cuda_device))
@@ -69,7 +70,7 @@ def test_update_kernel_matches_reference(built, cuda_device, g, chain):
     e_sum = torch.zeros((S, n), dtype=torch.float64, device=cuda_device)
     e_last, u = torch.zeros_like(e_sum), torch.zeros_like(e_sum)
     so = col(cat(g, "So0_"), n, cuda_device)
-    for c, a in enumerate(g["actions"]):
+    for c, a in enumerate(g["actions" if chain == "env" else "actions_learn"]):
         sp6 = col([0, 0, a[0], 0, a[1], a[2]], n, cuda_device)
         ilc.ilc_update(lay, wd, Dd, sp6, so, e_sum, e_last, u)
         assert np.allclose(e_last.cpu().numpy()[:, 1], cat(g, "%s_c%d_E" % (chain, c)), rtol=1e-9, atol=1e-12), c
@@ -89,7 +90,7 @@ def test_vec_env_closed_loop_matches_the_reference_chain(built, cuda_device, g, 
     obs = env.reset(influent=infl)
     # reset observation (gym_SBR_env0.py:150-176): (x_last + influent) / scale, first entry 1
     assert np.allclose(obs.cpu().numpy()[0], g["reset_obs"], rtol=1e-5, atol=1e-7)
-    for c, a in enumerate(g["actions"]):
+    for c, a in enumerate(g["actions" if chain == "env" else "actions_learn"]):
         act = np.tile(a[None, :], (n, 1))
         obs, reward, done, info = env.step(act, influent=infl)
         ok, worst = parity.state_close(info["x_last"].cpu().numpy()[:, 3], g["%s_c%d_x_last" % (chain, c)], rtol=3e-5)
@@ -227,3 +228,22 @@ def test_device_sampler_serves_buffer_tank2_bit_for_bit(built, cuda_device):
     assert torch.equal(env.influent[1:], first[1:]) and float(env.influent[0, 0]) == ilc.FILL_FLOW
     with pytest.raises(ValueError):
         core.influent_sample(8, cuda_device, seed, scenario=3, table_set="buffer_tank2")
+
+
+def test_zero_setpoint_memory_quirk_is_reproduced_and_flagged(built, cuda_device):
+    """gym_SBR_env0.py:251-253 rescales the previous set-point memory, sp_prev / sp_prev[0] * action: once a phase ran
+    with set-point 0, the next memory is 0 / 0 = NaN.  With the last cycle fed back (learn="feedback") that NaN reaches the
+    feed-forward KLa and the state -- here as in the reference's arithmetic -- and the env is flagged instead of raising;
+    with the module's frozen memories (learn="frozen") the previous set-point stays cycle 0's 2.0 and nothing happens."""
+    n = 4
+    a0 = torch.tensor([[0.0, 2.0, 2.0]] * n, dtype=torch.float64, device=cuda_device)
+    a1 = torch.tensor([[1.0, 2.0, 2.0]] * n, dtype=torch.float64, device=cuda_device)
+    for learn, expect_nan in (("feedback", True), ("frozen", False)):
+        env = ilc.SbrIlcVecEnv(n, device=cuda_device, seed=3, learn=learn)
+        env.reset()
+        _, _, _, info = env.step(a0)
+        assert int(info["status"].abs().sum()) == 0 and bool(torch.isfinite(info["x_last"]).all())
+        _, reward, _, info = env.step(a1)
+        nonfinite = (info["status"] & 1).bool()                     # SBR_ST_NONFINITE
+        assert bool(nonfinite.all()) == expect_nan and bool(torch.isnan(info["u_batch"]).any()) == expect_nan
+        assert bool(torch.isfinite(info["x_last"]).all()) != expect_nan

@@ -11,7 +11,7 @@ from gym_sbr2_b200 import ilc, parity, schedule
 from oracle import sbr_oracle_ilc as I
 from oracle.twin import binding as twin
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilc_seed0.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilc_seed%d.npz")
 NAMES = ("1", "2", "3", "4", "5", "8")
 T_FILL = schedule.T_CYCLE * schedule.T_RATIO[0]
 # So sits at 1e-6..1e-3 g/m3 in the unaerated phases.  Measured against LSODA at rtol = atol = 1e-12 on cycle 0, the
@@ -22,9 +22,10 @@ SO_RTOL, SO_ATOL = 1e-5, 1e-6
 KLA_ATOL = 2e-4            # KLa = Kc e + (Kc/tauI) ie + ...: the feedback KLa inherits So's noise through Kc/tauI = 283
 
 
-@pytest.fixture(scope="module")
-def g():
-    return np.load(GOLDEN, allow_pickle=True)
+@pytest.fixture(scope="module", params=[0, 1], ids=["seed0", "seed1_box_edges"])
+def g(request):
+    """Fixture 0: mid-range set-points; fixture 1: another influent draw and set-points at the edges of the action box."""
+    return np.load(GOLDEN % request.param, allow_pickle=True)
 
 
 @pytest.fixture(scope="module")
@@ -75,7 +76,7 @@ def test_batch_to_batch_update_matches_reference(g, setup, chain):
     S = lay.n_samples
     e_sum, e_last = np.zeros((S, 1)), np.zeros((S, 1))
     so = cat(g, "So0_")[:, None]
-    for c, a in enumerate(g["actions"]):
+    for c, a in enumerate(g["actions" if chain == "env" else "actions_learn"]):
         sp6 = np.array([0, 0, a[0], 0, a[1], a[2]], dtype=float)[:, None]
         u = twin.ilc_update(lay, w, D, sp6, so, e_sum, e_last, I.DT, ilc.KC_B, ilc.TAUI_B, ilc.TAUD_B)
         E_ref, u_ref = cat(g, "%s_c%d_E" % (chain, c)), cat(g, "%s_c%d_u" % (chain, c))
@@ -88,7 +89,7 @@ def test_batch_to_batch_update_matches_reference(g, setup, chain):
 @pytest.mark.parametrize("c", [0, 1, 2])
 def test_feed_forward_cycle_matches_reference(g, setup, c):
     p, sched, w, D, lay = setup
-    a = g["actions"][c]
+    a = g["actions_learn"][c]
     x_in = g["x_last0"] if c == 0 else g["learn_c%d_x_last" % (c - 1)]
     r = twin.cycle_ilc(x_in[:, None], g["influent"][:, None], a[:, None], p, sched, lay, T_FILL,
                        kla_base=cat(g, "kla0_")[:, None], u=cat(g, "learn_c%d_u" % c)[:, None])
@@ -109,7 +110,7 @@ def test_closed_loop_three_cycles_against_the_reference_chain(g, setup):
     r0 = twin.cycle_ilc(g["x0"][:, None], g["influent"][:, None], np.array([[2.0], [2.0], [2.0]]), p, sched, lay, T_FILL)
     kla_base, so, x = r0["kla_mem"], r0["so_mem"], r0["x_last"]
     e_sum, e_last = np.zeros((S, 1)), np.zeros((S, 1))
-    for c, a in enumerate(g["actions"]):
+    for c, a in enumerate(g["actions_learn"]):
         sp6 = np.array([0, 0, a[0], 0, a[1], a[2]], dtype=float)[:, None]
         u = twin.ilc_update(lay, w, D, sp6, so, e_sum, e_last, I.DT, ilc.KC_B, ilc.TAUI_B, ilc.TAUD_B)
         r = twin.cycle_ilc(x, g["influent"][:, None], a[:, None], p, sched, lay, T_FILL, kla_base=kla_base, u=u)
