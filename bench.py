@@ -522,44 +522,52 @@ def small_batch_leg(torch, device, n=4096):
 
 def ilc_leg(torch, device, n=1 << 16):
     """The batch-to-batch (ILC) feed-forward KLa path of `SBR-v0`: SbrIlcVecEnv.step = sbr_ilc_update (HBM-bound: seven
-    [4769][N] sample-row moves per update) + sbr_cycle_ilc (FP64-bound cycle that stops at every output point of the
-    reference's grid and stores So there).  CUDA events around each launch, three steps averaged."""
-    from gym_sbr2_b200 import _abi, ilc
+    [4769][N] sample-row moves per update) + sbr_cycle_ilc (FP64-bound cycle that stores So at every output point of the
+    reference's grid).  Three steps; CUDA events around the whole step and, inside the same steps, around each of its two
+    launches (the env's calls are wrapped for the duration of the leg)."""
+    from gym_sbr2_b200 import ilc
     env = ilc.SbrIlcVecEnv(n, device=device, seed=1, learn="feedback")
     env.reset()
     a = torch.rand((n, 3), dtype=torch.float64, device=device, generator=torch.Generator(device=device).manual_seed(5)) * 4 + 0.5
     env.step(a)
     torch.cuda.synchronize()
     S = int(env.layout.n_samples)
-    t_up = t_cy = t_step = 0.0
-    reps = 3
-    for _ in range(reps):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        env._sp.copy_(a.t())
-        env._sp6.zero_()
-        env._sp6[2], env._sp6[4], env._sp6[5] = a.t()[0], a.t()[1], a.t()[2]
-        e[0].record()
-        ilc.ilc_update(env.layout, env._w, env._D, env._sp6, env.so_learn, env.e_sum, env.e_last, env.u)
-        e[1].record()
-        ilc.cycle_ilc(env.x, env.influent, env._sp, env.params, env.sched, env.layout, kla_base=env.kla_base, u=env.u,
-                      out=env._cyc)
-        e[2].record()
+    marks = {"update": [], "cycle": []}
+
+    def timed(fn, key):
+        def wrapper(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kw)
+            e1.record()
+            marks[key].append((e0, e1))
+            return out
+        return wrapper
+
+    orig = ilc.ilc_update, ilc.cycle_ilc
+    ilc.ilc_update, ilc.cycle_ilc = timed(orig[0], "update"), timed(orig[1], "cycle")
+    try:
+        reps, steps = 3, []
+        for _ in range(reps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            env.step(a)
+            s1.record()
+            steps.append((s0, s1))
         torch.cuda.synchronize()
-        t_up += e[0].elapsed_time(e[1]) / reps
-        t_cy += e[1].elapsed_time(e[2]) / reps
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        env.step(a)
-        s1.record()
-        torch.cuda.synchronize()
-        t_step += s0.elapsed_time(s1) / reps
+    finally:
+        ilc.ilc_update, ilc.cycle_ilc = orig
+    mean = lambda ev: sum(e0.elapsed_time(e1) for e0, e1 in ev) / len(ev)
+    t_step, t_up, t_cy = mean(steps), mean(marks["update"]), mean(marks["cycle"])
     rhs = float(env._cyc.counters[0].double().mean())
     bad = int((env._cyc.status != 0).sum())
     return {"envs": n, "samples_per_env": S, "ms_per_step": t_step, "cycle_steps_per_sec": n / t_step * 1e3,
             "update_kernel_ms": t_up, "update_kernel_gbs": 7 * S * n * 8 / t_up / 1e6, "hbm_peak_gbs": _hbm_peak(),
             "cycle_kernel_ms": t_cy, "cycle_rhs_per_env": rhs, "bad_status": bad,
             "memory_gb": 6 * S * n * 8 / 1e9,
-            "note": "integrator: Dormand-Prince per PID interval (rtol 1e-9), So memory from its continuous extension; reward by construction, not pinned"}
+            "note": "integrator: Dormand-Prince per PID interval (rtol 1e-9), So memory from its continuous extension; "
+                    "update / cycle times are measured inside the same three steps as ms_per_step; reward by construction, "
+                    "not pinned"}
 
 
 def rollout_leg(torch, tdist, device, rank, world, args):
