@@ -1142,6 +1142,10 @@ SBR_HD double div_rn(double a, double b) {
 // true if the predicate holds for any env of the warp (CPU twin: for this env).  Used to pick the cheaper
 // react tail when no env of the warp doses carbon: with ec == 0 the EC tail IS the react tail.
 SBR_HD bool warp_any(bool pred) {
+#ifdef SBR_SINGLE_TAIL      // A/B build: always the dosing tail (one stepper instance instead of two, less code to stream):
+                            // measured slower, 0.250 against 0.224 ms per SBROS-v1 step (profiles/r02av_*), not taken
+    return true;
+#endif
 #ifdef __CUDA_ARCH__
     return __any_sync(__activemask(), pred) != 0;
 #else
