@@ -15,7 +15,7 @@ AUX_ROWS = 12
 PERMUTE_MAX = 8
 AUX_NAMES = ("OCI", "Qw", "EQI", "eff_Q", "eff_Ntot", "eff_COD", "eff_Snh", "eff_BOD5", "eff_Sno",
              "kla3_mean", "kla5_mean", "kla8_mean")
-ABI_VERSION = 7
+ABI_VERSION = 8
 # rows of the persistent per-env state of the interval-per-step path (enum SBR_OS_* in include/sbr_b200.h)
 OS_X, OS_T, OS_SO_PREV, OS_SNO_LAST, OS_SNO_PREV, OS_IE_DO, OS_IE_EC, OS_EC_LAST, OS_H, OS_KLA_RING = \
     0, 14, 15, 16, 17, 18, 19, 20, 21, 22
@@ -24,6 +24,8 @@ OS_NOBS, OS_NSTATE = 9, 15
 # rows of one trajectory record (enum SBR_TRAJ_*)
 TRAJ_T, TRAJ_X, TRAJ_KLA, TRAJ_EC, TRAJ_U_DO, TRAJ_U_EC, TRAJ_REWARD, TRAJ_EQI, TRAJ_OCI, TRAJ_AE, TRAJ_ECO, TRAJ_ROWS = \
     0, 1, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24
+# rows of one record of sbr_cycle_v2_traj (enum SBR_TRAJ2_*)
+TRAJ2_T, TRAJ2_X, TRAJ2_KLA, TRAJ2_ROWS = 0, 1, 15, 16
 # rows of the persistent state of the SBR-v4 env (enum SBR_V4_*)
 V4_T, V4_U, V4_SO_PREV, V4_IE, V4_KLA_LAST, V4_KLA_SUM, V4_H, V4_RETURN, V4_STEPS, V4_QW, V4_ROWS = \
     14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24
@@ -108,6 +110,9 @@ _PROTOS = {
     "sbr_params_default": (None, [C.POINTER(SbrParams)]),
     "sbr_cycle_v2": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrSchedule),
                                _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P, _P]),
+    "sbr_cycle_v2_traj_records": (C.c_int, [C.POINTER(SbrSchedule)]),
+    "sbr_cycle_v2_traj": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(SbrParams), C.POINTER(SbrSchedule),
+                                    C.POINTER(C.c_double), _P, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(SbrTol), _P]),
     "sbr_integrate_interval": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int,
                                          C.c_double, C.c_int, C.c_int, C.POINTER(SbrTol), _P, _P]),
     "sbr_rhs": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(SbrParams), C.c_int, _P, _P]),

@@ -84,6 +84,37 @@ def cycle_v2(x0, influent, action, params, sched, out=None, mode=_abi.MODE_RK4, 
     return out
 
 
+def cycle_v2_traj(x0, influent, action, params, sched, t_start, traj=None, out=None, mode=_abi.MODE_RK4, tol=None, stream=None):
+    """sbr_cycle_v2_traj: one whole cycle with a record [t, x[14], KLa] at the end of every PID interval (+ the post-draw
+    state) -- SBR_model_FB.run's `t`, `x` and KLa arrays sampled at the interval ends.  traj [R,16,n]; returns (out, traj)."""
+    lib = _abi.load()
+    n = x0.shape[1]
+    if out is None:
+        out = CycleV2Out(n, x0.device)
+    R = int(lib.sbr_cycle_v2_traj_records(C.byref(sched)))
+    if traj is None:
+        traj = torch.full((R, _abi.TRAJ2_ROWS, n), float("nan"), dtype=torch.float64, device=x0.device)
+    if tuple(traj.shape) != (R, _abi.TRAJ2_ROWS, n) or not traj.is_contiguous() or traj.dtype != torch.float64 or not traj.is_cuda:
+        raise ValueError("traj must be a contiguous CUDA float64 [%d, %d, %d] tensor" % (R, _abi.TRAJ2_ROWS, n))
+    px0, l0 = _dev_ptr(x0, _abi.NX, n, name="x0")
+    pin, l1 = _dev_ptr(influent, _abi.NX, n, name="influent")
+    pac, l2 = _dev_ptr(action, 3, n, name="action")
+    pxl, l3 = _dev_ptr(out.x_last, _abi.NX, n, name="x_last")
+    pob, l4 = _dev_ptr(out.obs, 3, n, name="obs")
+    prw, _ = _dev_ptr(out.reward, 1, n, name="reward")
+    pax, l5 = _dev_ptr(out.aux, _abi.AUX_ROWS, n, name="aux")
+    pst, _ = _dev_ptr(out.status, 1, n, dtype=torch.int32, name="status")
+    pct, l6 = _dev_ptr(out.counters, 2, n, dtype=torch.int32, name="counters")
+    ld = _same_ld([l0, l1, l2, l3, l4, l5, l6, n], "cycle_v2_traj")
+    ts = (C.c_double * _abi.NPHASE)(*[float(v) for v in t_start])
+    tol = tol or _abi.make_tol()
+    with torch.cuda.device(x0.device):
+        rc = lib.sbr_cycle_v2_traj(n, ld, px0, pin, pac, C.byref(params), C.byref(sched), ts, pxl, pob, prw, pax, pst, pct,
+                                   C.c_void_p(traj.data_ptr()), int(mode), C.byref(tol), _stream_ptr(stream))
+    _abi.check(rc, "sbr_cycle_v2_traj")
+    return out, traj
+
+
 def integrate_interval(x, kla, params, tail, T, n_sub, mode=_abi.MODE_RK4, tol=None, ec=None, loading=None,
                        counters=None, stream=None):
     """In-place advance of x [14,n] over one interval (replaces one odeint call, sub_phases_FB.py:252,480)."""

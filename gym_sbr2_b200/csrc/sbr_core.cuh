@@ -1103,6 +1103,97 @@ SBR_HD void cycle_v2(double (&x)[SBR_NX], const double (&action)[3], Loading loa
 }
 
 
+// One SoA column of an env: element j at p[j * stride].
+struct Column {
+    double* p;           // NULL: an output the caller did not ask for (set() is then a no-op)
+    int64_t stride;
+    SBR_HD double get(int j) const { return p[(int64_t)j * stride]; }
+    SBR_HD void set(int j, double v) const { if (p) p[(int64_t)j * stride] = v; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// The same cycle with a TRAJECTORY record (sbr_cycle_v2_traj): what SBR_model_FB.run stacks into its `t`, `x` return
+// values (SBR_model_FB.py:71-86 and the like after every phase) and its kla arrays, sampled at the END of every PID
+// interval: record k = [t, x[14], KLa of the interval], k counting the 528 intervals of phases 1-5 and 8 in order, plus one
+// record for the post-draw state (KLa row 0).  A separate function on purpose: the timed kernels above stay untouched.
+// It always runs interval by interval (pid_phase's form, both integrators) -- the passive components only exist per
+// interval there -- so in adaptive mode its step sequence is not the three-segment kernel's; both agree within the
+// tolerance.  traj: record r, row j at traj.p[(r * SBR_TRAJ2_ROWS + j) * traj.stride].
+// ---------------------------------------------------------------------------------------------------------
+template <int TAIL, int MODE>
+SBR_HD int pid_phase_traj(double (&x)[SBR_NX], int n_int, int n_sub, double T, double sp, double kla_in, const Coef& c,
+                          TailArgs a, const PidA& pid, const SbrTol& tol, Dp45State& st, PhaseOut& out, double t0,
+                          const Column& traj, int& rec) {
+    double bias = kla_in, ie = 0.0, so_prev = 0.0, so_i = x[iSo];
+    double ksum = 0.0, kla = kla_in;
+    int status = 0;
+    for (int i = 0; i < n_int; ++i) {
+        kla = pid_a_update(pid, sp, so_i, so_prev, i == 0, ie, bias);
+        a.kla = kla;
+        status |= integrate_interval<TAIL, MODE>(x, T, n_sub, c, a, tol, st);
+        ksum += kla;
+        so_prev = so_i;
+        so_i = x[iSo];
+        const int base = rec * SBR_TRAJ2_ROWS;
+        traj.set(base + SBR_TRAJ2_T, fma((double)(i + 1), T, t0));
+#pragma unroll
+        for (int j = 0; j < SBR_NX; ++j) traj.set(base + SBR_TRAJ2_X + j, x[j]);
+        traj.set(base + SBR_TRAJ2_KLA, kla);
+        ++rec;
+    }
+    out.kla_sum = ksum;
+    out.kla_last = kla;
+    return status;
+}
+
+template <int MODE>
+SBR_HD void cycle_v2_traj(double (&x)[SBR_NX], const double (&action)[3], Loading load, double q_fill,
+                          const SbrParams& p, const Coef& c, const SbrSchedule& s, const SbrTol& tol, Dp45State& st,
+                          CycleOut& o, const double (&t_start)[SBR_NPHASE], const Column& traj) {
+    PidA pid = make_pid_a(p, c);
+    pid.bypass = (tol.flags & SBR_FLAG_RAW_KLA) != 0;
+    double sp3[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        sp3[j] = clip_keep_nan(action[j], 0.0, 1.0) * (pid.bypass ? p.kla_max : p.action_scale);
+    TailArgs a;
+    a.kla = 0.0; a.q = q_fill; a.ec_conc = 0.0; a.load = load;
+    int status = 0, rec = 0;
+    double kla_mean[3] = {0.0, 0.0, 0.0};
+    DrawOut d;
+    PhaseOut po;
+    status |= pid_phase_traj<TAIL_FILL, MODE>(x, s.n_int[0], s.n_sub[0], s.interval[0], 0.0, p.kla0, c, a, pid, tol, st, po,
+                                              t_start[0], traj, rec);
+    double kla = po.kla_last;
+    a.q = 0.0;
+    for (int j = 0; j < 5; ++j) {
+        const int ph = j < 4 ? j + 1 : 7;
+        if (j == 4) {
+            double sX[10], Xf;
+            settle_closed_form(x, s.settle_time, p.settler_area, p.settler_vmax, sX, Xf);
+            draw_and_waste(x, sX, Xf, p.Qeff, p.biomass_setpoint, d);
+            status |= d.status;
+            // the post-draw state, stamped with the start of the idle phase
+            const int base = rec * SBR_TRAJ2_ROWS;
+            traj.set(base + SBR_TRAJ2_T, t_start[7]);
+#pragma unroll
+            for (int k = 0; k < SBR_NX; ++k) traj.set(base + SBR_TRAJ2_X + k, x[k]);
+            traj.set(base + SBR_TRAJ2_KLA, 0.0);
+            ++rec;
+        }
+        const double sp = j == 1 ? sp3[0] : (j == 3 ? sp3[1] : (j == 4 ? sp3[2] : 0.0));
+        status |= pid_phase_traj<TAIL_REACT, MODE>(x, s.n_int[ph], s.n_sub[ph], s.interval[ph], sp, kla, c, a, pid, tol, st,
+                                                   po, t_start[ph], traj, rec);
+        const double mean = po.kla_sum / (double)s.n_int[ph];
+        if (j < 4) kla = po.kla_last;
+        if (j == 1) kla_mean[0] = mean;
+        if (j == 3) kla_mean[1] = mean;
+        if (j == 4) kla_mean[2] = mean;
+    }
+    cycle_epilogue(x, p, d, kla_mean, status, o);
+}
+
+
 // =========================================================================================================
 // Path B: the interval-per-step env SbrOS (gym_SBR_oneshot.py).  One env.step = one (at phase boundaries two)
 // 72-s PID interval; DO-PID -> KLa in aerobic phases, NO3-PID -> external-carbon flow EC in anoxic phases; the
@@ -1153,13 +1244,6 @@ SBR_HD bool warp_any(bool pred) {
 #endif
 }
 
-// One SoA column of an env: element j at p[j * stride].
-struct Column {
-    double* p;           // NULL: an output the caller did not ask for (set() is then a no-op)
-    int64_t stride;
-    SBR_HD double get(int j) const { return p[(int64_t)j * stride]; }
-    SBR_HD void set(int j, double v) const { if (p) p[(int64_t)j * stride] = v; }
-};
 
 // The env's KLa history (the last 10 entries of the reference's ever-growing `Kla` list) as a CIRCULAR buffer: the
 // entry of the k-th interval since the reset sits in slot k % 10, so that a step writes one slot (two at a phase

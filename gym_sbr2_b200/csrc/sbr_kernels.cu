@@ -217,6 +217,52 @@ __global__ void __launch_bounds__(128) sbr_ilc_update_kernel(IlcUpdateArgs g, Sb
                           sbr::Column{g.e_last + base, g.ld}, sbr::Column{g.u + base, g.ld}, g.Kc, g.KcI, g.KcD);
 }
 
+struct CycleTrajArgs {
+    CycleArgs c;
+    double* traj;
+    double t_start[SBR_NPHASE];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) sbr_cycle_v2_traj_kernel(CycleTrajArgs h, SbrParams p, sbr::Coef c, SbrSchedule s,
+                                                                  SbrTol tol) {
+    __shared__ double s_load[SBR_NX * kBlock];
+    const CycleArgs& g = h.c;
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= g.n) return;
+    double x[SBR_NX], action[3];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) x[k] = g.x0[k * g.ld + i];
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) s_load[k * kBlock + threadIdx.x] = g.influent[k * g.ld + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) action[k] = g.action[k * g.ld + i];
+    sbr::Loading load{&s_load[threadIdx.x], kBlock};
+    sbr::Dp45State st;
+    st.h = s.interval[0] / (double)s.n_sub[0];
+    st.n_rhs = 0;
+    st.n_rej = 0;
+    sbr::CycleOut o;
+    double ts[SBR_NPHASE];
+#pragma unroll
+    for (int k = 0; k < SBR_NPHASE; ++k) ts[k] = h.t_start[k];
+    sbr::cycle_v2_traj<MODE>(x, action, load, load(0), p, c, s, tol, st, o, ts, sbr::Column{h.traj + i, g.ld});
+#pragma unroll
+    for (int k = 0; k < SBR_NX; ++k) g.x_last[k * g.ld + i] = x[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.obs[k * g.ld + i] = o.obs[k];
+    g.reward[i] = o.reward;
+    if (g.aux) {
+#pragma unroll
+        for (int k = 0; k < SBR_AUX_ROWS; ++k) g.aux[k * g.ld + i] = o.aux[k];
+    }
+    if (g.status) g.status[i] = o.status;
+    if (g.counters) {
+        g.counters[i] = st.n_rhs;
+        g.counters[g.ld + i] = st.n_rej;
+    }
+}
+
 struct IntervalArgs {
     int64_t n, ld;
     double* x;
@@ -1359,6 +1405,43 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
     else
         sbr_cycle_v2_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, st>>>(g, *p, c, *s, t);
     return check_launch("sbr_cycle_v2");
+}
+
+int sbr_cycle_v2_traj_records(const SbrSchedule* s) {
+    if (!s) return 0;
+    int r = 1;
+    for (int k = 0; k < SBR_NPHASE; ++k)
+        if (k != 5 && k != 6) r += s->n_int[k];
+    return r;
+}
+
+int sbr_cycle_v2_traj(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
+                      const SbrParams* p, const SbrSchedule* s, const double* t_start, double* x_last, double* obs,
+                      double* reward, double* aux, int32_t* status, uint32_t* counters, double* traj, int mode,
+                      const SbrTol* tol, void* stream) {
+    int rc = check_common(n, ld, p);
+    if (rc) return rc;
+    if (!x0 || !influent || !action || !s || !t_start || !x_last || !obs || !reward || !traj)
+        return fail(SBR_ERR_ARG, "sbr_cycle_v2_traj: NULL buffer%s");
+    if (mode != SBR_MODE_RK4 && mode != SBR_MODE_DP45) return fail(SBR_ERR_ARG, "sbr_cycle_v2_traj: bad mode%s");
+    for (int k = 0; k < SBR_NPHASE; ++k) {
+        if (k == 5 || k == 6) continue;
+        if (s->n_int[k] < 1 || s->n_sub[k] < 1 || !(s->interval[k] > 0))
+            return fail(SBR_ERR_ARG, "sbr_cycle_v2_traj: schedule needs n_int, n_sub >= 1 and interval > 0%s");
+    }
+    CycleTrajArgs h;
+    h.c = CycleArgs{n, ld, x0, influent, action, x_last, obs, reward, aux, status, counters, nullptr};
+    h.traj = traj;
+    for (int k = 0; k < SBR_NPHASE; ++k) h.t_start[k] = t_start[k];
+    const SbrTol t = tol_or_default(tol);
+    const sbr::Coef c = sbr::make_coef(*p);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SBR_MODE_RK4)
+        sbr_cycle_v2_traj_kernel<SBR_MODE_RK4><<<grid, kBlock, 0, st>>>(h, *p, c, *s, t);
+    else
+        sbr_cycle_v2_traj_kernel<SBR_MODE_DP45><<<grid, kBlock, 0, st>>>(h, *p, c, *s, t);
+    return check_launch("sbr_cycle_v2_traj");
 }
 
 static int check_ilc_layout(const SbrIlcLayout* lay, const SbrSchedule* s, const char* who) {

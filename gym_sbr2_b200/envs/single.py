@@ -40,10 +40,22 @@ class SbrEnv2(_Base):
         if self.influent_mixed is None:
             raise RuntimeError("step() before reset()")
         action = np.clip(np.asarray(action, dtype=np.float64), self.action_space.low, self.action_space.high)
+        self._last_action = action
         obs, reward, done, info = self._vec.step(torch.as_tensor(action, dtype=torch.float64)[None, :])
         self.reward = float(reward[0])
         self.info = {k: v[..., 0].cpu().numpy() for k, v in info.items()}
         return obs[0].cpu().numpy(), self.reward, True, {}
+
+    def trajectory(self):
+        """(t, x, kla) of the last step's cycle -- the first two return values of the reference's SBR_model_FB.run (`t`: list
+        of times in days, `x`: [14, len(t)]; SBR_model_FB.py:71-86, 295) sampled at the END of every PID interval (the
+        reference also lists the 8-9 interior output points of each), with the post-draw state at index 492, and the KLa
+        of each interval (the reference's kla3 / kla5 / kla8 are kla[72:295], kla[481:492], kla[493:529])."""
+        if getattr(self, "_last_action", None) is None:
+            raise RuntimeError("trajectory() before step()")
+        tr = self._vec.trajectory(torch.as_tensor(self._last_action, dtype=torch.float64)[None, :])
+        return (tr["t"][:, 0].cpu().numpy().tolist(), tr["x"][:, :, 0].cpu().numpy().T.copy(),
+                tr["kla"][:, 0].cpu().numpy())
 
     def render(self, mode="human", close=False):
         print("Reward for this episode: {}".format(self.reward))

@@ -196,6 +196,21 @@ class SbrV2VecEnv(object):
             info[name] = o.aux[k]
         return o.obs.t(), o.reward, self._done, info
 
+    def trajectory(self, action):
+        """The cycle `step(action)` runs, with its trajectory: what SBR_model_FB.run returns as `t`, `x` (SBR_model_FB.py:71-86)
+        and as its per-interval KLa arrays, sampled at the END of every PID interval of phases 1-5 and 8 (528 records) plus
+        the post-draw state (record 492, KLa 0).  For analysis and plotting, off the timed path (sbr_cycle_v2_traj: 67 kB per
+        env; it runs interval by interval, so in adaptive mode its steps are not the three-segment kernel's -- same results
+        within the tolerance).  Returns dict(t [R,N], x [R,14,N], kla [R,N], x_last [14,N], reward [N], obs [N,3])."""
+        if action.shape != (self.num_envs, 3):
+            raise ValueError("action must be [N,3], got %s" % (tuple(action.shape),))
+        a = action.to(self.device, torch.float64).t().contiguous()
+        t_start = [b[0] for b in schedule.phase_bounds()]
+        out, traj = core.cycle_v2_traj(self.x0, self._loading, a, self.params, self.sched, t_start, mode=self.mode,
+                                       tol=self.tol)
+        return dict(t=traj[:, _abi.TRAJ2_T], x=traj[:, _abi.TRAJ2_X:_abi.TRAJ2_X + _abi.NX], kla=traj[:, _abi.TRAJ2_KLA],
+                    x_last=out.x_last, reward=out.reward, obs=out.obs.t(), status=out.status)
+
     def render(self, mode="human", close=False):
         print("Reward for this episode: {}".format(self._out.reward))
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SBR_ABI_VERSION 7
+#define SBR_ABI_VERSION 8
 #define SBR_NX 14            /* state components per env */
 #define SBR_NPHASE 8         /* phases per cycle (Pons et al. B-SBR protocol) */
 
@@ -184,6 +184,26 @@ int sbr_cycle_v2(int64_t n, int64_t ld, const double* x0, const double* influent
                  const SbrParams* p, const SbrSchedule* s, double* x_last, double* obs, double* reward,
                  double* aux, int32_t* status, uint32_t* counters, int mode, const SbrTol* tol,
                  const int64_t* perm, void* stream);
+
+/*
+ * sbr_cycle_v2 with a trajectory record -- what SBR_model_FB.run returns as `t`, `x` (stacked phase by phase,
+ * SBR_model_FB.py:71-86 ...) and as its per-interval KLa arrays, sampled at the END of every PID interval:
+ *   traj [R][SBR_TRAJ2_ROWS][ld] out, R = sbr_cycle_v2_traj_records(s) = the PID intervals of phases 1-5 and 8 (528 with the
+ *   default schedule) + 1: records 0 .. 491 = phases 1-5 in order, record 492 = the post-draw state (t = start of the idle
+ *   phase, KLa row 0), records 493 .. 528 = the idle phase.  Row SBR_TRAJ2_T = time in days, rows SBR_TRAJ2_X .. +13 = the
+ *   14 state components, row SBR_TRAJ2_KLA = KLa of that interval.
+ *   t_start [8] (host): start time of each phase (phase k starts t_delta after phase k-1 ends, SBR_model_FB.py:92,118,...;
+ *   schedule.phase_bounds()).
+ * A separate, untimed entry point for analysis and plotting (67 kB per env): it runs the cycle interval by interval in
+ * both integrator modes, so in adaptive mode its step sequence differs from sbr_cycle_v2's three-segment kernel (same
+ * results within the tolerance); every other argument as sbr_cycle_v2 (no perm).
+ */
+enum { SBR_TRAJ2_T = 0, SBR_TRAJ2_X = 1, SBR_TRAJ2_KLA = 15, SBR_TRAJ2_ROWS = 16 };
+int sbr_cycle_v2_traj_records(const SbrSchedule* s);
+int sbr_cycle_v2_traj(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
+                      const SbrParams* p, const SbrSchedule* s, const double* t_start, double* x_last, double* obs,
+                      double* reward, double* aux, int32_t* status, uint32_t* counters, double* traj, int mode,
+                      const SbrTol* tol, void* stream);
 
 /*
  * Stage-level entry (unit tests, and the seam where the reference calls odeint): advance n envs over ONE

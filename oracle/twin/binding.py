@@ -261,3 +261,21 @@ def ilc_update(layout, w, D, sp6, so_mem, e_sum, e_last, dt, Kc, tauI, tauD):
                              C.c_double(tauD))
     assert rc == 0
     return u
+
+
+def cycle_v2_traj(x0, influent, action, params, sched, t_start, mode=0, tol=None):
+    """The cycle with its trajectory record: returns dict(x_last, obs, reward, traj [R, 16, n])."""
+    lib = load()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64); influent = np.ascontiguousarray(influent, dtype=np.float64)
+    action = np.ascontiguousarray(action, dtype=np.float64)
+    n = x0.shape[1]
+    R = 1 + sum(sched.n_int[k] for k in range(8) if k not in (5, 6))
+    traj = np.full((R, _abi.TRAJ2_ROWS, n), np.nan)
+    x_last = np.empty((14, n)); obs = np.empty((3, n)); reward = np.empty(n)
+    ts = (C.c_double * 8)(*[float(v) for v in t_start])
+    tol = tol or _abi.make_tol()
+    rc = lib.twin_cycle_v2_traj(C.c_int64(n), C.c_int64(n), _ptr(x0), _ptr(influent), _ptr(action), C.byref(params),
+                                C.byref(sched), ts, _ptr(x_last), _ptr(obs), _ptr(reward), _ptr(traj), C.c_int(mode),
+                                C.byref(tol))
+    assert rc == 0
+    return dict(x_last=x_last, obs=obs, reward=reward, traj=traj)

@@ -379,4 +379,28 @@ int twin_ilc_update(int64_t n, int64_t ld, const SbrIlcLayout* lay, const double
     return 0;
 }
 
+int twin_cycle_v2_traj(int64_t n, int64_t ld, const double* x0, const double* influent, const double* action,
+                       const SbrParams* p, const SbrSchedule* s, const double* t_start, double* x_last, double* obs,
+                       double* reward, double* traj, int mode, const SbrTol* tol) {
+    const Coef c = make_coef(*p);
+    SbrTol t;
+    t.rtol = 1e-8; t.atol = 1e-10; t.max_steps = 200; t.flags = 0;
+    if (tol) t = *tol;
+    for (int64_t i = 0; i < n; ++i) {
+        double x[SBR_NX], a[3], load[SBR_NX], ts[SBR_NPHASE];
+        for (int k = 0; k < SBR_NX; ++k) { x[k] = x0[k * ld + i]; load[k] = influent[k * ld + i]; }
+        for (int k = 0; k < 3; ++k) a[k] = action[k * ld + i];
+        for (int k = 0; k < SBR_NPHASE; ++k) ts[k] = t_start[k];
+        Dp45State st;
+        st.h = s->interval[0] / (double)s->n_sub[0]; st.n_rhs = 0; st.n_rej = 0;
+        CycleOut o;
+        if (mode == SBR_MODE_RK4) cycle_v2_traj<SBR_MODE_RK4>(x, a, Loading{load, 1}, load[0], *p, c, *s, t, st, o, ts, Column{traj + i, ld});
+        else cycle_v2_traj<SBR_MODE_DP45>(x, a, Loading{load, 1}, load[0], *p, c, *s, t, st, o, ts, Column{traj + i, ld});
+        for (int k = 0; k < SBR_NX; ++k) x_last[k * ld + i] = x[k];
+        for (int k = 0; k < 3; ++k) obs[k * ld + i] = o.obs[k];
+        reward[i] = o.reward;
+    }
+    return 0;
+}
+
 }  // extern "C"

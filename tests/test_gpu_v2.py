@@ -314,3 +314,39 @@ def test_config1_4096_envs_random_kla_actions(built, cuda_device, mode):
             assert abs(r[i] - ref["reward"]) <= 1e-5 * abs(ref["reward"]) + 1e-7, i
     with pytest.raises(ValueError):
         SbrV2VecEnv(8, device=cuda_device, action_kind="raw")
+
+
+def test_cycle_trajectory_kernel_matches_reference_run_outputs(built, cuda_device):
+    """sbr_cycle_v2_traj through the C ABI and SbrV2VecEnv.trajectory(): state at the end of every PID interval, post-draw
+    state and per-interval KLa against SBR_model_FB.run's `t`, `x`, kla3 / kla5 / kla8 of the UNMODIFIED reference
+    (tests/golden/sbr_v2_traj_seed0.npz); tolerances as argued in tests/test_twin_parity.py."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sbr_v2_traj_seed0.npz"))
+    n = 5
+    infl = torch.as_tensor(np.tile(g["influent"][:, None], (1, n)), dtype=torch.float64, device=cuda_device)
+    act = torch.as_tensor(np.tile(g["action"][None, :], (n, 1)), dtype=torch.float64, device=cuda_device)
+    for mode, kw, ref, rtol, floor in (("dp45", dict(rtol=1e-9, atol=1e-11), "tight", 1e-6, 1e-9),
+                                       ("dp45", dict(rtol=1e-9, atol=1e-11), "default", 1e-5, 1e-7),
+                                       ("rk4", {}, "default", 1e-5, 1e-6)):
+        env = SbrV2VecEnv(n, device=cuda_device, seed=0, mode=mode, **kw)
+        env.reset(influent=infl)
+        tr = env.trajectory(act)
+        t, x, kla = tr["t"].cpu().numpy(), tr["x"].cpu().numpy(), tr["kla"].cpu().numpy()
+        assert t.shape == (529, n) and x.shape == (529, 14, n) and not np.isnan(x).any()
+        assert np.array_equal(x[:, :, 0], x[:, :, n - 1])
+        ends_x = np.concatenate([x[:492, :, 2], x[493:, :, 2]])
+        ends_t, ends_k = np.concatenate([t[:492, 2], t[493:, 2]]), np.concatenate([kla[:492, 2], kla[493:, 2]])
+        assert np.allclose(ends_t, g[ref + "_t"], rtol=1e-12, atol=1e-15)
+        want = g[ref + "_x"].copy()
+        if mode == "rk4":
+            assert np.allclose(ends_x[:4, 8], want[:4, 8], rtol=2e-3, atol=5e-6)
+            ends_x[:4, 8] = want[:4, 8]
+        ok, worst = parity.state_close(ends_x, want, rtol=rtol, atol_frac=floor)
+        assert ok, (mode, ref, worst)
+        assert parity.state_close(x[492, :, 2], g[ref + "_x_post_draw"], rtol=rtol, atol_frac=floor)[0]
+        for name, lo, hi in (("kla3", 72, 295), ("kla5", 481, 492), ("kla8", 492, 528)):
+            assert np.allclose(ends_k[lo:hi], g[ref + "_" + name], rtol=1e-5, atol=2e-4), (mode, name)
+        # same end state and reward as the timed step of the same env
+        obs, reward, done, info = env.step(act)
+        assert parity.state_close(tr["x_last"].cpu().numpy().T, info["x_last"].cpu().numpy().T, rtol=1e-7)[0]
+        assert np.allclose(tr["reward"].cpu().numpy(), reward.cpu().numpy(), rtol=1e-7)

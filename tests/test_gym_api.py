@@ -210,3 +210,19 @@ def test_sbr_v1_env_through_make(built, cuda_device):
     assert np.array_equal(env.reset(), obs)                   # reset() does not touch the plant
     env.step([2.0, 2.0, 2.0])
     assert not np.array_equal(env.info["x_last"], x1) and int(env.info["status"]) == 0
+
+
+@pytest.mark.gpu
+def test_sbr_v2_trajectory_through_make(built, cuda_device):
+    """SbrEnv2.trajectory(): (t, x, kla) of the last step's cycle in the shapes of SBR_model_FB.run's `t`, `x`."""
+    env = sbr.make("SBR-v2")
+    np.random.seed(0)
+    env.reset()
+    with pytest.raises(RuntimeError):
+        env.trajectory()
+    obs, reward, done, info = env.step([0.25, 0.5, 0.75])
+    t, x, kla = env.trajectory()
+    assert isinstance(t, list) and len(t) == 529 and x.shape == (14, 529) and kla.shape == (529,)
+    assert t[0] > 0 and abs(t[-1] - 0.5) < 1e-2 and all(b >= a for a, b in zip(t, t[1:]))
+    assert np.allclose(x[:, -1], env.info["x_last"], rtol=1e-9)
+    assert abs(kla[72:295].mean() - env.info["kla3_mean"]) < 1e-9 * max(1.0, abs(env.info["kla3_mean"]))
