@@ -199,6 +199,13 @@ class SbrIlcVecEnv(object):
             raise ValueError("SbrIlcVecEnv draws its influent from the counter-based sampler only (rng='philox')")
         vec_env._init_rng(self, seed, rng, env_offset)
         n, S = self.num_envs, int(self.layout.n_samples)
+        # this path is sized by HBM capacity, not by throughput: refuse early instead of running the device out of memory
+        need = (6 + bool(record_feed_forward)) * S * n * 8
+        free, _total = torch.cuda.mem_get_info(self.device)
+        if need > 0.9 * free:
+            raise ValueError("SbrIlcVecEnv(%d envs) needs %.1f GB of sample memories (%d rows of %d samples per env), "
+                             "%.1f GB are free on %s" % (n, need / 1e9, 6 + bool(record_feed_forward), S, free / 1e9,
+                                                         self.device))
         self.x = torch.tensor(X0_ILC, **f)[:, None].repeat(1, n).contiguous()
         self.influent = torch.zeros((_abi.NX, n), **f)
         self._sp = torch.zeros((3, n), **f)

@@ -247,3 +247,10 @@ def test_zero_setpoint_memory_quirk_is_reproduced_and_flagged(built, cuda_device
         nonfinite = (info["status"] & 1).bool()                     # SBR_ST_NONFINITE
         assert bool(nonfinite.all()) == expect_nan and bool(torch.isnan(info["u_batch"]).any()) == expect_nan
         assert bool(torch.isfinite(info["x_last"]).all()) != expect_nan
+
+
+def test_batch_too_large_for_the_device_is_refused_before_allocating(built, cuda_device):
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    n = int(free / (6 * 4769 * 8)) + 4096
+    with pytest.raises(ValueError, match="sample memories"):
+        ilc.SbrIlcVecEnv(n, device=cuda_device, seed=0)
