@@ -225,6 +225,50 @@ def collect_episode_v4_fused(env, policy, K=8, resort_every=2):
     return dict(returns=ret, steps=steps, all_done=all_done, status=status)
 
 
+@torch.no_grad()
+def collect_episode_v4_sorted(env, policy, resort_every=8):
+    """One SBR-v4 episode STEP BY STEP (one policy evaluation and one sbr_v4_step launch per env.step, for policies that
+    cannot move into the fused kernel) with every device buffer of the rollout in SLOT order, as collect_episode_v4_fused
+    keeps them: slots fully re-sorted (single envs) by the last step's RHS count every `resort_every` steps with one
+    sbr_permute_rows of state, loading, observation and done flags.  A policy that maps each env's observation to that
+    env's action does not care in which order the envs come; the slot -> env map is applied to the returns at the end.
+    `policy` needs act_into(obs, None, action) (TinyPolicy) -- any per-env torch expression on obs [14, N] works the same
+    way.  Bit-identical to collect_episode_v4."""
+    from . import _abi
+    env.unsort()
+    env.reset()
+    b = env.buf
+    n, dev = env.num_envs, env.device
+    steps = env.max_episode_steps
+    act = torch.empty((1, n), dtype=torch.float64, device=dev)
+    load = env._loading
+    slot_env = None
+    alt = dict(st=torch.empty_like(b.st), load=torch.empty_like(load), obs=torch.empty_like(b.obs),
+               done=torch.empty((n,), dtype=torch.int32, device=dev))
+    for k in range(steps):
+        policy.act_into(b.obs, None, act)
+        core.v4_step(b, load, act[0], env.params, env.sched, mode=env.mode, tol=env.tol)
+        if resort_every and (k + 1) % resort_every == 0 and k + 1 < steps:
+            perm = torch.argsort(b.counters[0])
+            done32 = b.done.to(torch.int32)
+            core.permute_rows(perm, [(b.st, alt["st"]), (load, alt["load"]), (b.obs, alt["obs"]), (done32, alt["done"])])
+            b.st, alt["st"] = alt["st"], b.st
+            load, alt["load"] = alt["load"], load
+            b.obs, alt["obs"] = alt["obs"], b.obs
+            b.done.copy_(alt["done"].to(torch.uint8))
+            slot_env = perm if slot_env is None else slot_env[perm]
+    ret, all_done, status = b.st[_abi.V4_RETURN].clone(), b.done.bool().all(), b.status
+    if slot_env is not None:
+        out = torch.empty_like(ret)
+        out[slot_env] = ret
+        ret = out
+        core.permute_rows(slot_env, [(b.st, alt["st"]), (b.obs, alt["obs"])], scatter=True)
+        b.st, alt["st"] = alt["st"], b.st
+        b.obs, alt["obs"] = alt["obs"], b.obs
+    env._lockstep = False
+    return dict(returns=ret, steps=steps, all_done=all_done, status=status)
+
+
 def _cnt_policy_obs(env):
     """The observation rows the policy head of a SBRCnt / SBROS-v2 env reads (all of them; os2: obs_DO ++ obs_EC)."""
     o = env.buf.obs

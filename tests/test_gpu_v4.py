@@ -146,3 +146,21 @@ def test_fused_rollout_matches_stepwise_rollout(built, cuda_device, K, resort):
     u = env_f.buf.st[_abi.V4_U]
     assert float(u.min()) >= 0.0 and float(u.max()) <= 8.0 and float(u.max()) > 0.5
     assert torch.equal(env_f.buf.st[_abi.V4_U], env_s.buf.st[_abi.V4_U])
+
+
+@pytest.mark.parametrize("resort", [4, 32])
+def test_slot_ordered_stepwise_rollout_is_bit_identical(built, cuda_device, resort):
+    """collect_episode_v4_sorted: one policy launch and one sbr_v4_step per env.step with every buffer in slot order and a
+    full re-sort every few steps -- the same kernel on the same per-env inputs in another order: identical bits, in env
+    order again at the end."""
+    from gym_sbr2_b200 import rollout
+    n = 777
+    policy = rollout.TinyPolicy(cuda_device, n_in=14, lo=(-0.1,), span=(0.4,), seed=3)
+    env_s = SbrV4VecEnv(n, device=cuda_device, seed=21)
+    step = rollout.collect_episode_v4(env_s, policy)
+    env_s.unsort()
+    env_o = SbrV4VecEnv(n, device=cuda_device, seed=21)
+    srt = rollout.collect_episode_v4_sorted(env_o, policy, resort_every=resort)
+    assert bool(srt["all_done"]) and srt["steps"] == 493 and int(srt["status"].max()) == 0
+    assert torch.equal(step["returns"], srt["returns"])
+    assert torch.equal(env_o.buf.st, env_s.buf.st) and torch.equal(env_o.buf.obs, env_s.buf.obs)
