@@ -191,7 +191,7 @@ class SbrIlcVecEnv(object):
         self.lib = _abi.load()
         self.learn = learn
         self.params = apply_constants(params if params is not None else _abi.default_params())
-        self.sched = schedule.cycle_schedule()                 # the reference's output grid: one RK4 step per sample
+        self.sched = schedule.cycle_schedule()                 # the reference's output grid: one memory sample per point
         w, D, self.layout = weights(self.sched)
         f = dict(dtype=torch.float64, device=self.device)
         self._w, self._D = torch.as_tensor(w, **f), torch.as_tensor(D, **f)
