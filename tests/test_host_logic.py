@@ -72,6 +72,9 @@ def test_struct_layouts_match_header(built):
     assert fields == [f for f, _ in _abi.SbrParams._fields_]
     assert C.sizeof(_abi.SbrSchedule) == 8 * 4 + 8 * 4 + 8 * 8 + 8
     assert C.sizeof(_abi.SbrTol) == 24
+    assert C.sizeof(_abi.SbrIlcLayout) == 13 * 4
+    body = re.search(r"typedef struct SbrIlcLayout \{(.*?)\} SbrIlcLayout;", text, flags=re.S).group(1)
+    assert [m for m in re.findall(r"int32_t\s+(\w+)", body)] == [f for f, _ in _abi.SbrIlcLayout._fields_]
     body = re.search(r"typedef struct SbrOsSchedule \{(.*?)\} SbrOsSchedule;", text, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
@@ -114,6 +117,18 @@ def test_argument_errors_are_reported_without_gpu(built):
     assert rc == -1 and b"NULL" in lib.sbr_last_error()
     with pytest.raises(_abi.SbrLibraryError):
         _abi.check(rc, "sbr_cycle_v2")
+    # the batch-to-batch and trajectory entry points validate before they launch, too
+    from gym_sbr2_b200 import ilc
+    lay = ilc.layout(s)
+    rc = lib.sbr_cycle_ilc(4, 4, None, None, None, C.byref(p), C.byref(s), C.byref(lay), 0.021, None, None, None, None,
+                           None, None, None, None, 1, None, None)
+    assert rc == -1 and b"NULL" in lib.sbr_last_error()
+    rc = lib.sbr_ilc_update(4, 2, C.byref(lay), None, None, None, None, None, None, None, 1e-4, 1.0, 0.25, 0.1, None)
+    assert rc == -1 and b"ld" in lib.sbr_last_error()
+    assert lib.sbr_cycle_v2_traj_records(C.byref(s)) == 529
+    rc = lib.sbr_cycle_v2_traj(4, 4, None, None, None, C.byref(p), C.byref(s), None, None, None, None, None, None, None,
+                               None, 0, None, None)
+    assert rc == -1 and b"NULL" in lib.sbr_last_error()
 
 
 def test_no_cpu_fallback_in_product():
