@@ -10,8 +10,8 @@ oracle/extract_influent_tables.py into data/influent_tables.npz.  `SBR-v0` / `SB
 (96-point profiles with explicit standard deviations; see `mix_numpy_bt2` below).
 
 `mix_numpy` is bit-exact with the reference (sequential sums, same operation order) and serves the single-env
-Gym wrappers, where "identical seeds" means np.random.seed(s) before reset().  `mix_torch` is the batched
-device version used by the vector envs (same formula, parallel reduction order -> ~1e-16 relative).
+Gym wrappers, where "identical seeds" means np.random.seed(s) before reset().  The vector envs draw on the device
+(sbr_influent_sample / sbr_influent_mix, same arithmetic in the same order).
 """
 import os
 
@@ -109,21 +109,3 @@ def sample_numpy_bt2(rng=None):
     rng = np.random if rng is None else rng
     rng.choice(2, 1)
     return mix_numpy_bt2(rng.randn(BT2_POINTS))
-
-
-def mix_torch(switch, rnd):
-    """Batched device version: rnd [n, 48] (torch, float64) -> influent_mixed SoA [14, n]."""
-    import torch
-    t = tables()
-    mean = torch.as_tensor(t["mean"][int(switch)], dtype=torch.float64, device=rnd.device)          # [14,48]
-    std = torch.as_tensor(t["std_frac"][int(switch)][:, None] * t["mean"][int(switch)], dtype=torch.float64,
-                          device=rnd.device)
-    n = rnd.shape[0]
-    out = torch.empty((14, n), dtype=torch.float64, device=rnd.device)
-    out[0] = 0.66
-    q = mean[0][None, :] + std[0][None, :] * rnd                 # [n,48]
-    qsum = q.sum(dim=1)
-    for j in range(1, 14):
-        c = mean[j][None, :] + std[j][None, :] * rnd
-        out[j] = (c * q).sum(dim=1) / qsum
-    return out

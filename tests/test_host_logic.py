@@ -38,15 +38,6 @@ def test_influent_draw_counts():
     assert [influent.draws_per_reset(k) for k in range(8)] == [1, 2, 2, 2, 2, 2, 2, 2]
 
 
-def test_influent_torch_matches_numpy():
-    import torch
-    rnd = torch.randn(7, 48, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
-    for sw in range(8):
-        a = influent.mix_torch(sw, rnd).numpy()
-        b = np.stack([influent.mix_numpy(sw, r.numpy()) for r in rnd], axis=1)
-        assert np.allclose(a, b, rtol=1e-13, atol=0)
-
-
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "sbr_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
