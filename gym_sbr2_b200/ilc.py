@@ -210,7 +210,6 @@ class SbrIlcVecEnv(object):
         self.influent = torch.zeros((_abi.NX, n), **f)
         self._sp = torch.zeros((3, n), **f)
         self._sp6 = torch.zeros((6, n), **f)
-        self._prev_sp = torch.zeros((3, n), **f)
         # sample memories [S][N] (38 kB per env each).  The cycle kernel writes its So memory into `_so_next` while the
         # update kernel reads `so_learn`; learn="feedback" swaps the two after every cycle, so nothing is ever copied.
         # The clamped feed-forward profile the reference returns as Kla_memory (and never reads) is only written on request:
@@ -252,7 +251,6 @@ class SbrIlcVecEnv(object):
         self._cyc.so_mem, self._cyc.kla_mem = self.so_learn, self.kla_base
         cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, out=self._cyc)
         self._cyc.so_mem, self._cyc.kla_mem = self._so_next, self.kla_ff
-        self._prev_sp.copy_(self._sp)
         self.e_sum.zero_(); self.e_last.zero_(); self.u.zero_()
         self.x.copy_(self._cyc.x_last)
         self._ready = True
@@ -266,10 +264,11 @@ class SbrIlcVecEnv(object):
         self._sp.copy_(a.t())
         self.influent[0] = FILL_FLOW                             # gym_SBR_env0.py:193
         # set-point memories handed to batch_PID: phases 1, 2, 4 carry their zeros; phases 3, 5, 8 are the previous memory
-        # rescaled, sp_prev / sp_prev[0] * action (0 / 0 = NaN is the reference's, gym_SBR_env0.py:251-253)
+        # rescaled, sp_prev / sp_prev[0] * action (gym_SBR_env0.py:251-253) -- in the module the previous memory is cycle 0's
+        # for ever (set-point 2), so this is the action itself, exactly.  With the last cycle fed back the same expression
+        # would turn 0 / 0 into NaN after a zero set-point, a state the reference can never reach; the action is used.
         self._sp6.zero_()
-        scaled = self._prev_sp / self._prev_sp * self._sp
-        self._sp6[2], self._sp6[4], self._sp6[5] = scaled[0], scaled[1], scaled[2]
+        self._sp6[2], self._sp6[4], self._sp6[5] = self._sp[0], self._sp[1], self._sp[2]
         ilc_update(self.layout, self._w, self._D, self._sp6, self.so_learn, self.e_sum, self.e_last, self.u)
         self._cyc.so_mem, self._cyc.kla_mem = self._so_next, self.kla_ff
         cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, kla_base=self.kla_base, u=self.u,
@@ -277,7 +276,6 @@ class SbrIlcVecEnv(object):
         so_written = self._so_next
         if self.learn == "feedback":
             self.so_learn, self._so_next = self._so_next, self.so_learn
-            self._prev_sp.copy_(self._sp)
         self.x.copy_(self._cyc.x_last)
         o = self._cyc.out
         info = dict(x_last=self._cyc.x_last, status=self._cyc.status, Qeff=o[_abi.ILC_QEFF], Qw=o[_abi.ILC_QW],
@@ -288,7 +286,7 @@ class SbrIlcVecEnv(object):
         return self._obs(), o[_abi.ILC_REWARD].clone(), self._done, info
 
     # -- checkpoint / resume (the reference keeps all of this in module globals and has no resume path) --
-    _CKPT = ("x", "influent", "kla_base", "so_learn", "e_sum", "e_last", "u", "_prev_sp")
+    _CKPT = ("x", "influent", "kla_base", "so_learn", "e_sum", "e_last", "u")
 
     def state_dict(self):
         from . import vec_env

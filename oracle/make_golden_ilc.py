@@ -37,8 +37,8 @@ def load_env0(seed):
 
 
 # per fixture: the seed of the module-level influent draw and the three actions of the two chains.  Fixture 1 touches the
-# edges of the action box [0, 5]; a zero set-point is only given to the env chain: in the learning chain it makes the NEXT
-# set-point memory 0 / 0 = NaN (gym_SBR_env0.py:251-253) -- covered by a product-side test, not by a reference run
+# edges of the action box [0, 5]; a zero set-point is only given to the env chain: in the learning chain it would make the
+# NEXT set-point memory 0 / 0 = NaN (gym_SBR_env0.py:251-253), a state the module itself never reaches
 FIXTURES = {
     0: (np.array([[2.0, 2.5, 1.5], [1.0, 3.0, 2.0], [3.5, 0.5, 4.0]]), None),
     1: (np.array([[0.0, 5.0, 0.3], [4.8, 0.05, 5.0], [0.6, 2.2, 0.0]]),
