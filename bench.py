@@ -561,10 +561,26 @@ def ilc_leg(torch, device, n=1 << 16):
     t_step, t_up, t_cy = mean(steps), mean(marks["update"]), mean(marks["cycle"])
     rhs = float(env._cyc.counters[0].double().mean())
     bad = int((env._cyc.status != 0).sum())
+    del env
+    torch.cuda.empty_cache()
+    # `SBR-v1`: the same plant under the feedback PID alone (the cycle kernel without feed-forward and without memories)
+    v1 = ilc.SbrV1VecEnv(n, device=device, seed=1)
+    v1.reset()
+    v1.step(a)
+    torch.cuda.synchronize()
+    v1_steps = []
+    for _ in range(reps):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        v1.step(a)
+        s1.record()
+        v1_steps.append((s0, s1))
+    torch.cuda.synchronize()
+    t_v1 = mean(v1_steps)
     return {"envs": n, "samples_per_env": S, "ms_per_step": t_step, "cycle_steps_per_sec": n / t_step * 1e3,
             "update_kernel_ms": t_up, "update_kernel_gbs": 7 * S * n * 8 / t_up / 1e6, "hbm_peak_gbs": _hbm_peak(),
             "cycle_kernel_ms": t_cy, "cycle_rhs_per_env": rhs, "bad_status": bad,
-            "memory_gb": 6 * S * n * 8 / 1e9,
+            "memory_gb": 6 * S * n * 8 / 1e9, "sbr_v1_ms_per_step": t_v1, "sbr_v1_cycle_steps_per_sec": n / t_v1 * 1e3,
             "note": "integrator: Dormand-Prince per PID interval (rtol 1e-9), So memory from its continuous extension; "
                     "update / cycle times are measured inside the same three steps as ms_per_step; reward by construction, "
                     "not pinned"}
