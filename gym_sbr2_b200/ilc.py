@@ -321,8 +321,11 @@ class SbrV1VecEnv(object):
     scenario = 0
     influent_tables = "buffer_tank2"
 
-    def __init__(self, num_envs, device="cuda", seed=None, params=None, rng="philox", env_offset=0):
+    def __init__(self, num_envs, device="cuda", seed=None, params=None, rng="philox", env_offset=0, order="action"):
         from . import vec_env
+        if order not in ("action", "none"):
+            raise ValueError("order must be 'action' or 'none'")
+        self.order, self._sorted = order, None
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -361,12 +364,30 @@ class SbrV1VecEnv(object):
         a = torch.where(a < ACTION_LOW, torch.full_like(a, ACTION_LOW), torch.where(a > ACTION_HIGH, torch.full_like(a, ACTION_HIGH), a))
         self._sp.copy_(a.t())
         self.influent[0] = FILL_FLOW
-        cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, out=self._cyc)
-        self.x.copy_(self._cyc.x_last)
-        o = self._cyc.out
-        info = dict(x_last=self._cyc.x_last, status=self._cyc.status, Qeff=o[_abi.ILC_QEFF], Qw=o[_abi.ILC_QW],
+        c = self._cyc
+        if self.order == "action" and self.num_envs > 32:
+            # divergence-aware order, as SbrV2VecEnv: this env keeps no per-env memories, so its data can be handed to the
+            # adaptive kernel sorted by set-point (one coalesced gather in, one scatter out; results are unaffected)
+            if self._sorted is None:
+                f = dict(dtype=torch.float64, device=self.device)
+                self._sorted = dict(x=torch.empty_like(self.x), influent=torch.empty_like(self.influent),
+                                    sp=torch.empty_like(self._sp),
+                                    out=IlcCycleOut(self.num_envs, int(self.layout.n_samples), self.device, so_mem=False,
+                                                    kla_mem=False))
+            z = self._sorted
+            a0, a1 = self._sp[0] / ACTION_HIGH, self._sp[1] / ACTION_HIGH
+            perm = torch.argsort(torch.floor(a0 * 255.999) + 0.999 * a1)
+            core.permute_rows(perm, [(self.x, z["x"]), (self.influent, z["influent"]), (self._sp, z["sp"])])
+            zo = cycle_ilc(z["x"], z["influent"], z["sp"], self.params, self.sched, self.layout, out=z["out"])
+            core.permute_rows(perm, [(zo.x_last, c.x_last), (zo.out, c.out), (zo.status, c.status),
+                                     (zo.counters, c.counters)], scatter=True)
+        else:
+            cycle_ilc(self.x, self.influent, self._sp, self.params, self.sched, self.layout, out=c)
+        self.x.copy_(c.x_last)
+        o = c.out
+        info = dict(x_last=c.x_last, status=c.status, Qeff=o[_abi.ILC_QEFF], Qw=o[_abi.ILC_QW],
                     OCI=o[_abi.ILC_OCI], kla3_mean=o[_abi.ILC_KLA3_MEAN], kla5_mean=o[_abi.ILC_KLA5_MEAN],
-                    kla8_mean=o[_abi.ILC_KLA8_MEAN], counters=self._cyc.counters, reward_pinned=False)
+                    kla8_mean=o[_abi.ILC_KLA8_MEAN], counters=c.counters, reward_pinned=False)
         self._next_influent(influent)
         return self._obs(), o[_abi.ILC_REWARD].clone(), self._done, info
 

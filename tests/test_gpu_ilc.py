@@ -252,3 +252,18 @@ def test_batch_too_large_for_the_device_is_refused_before_allocating(built, cuda
     n = int(free / (6 * 4769 * 8)) + 4096
     with pytest.raises(ValueError, match="sample memories"):
         ilc.SbrIlcVecEnv(n, device=cuda_device, seed=0)
+
+
+def test_sbr_v1_ordered_launch_is_bit_identical(built, cuda_device):
+    """SbrV1VecEnv hands its envs to the adaptive kernel sorted by set-point (gather in, scatter out): same bits as the
+    launch in caller order, over chained cycles with drawn influent."""
+    n = 500
+    gen = torch.Generator(device="cpu").manual_seed(8)
+    acts = [(torch.rand((n, 3), generator=gen, dtype=torch.float64) * 5).to(cuda_device) for _ in range(3)]
+    a, b = ilc.SbrV1VecEnv(n, device=cuda_device, seed=4, order="action"), ilc.SbrV1VecEnv(n, device=cuda_device, seed=4, order="none")
+    assert torch.equal(a.reset(), b.reset())
+    for act in acts:
+        oa, ra, _, ia = a.step(act)
+        ob, rb, _, ib = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ia["x_last"], ib["x_last"])
+        assert torch.equal(ia["counters"], ib["counters"]) and torch.equal(ia["status"], ib["status"])
